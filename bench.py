@@ -1,0 +1,255 @@
+#!/usr/bin/env python3
+"""bench.py — agent-days/s of covid19abm.jl's simulation path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference (oracle port)
+
+Workload (config.workload): BASELINE.json configs[1] — an ensemble of the 10,000-agent x 500-day Ontario
+scenario with isolation on (fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3, tpreiso=0), 1000 replicates per GPU
+(weak scaling: replicates are independent, sharded over ranks with no data-path collective; one end-of-run
+NCCL gather of the summary curves). A step = one full pass of the hot path (main(ip) :104-142 for every
+replicate of the batch: initialize, seed, 500 x (dyntrans, time_update + snapshot), reductions).
+
+`value` is device time (CUDA events on the library's stream) with parameters and seeds already resident;
+`e2e` goes through the public API from host parameter structs to host result buffers (curves + scalars as
+runsim returns them, :77-101), copies included. The Julia reference cannot run in this image (no julia):
+the CPU arm is the C restatement in oracle/ ("port"), one replicate per core on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_AGENTS, T_DAYS = 10000, 500
+WORKLOAD = "configs[1]: Ontario beta=0.0345, 10000 agents x 500 days, isolation on (fmild=0.5 taumild=1 fsevere=1.0 fpreiso=0.3 tpreiso=0)"
+CFG = dict(β=0.0345, prov="ontario", initialinf=1, modeltime=T_DAYS, popsize=N_AGENTS,
+           fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3, tpreiso=0)
+METRIC, UNIT = "agent_days_per_sec", "agent-days/s"
+
+
+def seeds_for(step, rank, nrep):
+    base = 1 + (step * 64 + rank) * 100000
+    return [726 * (base + i) for i in range(nrep)]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_sample(nrep, threads):
+    """Times the oracle port (oracle/abm_oracle.c) on `nrep` replicates of the workload with `threads` workers."""
+    import oracle_api as O
+    from test_gpu_parity import to_oracle
+    import covid19abm_b200 as cv
+    p = to_oracle(O, cv.ModelParameters(**CFG))
+    seeds = seeds_for(0, 999, nrep)
+    t0 = time.perf_counter()
+    O.run_ensemble([p], [0] * nrep, seeds, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return nrep * N_AGENTS * T_DAYS / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path. Julia is absent from the image, so this is
+    the oracle port (kind "port"), all host threads, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nrep = max(threads, 16)
+    for _ in range(args.warmup):
+        cpu_sample(min(nrep, threads), threads)
+    tot = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_sample(nrep, threads)
+        tot += dt
+    value = args.steps * nrep * N_AGENTS * T_DAYS / tot
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32/i16 integer state, u32 Philox", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "replicates_per_step": nrep, "note": "CPU restatement of covid19abm.jl in C (oracle/), not Julia: no julia binary in the image"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{nrep} replicates per step, one per thread"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU per step")
+    ap.add_argument("--no-hmatrix", action="store_true", help="do not keep the state matrices in HBM (curves only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import covid19abm_b200 as cv
+
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    R = args.replicates
+    ip = cv.ModelParameters(**CFG)
+    pop = cv.Population(R, N_AGENTS, T_DAYS, store_hmatrix=not args.no_hmatrix, device=local)
+    shape = (R, 6, T_DAYS, 12)
+    pin_inc, pin_prev = cv.PinnedArray(shape, np.int32), cv.PinnedArray(shape, np.int32)
+    units = R * N_AGENTS * T_DAYS                      # agent-days per step per GPU
+
+    for w in range(args.warmup):
+        pop.configure(ip, seeds_for(1000 + w, rank, R))
+        pop.run()
+    pop.check_errors()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- value: device-resident, CUDA-event time of exactly K steps
+    barrier()
+    l0 = pop.launch_count
+    dev_ms, t0 = 0.0, time.perf_counter()
+    for k in range(args.steps):
+        pop.configure(ip, seeds_for(k, rank, R))       # seeds + thresholds: ~10 KB, resident before the timed run
+        pop.run(sync=False)
+        dev_ms += pop.last_run_ms                      # events recorded on the library's stream around the run
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    launches = pop.launch_count - l0
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    # ---- e2e: host params -> host curves/scalars through the public API, copies inside the timed region
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        pop.configure(ip, seeds_for(100 + k, rank, R))
+        pop.run(sync=False)
+        pop.curves(pin_inc.array, pin_prev.array)
+        sc = pop.scalars()
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h2d = R * 8 + R * 4 + 280 + 4 * T_DAYS * 8
+    d2h = 2 * int(np.prod(shape)) * 4 + R * (32 + 8 + 8 + 4)
+    assert (sc["err"] == 0).all()
+
+    # ---- end-of-run gather of the summary curves (the path's only collective): mean prevalence per day/state
+    mean_prev = torch.from_numpy(pin_prev.array[:, 0].astype(np.float64).mean(axis=0)).cuda()
+    if dist is not None:
+        gathered = [torch.empty_like(mean_prev) for _ in range(world)] if rank == 0 else None
+        dist.gather(mean_prev, gathered, dst=0)
+    attack = float(1.0 - pin_prev.array[:, 0, -1, 0].mean() / N_AGENTS)
+
+    # ---- per-kernel-class device time of one more (profiled) step -> roofline of the dominant kernel
+    pop.set_profiling(True)
+    pop.configure(ip, seeds_for(200, rank, R))
+    pop.run()
+    prof = pop.profile()
+    pop.set_profiling(False)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    # algorithmic bytes per agent-day of time_update in this layout: status 4 r + expday 2 r + hmatrix 2 w
+    tu_bytes = (6 + (0 if args.no_hmatrix else 2)) * R * N_AGENTS
+    kernels = {}
+    for name, (ms, n) in prof.items():
+        kernels[name] = {"ms_per_step": round(ms, 3), "launches": n, "avg_us": round(1e3 * ms / n, 2) if n else None}
+    dom = max(("dyntrans", "time_update"), key=lambda k: prof[k][0])
+    tu_ms, tu_n = prof["time_update"]
+    tu_gbs = tu_bytes / (tu_ms / tu_n * 1e-3) / 1e9 if tu_n else 0.0
+    kernels["time_update"]["algorithmic_GBps"] = round(tu_gbs, 1)
+    kernels["time_update"]["frac_of_hbm_peak"] = round(tu_gbs / peak, 4)
+    roofline = {"kernel": "k_time_update", "bound": "hbm", "achieved": round(tu_gbs, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(tu_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                "bytes_per_agent_day": tu_bytes / (R * N_AGENTS), "dominant_by_time": "k_" + dom + ("_exact" if dom == "dyntrans" else ""),
+                "note": "time_update is the HBM-streaming per-agent kernel; dyntrans is a latency-bound gather/scatter (see kernels)"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        nrep = max(2 * threads, 32)
+        v, dt = cpu_sample(nrep, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{nrep} replicates of the same workload, one per thread, {dt:.1f} s wall (C restatement of the reference, not Julia)"}
+
+    if rank == 0:
+        value = world * units * args.steps / (dev_ms * 1e-3)
+        e2e = world * units * args.steps / (e2e_ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32/i16 integer state, u32 Philox", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "replicates_per_gpu": R, "replicates_per_sec": world * R * args.steps / (dev_ms * 1e-3),
+                           "mode": "exact (bit-identical to the sequential reference order)", "hmatrix_in_hbm": not args.no_hmatrix,
+                           "l2": "inputs larger than L2: >=0.3 GB of agent state + 10 GB state matrix per step, rebuilt every step",
+                           "wall_ms_per_step": wall_ms / args.steps, "attack_rate_mean": attack},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] int32 x2 and per-replicate scalars (runsim :77-101), pinned host buffers"},
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    pop.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

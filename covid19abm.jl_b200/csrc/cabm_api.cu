@@ -1,0 +1,499 @@
+// cabm_api.cu — the C ABI of include/cabm.h: handle, parameter validation, the day loop of main (:104-142).
+// No CPU fallback: every entry point that computes needs the CUDA device the handle was created on.
+#include "../../include/cabm.h"
+#include "cabm_kernels.h"
+#include "cabm_tables.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace cabm;
+
+static_assert((int)CABM_UNDEF == (int)UNDEF && (int)CABM_DED == (int)DED, "HEALTH codes");
+
+struct cabm_handle {
+    int device = 0, R = 0, N = 0, Np = 0, T = 0, flags = 0;
+    int n_rep = 0, n_psets = 0, mode = 0, day = 1, any_ct = 0, configured = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Dev S{};
+    std::vector<void *> allocs;
+    DevPset *d_psets = nullptr; unsigned long long *d_beta = nullptr; int psets_cap = 0;
+    int *d_scratch = nullptr;          // 4*N ints for peeks
+    int64_t launches = 0;
+    bool ran = false;
+    // optional per-kernel-class timing (cabm_set_profiling): events around every launch of the next cabm_run
+    int profiling = 0;
+    std::vector<cudaEvent_t> pev; std::vector<int> pcls; size_t pev_used = 0;
+    float prof_ms[CABM_N_KCLASS] = {0}; int prof_n[CABM_N_KCLASS] = {0};
+    std::string err;
+};
+
+static std::string g_create_err;
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+            return CABM_E_CUDA;                                                                        \
+        }                                                                                              \
+    } while (0)
+
+static int fail(cabm_handle *h, int code, const std::string &msg) { h->err = msg; return code; }
+
+extern "C" const char *cabm_last_error(const cabm_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+extern "C" const char *cabm_version(void) { return "covid19abm-b200 0.1 (sm_100a)"; }
+
+template <class Tp> static cudaError_t dalloc(cabm_handle *h, Tp **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp) > 0 ? count * sizeof(Tp) : 16);
+    if (e == cudaSuccess) { h->allocs.push_back(q); *p = (Tp *)q; }
+    return e;
+}
+
+static ConstTables make_const_tables() {
+    const Tables &t = tables();
+    ConstTables c;
+    memset(&c, 0, sizeof c);
+    auto put = [](const Table &s, uint32_t *dst, int cap, int &len, int &base) {
+        len = (int)s.thr.size(); base = s.base;
+        for (int i = 0; i < len && i < cap; ++i) dst[i] = s.thr[i];
+    };
+    put(t.lat, c.lat_thr, 4, c.lat_len, c.lat_base); put(t.pre, c.pre_thr, 4, c.pre_len, c.pre_base);
+    put(t.asy, c.asy_thr, 40, c.asy_len, c.asy_base); put(t.inf, c.inf_thr, 40, c.inf_len, c.inf_base);
+    put(t.psi, c.psi_thr, 12, c.psi_len, c.psi_base); put(t.mu, c.mu_thr, 8, c.mu_len, c.mu_base);
+    for (int g = 0; g < 5; ++g) c.nb_len[g] = (int)t.nb[g].thr.size();
+    // move_to_inf :535-537 — Uniform(a,b) draws are a + (b-a)*rand()
+    const double hlo[5] = {0.02, 0.02, 0.28, 0.28, 0.60}, hhi[5] = {0.03, 0.03, 0.34, 0.34, 0.68};
+    const double clo[5] = {0.01, 0.01, 0.03, 0.05, 0.05}, chi[5] = {0.015, 0.015, 0.05, 0.20, 0.15};
+    const double mh_inf[5] = {0.01 / 5, 0.01 / 5, 0.0135 / 3, 0.01225 / 1.5, 0.04 / 2};
+    const double mh_hos[5] = {0.01 * 2, 0.01 * 2, 0.0135, 0.01225, 0.03 * 2};          // :585
+    for (int g = 0; g < 5; ++g) {
+        c.hlo[g] = hlo[g]; c.hspan[g] = hhi[g] - hlo[g]; c.clo[g] = clo[g]; c.cspan[g] = chi[g] - clo[g];
+        c.mh_inf_thr[g] = bernoulli_threshold(mh_inf[g]);
+        c.mh_hos_thr[g] = bernoulli_threshold(mh_hos[g]);
+        c.mh_icu_thr[g] = bernoulli_threshold(2 * mh_hos[g]);                           // :586
+    }
+    c.ct3_lat_thr = bernoulli_threshold(0.05); c.ct3_pre_thr = bernoulli_threshold(0.95); c.ct3_asymp_thr = bernoulli_threshold(0.70);
+    return c;
+}
+
+extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, int popsize, int modeltime, int flags) {
+    if (!out || max_replicates < 1 || popsize < 1 || modeltime < 1 || modeltime > 1000) {
+        g_create_err = popsize == 0 ? "no population size given" : "cabm_create: bad argument";
+        return CABM_E_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_err = std::string("cabm_create: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") + "); there is no CPU fallback";
+        return CABM_E_CUDA;
+    }
+    cabm_handle *h = new cabm_handle();
+    h->device = device; h->R = max_replicates; h->N = popsize; h->Np = (popsize + 31) / 32 * 32; h->T = modeltime; h->flags = flags;
+    auto bail = [&](cudaError_t er, const char *what) {
+        g_create_err = std::string("cabm_create: ") + what + ": " + cudaGetErrorString(er);
+        cabm_destroy(h);
+        return CABM_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "event");
+    Dev &S = h->S;
+    S.R = h->R; S.N = h->N; S.Np = h->Np; S.T = h->T; S.store_hm = (flags & CABM_STORE_HMATRIX) ? 1 : 0; S.nwords = h->Np / 32;
+    S.ct_cap = 0;
+    const size_t A = (size_t)h->R * h->Np, W = (size_t)h->R * S.nwords, C = (size_t)h->R * 6 * h->T * 12;
+#define DA(ptr, count) if ((e = dalloc(h, &(ptr), (count))) != cudaSuccess) return bail(e, #ptr)
+    DA(S.status, A); DA(S.expday, A); DA(S.entry, A); DA(S.dur, A); DA(S.sickfrom, A); DA(S.isovia, A);
+    DA(S.latday, A); DA(S.tracestart, A); DA(S.traceend, A); DA(S.tracedxp, A); DA(S.ct_head, A);
+    DA(S.mark_pre, W); DA(S.mark_post, W); DA(S.infmask, W); DA(S.ct_cnt, (size_t)h->R);
+    DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8);
+    DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);
+    DA(S.totalmet, (size_t)h->R); DA(S.totalinf, (size_t)h->R);
+    DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R);
+    if (S.store_hm) DA(S.hm, (size_t)h->R * h->T * h->N);
+    DA(h->d_scratch, (size_t)4 * h->N);
+    // shared tables
+    {
+        const Tables &t = tables();
+        std::vector<uint32_t> nb(5 * 256, 0xFFFFFFFFu);
+        std::vector<uint8_t> guide(5 * 256, 0);
+        std::vector<unsigned long long> gpw(5 * 256, 0);
+        for (int g = 0; g < 5; ++g) {
+            const auto &thr = t.nb[g].thr;
+            if (thr.size() > 255) return bail(cudaErrorInvalidValue, "negative-binomial table too long");
+            for (size_t k = 0; k < thr.size(); ++k) nb[g * 256 + k] = thr[k];
+            for (int b = 0; b < 256; ++b) {
+                uint32_t wmin = (uint32_t)b << 24; int k = 0;
+                while (k < (int)thr.size() && thr[k] <= wmin) ++k;
+                guide[g * 256 + b] = (uint8_t)k;
+            }
+            for (int cnt = 0; cnt < 256; ++cnt) {
+                int o[5]; gpw_split(g + 1, cnt, o);
+                unsigned long long v = 0;
+                for (int q = 0; q < 5; ++q) v |= (unsigned long long)(o[q] & 0xFF) << (8 * q);
+                gpw[g * 256 + cnt] = v;
+            }
+        }
+        uint32_t *d_nb; uint8_t *d_guide; unsigned long long *d_gpw;
+        DA(d_nb, nb.size()); DA(d_guide, guide.size()); DA(d_gpw, gpw.size());
+        cudaMemcpy(d_nb, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_guide, guide.data(), guide.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_gpw, gpw.data(), gpw.size() * 8, cudaMemcpyHostToDevice);
+        S.nb_thr = d_nb; S.nb_guide = d_guide; S.gpw = d_gpw;
+        ConstTables c = make_const_tables();
+        upload_const_tables(c, h->stream);
+        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(e, "table upload");
+    }
+#undef DA
+    *out = h;
+    return CABM_OK;
+}
+
+extern "C" void cabm_destroy(cabm_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->d_psets) cudaFree(h->d_psets);
+    if (h->d_beta) cudaFree(h->d_beta);
+    if (h->S.ct_log) cudaFree(h->S.ct_log);
+    for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// td_seasonality :204-215
+static void td_seasonality(int T, std::vector<double> &out) {
+    out.resize(T);
+    double mn = 0, mx = 0;
+    for (int t = 1; t <= T; ++t) {
+        double v = 6.261 + -11.81 * std::cos((80 - t) * 0.022) + 1.817 * std::sin((80 - t) * 0.022);
+        out[t - 1] = v;
+        if (t == 1 || v < mn) mn = v;
+        if (t == 1 || v > mx) mx = v;
+    }
+    for (int t = 0; t < T; ++t) out[t] = (out[t] - 2.5 * mn) / (mx - mn);
+}
+
+extern "C" int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_psets, const int32_t *pset_of_rep,
+                              int n_rep, const uint64_t *seeds, int mode) {
+    if (!h) return CABM_E_ARG;
+    if (!psets || n_psets < 1 || n_rep < 1 || n_rep > h->R || !seeds) return fail(h, CABM_E_ARG, "cabm_configure: bad argument");
+    if (mode != CABM_MODE_EXACT && mode != CABM_MODE_NATIVE) return fail(h, CABM_E_ARG, "cabm_configure: unknown mode");
+    CU(cudaSetDevice(h->device));
+    std::vector<DevPset> dp(n_psets);
+    std::vector<unsigned long long> beta((size_t)n_psets * h->T * 4);
+    int any_ct = 0;
+    for (int q = 0; q < n_psets; ++q) {
+        const cabm_params &p = psets[q];
+        if (p.popsize == 0) return fail(h, CABM_E_PARAM, "no population size given");                       // :164
+        if (!(p.ctstrat == 0 || p.ctstrat == 1 || p.ctstrat == 3)) return fail(h, CABM_E_PARAM, "invalid ct strategy");   // :165
+        if (p.prov_id < 0 || p.prov_id > 14) return fail(h, CABM_E_PARAM, "shame for not knowing your canadian provinces and territories");  // :334
+        if (p.popsize != h->N || p.modeltime != h->T) return fail(h, CABM_E_PARAM, "popsize/modeltime differ from the handle's");
+        if (p.tau_mild < -100 || p.tau_mild > 100 || p.cdaysback < 0 || p.strat3qdays < 0 || p.initialinf < 0 || p.initialhi < 0)
+            return fail(h, CABM_E_PARAM, "parameter out of range");
+        DevPset &d = dp[q];
+        memset(&d, 0, sizeof d);
+        for (int g = 0; g < 5; ++g) { d.asymp_thr[g] = bernoulli_threshold(p.asymp_props[g]); d.mild_thr[g] = bernoulli_threshold(p.mild_props[g]); }
+        double cp = 0;                                           // Categorical CDF walk :177: u >= cdf_k  <=>  w >= ceil(cdf_k 2^32)
+        for (int k = 0; k < 4; ++k) { cp = (k == 0) ? PROV_AG[p.prov_id][0] : cp + PROV_AG[p.prov_id][k]; d.age_thr[k] = bernoulli_threshold(cp); }
+        d.fmild_thr = bernoulli_threshold(p.fmild); d.fsevere_thr = bernoulli_threshold(p.fsevere);
+        d.fpreiso_thr = bernoulli_threshold(p.fpreiso); d.quar_thr = bernoulli_threshold(p.quar_grp_frac);
+        d.fctcap_thr = bernoulli_threshold((double)p.fctcapture); d.fcontact_thr = bernoulli_threshold((double)p.fcontactst);
+        d.tau_mild = p.tau_mild; d.tpreiso = p.tpreiso; d.quar_grp0 = p.quar_grp - 1; d.ctstrat = p.ctstrat;
+        d.cdaysback = p.cdaysback; d.strat3qdays = p.strat3qdays; d.calibration = p.calibration ? 1 : 0;
+        d.initialinf = p.initialinf; d.initialhi = p.initialhi;
+        d.qdays = p.ctstrat == 1 ? 14 : p.ctstrat == 3 ? p.strat3qdays : 0;                                  // :650-655
+        any_ct |= p.ctstrat != 0;
+        // init_betas :191-202 and _get_betavalue :756-769
+        std::vector<double> seas;
+        if (p.seasonal) td_seasonality(h->T, seas);
+        for (int t = 0; t < h->T; ++t) {
+            double bf = p.seasonal ? p.beta * seas[t] : p.beta * 1.0;
+            unsigned long long *b = &beta[((size_t)q * h->T + t) * 4];
+            b[0] = bernoulli_threshold(bf); b[1] = bernoulli_threshold(bf * p.frelasymp);
+            b[2] = bernoulli_threshold(bf * 0.44); b[3] = bernoulli_threshold(bf * 0.89);
+        }
+    }
+    std::vector<int> pof(n_rep, 0);
+    for (int r = 0; r < n_rep; ++r) {
+        if (pset_of_rep) pof[r] = pset_of_rep[r];
+        if (pof[r] < 0 || pof[r] >= n_psets) return fail(h, CABM_E_ARG, "pset_of_rep out of range");
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (n_psets > h->psets_cap) {
+        if (h->d_psets) cudaFree(h->d_psets);
+        if (h->d_beta) cudaFree(h->d_beta);
+        h->d_psets = nullptr; h->d_beta = nullptr;
+        CU(cudaMalloc((void **)&h->d_psets, sizeof(DevPset) * n_psets));
+        CU(cudaMalloc((void **)&h->d_beta, sizeof(unsigned long long) * (size_t)n_psets * h->T * 4));
+        h->psets_cap = n_psets;
+    }
+    CU(cudaMemcpy(h->d_psets, dp.data(), sizeof(DevPset) * n_psets, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_beta, beta.data(), beta.size() * 8, cudaMemcpyHostToDevice));
+    std::vector<uint2> keys(n_rep);
+    for (int r = 0; r < n_rep; ++r) keys[r] = make_uint2((uint32_t)seeds[r], (uint32_t)(seeds[r] >> 32));
+    CU(cudaMemcpy(h->S.key, keys.data(), sizeof(uint2) * n_rep, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->S.pset_of, pof.data(), sizeof(int) * n_rep, cudaMemcpyHostToDevice));
+    if (any_ct && !h->S.ct_log) {
+        // contact log: (target, next) per traced contact. 64 entries per agent covers a full epidemic with
+        // cdaysback of a few days (mean ~13 contacts/day for the ~half of infections that are captured).
+        size_t cap = (size_t)64 * h->N;
+        if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+        CU(cudaMalloc((void **)&h->S.ct_log, sizeof(uint2) * cap * h->R));
+        h->S.ct_cap = (uint32_t)cap;
+    }
+    h->S.psets = h->d_psets; h->S.beta_thr = h->d_beta; h->S.P = n_psets;
+    h->n_rep = n_rep; h->n_psets = n_psets; h->mode = mode; h->any_ct = any_ct; h->configured = 1; h->day = 1; h->ran = false;
+    h->S.R = n_rep;
+    return CABM_OK;
+}
+
+static int need_config(cabm_handle *h) {
+    if (!h) return CABM_E_ARG;
+    if (!h->configured) return fail(h, CABM_E_STATE, "cabm_configure has not been called");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(h, CABM_E_CUDA, cudaGetErrorString(e));
+    return CABM_OK;
+}
+
+static int reset_state(cabm_handle *h) {
+    Dev &S = h->S;
+    const size_t W = (size_t)S.R * S.nwords, C = (size_t)S.R * 6 * S.T * 12;
+    CU(cudaMemsetAsync(S.mark_pre, 0, W * 4, h->stream)); CU(cudaMemsetAsync(S.mark_post, 0, W * 4, h->stream));
+    CU(cudaMemsetAsync(S.infmask, 0, W * 4, h->stream)); CU(cudaMemsetAsync(S.ct_cnt, 0, (size_t)S.R * 4, h->stream));
+    CU(cudaMemsetAsync(S.err, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totiso, 0, (size_t)S.R * 8, h->stream));
+    CU(cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, h->stream));
+    CU(cudaMemsetAsync(S.inc, 0, C * 4, h->stream)); CU(cudaMemsetAsync(S.prev, 0, C * 4, h->stream));
+    CU(cudaMemsetAsync(S.infectors, 0, (size_t)S.R * 32, h->stream)); CU(cudaMemsetAsync(S.latsum, 0, (size_t)S.R * 8, h->stream));
+    h->day = 1;
+    return CABM_OK;
+}
+
+// wraps one launcher call; in profiling mode brackets it with events on the handle's stream
+template <class F> static void timed(cabm_handle *h, int cls, F f) {
+    if (!h->profiling) { h->launches += f(); return; }
+    while (h->pev.size() < h->pev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); h->pev.push_back(e); }
+    cudaEventRecord(h->pev[h->pev_used], h->stream);
+    h->launches += f();
+    cudaEventRecord(h->pev[h->pev_used + 1], h->stream);
+    h->pev_used += 2; h->pcls.push_back(cls);
+}
+
+static int do_dyntrans(cabm_handle *h, int day) {
+    // CABM_MODE_NATIVE currently shares the exact schedule (the relaxed per-infector kernel is a later row)
+    timed(h, CABM_K_DYNTRANS, [&] { return launch_dyntrans_exact(h->S, day, h->stream); });
+    return CABM_OK;
+}
+static int do_time_update(cabm_handle *h, int day) {
+    if (h->any_ct) timed(h, CABM_K_CT_IDENTIFY, [&] { return launch_ct_identify(h->S, day, h->stream); });
+    timed(h, CABM_K_TIME_UPDATE, [&] { return launch_time_update(h->S, day, h->stream); });
+    return CABM_OK;
+}
+
+extern "C" int cabm_run(cabm_handle *h) {
+    int rc = need_config(h); if (rc) return rc;
+    const Dev &S = h->S;
+    h->pev_used = 0; h->pcls.clear();
+    CU(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = reset_state(h))) return rc;
+    timed(h, CABM_K_OTHER, [&] { return launch_initialize(S, h->stream); });                                   // :112
+    timed(h, CABM_K_OTHER, [&] { return launch_insert_infected(S, 0, 0, 0, 0, 0, 0, h->stream); });            // :117/:119
+    timed(h, CABM_K_OTHER, [&] { return launch_insert_infected(S, 1, 0, 0, 0, 1, 0, h->stream); });            // :120
+    timed(h, CABM_K_OTHER, [&] { return launch_build_groups(S, h->stream); });                                 // :128
+    timed(h, CABM_K_OTHER, [&] { return launch_first_column(S, h->stream); });                                 // :136 for st = 1
+    for (int st = 1; st <= h->T; ++st) {                                              // :131
+        do_dyntrans(h, st);                                                           // :137
+        do_time_update(h, st);                                                        // :138 (+ snapshot of st+1)
+    }
+    timed(h, CABM_K_OTHER, [&] { return launch_curves_finalize(S, h->stream); });                              // :259-293
+    timed(h, CABM_K_OTHER, [&] { return launch_count_infectors(S, h->stream); });                              // :295-313
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaGetLastError());
+    h->day = h->T + 1; h->ran = true;
+    if (h->profiling) {
+        CU(cudaStreamSynchronize(h->stream));
+        for (int c = 0; c < CABM_N_KCLASS; ++c) { h->prof_ms[c] = 0; h->prof_n[c] = 0; }
+        for (size_t k = 0; k < h->pcls.size(); ++k) {
+            float ms = 0; cudaEventElapsedTime(&ms, h->pev[2 * k], h->pev[2 * k + 1]);
+            h->prof_ms[h->pcls[k]] += ms; h->prof_n[h->pcls[k]] += 1;
+        }
+    }
+    return CABM_OK;
+}
+
+extern "C" int cabm_set_profiling(cabm_handle *h, int on) { if (!h) return CABM_E_ARG; h->profiling = on ? 1 : 0; return CABM_OK; }
+extern "C" int cabm_get_profile(cabm_handle *h, float *ms, int32_t *launches) {
+    if (!h || !ms || !launches) return CABM_E_ARG;
+    for (int c = 0; c < CABM_N_KCLASS; ++c) { ms[c] = h->prof_ms[c]; launches[c] = h->prof_n[c]; }
+    return CABM_OK;
+}
+
+extern "C" int cabm_sync(cabm_handle *h) {
+    if (!h) return CABM_E_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return CABM_OK;
+}
+
+extern "C" int cabm_last_run_ms(cabm_handle *h, float *ms) {
+    if (!h || !ms) return CABM_E_ARG;
+    if (!h->ran) return fail(h, CABM_E_STATE, "no cabm_run yet");
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return CABM_OK;
+}
+extern "C" int64_t cabm_launch_count(const cabm_handle *h) { return h ? h->launches : 0; }
+extern "C" int cabm_get_day(const cabm_handle *h) { return h ? h->day : -1; }
+
+extern "C" int cabm_step_initialize(cabm_handle *h) {
+    int rc = need_config(h); if (rc) return rc;
+    if ((rc = reset_state(h))) return rc;
+    h->launches += launch_initialize(h->S, h->stream);
+    h->launches += launch_build_groups(h->S, h->stream);
+    CU(cudaGetLastError());
+    return CABM_OK;
+}
+extern "C" int cabm_step_insert_infected(cabm_handle *h, int health, int num, int ag, int call_id) {
+    int rc = need_config(h); if (rc) return rc;
+    if (!(health == PRE || health == LAT || health == INF || health == REC)) return fail(h, CABM_E_ARG, "can not insert human of this health");  // :389
+    if (num < 0 || ag < 1 || ag > 5) return fail(h, CABM_E_ARG, "cabm_step_insert_infected: bad argument");
+    h->launches += launch_insert_infected(h->S, 2, health, num, ag, call_id, h->day - 1, h->stream);
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<uint32_t> err(h->n_rep);
+    CU(cudaMemcpy(err.data(), h->S.err, 4 * (size_t)h->n_rep, cudaMemcpyDeviceToHost));
+    for (uint32_t e : err) if (e & ERR_NO_SUS) return fail(h, CABM_E_MODEL, "No susceptibles in the population to change status");     // :371-372
+    return CABM_OK;
+}
+extern "C" int cabm_step_dyntrans(cabm_handle *h) {
+    int rc = need_config(h); if (rc) return rc;
+    if (h->day > h->T) return fail(h, CABM_E_STATE, "day exceeds modeltime");
+    do_dyntrans(h, h->day);
+    CU(cudaGetLastError());
+    return CABM_OK;
+}
+extern "C" int cabm_step_time_update(cabm_handle *h) {
+    int rc = need_config(h); if (rc) return rc;
+    if (h->day > h->T) return fail(h, CABM_E_STATE, "day exceeds modeltime");
+    do_time_update(h, h->day);
+    h->day += 1;
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<uint32_t> err(h->n_rep);
+    CU(cudaMemcpy(err.data(), h->S.err, 4 * (size_t)h->n_rep, cudaMemcpyDeviceToHost));
+    for (uint32_t e : err) if (e & ERR_NO_SWAP) return fail(h, CABM_E_MODEL, "swap expired, but no swap set.");                          // :418
+    return CABM_OK;
+}
+extern "C" int cabm_get_dyntrans_counters(cabm_handle *h, int32_t *totalmet, int32_t *totalinf) {
+    int rc = need_config(h); if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    if (totalmet) CU(cudaMemcpy(totalmet, h->S.totalmet, 4 * (size_t)h->n_rep, cudaMemcpyDeviceToHost));
+    if (totalinf) CU(cudaMemcpy(totalinf, h->S.totalinf, 4 * (size_t)h->n_rep, cudaMemcpyDeviceToHost));
+    return CABM_OK;
+}
+
+extern "C" int cabm_get_hmatrix(cabm_handle *h, int replicate, int16_t *out) {
+    int rc = need_config(h); if (rc) return rc;
+    if (!h->S.store_hm) return fail(h, CABM_E_STATE, "handle was created without CABM_STORE_HMATRIX");
+    if (replicate < 0 || replicate >= h->n_rep || !out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix: bad argument");
+    const size_t n = (size_t)h->T * h->N;
+    CU(cudaMemcpyAsync(out, h->S.hm + (size_t)replicate * n, n * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CABM_OK;
+}
+extern "C" int cabm_get_hmatrix_all(cabm_handle *h, int16_t *out) {
+    int rc = need_config(h); if (rc) return rc;
+    if (!h->S.store_hm) return fail(h, CABM_E_STATE, "handle was created without CABM_STORE_HMATRIX");
+    if (!out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix_all: bad argument");
+    CU(cudaMemcpyAsync(out, h->S.hm, (size_t)h->n_rep * h->T * h->N * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CABM_OK;
+}
+extern "C" int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev) {
+    int rc = need_config(h); if (rc) return rc;
+    if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");
+    const size_t bytes = (size_t)h->n_rep * 6 * h->T * 12 * 4;
+    if (inc) CU(cudaMemcpyAsync(inc, h->S.inc, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (prev) CU(cudaMemcpyAsync(prev, h->S.prev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CABM_OK;
+}
+extern "C" int cabm_get_scalars(cabm_handle *h, int64_t *infectors, int64_t *totalisolated, int64_t *lat_inc_sum, uint32_t *err) {
+    int rc = need_config(h); if (rc) return rc;
+    if ((infectors || lat_inc_sum) && !h->ran) return fail(h, CABM_E_STATE, "infectors/lat_inc_sum exist after cabm_run");
+    const size_t R = (size_t)h->n_rep;
+    if (infectors) CU(cudaMemcpyAsync(infectors, h->S.infectors, R * 32, cudaMemcpyDeviceToHost, h->stream));
+    if (totalisolated) CU(cudaMemcpyAsync(totalisolated, h->S.totiso, R * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (lat_inc_sum) CU(cudaMemcpyAsync(lat_inc_sum, h->S.latsum, R * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (err) CU(cudaMemcpyAsync(err, h->S.err, R * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CABM_OK;
+}
+extern "C" int cabm_get_field(cabm_handle *h, int field, int replicate, int32_t *out) {
+    int rc = need_config(h); if (rc) return rc;
+    if (field < 0 || field > CABM_F_NCONTACTS || replicate < 0 || replicate >= h->n_rep || !out) return fail(h, CABM_E_ARG, "cabm_get_field: bad argument");
+    if (field >= CABM_F_NCONTACTS && !h->S.ct_log) { memset(out, 0, 4 * (size_t)h->N); return CABM_OK; }
+    h->launches += launch_peek(h->S, field, replicate, h->day, h->d_scratch, h->stream);
+    const size_t n = (size_t)h->N * (field == CABM_F_DUR ? 4 : 1);
+    CU(cudaMemcpyAsync(out, h->d_scratch, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CABM_OK;
+}
+extern "C" int cabm_set_field(cabm_handle *h, int field, int replicate, int agent, int32_t value) {
+    int rc = need_config(h); if (rc) return rc;
+    if (field < 0 || field > CABM_F_TRACEDXP || field == CABM_F_AG || field == CABM_F_DUR || replicate < 0 || replicate >= h->n_rep || agent < 0 || agent >= h->N)
+        return fail(h, CABM_E_ARG, "cabm_set_field: bad argument");
+    h->launches += launch_poke(h->S, field, replicate, agent, h->day, value, h->stream);
+    CU(cudaStreamSynchronize(h->stream));
+    return CABM_OK;
+}
+
+extern "C" int cabm_reduce_hmatrix(cabm_handle *h, const int16_t *hm, int n_mat, int n, int t, const int32_t *ags,
+                                   int32_t *inc, int32_t *prev) {
+    if (!h) return CABM_E_ARG;
+    if (!hm || !ags || !inc || !prev || n_mat < 1 || n < 1 || t < 1) return fail(h, CABM_E_ARG, "cabm_reduce_hmatrix: bad argument");
+    CU(cudaSetDevice(h->device));
+    const size_t hb = (size_t)n_mat * n * t * 2, ab = (size_t)n_mat * n * 4, cb = (size_t)n_mat * 6 * t * 12 * 4;
+    int16_t *d_hm = nullptr; int *d_ags = nullptr, *d_inc = nullptr, *d_prev = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_hm, hb);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_ags, ab);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_inc, cb);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_prev, cb);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_hm, hm, hb, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ags, ags, ab, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_inc, 0, cb, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_prev, 0, cb, h->stream);
+    if (e == cudaSuccess) { h->launches += launch_reduce_hmatrix(d_hm, d_ags, n_mat, n, t, d_inc, d_prev, h->stream); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(inc, d_inc, cb, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(prev, d_prev, cb, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_hm); cudaFree(d_ags); cudaFree(d_inc); cudaFree(d_prev);
+    if (e != cudaSuccess) return fail(h, CABM_E_CUDA, std::string("cabm_reduce_hmatrix: ") + cudaGetErrorString(e));
+    return CABM_OK;
+}
+
+extern "C" void *cabm_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void cabm_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int cabm_get_table(const char *name, int32_t *base, uint32_t *thr, int cap) {
+    const Table *t = name ? table_by_name(name) : nullptr;
+    if (!t) return -1;
+    if (base) *base = t->base;
+    for (int i = 0; i < (int)t->thr.size() && i < cap && thr; ++i) thr[i] = t->thr[i];
+    return (int)t->thr.size();
+}
+extern "C" void cabm_get_gpw(int ag, int cnts, int32_t out[5]) {
+    int o[5]; gpw_split(ag, cnts, o);
+    for (int g = 0; g < 5; ++g) out[g] = o[g];
+}

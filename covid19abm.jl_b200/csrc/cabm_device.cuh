@@ -1,0 +1,213 @@
+// cabm_device.cuh — HBM data layout, draw contract and per-agent device functions (sm_100a).
+//
+// Layout: the reference's array-of-structs `humans` (src/covid19abm.jl:8-27,69) becomes a
+// struct-of-arrays with a replicate dimension, every array [R][Np] (Np = popsize padded to 32):
+//   status  u32  : rem[0:8) health[8:12) swap[12:16) ag[16:19) iso[19] isob[20] tracing[21] tag[22:32)
+//                  - everything dyntrans gathers about a contact target is in this one word, so one
+//                    32-bit load (or one atomicCAS in native mode) resolves a contact event;
+//                  - (tag, rem) is the agent's *remaining* contact budget, valid only when tag == day:
+//                    nextday_meetcnt (:13,:786) is a pure function of the keyed draw, so it is evaluated
+//                    lazily for infectors and their targets instead of once per agent-day (:425,:781);
+//                  - isob is `iso` as of the agent's own last update step (the value :778 used).
+//   expday  i16  : absolute day on which tis >= exp (:405) becomes true   (replaces tis/exp :16-17)
+//   entry   i16  : day of entry to the current state (tis = updates_done - entry)
+//   dur     u32  : 4 x u8 (latents, asymps, pres, infs) :18
+//   sickfrom/isovia u8, latday i16 (doi = updates_done - latday :19), tracestart/traceend/tracedxp i16,
+//   ct_head u32 -> per-replicate contact log (linked list replacing the Bool[10000] of :25).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cabm {
+
+enum : int { SUS = 0, LAT, PRE, ASYMP, MILD, MISO, INF, IISO, HOS, ICU, REC, DED, UNDEF };
+enum : int { VIA_NULL = 0, VIA_QU, VIA_PI, VIA_MI, VIA_CT };
+// draw-contract streams
+enum : uint32_t { S_INIT = 1, S_COUNT = 2, S_SEED = 3, S_TRANS = 4, S_CTWIN = 5, S_CTCON = 6, S_CT3 = 7, S_DT = 8 };
+enum : uint32_t { ERR_NO_SWAP = 1, ERR_NO_SUS = 2, ERR_TRACED_NOT_ISO = 4, ERR_EMPTY_GROUP = 8, ERR_CT_LOG_FULL = 16, ERR_SICKFROM = 32 };
+
+constexpr uint32_t ST_ISO = 1u << 19, ST_ISOB = 1u << 20, ST_TRACING = 1u << 21;
+constexpr uint32_t ST_TAGMASK = 0xFFC00000u, ST_REMMASK = 0xFFu;
+constexpr uint32_t CT_NONE = 0xFFFFFFFFu;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__host__ __device__ inline int st_rem(uint32_t s) { return (int)(s & 0xFF); }
+__host__ __device__ inline int st_health(uint32_t s) { return (int)((s >> 8) & 0xF); }
+__host__ __device__ inline int st_swap(uint32_t s) { return (int)((s >> 12) & 0xF); }
+__host__ __device__ inline int st_ag(uint32_t s) { return (int)((s >> 16) & 0x7); }   // 0..4
+__host__ __device__ inline int st_tag(uint32_t s) { return (int)(s >> 22); }
+__host__ __device__ inline uint32_t st_set_health(uint32_t s, int h) { return (s & ~0xF00u) | ((uint32_t)h << 8); }
+__host__ __device__ inline uint32_t st_set_swap(uint32_t s, int h) { return (s & ~0xF000u) | ((uint32_t)h << 12); }
+__host__ __device__ inline uint32_t st_make(int health, int swap, int ag0, bool iso) {
+    return ((uint32_t)health << 8) | ((uint32_t)swap << 12) | ((uint32_t)ag0 << 16) | (iso ? (ST_ISO | ST_ISOB) : 0u);
+}
+__host__ __device__ inline bool is_infectious(int h) { return h >= PRE && h <= IISO; }  // :794
+// _get_betavalue class :761-767: 0 PRE, 1 ASYMP, 2 MILD/MISO, 3 INF/IISO
+__host__ __device__ inline int beta_class(int h) { return h == PRE ? 0 : h == ASYMP ? 1 : (h == MILD || h == MISO) ? 2 : 3; }
+
+// per-parameter-set constants, thresholds are "w < thr  <=>  rand() < p"
+struct DevPset {
+    unsigned long long asymp_thr[5], mild_thr[5], age_thr[4];
+    unsigned long long fmild_thr, fsevere_thr, fpreiso_thr, quar_thr, fctcap_thr, fcontact_thr;
+    int tau_mild, tpreiso, quar_grp0, ctstrat, cdaysback, strat3qdays, calibration, initialinf, initialhi, qdays;
+};
+
+// small tables in constant memory
+struct ConstTables {
+    uint32_t lat_thr[4], pre_thr[4], asy_thr[40], inf_thr[40], psi_thr[12], mu_thr[8];
+    int lat_len, pre_len, asy_len, inf_len, psi_len, mu_len;
+    int lat_base, pre_base, asy_base, inf_base, psi_base, mu_base;
+    int nb_len[5];
+    double hlo[5], hspan[5], clo[5], cspan[5];                 // move_to_inf :535-536
+    unsigned long long mh_inf_thr[5];                          // :537
+    unsigned long long mh_hos_thr[5], mh_icu_thr[5];           // :585-586
+    unsigned long long ct3_lat_thr, ct3_pre_thr, ct3_asymp_thr; // :741
+};
+
+struct Dev {
+    int R, N, Np, T, P, store_hm, nwords;
+    uint32_t ct_cap;
+    uint32_t *status; int16_t *expday; int16_t *entry; uint32_t *dur; uint8_t *sickfrom; uint8_t *isovia;
+    int16_t *latday, *tracestart, *traceend, *tracedxp; uint32_t *ct_head;
+    uint32_t *mark_pre, *mark_post;          // [R][nwords] bitmasks
+    uint2 *ct_log; uint32_t *ct_cnt;         // [R][ct_cap] (y, next), [R]
+    uint32_t *grp_idx; int *grp_off;         // [R][Np], [R][8]
+    uint32_t *infmask;                       // [R][nwords]
+    uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;
+    int *inc, *prev;                         // [R][6][T][12]
+    long long *infectors, *latsum;           // [R][4], [R]
+    int16_t *hm;                             // [R][T][N]
+    const DevPset *psets; const unsigned long long *beta_thr;    // [P], [P][T][4]
+    const uint32_t *nb_thr; const uint8_t *nb_guide;             // [5][256], [5][256]
+    const unsigned long long *gpw;                               // [5][256] five u8 counts packed
+};
+
+#ifdef CABM_KERNELS_TU   // device code below is compiled only in cabm_kernels.cu (no -rdc: constants are per-TU)
+__constant__ ConstTables c_tab;
+
+// ---------------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint2 key) {
+    uint32_t k0 = key.x, k1 = key.y;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint32_t pick(uint4 w, uint32_t k) { return k == 0 ? w.x : k == 1 ? w.y : k == 2 ? w.z : w.w; }
+__device__ __forceinline__ int below(uint32_t w, int n) { return (int)__umulhi(w, (uint32_t)n); }
+__device__ __forceinline__ bool bern(uint32_t w, unsigned long long thr) { return (unsigned long long)w < thr; }
+__device__ __forceinline__ double u01(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+__device__ __forceinline__ int table_draw(uint32_t w, int base, const uint32_t *thr, int len) {
+    int v = 0;
+    while (v < len && thr[v] <= w) ++v;
+    return base + v;
+}
+
+// get_nextday_counts :772-788, evaluated on demand for day `day` from the agent's status word
+__device__ __forceinline__ int fresh_budget(const Dev &S, uint2 key, uint32_t i, uint32_t day, uint32_t st) {
+    if (st_health(st) == DED) return 0;                                    // :783-785
+    uint32_t w = pick(philox(i >> 2, day, S_COUNT, 0, key), i & 3u);
+    if (st & ST_ISOB)                                                      // :778-779
+        return (w < 0x80000000u) ? 0 : 1 + (int)(((unsigned long long)(w & 0x7fffffffu) * 3ull) >> 31);
+    int ag = st_ag(st);                                                    // :781
+    const uint32_t *thr = S.nb_thr + ag * 256;
+    int k = __ldg(&S.nb_guide[ag * 256 + (w >> 24)]), len = c_tab.nb_len[ag];
+    while (k < len && __ldg(&thr[k]) <= w) ++k;
+    return k;
+}
+__device__ __forceinline__ int budget_of(const Dev &S, uint2 key, uint32_t i, int day, uint32_t st) {
+    return st_tag(st) == day ? st_rem(st) : fresh_budget(S, key, i, (uint32_t)day, st);
+}
+
+__device__ __forceinline__ void curve_move(const Dev &S, int r, int ag0, int col, int oldh, int newh) {
+    // column `col` (0-based) is the first snapshot that shows the new state (:136,:218-223)
+    if (col >= S.T || oldh == newh) return;
+    size_t b = (((size_t)r * 6 + (size_t)(ag0 + 1)) * (size_t)S.T + (size_t)col) * 12;
+    atomicAdd(&S.inc[b + newh], 1);
+    atomicAdd(&S.prev[b + oldh], 1);   // exits are parked in prev[] until k_curves_finalize
+}
+
+// One expired agent: time_update's @match :405-419 and the move_to_* functions :446-644.
+// Returns the new status word (not stored); writes expday/entry/latday/isovia, the infectious bitmask
+// and the incidence counters. `day` is st; for seeding it is 0.
+__device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
+                                      int target /* swap to apply */, bool seed_simple_inf, bool count_curves) {
+    size_t a = (size_t)r * S.Np + i;
+    const int oldh = st_health(st), ag = st_ag(st);
+    const uint32_t d4 = S.dur[a];
+    const int d_lat = d4 & 0xFF, d_asy = (d4 >> 8) & 0xFF, d_pre = (d4 >> 16) & 0xFF, d_inf = d4 >> 24;
+    bool iso = st & ST_ISO;
+    int via = -1;                       // -1: unchanged
+    int newh = target, newsw = UNDEF, exp = 999;
+    switch (target) {
+    case LAT: {                          // move_to_latent :446-461
+        uint4 w = philox(i, day, S_TRANS, 0, key);
+        exp = d_lat; newsw = bern(w.x, P.asymp_thr[ag]) ? ASYMP : PRE;
+        if (P.calibration) { newsw = LAT; exp = 999; }
+        S.latday[a] = (int16_t)day;
+        break; }
+    case ASYMP: exp = d_asy; newsw = REC; break;                       // :464-472
+    case PRE: {                          // move_to_pre :475-488
+        uint4 w = philox(i, day, S_TRANS, 0, key);
+        exp = d_pre; newsw = bern(w.x, P.mild_thr[ag]) ? MILD : INF;
+        bool active = (day == 0) || (P.tpreiso >= 1 && day >= P.tpreiso);   // main :124-125,:133-135
+        if (active && bern(w.y, P.fpreiso_thr)) { iso = true; via = VIA_PI; }
+        break; }
+    case MILD: {                         // move_to_mild :491-507
+        exp = d_inf; newsw = REC;
+        bool go = iso;
+        if (!go) { uint4 w = philox(i, day, S_TRANS, 0, key); go = bern(w.x, P.fmild_thr); }
+        if (go) { newsw = MISO; exp = P.tau_mild; }
+        break; }
+    case MISO: exp = d_inf - P.tau_mild; newsw = REC; iso = true; via = VIA_MI; break;   // :510-517
+    case INF: {
+        if (seed_simple_inf) {           // move_to_infsimple :520-528
+            exp = d_inf; newsw = REC; iso = false; break;    // _set_isolation(x, false, :null) leaves isovia as is
+        }
+        // move_to_inf :530-569
+        uint4 wa = philox(i, day, S_TRANS, 0, key), wb = philox(i, day, S_TRANS, 1, key);
+        double h = __dadd_rn(c_tab.hlo[ag], __dmul_rn(c_tab.hspan[ag], u01(wa.x)));
+        double c = __dadd_rn(c_tab.clo[ag], __dmul_rn(c_tab.cspan[ag], u01(wa.y)));
+        unsigned long long mthr = c_tab.mh_inf_thr[ag];
+        if (P.calibration) { h = 0; c = 0; mthr = 0; }
+        int tth = (int)rint(__dadd_rn(2.0, __dmul_rn(3.0, u01(wa.z))));
+        if (u01(wa.w) < h) { exp = tth; newsw = (u01(wb.x) < c) ? ICU : HOS; }
+        else if (bern(wb.y, mthr)) { exp = d_inf; newsw = DED; }
+        else {
+            exp = d_inf; newsw = REC;
+            if (iso || bern(wb.z, P.fsevere_thr)) { exp = 1; newsw = IISO; }
+        }
+        break; }
+    case IISO: exp = d_inf - 1; newsw = REC; iso = true; via = VIA_MI; break;            // :571-578
+    case HOS: case ICU: {                // move_to_hospicu :580-622
+        uint4 w = philox(i, day, S_TRANS, 0, key);
+        int psi = table_draw(w.x, c_tab.psi_base, c_tab.psi_thr, c_tab.psi_len);
+        int mu = table_draw(w.y, c_tab.mu_base, c_tab.mu_thr, c_tab.mu_len);
+        iso = true;                                                                        // :599
+        if (target == HOS) { if (bern(w.z, c_tab.mh_hos_thr[ag])) { exp = mu; newsw = DED; } else { exp = psi; newsw = REC; } }
+        else { if (bern(w.z, c_tab.mh_icu_thr[ag])) { exp = mu + 2; newsw = DED; } else { exp = psi + 2; newsw = REC; } }
+        break; }
+    case REC: exp = 999; newsw = UNDEF; break;                                             // :635-644
+    case DED: exp = 999; newsw = UNDEF; iso = true; break;                                 // :624-633
+    default:                              // :418 "swap expired, but no swap set."
+        atomicOr(&S.err[r], ERR_NO_SWAP);
+        S.expday[a] = 32767;
+        return st;
+    }
+    if (via >= 0 && S.isovia[a] == VIA_NULL) S.isovia[a] = (uint8_t)via;   // _set_isolation :432-444 only fills a :null isovia
+    S.expday[a] = (int16_t)(day + exp);
+    S.entry[a] = (int16_t)day;
+    if (is_infectious(newh) != is_infectious(oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
+    if (count_curves) curve_move(S, r, ag, day, oldh, newh);
+    st = st_set_swap(st_set_health(st, newh), newsw);
+    st = iso ? (st | ST_ISO | ST_ISOB) : (st & ~(ST_ISO | ST_ISOB));
+    return st;
+}
+
+#endif  // CABM_KERNELS_TU
+
+}  // namespace cabm

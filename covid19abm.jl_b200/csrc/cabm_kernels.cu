@@ -1,0 +1,585 @@
+// cabm_kernels.cu — the sm_100a kernels of the simulation path.
+// One launch advances every configured replicate; grid.y (or the warp index) is the replicate.
+#define CABM_KERNELS_TU
+#include "cabm_device.cuh"
+#include "cabm_kernels.h"
+
+namespace cabm {
+
+void upload_const_tables(const ConstTables &t, cudaStream_t s) {
+    cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, s);
+}
+
+// ============================================================================ initialize :171-188
+// thread per (replicate, agent). Draw words: S_INIT block 0 = (ag, lat, pre, asymp), block 1 = (inf, quarantine).
+__global__ void __launch_bounds__(256) k_initialize(Dev S) {
+    const int r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.Np) return;
+    const size_t a = (size_t)r * S.Np + i;
+    const DevPset &P = S.psets[S.pset_of[r]];
+    uint32_t st = st_make(SUS, UNDEF, 0, false), d4 = 0;
+    if (i < S.N) {
+        const uint2 key = S.key[r];
+        uint4 wa = philox(i, 0, S_INIT, 0, key), wb = philox(i, 0, S_INIT, 1, key);
+        int ag0 = 0;                                                   // :177 rand(Categorical)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ag0 += ((unsigned long long)wa.x >= P.age_thr[k]);
+        int latents = table_draw(wa.y, c_tab.lat_base, c_tab.lat_thr, c_tab.lat_len);   // :347,352
+        int pres = table_draw(wa.z, c_tab.pre_base, c_tab.pre_thr, c_tab.pre_len);      // :348,353
+        int asymps = table_draw(wa.w, c_tab.asy_base, c_tab.asy_thr, c_tab.asy_len);    // :349,355
+        int infs = table_draw(wb.x, c_tab.inf_base, c_tab.inf_thr, c_tab.inf_len);      // :350,356
+        latents -= pres;                                                                // :354
+        d4 = (uint32_t)latents | ((uint32_t)asymps << 8) | ((uint32_t)pres << 16) | ((uint32_t)infs << 24);
+        bool quar = bern(wb.y, P.quar_thr) && ag0 == P.quar_grp0;                       // :181
+        st = st_make(SUS, UNDEF, ag0, quar);
+        S.isovia[a] = quar ? VIA_QU : VIA_NULL;                                          // :183
+    } else {
+        S.isovia[a] = VIA_NULL;
+    }
+    S.status[a] = st;
+    S.dur[a] = d4;
+    S.expday[a] = (i < S.N) ? (int16_t)999 : (int16_t)32767;                             // :179
+    S.entry[a] = 0;
+    S.sickfrom[a] = UNDEF;
+    S.latday[a] = -999;                                                                   // doi = 999 (:19)
+    S.tracestart[a] = -1; S.traceend[a] = -1; S.tracedxp[a] = 0;
+    S.ct_head[a] = CT_NONE;
+}
+
+// ============================================================================ get_ag_dist :339-343
+// CTA per replicate: ascending agent indices of each age group, concatenated; offsets in grp_off[r][0..5].
+__global__ void __launch_bounds__(256) k_build_groups(Dev S) {
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ int wcnt[8][5];
+    __shared__ int base[5];
+    __shared__ int total[5];
+    const size_t rb = (size_t)r * S.Np;
+    if (tid < 5) total[tid] = 0;
+    __syncthreads();
+    // pass 1: group sizes
+    int c[5] = {0, 0, 0, 0, 0};
+    for (int i = tid; i < S.N; i += 256) c[st_ag(S.status[rb + i])]++;
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+        int v = c[g];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0) atomicAdd(&total[g], v);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int o = 0;
+        for (int g = 0; g < 5; ++g) { S.grp_off[r * 8 + g] = o; base[g] = o; o += total[g]; }
+        S.grp_off[r * 8 + 5] = o;
+    }
+    __syncthreads();
+    // pass 2: ordered scatter, 256 agents per round
+    for (int i0 = 0; i0 < S.N; i0 += 256) {
+        const int i = i0 + tid;
+        const int ag = (i < S.N) ? st_ag(S.status[rb + i]) : -1;
+        unsigned m[5];
+#pragma unroll
+        for (int g = 0; g < 5; ++g) { m[g] = __ballot_sync(FULL, ag == g); if (lane == 0) wcnt[wid][g] = __popc(m[g]); }
+        __syncthreads();
+        if (ag >= 0) {
+            int pos = base[ag];
+            for (int w = 0; w < wid; ++w) pos += wcnt[w][ag];
+            unsigned mm = ag == 0 ? m[0] : ag == 1 ? m[1] : ag == 2 ? m[2] : ag == 3 ? m[3] : m[4];
+            pos += __popc(mm & ((1u << lane) - 1u));
+            S.grp_idx[rb + pos] = (uint32_t)i;
+        }
+        __syncthreads();
+        if (tid < 5) { int s = 0; for (int w = 0; w < 8; ++w) s += wcnt[w][tid]; base[tid] += s; }
+        __syncthreads();
+    }
+}
+
+// ============================================================================ insert_infected :360-395
+// CTA per replicate. Pick j takes the floor(u_j*(L-j))-th remaining susceptible in ascending index order.
+// which: 0 = main's insert_infected(PRE, initialinf, 4) :117/:119; 1 = insert_infected(REC, initialhi, 4) :120
+//        (skipped in calibration); 2 = explicit (health, num, ag) for the step API.
+__global__ void __launch_bounds__(256) k_insert_infected(Dev S, int which, int health, int num, int ag, int call_id, int day) {
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const DevPset &P = S.psets[S.pset_of[r]];
+    if (which == 0) { health = PRE; num = P.initialinf; call_id = 0; }
+    if (which == 1) { if (P.calibration) return; health = REC; num = P.initialhi; call_id = 1; }
+    const size_t rb = (size_t)r * S.Np;
+    const uint2 key = S.key[r];
+    const int seg = (S.N + 255) / 256, lo = tid * seg, hi = min(S.N, lo + seg);
+    __shared__ int cnt[256];
+    __shared__ int sel_tid, sel_k;
+    int mine = 0;
+    for (int i = lo; i < hi; ++i) {
+        uint32_t st = S.status[rb + i];
+        mine += (st_health(st) == SUS && (health != INF || st_ag(st) == ag - 1));       // :365-369
+    }
+    cnt[tid] = mine;
+    __syncthreads();
+    __shared__ int Ltot;
+    if (tid == 0) { int L = 0; for (int t = 0; t < 256; ++t) L += cnt[t]; Ltot = L; }
+    __syncthreads();
+    if (Ltot == 0 || num > Ltot) { if (tid == 0 && (num > 0 || Ltot == 0)) atomicOr(&S.err[r], ERR_NO_SUS); return; }   // :371-372
+    for (int j = 0; j < num; ++j) {
+        if (tid == 0) {
+            uint4 w = philox(j, 0, S_SEED, call_id, key);
+            int k = below(w.x, Ltot - j), t = 0;
+            while (k >= cnt[t]) { k -= cnt[t]; ++t; }
+            sel_tid = t; sel_k = k;
+        }
+        __syncthreads();
+        if (tid == sel_tid) {
+            int k = sel_k;
+            for (int i = lo; i < hi; ++i) {
+                uint32_t st = S.status[rb + i];
+                if (!(st_health(st) == SUS && (health != INF || st_ag(st) == ag - 1))) continue;
+                if (k-- > 0) continue;
+                uint32_t ns = transition(S, P, r, i, day, st, key, health, /*seed_simple_inf=*/true, /*count_curves=*/false);
+                if (health == LAT) {                                                     // x.tis = x.exp :383
+                    const int ex = (int)S.expday[rb + i] - day;
+                    S.entry[rb + i] = (int16_t)(day - ex); S.expday[rb + i] = (int16_t)day;
+                }
+                // the contact budget already drawn for the coming day (:186 / :425) used the agent's old `iso`
+                ns = (ns & ~ST_ISOB) | (st & ST_ISOB);
+                S.status[rb + i] = ns;
+                S.sickfrom[rb + i] = INF;                                                // :391
+                break;
+            }
+            cnt[tid] -= 1;
+        }
+        __syncthreads();
+    }
+}
+
+// ============================================================================ first column of hmatrix + day-1 curves
+// _get_model_state(1, hmatrix) :136,:218-223 and the t=1 entries of :270-293 (every agent "first occurs" in
+// its initial state on day 1).
+__global__ void __launch_bounds__(256) k_first_column(Dev S) {
+    const int r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int hist[5][12];
+    if (threadIdx.x < 60) (&hist[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    if (i < S.N) {
+        uint32_t st = S.status[(size_t)r * S.Np + i];
+        int h = st_health(st);
+        atomicAdd(&hist[st_ag(st)][h], 1);
+        if (S.store_hm) S.hm[(size_t)r * S.T * S.N + i] = (int16_t)h;
+    }
+    __syncthreads();
+    if (threadIdx.x < 60) {
+        int v = (&hist[0][0])[threadIdx.x];
+        if (v) {
+            int g = threadIdx.x / 12, s = threadIdx.x % 12;
+            size_t b = (((size_t)r * 6 + (g + 1)) * (size_t)S.T + 0) * 12 + s;
+            atomicAdd(&S.inc[b], v);
+            atomicAdd(&S.prev[b], v);
+        }
+    }
+}
+
+// ============================================================================ dyntrans :790-834 (exact schedule)
+// One warp per replicate walks the infectious agents in ascending index order (the reference's order, on which
+// the result depends through the shared contact budgets :811-813); the lanes take that infector's contact
+// events 32 at a time. Duplicate targets inside a batch are ranked with __match_any_sync so that the outcome
+// equals processing the events one after another.
+__global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
+    const int r = blockIdx.x, lane = threadIdx.x;
+    const DevPset &P = S.psets[S.pset_of[r]];
+    const uint2 key = S.key[r];
+    const size_t rb = (size_t)r * S.Np;
+    const unsigned long long *bt = S.beta_thr + ((size_t)S.pset_of[r] * S.T + (size_t)(day - 1)) * 4;
+    const int o0 = S.grp_off[r * 8 + 0], o1 = S.grp_off[r * 8 + 1], o2 = S.grp_off[r * 8 + 2],
+              o3 = S.grp_off[r * 8 + 3], o4 = S.grp_off[r * 8 + 4], o5 = S.grp_off[r * 8 + 5];
+    const bool ct = P.ctstrat != 0;
+    uint32_t logn = ct ? S.ct_cnt[r] : 0;
+    int met = 0, ninf = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t *mask = S.infmask + (size_t)r * S.nwords;
+    for (int wb = 0; wb < S.nwords; wb += 32) {
+        const uint32_t mw = (wb + lane < S.nwords) ? mask[wb + lane] : 0u;
+        unsigned any = __ballot_sync(FULL, mw != 0);
+        while (any) {
+            const int L = __ffs(any) - 1; any &= any - 1;
+            uint32_t m = __shfl_sync(FULL, mw, L);
+            while (m) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                const int x = ((wb + L) << 5) + b;
+                // ---- one infector (:798-803)
+                const uint32_t sx = __ldcg(&S.status[rb + x]);
+                const int xh = st_health(sx);
+                const int cnts = budget_of(S, key, x, day, sx);
+                if (cnts == 0) continue;
+                const unsigned long long gp = __ldg(&S.gpw[st_ag(sx) * 256 + cnts]);     // :804
+                const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF),
+                          p4 = p3 + (int)((gp >> 24) & 0xFF), E = p4 + (int)((gp >> 32) & 0xFF);
+                const unsigned long long bthr = bt[beta_class(xh)];                      // :800
+                const bool tracing = ct && (sx & ST_TRACING);
+                uint32_t head = tracing ? S.ct_head[rb + x] : CT_NONE;
+                for (int e0 = 0; e0 < E; e0 += 32) {
+                    const int e = e0 + lane;
+                    bool act = e < E;
+                    const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
+                    const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
+                    const int go = g == 0 ? o0 : g == 1 ? o1 : g == 2 ? o2 : g == 3 ? o3 : o4;
+                    const int ge = g == 0 ? o1 : g == 1 ? o2 : g == 2 ? o3 : g == 3 ? o4 : o5;
+                    const int len = ge - go;
+                    if (act && len == 0) { atomicOr(&S.err[r], ERR_EMPTY_GROUP); act = false; }
+                    uint32_t j = 0x80000000u + lane, sy = 0, w1 = 0;
+                    int remy = 0;
+                    if (act) {
+                        const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                        w1 = w.y;
+                        j = S.grp_idx[rb + go + below(w.x, len)];                        // :807
+                        sy = __ldcg(&S.status[rb + j]);
+                        remy = budget_of(S, key, j, day, sy);                            // :811
+                    }
+                    const unsigned peers = __match_any_sync(FULL, j);
+                    const int rank = __popc(peers & lt), cntp = __popc(peers);
+                    const bool adm = act && rank < remy;                                 // :812
+                    const bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;      // :822
+                    const bool succ = adm && sus && bern(w1, bthr);                      // :823
+                    const unsigned succm = __ballot_sync(FULL, succ) & peers;
+                    const unsigned admm = __ballot_sync(FULL, adm);
+                    if (act && rank == 0) {
+                        const int used = min(cntp, remy);
+                        uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)(remy - used) | ((uint32_t)day << 22);   // :813
+                        if (succm) {                                                      // :824-827
+                            ns = st_set_swap(ns, LAT);
+                            S.sickfrom[rb + j] = (uint8_t)xh;
+                            S.expday[rb + j] = (int16_t)day;                              // y.exp = y.tis: fires in today's time_update
+                            ++ninf;
+                        }
+                        __stcg(&S.status[rb + j], ns);
+                    }
+                    met += adm;
+                    if (tracing && admm) {                                                // :817-819
+                        unsigned am = admm;
+                        while (am) {
+                            const int src = __ffs(am) - 1; am &= am - 1;
+                            const uint32_t jj = __shfl_sync(FULL, j, src);
+                            if (lane == 0) {
+                                if (logn < S.ct_cap) { S.ct_log[(size_t)r * S.ct_cap + logn] = make_uint2(jj, head); head = logn; ++logn; }
+                                else atomicOr(&S.err[r], ERR_CT_LOG_FULL);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (tracing && lane == 0) S.ct_head[rb + x] = head;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) { met += __shfl_xor_sync(FULL, met, o); ninf += __shfl_xor_sync(FULL, ninf, o); }
+    if (lane == 0) { S.totalmet[r] = met; S.totalinf[r] = ninf; if (ct) S.ct_cnt[r] = logn; }
+}
+
+// ============================================================================ contact tracing, pass A
+// The identification branch of ct_dynamics :705-716 writes *other* agents from inside the sequential agent loop.
+// An index case x identifies on a day fixed when it became latent (doi == traceend), so the cross-agent writes are
+// hoisted: this kernel draws Bernoulli(fcontactst) once per distinct traced contact y (:709-713) and leaves a mark —
+// "pre" if y > x (y sees the isolation in its own update today), "post" if y < x (y was already updated today).
+__global__ void __launch_bounds__(256) k_ct_identify(Dev S, int day) {
+    const int r = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+    const DevPset &P = S.psets[S.pset_of[r]];
+    if (P.ctstrat == 0 || x >= S.N) return;
+    const size_t a = (size_t)r * S.Np + x;
+    const int te = S.traceend[a];
+    if (te < 0 || day - (int)S.latday[a] != te) return;
+    const uint2 key = S.key[r];
+    const uint2 *log = S.ct_log + (size_t)r * S.ct_cap;
+    const uint32_t head = S.ct_head[a];
+    for (uint32_t e = head; e != CT_NONE; e = log[e].y) {
+        const uint32_t y = log[e].x;
+        bool dup = false;                                     // the reference's contact set is a Bool vector (:25)
+        for (uint32_t f = head; f != e; f = log[f].y) if (log[f].x == y) { dup = true; break; }
+        if (dup) continue;
+        const uint4 w = philox(x, day, S_CTCON, y, key);
+        if (!bern(w.x, P.fcontact_thr)) continue;             // :711
+        atomicAdd(&S.totiso[r], 1ull);                        // :649
+        if (y > (uint32_t)x) atomicOr(&S.mark_pre[(size_t)r * S.nwords + (y >> 5)], 1u << (y & 31));
+        else if (y < (uint32_t)x) atomicOr(&S.mark_post[(size_t)r * S.nwords + (y >> 5)], 1u << (y & 31));
+    }
+}
+
+// ct_dynamics :658-752 for one agent, with the hoisted marks applied where the sequential loop would have.
+__device__ inline uint32_t agent_update_ct(const Dev &S, const DevPset &P, int r, int i, int day, uint2 key,
+                                           uint32_t st, bool fire, bool pre, bool post) {
+    const size_t a = (size_t)r * S.Np + i;
+    int txp = S.tracedxp[a];
+    const int txp0 = txp;
+    auto isolate_ct = [&](uint32_t s) {                       // apply_ct_strategy :647-656
+        if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+        txp = P.qdays;
+        return s | ST_ISO;
+    };
+    if (pre) st = isolate_ct(st);
+    if (fire) st = transition(S, P, r, i, day, st, key, st_swap(st), false, true);
+    const int doi = day - (int)S.latday[a];
+    int ts = S.tracestart[a], te = S.traceend[a];
+    if (st_health(st) == LAT && st_swap(st) != ASYMP && doi == 0) {          // :678
+        const uint4 w = philox(i, day, S_CTWIN, 0, key);
+        if (bern(w.x, P.fctcap_thr)) {
+            const uint32_t d4 = S.dur[a];
+            const int tid = 1 + below(w.y, (int)(d4 >> 24));                  // :680
+            const int delta = (int)(d4 & 0xFF) + (int)((d4 >> 16) & 0xFF) + tid;
+            const int q = delta - P.cdaysback;
+            ts = q > 0 ? q : 0; te = delta;
+            S.tracestart[a] = (int16_t)ts; S.traceend[a] = (int16_t)te;
+            st &= ~ST_TRACING;
+            S.ct_head[a] = CT_NONE;                                            // :687
+        }
+    }
+    if (doi >= ts && doi < te) st |= ST_TRACING;                              // :699-701
+    if (doi == te) {                                                          // :705-716 (contacts were handled in pass A)
+        st &= ~ST_TRACING;
+        st = isolate_ct(st);
+        atomicAdd(&S.totiso[r], 1ull);
+        S.ct_head[a] = CT_NONE;
+    }
+    if (txp > 0) {                                                            // :718-750
+        if (!(st & ST_ISO)) atomicOr(&S.err[r], ERR_TRACED_NOT_ISO);
+        txp -= 1;
+        if (txp == 0) {
+            st &= ~ST_ISO;
+            S.isovia[a] = VIA_NULL;
+            if (P.ctstrat == 3) {
+                const uint4 w = philox(i, day, S_CT3, 0, key);
+                const int h = st_health(st);
+                if ((h == LAT && bern(w.x, c_tab.ct3_lat_thr)) || (h == PRE && bern(w.x, c_tab.ct3_pre_thr)) ||
+                    (h == ASYMP && bern(w.x, c_tab.ct3_asymp_thr)) || h == MILD || h == INF || h == MISO || h == IISO) {
+                    st |= ST_ISO; S.isovia[a] = VIA_CT; txp = 14;
+                }
+            }
+        }
+    }
+    st = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);                    // the iso that :778 sees
+    if (post) st = isolate_ct(st);
+    if (txp != txp0) S.tracedxp[a] = (int16_t)txp;
+    return st;
+}
+
+// ============================================================================ time_update :399-428 (+ snapshot :218-223)
+// Thread per 8 consecutive agents: 128-bit loads of the expiry days and status words, 128-bit store of the next
+// hmatrix column. tis/doi are not stored (absolute days), and the next-day contact count (:425) is drawn lazily by
+// dyntrans, so an agent-day costs one compare unless the agent's state expires (or tracing is on).
+__global__ void __launch_bounds__(256) k_time_update(Dev S, int day) {
+    const int r = blockIdx.y;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 >= S.N) return;
+    const size_t a0 = (size_t)r * S.Np + i0;
+    const DevPset &P = S.psets[S.pset_of[r]];
+    union { uint4 v; int16_t e[8]; } ex;
+    union { uint4 v[2]; uint32_t s[8]; } st;
+    ex.v = *reinterpret_cast<const uint4 *>(S.expday + a0);
+    st.v[0] = *reinterpret_cast<const uint4 *>(S.status + a0);
+    st.v[1] = *reinterpret_cast<const uint4 *>(S.status + a0 + 4);
+    unsigned fire = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fire |= (unsigned)((int)ex.e[k] <= day && i0 + k < S.N) << k;
+    if (P.ctstrat != 0) {
+        const uint2 key = S.key[r];
+        const size_t wi = (size_t)r * S.nwords + (i0 >> 5);
+        const unsigned sh = i0 & 31;
+        const unsigned pre = (S.mark_pre[wi] >> sh) & 0xFF, post = (S.mark_post[wi] >> sh) & 0xFF;
+        if (pre) atomicAnd(&S.mark_pre[wi], ~(0xFFu << sh));          // marks are consumed by this update
+        if (post) atomicAnd(&S.mark_post[wi], ~(0xFFu << sh));
+        for (int k = 0; k < 8 && i0 + k < S.N; ++k) {
+            const uint32_t ns = agent_update_ct(S, P, r, i0 + k, day, key, st.s[k], (fire >> k) & 1, (pre >> k) & 1, (post >> k) & 1);
+            if (ns != st.s[k]) { st.s[k] = ns; S.status[a0 + k] = ns; }
+        }
+    } else {
+        // isob trails iso only for agents isolated by seeding (their day-1 budget predates it, :186): resync
+        unsigned stale = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) stale |= (((st.s[k] >> 19) ^ (st.s[k] >> 20)) & 1u) << k;
+        if (fire | stale) {
+            const uint2 key = S.key[r];
+            for (int k = 0; k < 8; ++k) {
+                if (!(((fire | stale) >> k) & 1)) continue;
+                uint32_t ns = st.s[k];
+                if ((fire >> k) & 1) ns = transition(S, P, r, i0 + k, day, ns, key, st_swap(ns), false, true);
+                ns = (ns & ST_ISO) ? (ns | ST_ISOB) : (ns & ~ST_ISOB);
+                st.s[k] = ns; S.status[a0 + k] = ns;
+            }
+        }
+    }
+    if (S.store_hm && day < S.T) {                            // column st+1 = state at the start of the next day
+        int16_t *col = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
+        if ((S.N & 7) == 0) {
+            union { uint4 v; int16_t h[8]; } o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.h[k] = (int16_t)st_health(st.s[k]);
+            *reinterpret_cast<uint4 *>(col) = o.v;
+        } else {
+            for (int k = 0; k < 8 && i0 + k < S.N; ++k) col[k] = (int16_t)st_health(st.s[k]);
+        }
+    }
+}
+
+// clears the pass-A marks after time_update consumed them
+__global__ void k_clear_marks(Dev S) {
+    const size_t n = (size_t)S.R * S.nwords;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        S.mark_pre[i] = 0; S.mark_post[i] = 0;
+    }
+}
+
+// ============================================================================ curves: :259-293 from the transition counters
+// During the run inc[r][g][t][s] counted entries into s first visible in column t and prev[] parked the exits.
+// Every state is entered at most once per agent (SUS->LAT->PRE|ASYMP->...->REC|DED), so first-occurrence incidence
+// (:270-280) is the entry count and prevalence (:282-293) is the running sum entries - exits. Group 0 = all agents.
+__global__ void __launch_bounds__(64) k_curves_finalize(Dev S) {
+    const int r = blockIdx.x, s = threadIdx.x;
+    if (s >= 12) return;
+    const size_t T = S.T;
+    int *inc0 = S.inc + (size_t)r * 6 * T * 12, *prev0 = S.prev + (size_t)r * 6 * T * 12;
+    for (size_t t = 0; t < T; ++t) { inc0[t * 12 + s] = 0; prev0[t * 12 + s] = 0; }
+    long long lat = 0;
+    for (int g = 1; g <= 5; ++g) {
+        int *inc = inc0 + (size_t)g * T * 12, *prev = prev0 + (size_t)g * T * 12;
+        int run = prev[s];
+        inc0[s] += inc[s]; prev0[s] += run;
+        for (size_t t = 1; t < T; ++t) {
+            const int in = inc[t * 12 + s];
+            run += in - prev[t * 12 + s];
+            prev[t * 12 + s] = run;
+            inc0[t * 12 + s] += in; prev0[t * 12 + s] += run;
+        }
+    }
+    if (s == LAT) { for (size_t t = 0; t < T; ++t) lat += inc0[t * 12 + LAT]; S.latsum[r] = lat; }
+}
+
+// ============================================================================ _count_infectors :295-313
+__global__ void __launch_bounds__(256) k_count_infectors(Dev S) {
+    const int r = blockIdx.x;
+    __shared__ int c[4];
+    if (threadIdx.x < 4) c[threadIdx.x] = 0;
+    __syncthreads();
+    int l[4] = {0, 0, 0, 0};
+    bool bad = false;
+    for (int i = threadIdx.x; i < S.N; i += blockDim.x) {
+        const size_t a = (size_t)r * S.Np + i;
+        if (st_health(S.status[a]) == SUS) continue;
+        const int f = S.sickfrom[a];
+        if (f == PRE) l[0]++; else if (f == ASYMP) l[1]++; else if (f == MILD || f == MISO) l[2]++;
+        else if (f == INF || f == IISO) l[3]++; else bad = true;
+    }
+    for (int k = 0; k < 4; ++k) if (l[k]) atomicAdd(&c[k], l[k]);
+    if (bad) atomicOr(&S.err[r], ERR_SICKFROM);
+    __syncthreads();
+    if (threadIdx.x < 4) S.infectors[r * 4 + threadIdx.x] = c[threadIdx.x];
+}
+
+// ============================================================================ literal reductions over given matrices
+// _get_column_incidence :270-280 (first occurrence along each row) and _get_column_prevalence :282-293 (count per
+// column), for "all" and the five _splitstate groups :247-256. hm is [M][T][N]; thread per agent walks its row.
+__global__ void __launch_bounds__(256) k_reduce_hmatrix(const int16_t *hm, const int *ags, int N, int T, int *inc, int *prev) {
+    const int m = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool valid = i < N;
+    const int g = valid ? ags[(size_t)m * N + i] : 0;          // 1..5
+    const int16_t *row = hm + (size_t)m * T * N + i;
+    int *incm = inc + (size_t)m * 6 * T * 12, *prevm = prev + (size_t)m * 6 * T * 12;
+    unsigned seen = 0;
+    for (int t = 0; t < T; ++t) {
+        int h = valid ? row[(size_t)t * N] : -1;
+        if (h < 0 || h > 11) h = -1;
+        const bool first = h >= 0 && !((seen >> h) & 1);
+        if (h >= 0) seen |= 1u << h;
+        // warp-aggregate equal (group, state, first) triples before touching global memory
+        const int keyv = h < 0 ? -1 : (g * 12 + h) * 2 + (first ? 1 : 0);
+        const unsigned peers = __match_any_sync(FULL, keyv);
+        if (h >= 0 && (__ffs(peers) - 1) == lane) {
+            const int c = __popc(peers);
+            atomicAdd(&prevm[((size_t)g * T + t) * 12 + h], c);
+            atomicAdd(&prevm[((size_t)0 * T + t) * 12 + h], c);
+            if (first) { atomicAdd(&incm[((size_t)g * T + t) * 12 + h], c); atomicAdd(&incm[((size_t)0 * T + t) * 12 + h], c); }
+        }
+    }
+}
+
+// ============================================================================ peek / poke (tests read `humans` like test/runtests.jl)
+__global__ void __launch_bounds__(256) k_peek(Dev S, int field, int r, int day, int *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.N) return;
+    const size_t a = (size_t)r * S.Np + i;
+    const uint32_t st = S.status[a];
+    const int done = day - 1;                    // number of time_updates so far
+    const int tis = done - S.entry[a];
+    int v = 0;
+    switch (field) {
+    case 0: v = st_health(st); break;
+    case 1: v = st_swap(st); break;
+    case 2: v = S.sickfrom[a]; break;
+    case 3: v = budget_of(S, S.key[r], i, day, st); break;
+    case 4: v = st_ag(st) + 1; break;
+    case 5: v = tis; break;
+    case 6: v = (st_health(st) == SUS && st_swap(st) == LAT) ? tis : (int)S.expday[a] - (int)S.entry[a]; break;
+    case 7: { const uint32_t d4 = S.dur[a]; out[4 * i] = d4 & 0xFF; out[4 * i + 1] = (d4 >> 8) & 0xFF; out[4 * i + 2] = (d4 >> 16) & 0xFF; out[4 * i + 3] = d4 >> 24; return; }
+    case 8: v = done - S.latday[a]; break;
+    case 9: v = (st & ST_ISO) ? 1 : 0; break;
+    case 10: v = S.isovia[a]; break;
+    case 11: v = (st & ST_TRACING) ? 1 : 0; break;
+    case 12: v = S.tracestart[a]; break;
+    case 13: v = S.traceend[a]; break;
+    case 14: v = S.tracedxp[a]; break;
+    case 15: {
+        const uint2 *log = S.ct_log + (size_t)r * S.ct_cap;
+        const uint32_t head = S.ct_head[a];
+        for (uint32_t e = head; e != CT_NONE; e = log[e].y) {
+            bool dup = false;
+            for (uint32_t f = head; f != e; f = log[f].y) if (log[f].x == log[e].x) { dup = true; break; }
+            v += !dup;
+        }
+        break; }
+    }
+    out[i] = v;
+}
+
+__global__ void k_poke(Dev S, int field, int r, int i, int day, int value) {
+    const size_t a = (size_t)r * S.Np + i;
+    uint32_t st = S.status[a];
+    const int done = day - 1;
+    switch (field) {
+    case 0: {
+        const int oldh = st_health(st);
+        if (is_infectious(oldh) != is_infectious(value)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
+        st = st_set_health(st, value); break; }
+    case 1: st = st_set_swap(st, value); break;
+    case 2: S.sickfrom[a] = (uint8_t)value; break;
+    case 3: st = (st & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)(value & 0xFF) | ((uint32_t)day << 22); break;
+    case 5: { const int exp = (int)S.expday[a] - (int)S.entry[a]; S.entry[a] = (int16_t)(done - value); S.expday[a] = (int16_t)(done - value + exp); break; }
+    case 6: S.expday[a] = (int16_t)((int)S.entry[a] + value); break;
+    case 8: S.latday[a] = (int16_t)(done - value); break;
+    case 9: st = value ? (st | ST_ISO | ST_ISOB) : (st & ~(ST_ISO | ST_ISOB)); break;
+    case 10: S.isovia[a] = (uint8_t)value; break;
+    case 11: st = value ? (st | ST_TRACING) : (st & ~ST_TRACING); break;
+    case 12: S.tracestart[a] = (int16_t)value; break;
+    case 13: S.traceend[a] = (int16_t)value; break;
+    case 14: S.tracedxp[a] = (int16_t)value; break;
+    default: break;
+    }
+    S.status[a] = st;
+}
+
+// ============================================================================ launchers
+static inline dim3 agent_grid(const Dev &S, int per_thread) {
+    return dim3((unsigned)((S.Np + 256 * per_thread - 1) / (256 * per_thread)), (unsigned)S.R);
+}
+
+int launch_initialize(const Dev &S, cudaStream_t s) { k_initialize<<<agent_grid(S, 1), 256, 0, s>>>(S); return 1; }
+int launch_build_groups(const Dev &S, cudaStream_t s) { k_build_groups<<<S.R, 256, 0, s>>>(S); return 1; }
+int launch_insert_infected(const Dev &S, int which, int health, int num, int ag, int call_id, int day, cudaStream_t s) {
+    k_insert_infected<<<S.R, 256, 0, s>>>(S, which, health, num, ag, call_id, day); return 1;
+}
+int launch_first_column(const Dev &S, cudaStream_t s) { k_first_column<<<agent_grid(S, 1), 256, 0, s>>>(S); return 1; }
+int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s) { k_dyntrans_exact<<<S.R, 32, 0, s>>>(S, day); return 1; }
+int launch_ct_identify(const Dev &S, int day, cudaStream_t s) { k_ct_identify<<<agent_grid(S, 1), 256, 0, s>>>(S, day); return 1; }
+int launch_time_update(const Dev &S, int day, cudaStream_t s) { k_time_update<<<agent_grid(S, 8), 256, 0, s>>>(S, day); return 1; }
+int launch_clear_marks(const Dev &S, cudaStream_t s) { k_clear_marks<<<296, 256, 0, s>>>(S); return 1; }
+int launch_curves_finalize(const Dev &S, cudaStream_t s) { k_curves_finalize<<<S.R, 64, 0, s>>>(S); return 1; }
+int launch_count_infectors(const Dev &S, cudaStream_t s) { k_count_infectors<<<S.R, 256, 0, s>>>(S); return 1; }
+int launch_reduce_hmatrix(const int16_t *hm, const int *ags, int M, int N, int T, int *inc, int *prev, cudaStream_t s) {
+    k_reduce_hmatrix<<<dim3((unsigned)((N + 255) / 256), (unsigned)M), 256, 0, s>>>(hm, ags, N, T, inc, prev); return 1;
+}
+int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s) { k_peek<<<(S.N + 255) / 256, 256, 0, s>>>(S, field, r, day, out); return 1; }
+int launch_poke(const Dev &S, int field, int r, int i, int day, int value, cudaStream_t s) { k_poke<<<1, 1, 0, s>>>(S, field, r, i, day, value); return 1; }
+
+}  // namespace cabm

@@ -1,0 +1,23 @@
+// cabm_kernels.h — host-callable launchers of the kernels in cabm_kernels.cu. Each returns the number of
+// kernel launches it issued (for cabm_launch_count).
+#pragma once
+#include "cabm_device.cuh"
+
+namespace cabm {
+
+void upload_const_tables(const ConstTables &t, cudaStream_t s);
+int launch_initialize(const Dev &S, cudaStream_t s);
+int launch_build_groups(const Dev &S, cudaStream_t s);
+int launch_insert_infected(const Dev &S, int which, int health, int num, int ag, int call_id, int day, cudaStream_t s);
+int launch_first_column(const Dev &S, cudaStream_t s);
+int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s);
+int launch_ct_identify(const Dev &S, int day, cudaStream_t s);
+int launch_time_update(const Dev &S, int day, cudaStream_t s);
+int launch_clear_marks(const Dev &S, cudaStream_t s);
+int launch_curves_finalize(const Dev &S, cudaStream_t s);
+int launch_count_infectors(const Dev &S, cudaStream_t s);
+int launch_reduce_hmatrix(const int16_t *hm, const int *ags, int M, int N, int T, int *inc, int *prev, cudaStream_t s);
+int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s);
+int launch_poke(const Dev &S, int field, int r, int i, int day, int value, cudaStream_t s);
+
+}  // namespace cabm

@@ -1,0 +1,159 @@
+/* cabm.h — C ABI of libcabm_b200.so: covid19abm.jl's simulation path on B200 (sm_100a).
+ *
+ * The reference has no FFI: its boundary is the Julia API of /root/reference/src/covid19abm.jl.
+ * Each entry point below names the Julia interface it replaces (file:line under /root/reference).
+ * Plain C types only; no exceptions cross the ABI: every call returns 0 or a CABM_E_* code and
+ * cabm_last_error() gives the message (the reference's error("...") strings where one exists).
+ * One handle = one GPU = one stream; a handle is not thread-safe, distinct handles are independent.
+ * There is no CPU fallback: without a CUDA device cabm_create fails with CABM_E_CUDA.
+ */
+#ifndef CABM_H
+#define CABM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* HEALTH enum — src/covid19abm.jl:5 (0-based like Julia's @enum; these are the hmatrix codes :221) */
+enum { CABM_SUS = 0, CABM_LAT, CABM_PRE, CABM_ASYMP, CABM_MILD, CABM_MISO, CABM_INF, CABM_IISO,
+       CABM_HOS, CABM_ICU, CABM_REC, CABM_DED, CABM_UNDEF };
+/* isovia symbols — src/covid19abm.jl:21 */
+enum { CABM_VIA_NULL = 0, CABM_VIA_QU, CABM_VIA_PI, CABM_VIA_MI, CABM_VIA_CT };
+
+/* error codes */
+enum { CABM_OK = 0, CABM_E_ARG = 1, CABM_E_CUDA = 2, CABM_E_PARAM = 3, CABM_E_STATE = 4, CABM_E_MODEL = 5 };
+
+/* per-replicate device error word (cabm_get_scalars): one bit per in-model error() of the reference */
+enum { CABM_ERR_NO_SWAP = 1,        /* :418 "swap expired, but no swap set." */
+       CABM_ERR_NO_SUSCEPTIBLE = 2, /* :371-372 */
+       CABM_ERR_TRACED_NOT_ISO = 4, /* :719 */
+       CABM_ERR_EMPTY_GROUP = 8,    /* rand(grps[i], g) on an empty group (:807 would throw) */
+       CABM_ERR_CT_LOG_FULL = 16,   /* contact log capacity exceeded (implementation limit) */
+       CABM_ERR_SICKFROM = 32 };    /* :308 */
+
+/* ModelParameters — src/covid19abm.jl:31-55, field for field.
+ * prov_id indexes the rows of get_province_ag (:319-333): 0 alberta, 1 bc, 2 canada, 3 manitoba,
+ * 4 newbruns, 5 newfdland, 6 nwterrito, 7 novasco, 8 nunavut, 9 ontario, 10 pei, 11 quebec,
+ * 12 saskat, 13 yukon, 14 newyork. fctcapture/fcontactst are Float16 in Julia (:51-52): pass the
+ * binary16-rounded value widened to float. */
+typedef struct cabm_params {
+    double beta;              /* β :32 */
+    double frelasymp;         /* :33 */
+    int32_t seasonal;         /* :34 */
+    int32_t popsize;          /* :35 */
+    int32_t prov_id;          /* :36 */
+    int32_t calibration;      /* :37 */
+    int32_t modeltime;        /* :38 */
+    int32_t initialinf;       /* :39 */
+    int32_t initialhi;        /* :40 */
+    int32_t tau_mild;         /* τmild :43 */
+    double asymp_props[5];    /* :41 */
+    double mild_props[5];     /* :42 */
+    double fmild;             /* :44 */
+    double fsevere;           /* :45 */
+    double fpreiso;           /* :47 */
+    double quar_grp_frac;     /* :49 */
+    int32_t tpreiso;          /* :46 */
+    int32_t quar_grp;         /* :48 (1..5) */
+    int32_t ctstrat;          /* :50 (0, 1 or 3; anything else is "invalid ct strategy" :165) */
+    int32_t cdaysback;        /* :53 */
+    int32_t strat3qdays;      /* :54 */
+    float fctcapture;         /* :51 */
+    float fcontactst;         /* :52 */
+    int32_t _pad;
+} cabm_params;
+
+typedef struct cabm_handle cabm_handle;
+
+/* cabm_create flags */
+enum { CABM_STORE_HMATRIX = 1 };   /* keep the popsize x modeltime state matrix of every replicate in HBM */
+/* dyntrans schedule */
+enum { CABM_MODE_EXACT = 0,        /* serial-equivalent: bit-identical to the sequential reference order */
+       CABM_MODE_NATIVE = 1 };     /* per-infector parallel with atomics: ensemble-equivalent */
+
+/* field ids for cabm_get_field / cabm_set_field — the members of `Human` (src/covid19abm.jl:8-27) */
+enum { CABM_F_HEALTH = 0, CABM_F_SWAP, CABM_F_SICKFROM, CABM_F_NEXTDAY_MEETCNT, CABM_F_AG, CABM_F_TIS,
+       CABM_F_EXP, CABM_F_DUR /* 4 per agent */, CABM_F_DOI, CABM_F_ISO, CABM_F_ISOVIA, CABM_F_TRACING,
+       CABM_F_TRACESTART, CABM_F_TRACEEND, CABM_F_TRACEDXP, CABM_F_NCONTACTS /* |tracecontacts| */ };
+
+/* message of the last failing call on this handle (or of the last failing cabm_create if h == NULL) */
+const char *cabm_last_error(const cabm_handle *h);
+
+/* Replaces the module-level state `humans`, `p`, `BETAS`, `ct_data` (:69-73) by device buffers sized for
+ * max_replicates independent copies of a popsize-agent population. */
+int cabm_create(cabm_handle **out, int device, int max_replicates, int popsize, int modeltime, int flags);
+void cabm_destroy(cabm_handle *h);
+
+/* reset_params(ip) :146-168 + init_betas :191-215 for n_rep replicates at once. psets[pset_of_rep[r]] is the
+ * ModelParameters of replicate r (pset_of_rep == NULL: all use psets[0]); seeds[r] plays Random.seed! (:78).
+ * All psets must share the handle's popsize and modeltime. Errors :164-165, :334 -> CABM_E_PARAM. */
+int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_psets, const int32_t *pset_of_rep,
+                   int n_rep, const uint64_t *seeds, int mode);
+
+/* main(ip) :104-142 for every configured replicate: initialize, seed, the day loop, then the
+ * incidence/prevalence reductions (:259-293) and _count_infectors (:295-313), all on device.
+ * Asynchronous on the handle's stream; cabm_sync or any cabm_get_* waits. */
+int cabm_run(cabm_handle *h);
+int cabm_sync(cabm_handle *h);
+/* device time of the last cabm_run in milliseconds (CUDA events on the handle's stream) */
+int cabm_last_run_ms(cabm_handle *h, float *ms);
+/* Per-kernel-class device time of a run: with profiling on, cabm_run brackets every launch with CUDA events on
+ * the handle's stream (and synchronises at the end); cabm_get_profile returns the summed milliseconds and the launch
+ * count per class. Classes: dyntrans :790-834, time_update :399-428 (+snapshot), ct_dynamics pass A :705-716,
+ * everything else (initialize, seeding, group tables, reductions). */
+enum { CABM_K_DYNTRANS = 0, CABM_K_TIME_UPDATE = 1, CABM_K_CT_IDENTIFY = 2, CABM_K_OTHER = 3, CABM_N_KCLASS = 4 };
+int cabm_set_profiling(cabm_handle *h, int on);
+int cabm_get_profile(cabm_handle *h, float *ms /*[CABM_N_KCLASS]*/, int32_t *launches /*[CABM_N_KCLASS]*/);
+/* number of kernel launches issued by this handle so far */
+int64_t cabm_launch_count(const cabm_handle *h);
+
+/* The individual phases, as the reference's tests drive them on `cv.humans` (test/runtests.jl):
+ * initialize() :171-188; insert_infected(health, num, ag) :360-395 (call_id names the seeding call in the
+ * draw contract: 0 and 1 are the two calls main makes); dyntrans(st, grps) :790-834;
+ * time_update() :399-428. The handle keeps the day index st (1-based), advanced by time_update. */
+int cabm_step_initialize(cabm_handle *h);
+int cabm_step_insert_infected(cabm_handle *h, int health, int num, int ag, int call_id);
+int cabm_step_dyntrans(cabm_handle *h);
+int cabm_step_time_update(cabm_handle *h);
+int cabm_get_day(const cabm_handle *h);
+/* (totalmet, totalinf) returned by the last dyntrans :833, per replicate */
+int cabm_get_dyntrans_counters(cabm_handle *h, int32_t *totalmet, int32_t *totalinf);
+
+/* hmatrix of one replicate: Int16, popsize x modeltime, column-major (:111,:141). Needs CABM_STORE_HMATRIX. */
+int cabm_get_hmatrix(cabm_handle *h, int replicate, int16_t *out);
+/* every replicate's matrix, [n_rep][modeltime][popsize] */
+int cabm_get_hmatrix_all(cabm_handle *h, int16_t *out);
+/* _get_incidence_and_prev :259-268 for "all" (group 0) and the five _splitstate groups (:247-256), as
+ * runsim collects them (:91-97): inc and prev are int32 [n_rep][6][modeltime][12]. */
+int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev);
+/* infectors = _count_infectors() :295-313 [n_rep][4]; totalisolated = ct_data.totalisolated :61,649 [n_rep];
+ * lat_inc_sum = sum(_get_column_incidence(h, LAT)) (scripts/local_run.jl:143) [n_rep]; err = CABM_ERR_* bits.
+ * Any pointer may be NULL. */
+int cabm_get_scalars(cabm_handle *h, int64_t *infectors, int64_t *totalisolated, int64_t *lat_inc_sum,
+                     uint32_t *err);
+/* one member of every Human of one replicate, widened to int32 (CABM_F_DUR: 4 per agent) */
+int cabm_get_field(cabm_handle *h, int field, int replicate, int32_t *out);
+int cabm_set_field(cabm_handle *h, int field, int replicate, int agent, int32_t value);
+
+/* _get_column_incidence :270-280 and _get_column_prevalence :282-293 over caller-supplied matrices:
+ * hm is Int16 [n_mat][t][n] (each popsize x modeltime column-major), ags[n_mat][n] in 1..5;
+ * inc/prev are int32 [n_mat][6][t][12]. Runs on the handle's device and stream. */
+int cabm_reduce_hmatrix(cabm_handle *h, const int16_t *hm, int n_mat, int n, int t, const int32_t *ags,
+                        int32_t *inc, int32_t *prev);
+
+/* pinned host memory for result buffers (optional; any host pointer is accepted by cabm_get_*) */
+void *cabm_host_alloc(uint64_t bytes);
+void cabm_host_free(void *p);
+
+/* draw-contract tables for cross-checking: name in {"lat","pre","asy","inf","psi","mu",
+ * "nb1".."nb5"}; writes up to cap thresholds, returns the table length or -1. Host-only, needs no GPU. */
+int cabm_get_table(const char *name, int32_t *base, uint32_t *thr, int cap);
+/* gpw = Int.(round.(cm[ag]*cnts)) :804, ag 1..5. Host-only. */
+void cabm_get_gpw(int ag, int cnts, int32_t out[5]);
+const char *cabm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,135 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs — bit-exact.
+
+The reference's own tests hold no golden vectors (test/runtests.jl is invariants only), so the
+oracle (oracle/abm_oracle.c, pinned in tests/test_oracle_*.py) is the comparison; tolerance is zero:
+every element of the Int16 state matrix, every curve entry and every scalar must be equal.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def to_oracle(O, ip):
+    return O.make_params(beta=ip.β, frelasymp=ip.frelasymp, seasonal=ip.seasonal, popsize=ip.popsize, prov=ip.prov,
+                         calibration=ip.calibration, modeltime=ip.modeltime, initialinf=ip.initialinf,
+                         initialhi=ip.initialhi, asymp_props=ip.asymp_props, mild_props=ip.mild_props,
+                         tau_mild=ip.τmild, fmild=ip.fmild, fsevere=ip.fsevere, tpreiso=ip.tpreiso,
+                         fpreiso=ip.fpreiso, quar_grp=ip.quar_grp, quar_grp_frac=ip.quar_grp_frac,
+                         ctstrat=ip.ctstrat, fctcapture=ip.fctcapture, fcontactst=ip.fcontactst,
+                         cdaysback=ip.cdaysback, strat3qdays=ip.strat3qdays)
+
+
+def first_mismatch(a, b):
+    bad = np.argwhere(a != b)
+    if len(bad) == 0:
+        return None
+    k = bad[np.argmin(bad[:, 1])] if a.ndim == 2 else bad[0]
+    return tuple(int(x) for x in k), a[tuple(k)], b[tuple(k)]
+
+
+CONFIGS = {
+    # BASELINE.json configs[0]: single replicate Ontario, no isolation or tracing
+    "A_ontario": dict(β=0.0345, prov="ontario", initialinf=1, modeltime=500),
+    # configs[1]: isolation on (tpreiso=0 never activates fpreiso in the loop: SURVEY Q1; the tpreiso=1 variant does)
+    "B_isolation": dict(β=0.0345, prov="ontario", initialinf=1, modeltime=500, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3, tpreiso=0),
+    "B_isolation_tpre1": dict(β=0.05, prov="ontario", initialinf=5, modeltime=300, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3, tpreiso=1),
+    # configs[2]: contact tracing (ctstrat 2 does not exist in the source, :165)
+    "C_ct1": dict(β=0.05, prov="ontario", initialinf=5, modeltime=300, fmild=0.5, τmild=1, fsevere=1.0, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3),
+    "C_ct3": dict(β=0.05, prov="ontario", initialinf=5, modeltime=300, fmild=0.5, τmild=1, fsevere=1.0, ctstrat=3, strat3qdays=7, fctcapture=0.5, fcontactst=0.5, cdaysback=3),
+    "C_ct1_full": dict(β=0.06, prov="newyork", initialinf=10, modeltime=200, ctstrat=1, fctcapture=1.0, fcontactst=1.0, cdaysback=5),
+    # configs[3]: calibration mode
+    "D_calibration": dict(β=0.0525, prov="newyork", calibration=True, modeltime=50, initialinf=1),
+    # configs[4] ingredients at the reference's population size: quarantine group, herd immunity, seasonality
+    "E_quarantine": dict(β=0.06, prov="ontario", initialinf=10, modeltime=300, quar_grp_frac=0.5, quar_grp=5),
+    "seasonal_hi": dict(β=0.08, prov="bc", initialinf=3, initialhi=2000, modeltime=250, seasonal=True, frelasymp=0.3),
+    "hot": dict(β=0.2, prov="nunavut", initialinf=20, modeltime=120, fsevere=0.8, fmild=0.3, τmild=2),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("seed", [726, 1452])
+def test_main_bit_exact(cv, O, name, seed):
+    ip = cv.ModelParameters(**CONFIGS[name])
+    hm = cv.main(ip, seed=seed)
+    sim = O.Sim(to_oracle(O, ip), seed)
+    ref = sim.main()
+    mm = first_mismatch(np.asarray(hm), np.asarray(ref))
+    assert mm is None, f"first mismatch (agent, day) {mm}"
+    pop = cv.humans()
+    for f in ["health", "swap", "sickfrom", "ag", "iso", "isovia", "nextday_meetcnt", "tis", "exp", "doi",
+              "tracing", "tracestart", "traceend", "tracedxp"]:
+        assert (pop.field(f) == sim.field(f)).all(), f
+    assert (pop.field("dur") == sim.field("dur")).all()
+    sc = pop.scalars()
+    assert (sc["infectors"][0] == sim.count_infectors()).all()
+    assert sc["totalisolated"][0] == sim.totalisolated
+    inc, prev = pop.curves()
+    rinc, rprev = O.collect_curves(ref, sim.field("ag"))
+    assert (inc[0] == rinc).all() and (prev[0] == rprev).all()
+    assert sc["lat_inc_sum"][0] == O.get_column_incidence(ref, O.LAT).sum()
+    sim.close()
+
+
+def test_ensemble_bit_exact(cv, O):
+    """64 replicates x 2 parameter sets in one launch sequence, against the oracle's replicate loop."""
+    a = cv.ModelParameters(β=0.0345, prov="ontario", modeltime=200, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3)
+    b = cv.ModelParameters(β=0.07, prov="ontario", modeltime=200, initialinf=3, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3)
+    nrep = 64
+    seeds = [726 * (i + 1) for i in range(nrep)]
+    pof = [i % 2 for i in range(nrep)]
+    got = cv.run_ensemble([a, b], nrep, seeds=seeds, pset_of_rep=pof, want_hmatrix=True)
+    ref = O.run_ensemble([to_oracle(O, a), to_oracle(O, b)], pof, seeds, nthreads=8, want_hmatrix=True)
+    assert (got["err"] == 0).all()
+    assert (got["hmatrix"] == ref["hmatrix"]).all()
+    assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all()
+    assert (got["infectors"] == ref["infectors"]).all()
+    assert (got["totalisolated"] == ref["totalisolated"]).all()
+
+
+def test_reduce_hmatrix_matches_literal_reductions(cv, O):
+    """_get_column_incidence / _get_column_prevalence (:270-293) on device for arbitrary matrices, including
+    rows that revisit a state (first occurrence only) — against the oracle's literal findfirst/findall scans."""
+    rng = np.random.default_rng(5)
+    M, N, T = 3, 1000, 40
+    hm = rng.integers(0, 12, size=(M, T, N)).astype(np.int16)
+    ags = rng.integers(1, 6, size=(M, N)).astype(np.int32)
+    with cv.Population(1, N, T) as pop:
+        inc, prev = pop.reduce_hmatrix(hm, ags)
+    for m in range(M):
+        rinc, rprev = O.collect_curves(hm[m].T, ags[m])
+        assert (inc[m] == rinc).all() and (prev[m] == rprev).all()
+        for s in range(12):
+            assert (inc[m, 0, :, s] == O.get_column_incidence(hm[m].T, s)).all()
+            assert (prev[m, 0, :, s] == O.get_column_prevalence(hm[m].T, s)).all()
+
+
+def test_stepwise_fields_follow_oracle(cv, O):
+    """initialize / insert_infected / dyntrans / time_update one phase at a time, all agent fields compared."""
+    ip = cv.ModelParameters(β=0.3, prov="ontario", modeltime=60, initialinf=1, fmild=0.5, τmild=1, fsevere=0.7,
+                            ctstrat=1, fctcapture=1.0, fcontactst=0.7, cdaysback=3, quar_grp_frac=0.3, quar_grp=3)
+    seed = 99
+    names = ["health", "swap", "sickfrom", "ag", "iso", "isovia", "nextday_meetcnt", "tis", "exp", "doi",
+             "tracing", "tracestart", "traceend", "tracedxp"]
+    with cv.Population(1, ip.popsize, ip.modeltime) as pop:
+        pop.configure(ip, [seed])
+        sim = O.Sim(to_oracle(O, ip), seed)
+        pop.initialize(); sim.initialize()
+        for f in names:
+            assert (pop.field(f) == sim.field(f)).all(), ("init", f)
+        pop.insert_infected(cv.PRE, 30, 4, call_id=0); sim.insert_infected(O.PRE, 30, 4, 0)
+        sim.p.fpreiso = 0.0
+        for f in names:
+            assert (pop.field(f) == sim.field(f)).all(), ("seed", f)
+        for day in range(1, 31):
+            met, inf = pop.dyntrans()
+            rmet, rinf = sim.dyntrans()
+            assert (int(met[0]), int(inf[0])) == (rmet, rinf), day
+            for f in ["nextday_meetcnt", "swap", "sickfrom", "exp"]:
+                assert (pop.field(f) == sim.field(f)).all(), (day, "dyntrans", f)
+            pop.time_update(); sim.time_update()
+            for f in names:
+                g, r = pop.field(f), sim.field(f)
+                assert (g == r).all(), (day, "time_update", f, np.nonzero(g != r)[0][:5])
+        assert pop.totalisolated()[0] == sim.totalisolated
+        sim.close()
