@@ -144,6 +144,8 @@ def lib():
     L.cabm_last_run_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.cabm_launch_count.argtypes = [vp]; L.cabm_launch_count.restype = i64
     L.cabm_set_profiling.argtypes = [vp, i32]
+    L.cabm_set_path.argtypes = [vp, i32]
+    L.cabm_get_last_path.argtypes = [vp]
     L.cabm_get_profile.argtypes = [vp, vp, vp]
     L.cabm_step_initialize.argtypes = [vp]
     L.cabm_step_insert_infected.argtypes = [vp, i32, i32, i32, i32]
@@ -267,10 +269,18 @@ class Population:
 
     def profile(self):
         """{class: (milliseconds, launches)} of the last profiled run."""
-        ms = np.zeros(4, dtype=np.float32)
-        n = np.zeros(4, dtype=np.int32)
+        ms = np.zeros(5, dtype=np.float32)
+        n = np.zeros(5, dtype=np.int32)
         self._chk(self.L.cabm_get_profile(self.h, ms.ctypes.data, n.ctypes.data))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(["dyntrans", "time_update", "ct_identify", "other"])}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(["dyntrans", "time_update", "ct_identify", "other", "fused"])}
+
+    def set_path(self, path):
+        """'auto' | 'multikernel' | 'fused' (include/cabm.h CABM_PATH_*)."""
+        self._chk(self.L.cabm_set_path(self.h, {"auto": 0, "multikernel": 1, "fused": 2}[path]))
+
+    @property
+    def last_path(self):
+        return {0: None, 1: "multikernel", 2: "fused"}[self.L.cabm_get_last_path(self.h)]
 
     @property
     def day(self):
@@ -368,13 +378,14 @@ class Population:
 _last = {}
 
 
-def main(ip, seed=0, device=0):
+def main(ip, seed=0, device=0, path="auto"):
     """main(ip::ModelParameters) :104-142 -> Matrix{Int16}(popsize, modeltime).
 
     Julia seeds its global RNG outside main (runsim :78); here the replicate's Philox key is `seed`.
     The final agent state stays readable through `humans()` like the reference's global `humans`."""
     pop = Population(1, ip.popsize, ip.modeltime, store_hmatrix=True, device=device)
     pop.configure(ip, [seed])
+    pop.set_path(path)
     pop.run()
     pop.check_errors()
     old = _last.pop("pop", None)
@@ -427,7 +438,7 @@ def runsim(simnum, ip, device=0):
     return res
 
 
-def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_hmatrix=False, device=0, pop=None):
+def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_hmatrix=False, device=0, pop=None, path="auto"):
     """pmap(x -> runsim(x, ip), 1:nsims) (scripts/local_run.jl:28-30) as one device launch sequence.
     ip may be a list of ModelParameters with pset_of_rep choosing one per replicate (β sweeps)."""
     first = ip[0] if isinstance(ip, (list, tuple)) else ip
@@ -438,12 +449,14 @@ def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_
         pop = Population(nsims, first.popsize, first.modeltime, store_hmatrix=want_hmatrix, device=device)
     try:
         pop.configure(ip, seeds, pset_of_rep=pset_of_rep, mode=mode)
+        pop.set_path(path)
         pop.run()
         inc, prev = pop.curves()
         out = dict(inc=inc, prev=prev, **pop.scalars())
         if want_hmatrix:
             out["hmatrix"] = pop.hmatrix_all()
         out["device_ms"] = pop.last_run_ms
+        out["path"] = pop.last_path
     finally:
         if own:
             pop.close()

@@ -23,6 +23,9 @@ struct cabm_handle {
     std::vector<void *> allocs;
     DevPset *d_psets = nullptr; unsigned long long *d_beta = nullptr; int psets_cap = 0;
     int *d_scratch = nullptr;          // 4*N ints for peeks
+    unsigned *d_work = nullptr;        // work counter of the fused kernel
+    int16_t *d_stage = nullptr; size_t stage_elems = 0;   // Int16 staging for hmatrix read-back
+    int n_sm = 148, path = CABM_PATH_AUTO, last_path = 0;
     int64_t launches = 0;
     bool ran = false;
     // optional per-kernel-class timing (cabm_set_profiling): events around every launch of the next cabm_run
@@ -117,6 +120,8 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R);
     if (S.store_hm) DA(S.hm, (size_t)h->R * h->T * h->N);
     DA(h->d_scratch, (size_t)4 * h->N);
+    DA(h->d_work, 4);
+    { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) h->n_sm = pr.multiProcessorCount; }
     // shared tables
     {
         const Tables &t = tables();
@@ -162,6 +167,7 @@ extern "C" void cabm_destroy(cabm_handle *h) {
     if (h->d_psets) cudaFree(h->d_psets);
     if (h->d_beta) cudaFree(h->d_beta);
     if (h->S.ct_log) cudaFree(h->S.ct_log);
+    if (h->d_stage) cudaFree(h->d_stage);
     for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -304,17 +310,27 @@ extern "C" int cabm_run(cabm_handle *h) {
     h->pev_used = 0; h->pcls.clear();
     CU(cudaEventRecord(h->ev0, h->stream));
     if ((rc = reset_state(h))) return rc;
-    timed(h, CABM_K_OTHER, [&] { return launch_initialize(S, h->stream); });                                   // :112
-    timed(h, CABM_K_OTHER, [&] { return launch_insert_infected(S, 0, 0, 0, 0, 0, 0, h->stream); });            // :117/:119
-    timed(h, CABM_K_OTHER, [&] { return launch_insert_infected(S, 1, 0, 0, 0, 1, 0, h->stream); });            // :120
-    timed(h, CABM_K_OTHER, [&] { return launch_build_groups(S, h->stream); });                                 // :128
-    timed(h, CABM_K_OTHER, [&] { return launch_first_column(S, h->stream); });                                 // :136 for st = 1
-    for (int st = 1; st <= h->T; ++st) {                                              // :131
-        do_dyntrans(h, st);                                                           // :137
-        do_time_update(h, st);                                                        // :138 (+ snapshot of st+1)
+    // The fused kernel keeps a replicate's hot state in shared memory: usable when it fits two CTAs per SM budget
+    // (popsize <= ~21k agents), with the exact schedule and no contact tracing; otherwise one kernel per phase per day.
+    const bool fused_ok = !h->any_ct && h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 226 * 1024;
+    const bool use_fused = h->path == CABM_PATH_FUSED ? fused_ok : (h->path == CABM_PATH_AUTO && fused_ok);
+    if (h->path == CABM_PATH_FUSED && !fused_ok) return fail(h, CABM_E_STATE, "fused path needs ctstrat == 0, exact mode and a population that fits shared memory");
+    h->last_path = use_fused ? CABM_PATH_FUSED : CABM_PATH_MULTIKERNEL;
+    if (use_fused) {
+        timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->stream); });            // :104-142 in one launch
+    } else {
+        timed(h, CABM_K_OTHER, [&] { return launch_initialize(S, h->stream); });                                   // :112
+        timed(h, CABM_K_OTHER, [&] { return launch_insert_infected(S, 0, 0, 0, 0, 0, 0, h->stream); });            // :117/:119
+        timed(h, CABM_K_OTHER, [&] { return launch_insert_infected(S, 1, 0, 0, 0, 1, 0, h->stream); });            // :120
+        timed(h, CABM_K_OTHER, [&] { return launch_build_groups(S, h->stream); });                                 // :128
+        timed(h, CABM_K_OTHER, [&] { return launch_first_column(S, h->stream); });                                 // :136 for st = 1
+        for (int st = 1; st <= h->T; ++st) {                                              // :131
+            do_dyntrans(h, st);                                                           // :137
+            do_time_update(h, st);                                                        // :138 (+ snapshot of st+1)
+        }
+        timed(h, CABM_K_OTHER, [&] { return launch_curves_finalize(S, h->stream); });                              // :259-293
+        timed(h, CABM_K_OTHER, [&] { return launch_count_infectors(S, h->stream); });                              // :295-313
     }
-    timed(h, CABM_K_OTHER, [&] { return launch_curves_finalize(S, h->stream); });                              // :259-293
-    timed(h, CABM_K_OTHER, [&] { return launch_count_infectors(S, h->stream); });                              // :295-313
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaGetLastError());
     h->day = h->T + 1; h->ran = true;
@@ -329,6 +345,11 @@ extern "C" int cabm_run(cabm_handle *h) {
     return CABM_OK;
 }
 
+extern "C" int cabm_set_path(cabm_handle *h, int path) {
+    if (!h || path < CABM_PATH_AUTO || path > CABM_PATH_FUSED) return CABM_E_ARG;
+    h->path = path; return CABM_OK;
+}
+extern "C" int cabm_get_last_path(const cabm_handle *h) { return h ? h->last_path : -1; }
 extern "C" int cabm_set_profiling(cabm_handle *h, int on) { if (!h) return CABM_E_ARG; h->profiling = on ? 1 : 0; return CABM_OK; }
 extern "C" int cabm_get_profile(cabm_handle *h, float *ms, int32_t *launches) {
     if (!h || !ms || !launches) return CABM_E_ARG;
@@ -399,22 +420,34 @@ extern "C" int cabm_get_dyntrans_counters(cabm_handle *h, int32_t *totalmet, int
     return CABM_OK;
 }
 
+// hmatrix is kept as one byte per element on the device and leaves as Int16 (:111): widen through a staging buffer
+static int copy_hmatrix(cabm_handle *h, size_t first_elem, size_t n_elem, int16_t *out) {
+    const size_t chunk = (size_t)32 << 20;
+    if (!h->d_stage) {
+        h->stage_elems = n_elem < chunk ? n_elem : chunk;
+        if (h->stage_elems < (size_t)h->T * h->N) h->stage_elems = (size_t)h->T * h->N;
+        CU(cudaMalloc((void **)&h->d_stage, h->stage_elems * 2));
+    }
+    for (size_t o = 0; o < n_elem; o += h->stage_elems) {
+        const size_t n = n_elem - o < h->stage_elems ? n_elem - o : h->stage_elems;
+        h->launches += launch_widen(h->S.hm + first_elem + o, h->d_stage, n, h->stream);
+        CU(cudaMemcpyAsync(out + o, h->d_stage, n * 2, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return CABM_OK;
+}
 extern "C" int cabm_get_hmatrix(cabm_handle *h, int replicate, int16_t *out) {
     int rc = need_config(h); if (rc) return rc;
     if (!h->S.store_hm) return fail(h, CABM_E_STATE, "handle was created without CABM_STORE_HMATRIX");
     if (replicate < 0 || replicate >= h->n_rep || !out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix: bad argument");
     const size_t n = (size_t)h->T * h->N;
-    CU(cudaMemcpyAsync(out, h->S.hm + (size_t)replicate * n, n * 2, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return CABM_OK;
+    return copy_hmatrix(h, (size_t)replicate * n, n, out);
 }
 extern "C" int cabm_get_hmatrix_all(cabm_handle *h, int16_t *out) {
     int rc = need_config(h); if (rc) return rc;
     if (!h->S.store_hm) return fail(h, CABM_E_STATE, "handle was created without CABM_STORE_HMATRIX");
     if (!out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix_all: bad argument");
-    CU(cudaMemcpyAsync(out, h->S.hm, (size_t)h->n_rep * h->T * h->N * 2, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return CABM_OK;
+    return copy_hmatrix(h, 0, (size_t)h->n_rep * h->T * h->N, out);
 }
 extern "C" int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev) {
     int rc = need_config(h); if (rc) return rc;

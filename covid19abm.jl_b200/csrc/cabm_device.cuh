@@ -76,7 +76,7 @@ struct Dev {
     uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;
     int *inc, *prev;                         // [R][6][T][12]
     long long *infectors, *latsum;           // [R][4], [R]
-    int16_t *hm;                             // [R][T][N]
+    uint8_t *hm;                             // [R][T][N] health codes (widened to Int16 by cabm_get_hmatrix)
     const DevPset *psets; const unsigned long long *beta_thr;    // [P], [P][T][4]
     const uint32_t *nb_thr; const uint8_t *nb_guide;             // [5][256], [5][256]
     const unsigned long long *gpw;                               // [5][256] five u8 counts packed
@@ -132,10 +132,14 @@ __device__ __forceinline__ void curve_move(const Dev &S, int r, int ag0, int col
 }
 
 // One expired agent: time_update's @match :405-419 and the move_to_* functions :446-644.
-// Returns the new status word (not stored); writes expday/entry/latday/isovia, the infectious bitmask
-// and the incidence counters. `day` is st; for seeding it is 0.
-__device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
-                                      int target /* swap to apply */, bool seed_simple_inf, bool count_curves) {
+// transition_core returns the new status word and expiry day; it writes only the rarely-touched per-agent fields
+// that always live in HBM (entry, latday, isovia). The caller stores status/expday (HBM arrays in the per-day
+// kernels, shared memory in the fused kernel) and keeps the infectious bitmask and the incidence counters.
+// `day` is st; for seeding it is 0.
+struct Tr { uint32_t st; int expday; int oldh, newh; };
+
+__device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
+                                     int target /* swap to apply */, bool seed_simple_inf) {
     size_t a = (size_t)r * S.Np + i;
     const int oldh = st_health(st), ag = st_ag(st);
     const uint32_t d4 = S.dur[a];
@@ -195,17 +199,23 @@ __device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int
     case DED: exp = 999; newsw = UNDEF; iso = true; break;                                 // :624-633
     default:                              // :418 "swap expired, but no swap set."
         atomicOr(&S.err[r], ERR_NO_SWAP);
-        S.expday[a] = 32767;
-        return st;
+        return Tr{st, 32767, oldh, oldh};
     }
     if (via >= 0 && S.isovia[a] == VIA_NULL) S.isovia[a] = (uint8_t)via;   // _set_isolation :432-444 only fills a :null isovia
-    S.expday[a] = (int16_t)(day + exp);
     S.entry[a] = (int16_t)day;
-    if (is_infectious(newh) != is_infectious(oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
-    if (count_curves) curve_move(S, r, ag, day, oldh, newh);
     st = st_set_swap(st_set_health(st, newh), newsw);
     st = iso ? (st | ST_ISO | ST_ISOB) : (st & ~(ST_ISO | ST_ISOB));
-    return st;
+    return Tr{st, day + exp, oldh, newh};
+}
+
+// HBM-resident variant used by the per-day kernels: stores expday, flips the infectious bitmask, counts the curves.
+__device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
+                                      int target, bool seed_simple_inf, bool count_curves) {
+    const Tr t = transition_core(S, P, r, i, day, st, key, target, seed_simple_inf);
+    S.expday[(size_t)r * S.Np + i] = (int16_t)t.expday;
+    if (is_infectious(t.newh) != is_infectious(t.oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
+    if (count_curves) curve_move(S, r, st_ag(st), day, t.oldh, t.newh);
+    return t.st;
 }
 
 #endif  // CABM_KERNELS_TU

@@ -1,0 +1,479 @@
+// cabm_fused.cuh — k_sim_fused: one persistent CTA runs a whole replicate of main() (:104-142) out of shared memory.
+// Included by cabm_kernels.cu (same translation unit: shares c_tab).
+//
+// Replicates are independent (the reference parallelises only over them, scripts/local_run.jl:28-30), so a CTA
+// needs no grid-wide synchronisation: it initialises its population, seeds it, and loops over all modeltime days
+// with the hot per-agent state resident in shared memory:
+//     s_status u32[Np]  (the word dyntrans gathers/scatters; cabm_device.cuh)
+//     s_expday i16[Np]  (time_update's only per-agent-day read)
+//     s_col    u8[Np]   (the current hmatrix column; transitions patch it, one TMA bulk store per day writes it)
+//     s_grp    u16[Np]  (get_ag_dist index tables :339-343, "staged in shared memory")
+// HBM traffic per agent-day is therefore just the 1-byte hmatrix element (:221, widened to Int16 on the way out); the rarely-touched fields
+// (dur, entry, sickfrom, isovia, latday) stay in HBM and are read on state transitions only.
+// CTAs pull replicate indices from an atomic work counter (grid = resident CTAs), so long epidemics and early
+// extinctions balance across SMs.
+//
+// dyntrans keeps the reference's sequential semantics (:797-832): infectious agents are taken in ascending index
+// order in batches of up to 32 whose contact events (<= NT, one per thread) are drawn in parallel; a batch is cut
+// before the first infector that an earlier infector of the same batch contacts (its budget :802 would change), and
+// events that share a target are resolved in event order by the lowest event of the group.
+#pragma once
+
+namespace cabm {
+
+constexpr int FUSED_NT = 512;          // threads per CTA = max events per batch
+constexpr int FUSED_NCAND = 32;        // infectors per batch
+constexpr int FUSED_SLOTS = 1024;      // duplicate-detection hash slots
+
+struct FusedSmem {
+    uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
+    uint32_t *nb_thr; uint8_t *nb_guide;
+    uint32_t *Y, *W1; uint8_t *Q; uint32_t *slot;
+    int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
+};
+
+__host__ __device__ inline size_t fused_smem_bytes(int Np) {
+    size_t b = 0;
+    b += (size_t)Np * 4;                 // status
+    b += (size_t)Np * 2 * 2;             // expday, grp
+    b += (size_t)Np;                     // col
+    b += (size_t)(Np / 32) * 4;          // inf
+    b += 5 * 256 * 4 + 5 * 256;          // nb tables
+    b += FUSED_NT * 4 * 2 + FUSED_NT;    // Y (= cnt), W1, Q
+    b += FUSED_SLOTS * 4;                // slot counters
+    return (b + 15) / 16 * 16 + 64;
+}
+
+// get_nextday_counts :772-788 with the NB tables in shared memory
+__device__ __forceinline__ int fresh_budget_s(const FusedSmem &M, uint2 key, uint32_t i, uint32_t day, uint32_t st) {
+    if (st_health(st) == DED) return 0;
+    uint32_t w = pick(philox(i >> 2, day, S_COUNT, 0, key), i & 3u);
+    if (st & ST_ISOB) return (w < 0x80000000u) ? 0 : 1 + (int)(((unsigned long long)(w & 0x7fffffffu) * 3ull) >> 31);
+    const int ag = st_ag(st);
+    const uint32_t *thr = M.nb_thr + ag * 256;
+    int k = M.nb_guide[ag * 256 + (w >> 24)];
+    const int len = c_tab.nb_len[ag];
+    while (k < len && thr[k] <= w) ++k;
+    return k;
+}
+__device__ __forceinline__ int budget_of_s(const FusedSmem &M, uint2 key, uint32_t i, int day, uint32_t st) {
+    return st_tag(st) == day ? st_rem(st) : fresh_budget_s(M, key, i, (uint32_t)day, st);
+}
+
+// TMA bulk store of one hmatrix column from shared memory (UBLKCP in SASS)
+__device__ __forceinline__ void bulk_store_g2s_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = FUSED_NT, NW = FUSED_NT / 32;
+    const int N = S.N, Np = S.Np, T = S.T, nwords = S.nwords;
+    FusedSmem M;
+    {
+        unsigned char *p = smem_raw;
+        M.status = (uint32_t *)p; p += (size_t)Np * 4;
+        M.expday = (int16_t *)p; p += (size_t)Np * 2;
+        M.grp = (uint16_t *)p; p += (size_t)Np * 2;
+        M.col = (uint8_t *)p; p += (size_t)Np;
+        M.inf = (uint32_t *)p; p += (size_t)nwords * 4;
+        M.nb_thr = (uint32_t *)p; p += 5 * 256 * 4;
+        M.Y = (uint32_t *)p; M.cnt = (int *)p; p += NT * 4;
+        M.W1 = (uint32_t *)p; p += NT * 4;
+        M.slot = (uint32_t *)p; p += FUSED_SLOTS * 4;
+        M.nb_guide = (uint8_t *)p; p += 5 * 256;
+        M.Q = (uint8_t *)p; p += NT;
+    }
+    __shared__ int s_r, s_off[8], s_wcnt[FUSED_NT / 32][5], s_base[5], s_total[5];
+    __shared__ int s_sel_tid, s_sel_k, s_Ltot, s_ninf;
+    __shared__ int s_inc[60], s_out[60];
+    __shared__ int s_infectors[4];
+    // dyntrans batch
+    __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_ncand, s_nb, s_cut, s_cursor;
+    __shared__ unsigned long long s_gp[FUSED_NCAND], s_bthr[FUSED_NCAND];
+    __shared__ uint8_t s_xh[FUSED_NCAND];
+
+    for (int k = tid; k < 5 * 256; k += NT) { M.nb_thr[k] = S.nb_thr[k]; M.nb_guide[k] = S.nb_guide[k]; }
+    for (int k = tid; k < FUSED_SLOTS; k += NT) M.slot[k] = 0;
+    const bool tma_ok = S.store_hm && (N % 16 == 0);     // cp.async.bulk needs 16-byte size and alignment
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_r = (int)atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const int r = s_r;
+        if (r >= S.R) break;
+        const DevPset &P = S.psets[S.pset_of[r]];
+        const uint2 key = S.key[r];
+        const size_t rb = (size_t)r * Np;
+        const unsigned long long *beta = S.beta_thr + (size_t)S.pset_of[r] * T * 4;
+        uint8_t *hm = S.store_hm ? S.hm + (size_t)r * T * N : nullptr;
+
+        // ------------------------------------------------------------ initialize :171-188
+        for (int i = tid; i < Np; i += NT) {
+            const size_t a = rb + i;
+            uint32_t st = st_make(SUS, UNDEF, 0, false), d4 = 0;
+            uint8_t via = VIA_NULL;
+            if (i < N) {
+                const uint4 wa = philox(i, 0, S_INIT, 0, key), wb = philox(i, 0, S_INIT, 1, key);
+                int ag0 = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ag0 += ((unsigned long long)wa.x >= P.age_thr[k]);
+                int latents = table_draw(wa.y, c_tab.lat_base, c_tab.lat_thr, c_tab.lat_len);
+                const int pres = table_draw(wa.z, c_tab.pre_base, c_tab.pre_thr, c_tab.pre_len);
+                const int asymps = table_draw(wa.w, c_tab.asy_base, c_tab.asy_thr, c_tab.asy_len);
+                const int infs = table_draw(wb.x, c_tab.inf_base, c_tab.inf_thr, c_tab.inf_len);
+                latents -= pres;
+                d4 = (uint32_t)latents | ((uint32_t)asymps << 8) | ((uint32_t)pres << 16) | ((uint32_t)infs << 24);
+                const bool quar = bern(wb.y, P.quar_thr) && ag0 == P.quar_grp0;
+                st = st_make(SUS, UNDEF, ag0, quar);
+                via = quar ? VIA_QU : VIA_NULL;
+            }
+            M.status[i] = st;
+            M.expday[i] = (i < N) ? (int16_t)999 : (int16_t)32767;
+            M.col[i] = SUS;
+            S.dur[a] = d4; S.isovia[a] = via; S.entry[a] = 0; S.sickfrom[a] = UNDEF; S.latday[a] = -999;
+            S.tracestart[a] = -1; S.traceend[a] = -1; S.tracedxp[a] = 0; S.ct_head[a] = CT_NONE;
+        }
+        for (int k = tid; k < nwords; k += NT) M.inf[k] = 0;
+        if (tid < 60) { s_inc[tid] = 0; s_out[tid] = 0; }
+        if (tid < 5) s_total[tid] = 0;
+        if (tid < 4) s_infectors[tid] = 0;
+        if (tid == 0) s_ninf = 0;
+        __syncthreads();
+
+        // ------------------------------------------------------------ get_ag_dist :339-343 (ordered counting sort)
+        {
+            int c[5] = {0, 0, 0, 0, 0};
+            for (int i = tid; i < N; i += NT) c[st_ag(M.status[i])]++;
+#pragma unroll
+            for (int g = 0; g < 5; ++g) {
+                int v = c[g];
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                if (lane == 0) atomicAdd(&s_total[g], v);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int o = 0;
+                for (int g = 0; g < 5; ++g) { s_off[g] = o; s_base[g] = o; o += s_total[g]; }
+                s_off[5] = o;
+            }
+            __syncthreads();
+            for (int i0 = 0; i0 < N; i0 += NT) {
+                const int i = i0 + tid;
+                const int ag = (i < N) ? st_ag(M.status[i]) : -1;
+                unsigned m[5];
+#pragma unroll
+                for (int g = 0; g < 5; ++g) { m[g] = __ballot_sync(FULL, ag == g); if (lane == 0) s_wcnt[wid][g] = __popc(m[g]); }
+                __syncthreads();
+                if (ag >= 0) {
+                    int pos = s_base[ag];
+                    for (int w = 0; w < wid; ++w) pos += s_wcnt[w][ag];
+                    const unsigned mm = ag == 0 ? m[0] : ag == 1 ? m[1] : ag == 2 ? m[2] : ag == 3 ? m[3] : m[4];
+                    pos += __popc(mm & ((1u << lane) - 1u));
+                    M.grp[pos] = (uint16_t)i;
+                }
+                __syncthreads();
+                if (tid < 5) { int s = 0; for (int w = 0; w < NW; ++w) s += s_wcnt[w][tid]; s_base[tid] += s; }
+                __syncthreads();
+            }
+        }
+
+        // ------------------------------------------------------------ insert_infected :360-395 (PRE seeds, then REC seeds)
+        for (int which = 0; which < 2; ++which) {
+            if (which == 1 && P.calibration) break;                                          // :116-121
+            const int health = which == 0 ? PRE : REC, num = which == 0 ? P.initialinf : P.initialhi;
+            const int seg = (N + NT - 1) / NT, lo = tid * seg, hi = min(N, lo + seg);
+            int mine = 0;
+            for (int i = lo; i < hi; ++i) mine += (st_health(M.status[i]) == SUS);
+            M.cnt[tid] = mine;
+            __syncthreads();
+            if (tid == 0) { int L = 0; for (int t = 0; t < NT; ++t) L += M.cnt[t]; s_Ltot = L; }
+            __syncthreads();
+            if (s_Ltot == 0 || num > s_Ltot) { if (tid == 0 && (num > 0 || s_Ltot == 0)) atomicOr(&S.err[r], ERR_NO_SUS); continue; }
+            for (int j = 0; j < num; ++j) {
+                if (tid == 0) {
+                    const uint4 w = philox(j, 0, S_SEED, which, key);
+                    int k = below(w.x, s_Ltot - j), t = 0;
+                    while (k >= M.cnt[t]) { k -= M.cnt[t]; ++t; }
+                    s_sel_tid = t; s_sel_k = k;
+                }
+                __syncthreads();
+                if (tid == s_sel_tid) {
+                    int k = s_sel_k;
+                    for (int i = lo; i < hi; ++i) {
+                        const uint32_t st = M.status[i];
+                        if (st_health(st) != SUS) continue;
+                        if (k-- > 0) continue;
+                        const Tr t = transition_core(S, P, r, i, 0, st, key, health, true);
+                        M.status[i] = (t.st & ~ST_ISOB) | (st & ST_ISOB);    // day-1 budget was drawn with the old iso (:186)
+                        M.expday[i] = (int16_t)t.expday;
+                        M.col[i] = (uint8_t)t.newh;
+                        S.sickfrom[rb + i] = INF;                             // :391
+                        if (is_infectious(t.newh)) { M.inf[i >> 5] |= 1u << (i & 31); s_ninf += 1; }
+                        break;
+                    }
+                    M.cnt[tid] -= 1;
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------ column 1 (:136 at st = 1) and its curve entries
+        // every agent first occurs in its initial state on day 1 (:270-280); nearly all are SUS, so count the others
+        for (int i = tid; i < N; i += NT) {
+            const uint32_t st = M.status[i];
+            const int h = st_health(st);
+            if (h != SUS) { atomicAdd(&s_inc[st_ag(st) * 12 + h], 1); atomicAdd(&s_out[st_ag(st) * 12 + SUS], 1); }
+        }
+        __syncthreads();
+        int run = 0;                              // running prevalence of (group, state) = (tid/12, tid%12), tid < 60; group 0 in tid 60..71
+        if (tid < 60) {
+            const int g = tid / 12, s = tid % 12;
+            run = s_inc[tid] + (s == SUS ? (s_off[g + 1] - s_off[g]) - s_out[tid] : 0);
+            const size_t b = (((size_t)r * 6 + (g + 1)) * (size_t)T + 0) * 12 + s;
+            S.inc[b] = run; S.prev[b] = run;
+            M.cnt[tid] = run;
+        }
+        __syncthreads();
+        long long latsum = 0;
+        if (tid >= 60 && tid < 72) {
+            const int s = tid - 60;
+            for (int g = 0; g < 5; ++g) run += M.cnt[g * 12 + s];
+            const size_t b = (((size_t)r * 6 + 0) * (size_t)T + 0) * 12 + s;
+            S.inc[b] = run; S.prev[b] = run;
+            if (s == LAT) latsum = run;
+        }
+        __syncthreads();
+        if (tid < 60) { s_inc[tid] = 0; s_out[tid] = 0; }
+        if (hm) {
+            if (tma_ok) { bulk_store_g2s_fence(); __syncthreads(); if (tid == 0) bulk_store(hm, M.col, (uint32_t)N); }
+            else for (int i = tid; i < N; i += NT) hm[i] = M.col[i];
+        }
+        __syncthreads();
+
+        // ============================================================ the day loop :131-140
+        for (int day = 1; day <= T; ++day) {
+            // -------------------------------------------------------- dyntrans(st) :790-834
+            if (s_ninf > 0) {
+                if (tid == 0) s_cursor = 0;
+                __syncthreads();
+                for (;;) {
+                    // (a) warp 0: next <=32 infectious agents at or after the cursor, in ascending order, with their
+                    //     contact budget (:802) and its split over the age groups (:804)
+                    if (wid == 0) {
+                        int found = 0;
+                        const int cw = s_cursor >> 5, cb = s_cursor & 31;
+                        for (int w0 = cw; w0 < nwords && found < FUSED_NCAND; w0 += 32) {
+                            uint32_t m = (w0 + lane < nwords) ? M.inf[w0 + lane] : 0u;
+                            if (w0 + lane == cw) m &= ~((1u << cb) - 1u);
+                            const int c = __popc(m);
+                            int incl = c;
+                            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                            int pos = found + incl - c;
+                            while (m && pos < FUSED_NCAND) { const int b = __ffs(m) - 1; m &= m - 1; s_cand[pos++] = ((w0 + lane) << 5) + b; }
+                            found += __shfl_sync(FULL, incl, 31);
+                        }
+                        const int ncand = min(found, FUSED_NCAND);
+                        __syncwarp();
+                        int E = 0;
+                        if (lane < ncand) {
+                            const int x = s_cand[lane];
+                            const uint32_t sx = M.status[x];
+                            const int cnts = budget_of_s(M, key, x, day, sx);
+                            const unsigned long long gp = __ldg(&S.gpw[st_ag(sx) * 256 + cnts]);
+                            E = (int)(gp & 0xFF) + (int)((gp >> 8) & 0xFF) + (int)((gp >> 16) & 0xFF) + (int)((gp >> 24) & 0xFF) + (int)((gp >> 32) & 0xFF);
+                            s_gp[lane] = gp;
+                            s_xh[lane] = (uint8_t)st_health(sx);
+                            s_bthr[lane] = beta[(size_t)(day - 1) * 4 + beta_class(st_health(sx))];   // :800
+                        }
+                        int incl = E;
+                        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                        s_pref[lane + 1] = incl;
+                        const unsigned fits = __ballot_sync(FULL, lane < ncand && incl <= NT);
+                        if (lane == 0) {
+                            s_pref[0] = 0;
+                            int nb = 0;
+                            while (nb < ncand && ((fits >> nb) & 1)) ++nb;      // prefix of candidates whose events fit (E <= 260 < NT: nb >= 1)
+                            s_ncand = ncand; s_nb = nb; s_cut = nb;
+                        }
+                    }
+                    __syncthreads();
+                    const int nb = s_nb;
+                    if (s_ncand == 0) break;
+                    const int Etot = s_pref[nb];
+                    // (b) one contact event per thread: target draw (:807) and transmission word (:823)
+                    uint32_t y = 0, w1 = 0; int q = 0; bool ev = tid < Etot;
+                    if (ev) {
+                        int lo = 0, hi = nb - 1;                               // last q with pref[q] <= tid
+                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= tid) lo = mid; else hi = mid - 1; }
+                        q = lo;
+                        const int e = tid - s_pref[q];
+                        const unsigned long long gp = s_gp[q];
+                        const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF), p4 = p3 + (int)((gp >> 24) & 0xFF);
+                        const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
+                        const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
+                        const int go = s_off[g], len = s_off[g + 1] - go;
+                        const int x = s_cand[q];
+                        if (len == 0) { atomicOr(&S.err[r], ERR_EMPTY_GROUP); ev = false; }
+                        else {
+                            const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                            y = M.grp[go + below(w.x, len)]; w1 = w.y;
+                            // an infector later in this batch that gets contacted must re-read its budget: cut the batch there
+                            if ((int)y > x && (int)y <= s_cand[nb - 1] && ((M.inf[y >> 5] >> (y & 31)) & 1u)) {
+                                int a = q + 1, b = nb - 1;
+                                while (a < b) { const int mid = (a + b) >> 1; if (s_cand[mid] < (int)y) a = mid + 1; else b = mid; }
+                                atomicMin(&s_cut, a);
+                            }
+                        }
+                    }
+                    M.Y[tid] = ev ? y : 0xFFFFFFFFu; M.W1[tid] = w1; M.Q[tid] = (uint8_t)q;
+                    __syncthreads();
+                    const int cut = s_cut;
+                    const int Ev = s_pref[cut];                                // events of infectors [0, cut) are final
+                    ev = ev && tid < Ev;
+                    // (c) duplicate targets are rare: count events per hash slot, resolve shared slots in event order
+                    const int slot = (int)(y & (FUSED_SLOTS - 1));
+                    if (ev) atomicAdd(&M.slot[slot], 1u);
+                    __syncthreads();
+                    if (ev) {
+                        bool leader = true;
+                        const bool shared = M.slot[slot] > 1;
+                        if (shared) for (int e2 = 0; e2 < tid; ++e2) if (M.Y[e2] == y) { leader = false; break; }
+                        if (leader) {
+                            uint32_t sy = M.status[y];
+                            int rem = budget_of_s(M, key, y, day, sy);                                   // :811
+                            bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;                     // :822
+                            int xh_inf = -1;
+                            // own event first, then (rarely) the later events on the same target, in event order
+                            for (int e2 = tid; e2 < Ev; ++e2) {
+                                if (e2 != tid) { if (!shared) break; if (M.Y[e2] != y) continue; }
+                                if (rem == 0) break;                                                      // :812
+                                rem -= 1;                                                                 // :813
+                                const int q2 = M.Q[e2];
+                                if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }   // :823-827
+                            }
+                            uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
+                            if (xh_inf >= 0) {
+                                ns = st_set_swap(ns, LAT);
+                                S.sickfrom[rb + y] = (uint8_t)xh_inf;
+                                M.expday[y] = (int16_t)day;                    // y.exp = y.tis :826 — fires in today's time_update
+                            }
+                            M.status[y] = ns;
+                        }
+                    }
+                    __syncthreads();
+                    if (tid < Etot && M.Y[tid] != 0xFFFFFFFFu) M.slot[M.Y[tid] & (FUSED_SLOTS - 1)] = 0;
+                    if (tid == 0) s_cursor = s_cand[cut - 1] + 1;
+                    __syncthreads();
+                }
+            }
+            __syncthreads();
+
+            // -------------------------------------------------------- time_update() :399-428
+            if (hm && tma_ok && tid == 0) bulk_store_wait_read();              // previous column has left shared memory
+            __syncthreads();
+            for (int i0 = tid * 8; i0 < N; i0 += NT * 8) {
+                union { uint4 v; int16_t e[8]; } ex;
+                ex.v = *reinterpret_cast<const uint4 *>(M.expday + i0);
+                unsigned fire = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) fire |= (unsigned)((int)ex.e[k] <= day) << k;
+                if (day == 1) {                                                // seeds isolated by fpreiso: resync isob (see k_time_update)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const uint32_t st = M.status[i0 + k]; fire |= (((st >> 19) ^ (st >> 20)) & 1u) << k; }
+                }
+                while (fire) {
+                    const int k = __ffs(fire) - 1; fire &= fire - 1;
+                    const int i = i0 + k;
+                    if (i >= N) break;
+                    uint32_t st = M.status[i];
+                    if ((int)ex.e[k] <= day) {
+                        const Tr t = transition_core(S, P, r, i, day, st, key, st_swap(st), false);
+                        st = t.st;
+                        M.expday[i] = (int16_t)t.expday;
+                        if (t.newh != t.oldh) {
+                            M.col[i] = (uint8_t)t.newh;
+                            if (day < T) { atomicAdd(&s_inc[st_ag(st) * 12 + t.newh], 1); atomicAdd(&s_out[st_ag(st) * 12 + t.oldh], 1); }
+                            if (is_infectious(t.newh) != is_infectious(t.oldh)) {
+                                atomicXor(&M.inf[i >> 5], 1u << (i & 31));
+                                atomicAdd(&s_ninf, is_infectious(t.newh) ? 1 : -1);
+                            }
+                        }
+                    }
+                    st = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);
+                    M.status[i] = st;
+                }
+            }
+            __syncthreads();
+            // -------------------------------------------------------- column st+1 (:136 of the next day) and its curves
+            if (day < T) {
+                if (tid < 60) {
+                    const int g = tid / 12, s = tid % 12, in = s_inc[tid];
+                    run += in - s_out[tid];
+                    const size_t b = (((size_t)r * 6 + (g + 1)) * (size_t)T + (size_t)day) * 12 + s;
+                    S.inc[b] = in; S.prev[b] = run;
+                } else if (tid < 72) {
+                    const int s = tid - 60;
+                    int in = 0, out = 0;
+                    for (int g = 0; g < 5; ++g) { in += s_inc[g * 12 + s]; out += s_out[g * 12 + s]; }
+                    run += in - out;
+                    const size_t b = (((size_t)r * 6 + 0) * (size_t)T + (size_t)day) * 12 + s;
+                    S.inc[b] = in; S.prev[b] = run;
+                    if (s == LAT) latsum += in;
+                }
+                if (hm) {
+                    if (tma_ok) { bulk_store_g2s_fence(); __syncthreads(); if (tid == 0) bulk_store(hm + (size_t)day * N, M.col, (uint32_t)N); }
+                    else for (int i = tid; i < N; i += NT) hm[(size_t)day * N + i] = M.col[i];
+                }
+                __syncthreads();
+                if (tid < 60) { s_inc[tid] = 0; s_out[tid] = 0; }
+            }
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------ final state back to HBM, _count_infectors :295-313
+        if (tid == 60 + LAT) S.latsum[r] = latsum;
+        int l[4] = {0, 0, 0, 0};
+        bool bad = false;
+        for (int i = tid; i < Np; i += NT) {
+            const uint32_t st = M.status[i];
+            S.status[rb + i] = st;
+            S.expday[rb + i] = M.expday[i];
+            if (i < N && st_health(st) != SUS) {
+                const int f = S.sickfrom[rb + i];
+                if (f == PRE) l[0]++; else if (f == ASYMP) l[1]++; else if (f == MILD || f == MISO) l[2]++;
+                else if (f == INF || f == IISO) l[3]++; else bad = true;
+            }
+        }
+        for (int k = tid; k < nwords; k += NT) S.infmask[(size_t)r * nwords + k] = M.inf[k];
+        for (int k = 0; k < 4; ++k) if (l[k]) atomicAdd(&s_infectors[k], l[k]);
+        if (bad) atomicOr(&S.err[r], ERR_SICKFROM);
+        __syncthreads();
+        if (tid < 4) S.infectors[r * 4 + tid] = s_infectors[tid];
+        if (tid == 0) { S.totalmet[r] = 0; S.totalinf[r] = 0; }
+        if (hm && tma_ok && tid == 0) bulk_store_wait_all();
+    }
+}
+
+size_t fused_smem_bytes_host(int Np) { return fused_smem_bytes(Np); }
+
+int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, cudaStream_t s) {
+    const size_t bytes = fused_smem_bytes(S.Np);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_sim_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes > 200 * 1024 ? 227 * 1024 : 200 * 1024); attr_set = true; }
+    const int per_sm = bytes <= 113 * 1024 ? 2 : 1;
+    int grid = n_sm * per_sm;
+    if (grid > S.R) grid = S.R;
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned), s);
+    k_sim_fused<<<grid, FUSED_NT, bytes, s>>>(S, work_counter);
+    return 1;
+}
+
+}  // namespace cabm

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_first_column(Dev S) {
         uint32_t st = S.status[(size_t)r * S.Np + i];
         int h = st_health(st);
         atomicAdd(&hist[st_ag(st)][h], 1);
-        if (S.store_hm) S.hm[(size_t)r * S.T * S.N + i] = (int16_t)h;
+        if (S.store_hm) S.hm[(size_t)r * S.T * S.N + i] = (uint8_t)h;
     }
     __syncthreads();
     if (threadIdx.x < 60) {
@@ -402,14 +402,29 @@ __global__ void __launch_bounds__(256) k_time_update(Dev S, int day) {
         }
     }
     if (S.store_hm && day < S.T) {                            // column st+1 = state at the start of the next day
-        int16_t *col = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
+        uint8_t *col = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
         if ((S.N & 7) == 0) {
-            union { uint4 v; int16_t h[8]; } o;
+            union { uint2 v; uint8_t h[8]; } o;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o.h[k] = (int16_t)st_health(st.s[k]);
-            *reinterpret_cast<uint4 *>(col) = o.v;
+            for (int k = 0; k < 8; ++k) o.h[k] = (uint8_t)st_health(st.s[k]);
+            *reinterpret_cast<uint2 *>(col) = o.v;
         } else {
-            for (int k = 0; k < 8 && i0 + k < S.N; ++k) col[k] = (int16_t)st_health(st.s[k]);
+            for (int k = 0; k < 8 && i0 + k < S.N; ++k) col[k] = (uint8_t)st_health(st.s[k]);
+        }
+    }
+}
+
+// hmatrix leaves the device as Int16 (:111): widen a span of the stored health bytes
+__global__ void k_widen_u8_i16(const uint8_t *src, int16_t *dst, size_t n) {
+    for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 16; i < n; i += (size_t)gridDim.x * blockDim.x * 16) {
+        if (i + 16 <= n && ((reinterpret_cast<uintptr_t>(src + i) | reinterpret_cast<uintptr_t>(dst + i)) & 15) == 0) {
+            union { uint4 v; uint8_t b[16]; } in; in.v = *reinterpret_cast<const uint4 *>(src + i);
+            union { uint4 v[2]; int16_t h[16]; } out;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) out.h[k] = in.b[k];
+            reinterpret_cast<uint4 *>(dst + i)[0] = out.v[0]; reinterpret_cast<uint4 *>(dst + i)[1] = out.v[1];
+        } else {
+            for (size_t k = i; k < n && k < i + 16; ++k) dst[k] = src[k];
         }
     }
 }
@@ -579,7 +594,13 @@ int launch_count_infectors(const Dev &S, cudaStream_t s) { k_count_infectors<<<S
 int launch_reduce_hmatrix(const int16_t *hm, const int *ags, int M, int N, int T, int *inc, int *prev, cudaStream_t s) {
     k_reduce_hmatrix<<<dim3((unsigned)((N + 255) / 256), (unsigned)M), 256, 0, s>>>(hm, ags, N, T, inc, prev); return 1;
 }
+int launch_widen(const uint8_t *src, int16_t *dst, size_t n, cudaStream_t s) {
+    size_t blocks = (n / 16 + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+    k_widen_u8_i16<<<(unsigned)blocks, 256, 0, s>>>(src, dst, n); return 1;
+}
 int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s) { k_peek<<<(S.N + 255) / 256, 256, 0, s>>>(S, field, r, day, out); return 1; }
 int launch_poke(const Dev &S, int field, int r, int i, int day, int value, cudaStream_t s) { k_poke<<<1, 1, 0, s>>>(S, field, r, i, day, value); return 1; }
 
 }  // namespace cabm
+
+#include "cabm_fused.cuh"

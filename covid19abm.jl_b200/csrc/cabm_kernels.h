@@ -17,6 +17,9 @@ int launch_clear_marks(const Dev &S, cudaStream_t s);
 int launch_curves_finalize(const Dev &S, cudaStream_t s);
 int launch_count_infectors(const Dev &S, cudaStream_t s);
 int launch_reduce_hmatrix(const int16_t *hm, const int *ags, int M, int N, int T, int *inc, int *prev, cudaStream_t s);
+int launch_widen(const uint8_t *src, int16_t *dst, size_t n, cudaStream_t s);
+int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, cudaStream_t s);
+size_t fused_smem_bytes_host(int Np);
 int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s);
 int launch_poke(const Dev &S, int field, int r, int i, int day, int value, cudaStream_t s);
 

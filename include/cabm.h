@@ -101,10 +101,17 @@ int cabm_last_run_ms(cabm_handle *h, float *ms);
 /* Per-kernel-class device time of a run: with profiling on, cabm_run brackets every launch with CUDA events on
  * the handle's stream (and synchronises at the end); cabm_get_profile returns the summed milliseconds and the launch
  * count per class. Classes: dyntrans :790-834, time_update :399-428 (+snapshot), ct_dynamics pass A :705-716,
- * everything else (initialize, seeding, group tables, reductions). */
-enum { CABM_K_DYNTRANS = 0, CABM_K_TIME_UPDATE = 1, CABM_K_CT_IDENTIFY = 2, CABM_K_OTHER = 3, CABM_N_KCLASS = 4 };
+ * everything else (initialize, seeding, group tables, reductions), the fused whole-run kernel. */
+enum { CABM_K_DYNTRANS = 0, CABM_K_TIME_UPDATE = 1, CABM_K_CT_IDENTIFY = 2, CABM_K_OTHER = 3, CABM_K_FUSED = 4, CABM_N_KCLASS = 5 };
 int cabm_set_profiling(cabm_handle *h, int on);
 int cabm_get_profile(cabm_handle *h, float *ms /*[CABM_N_KCLASS]*/, int32_t *launches /*[CABM_N_KCLASS]*/);
+/* Execution path of cabm_run. FUSED: one persistent CTA per replicate runs all of main() with the per-agent state in
+ * shared memory (needs ctstrat == 0, exact mode, popsize that fits ~21k agents). MULTIKERNEL: one launch per phase per
+ * day over HBM-resident state (any popsize, contact tracing). AUTO (default) picks FUSED when eligible. Both give
+ * bit-identical results. */
+enum { CABM_PATH_AUTO = 0, CABM_PATH_MULTIKERNEL = 1, CABM_PATH_FUSED = 2 };
+int cabm_set_path(cabm_handle *h, int path);
+int cabm_get_last_path(const cabm_handle *h);
 /* number of kernel launches issued by this handle so far */
 int64_t cabm_launch_count(const cabm_handle *h);
 

@@ -47,11 +47,20 @@ CONFIGS = {
 }
 
 
-@pytest.mark.parametrize("name", list(CONFIGS))
+def _cases():
+    for name, kw in CONFIGS.items():
+        for path in ("multikernel", "fused"):
+            if path == "fused" and kw.get("ctstrat", 0) != 0:
+                continue          # the fused kernel does not carry contact tracing (cabm.h CABM_PATH_*)
+            yield pytest.param(name, path, id=f"{name}-{path}")
+
+
+@pytest.mark.parametrize("name,path", list(_cases()))
 @pytest.mark.parametrize("seed", [726, 1452])
-def test_main_bit_exact(cv, O, name, seed):
+def test_main_bit_exact(cv, O, name, path, seed):
     ip = cv.ModelParameters(**CONFIGS[name])
-    hm = cv.main(ip, seed=seed)
+    hm = cv.main(ip, seed=seed, path=path)
+    assert cv.humans().last_path == path
     sim = O.Sim(to_oracle(O, ip), seed)
     ref = sim.main()
     mm = first_mismatch(np.asarray(hm), np.asarray(ref))
@@ -69,6 +78,23 @@ def test_main_bit_exact(cv, O, name, seed):
     assert (inc[0] == rinc).all() and (prev[0] == rprev).all()
     assert sc["lat_inc_sum"][0] == O.get_column_incidence(ref, O.LAT).sum()
     sim.close()
+
+
+def test_ensemble_fused_bit_exact(cv, O):
+    """400 replicates (more than the resident CTAs: exercises the work queue) x 2 parameter sets, fused kernel."""
+    a = cv.ModelParameters(β=0.0345, prov="ontario", modeltime=120, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3)
+    b = cv.ModelParameters(β=0.09, prov="quebec", modeltime=120, initialinf=4, initialhi=500, quar_grp_frac=0.4, quar_grp=2)
+    nrep = 400
+    seeds = [726 * (i + 1) for i in range(nrep)]
+    pof = [i % 2 for i in range(nrep)]
+    got = cv.run_ensemble([a, b], nrep, seeds=seeds, pset_of_rep=pof, want_hmatrix=True, path="fused")
+    assert got["path"] == "fused"
+    ref = O.run_ensemble([to_oracle(O, a), to_oracle(O, b)], pof, seeds, nthreads=16, want_hmatrix=True)
+    assert (got["err"] == 0).all()
+    assert (got["hmatrix"] == ref["hmatrix"]).all()
+    assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all()
+    assert (got["infectors"] == ref["infectors"]).all()
+    assert (got["lat_inc_sum"] == ref["inc"][:, 0, :, 1].sum(axis=1)).all()
 
 
 def test_ensemble_bit_exact(cv, O):
