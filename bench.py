@@ -116,6 +116,7 @@ def main():
     ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU per step")
     ap.add_argument("--no-hmatrix", action="store_true", help="do not keep the state matrices in HBM (curves only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--path", default="auto", choices=["auto", "multikernel", "fused"], help="execution path (include/cabm.h CABM_PATH_*)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -150,6 +151,7 @@ def main():
     R = args.replicates
     ip = cv.ModelParameters(**CFG)
     pop = cv.Population(R, N_AGENTS, T_DAYS, store_hmatrix=not args.no_hmatrix, device=local)
+    pop.set_path(args.path)
     shape = (R, 6, T_DAYS, 12)
     pin_inc, pin_prev = cv.PinnedArray(shape, np.int32), cv.PinnedArray(shape, np.int32)
     units = R * N_AGENTS * T_DAYS                      # agent-days per step per GPU
@@ -208,20 +210,35 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    # algorithmic bytes per agent-day of time_update in this layout: status 4 r + expday 2 r + hmatrix 2 w
-    tu_bytes = (6 + (0 if args.no_hmatrix else 2)) * R * N_AGENTS
     kernels = {}
     for name, (ms, n) in prof.items():
-        kernels[name] = {"ms_per_step": round(ms, 3), "launches": n, "avg_us": round(1e3 * ms / n, 2) if n else None}
-    dom = max(("dyntrans", "time_update"), key=lambda k: prof[k][0])
-    tu_ms, tu_n = prof["time_update"]
-    tu_gbs = tu_bytes / (tu_ms / tu_n * 1e-3) / 1e9 if tu_n else 0.0
-    kernels["time_update"]["algorithmic_GBps"] = round(tu_gbs, 1)
-    kernels["time_update"]["frac_of_hbm_peak"] = round(tu_gbs / peak, 4)
-    roofline = {"kernel": "k_time_update", "bound": "hbm", "achieved": round(tu_gbs, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(tu_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
-                "bytes_per_agent_day": tu_bytes / (R * N_AGENTS), "dominant_by_time": "k_" + dom + ("_exact" if dom == "dyntrans" else ""),
-                "note": "time_update is the HBM-streaming per-agent kernel; dyntrans is a latency-bound gather/scatter (see kernels)"}
+        if n:
+            kernels[name] = {"ms_per_step": round(ms, 3), "launches": n, "avg_us": round(1e3 * ms / n, 2)}
+    if pop.last_path == "fused":
+        # k_sim_fused: per-agent state lives in shared memory; what must cross HBM per step:
+        #   the state matrix, 1 B per agent-day (u8 health code, :221); per agent once: the HBM-resident fields written at
+        #   initialize and the final status/expday (26 B); the curves [R][6][T][12] int32 x 2.
+        hm_b = 0 if args.no_hmatrix else R * N_AGENTS * T_DAYS
+        alg_bytes = hm_b + R * N_AGENTS * 26 + 2 * R * 6 * T_DAYS * 12 * 4
+        ms, n = prof["fused"]
+        gbs = alg_bytes / (ms / n * 1e-3) / 1e9
+        roofline = {"kernel": "k_sim_fused", "bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": alg_bytes, "bytes_per_agent_day": round(alg_bytes / (R * N_AGENTS * T_DAYS), 3),
+                    "note": "algorithmic bytes = u8 state matrix + per-agent HBM fields + curves; agent state itself never leaves shared memory. "
+                            "At the reference-width figure of SURVEY 8(d) (14 B/agent-day) the same launch would read "
+                            f"{round(14 * R * N_AGENTS * T_DAYS / (ms / n * 1e-3) / 1e9, 1)} GB/s"}
+    else:
+        # algorithmic bytes per agent-day of k_time_update in the HBM layout: status 4 r + expday 2 r + hmatrix 1 w
+        tu_bytes = (6 + (0 if args.no_hmatrix else 1)) * R * N_AGENTS
+        dom = max(("dyntrans", "time_update"), key=lambda k: prof[k][0])
+        tu_ms, tu_n = prof["time_update"]
+        tu_gbs = tu_bytes / (tu_ms / tu_n * 1e-3) / 1e9 if tu_n else 0.0
+        kernels["time_update"]["algorithmic_GBps"] = round(tu_gbs, 1)
+        roofline = {"kernel": "k_time_update", "bound": "hbm", "achieved": round(tu_gbs, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(tu_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "bytes_per_agent_day": tu_bytes / (R * N_AGENTS), "dominant_by_time": "k_" + dom + ("_exact" if dom == "dyntrans" else ""),
+                    "note": "time_update is the HBM-streaming per-agent kernel; dyntrans is a latency-bound gather/scatter (see kernels)"}
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -238,8 +255,8 @@ def main():
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32/i16 integer state, u32 Philox", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "replicates_per_gpu": R, "replicates_per_sec": world * R * args.steps / (dev_ms * 1e-3),
-                           "mode": "exact (bit-identical to the sequential reference order)", "hmatrix_in_hbm": not args.no_hmatrix,
-                           "l2": "inputs larger than L2: >=0.3 GB of agent state + 10 GB state matrix per step, rebuilt every step",
+                           "mode": "exact (bit-identical to the sequential reference order)", "path": pop.last_path, "hmatrix_in_hbm": not args.no_hmatrix,
+                           "l2": "inputs larger than L2: 0.3 GB of agent state + 5 GB state matrix + 0.3 GB curves written per step, rebuilt every step",
                            "wall_ms_per_step": wall_ms / args.steps, "attack_rate_mean": attack},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] int32 x2 and per-replicate scalars (runsim :77-101), pinned host buffers"},

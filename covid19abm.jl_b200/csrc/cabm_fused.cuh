@@ -23,12 +23,11 @@ namespace cabm {
 
 constexpr int FUSED_NT = 512;          // threads per CTA = max events per batch
 constexpr int FUSED_NCAND = 32;        // infectors per batch
-constexpr int FUSED_SLOTS = 1024;      // duplicate-detection hash slots
 
 struct FusedSmem {
     uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
     uint32_t *nb_thr; uint8_t *nb_guide;
-    uint32_t *Y, *W1; uint8_t *Q; uint32_t *slot;
+    uint32_t *Y, *W1; uint8_t *Q; uint32_t *touch, *dupm; uint16_t *D;
     int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
 };
 
@@ -40,7 +39,8 @@ __host__ __device__ inline size_t fused_smem_bytes(int Np) {
     b += (size_t)(Np / 32) * 4;          // inf
     b += 5 * 256 * 4 + 5 * 256;          // nb tables
     b += FUSED_NT * 4 * 2 + FUSED_NT;    // Y (= cnt), W1, Q
-    b += FUSED_SLOTS * 4;                // slot counters
+    b += (size_t)(Np / 32) * 4 * 2;      // touch, dupm bitmasks
+    b += FUSED_NT * 2;                   // D (compacted duplicate events)
     return (b + 15) / 16 * 16 + 64;
 }
 
@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         M.nb_thr = (uint32_t *)p; p += 5 * 256 * 4;
         M.Y = (uint32_t *)p; M.cnt = (int *)p; p += NT * 4;
         M.W1 = (uint32_t *)p; p += NT * 4;
-        M.slot = (uint32_t *)p; p += FUSED_SLOTS * 4;
+        M.touch = (uint32_t *)p; p += (size_t)nwords * 4;
+        M.dupm = (uint32_t *)p; p += (size_t)nwords * 4;
+        M.D = (uint16_t *)p; p += NT * 2;
         M.nb_guide = (uint8_t *)p; p += 5 * 256;
         M.Q = (uint8_t *)p; p += NT;
     }
@@ -97,9 +99,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_ncand, s_nb, s_cut, s_cursor;
     __shared__ unsigned long long s_gp[FUSED_NCAND], s_bthr[FUSED_NCAND];
     __shared__ uint8_t s_xh[FUSED_NCAND];
+    __shared__ int s_wdup[FUSED_NT / 32];
 
     for (int k = tid; k < 5 * 256; k += NT) { M.nb_thr[k] = S.nb_thr[k]; M.nb_guide[k] = S.nb_guide[k]; }
-    for (int k = tid; k < FUSED_SLOTS; k += NT) M.slot[k] = 0;
+    for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }
     const bool tma_ok = S.store_hm && (N % 16 == 0);     // cp.async.bulk needs 16-byte size and alignment
 
     for (;;) {
@@ -108,6 +111,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         __syncthreads();
         const int r = s_r;
         if (r >= S.R) break;
+        const long long t_start = clock64();
+        int n_rounds = 0;
         const DevPset &P = S.psets[S.pset_of[r]];
         const uint2 key = S.key[r];
         const size_t rb = (size_t)r * Np;
@@ -307,6 +312,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                     __syncthreads();
                     const int nb = s_nb;
                     if (s_ncand == 0) break;
+                    ++n_rounds;
                     const int Etot = s_pref[nb];
                     // (b) one contact event per thread: target draw (:807) and transmission word (:823)
                     uint32_t y = 0, w1 = 0; int q = 0; bool ev = tid < Etot;
@@ -338,26 +344,41 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                     const int cut = s_cut;
                     const int Ev = s_pref[cut];                                // events of infectors [0, cut) are final
                     ev = ev && tid < Ev;
-                    // (c) duplicate targets are rare: count events per hash slot, resolve shared slots in event order
-                    const int slot = (int)(y & (FUSED_SLOTS - 1));
-                    if (ev) atomicAdd(&M.slot[slot], 1u);
+                    // (c) events that share a target must be applied in event order (:809-830). Exact detection with two
+                    //     agent bitmasks; the (few) duplicate events are compacted in event order and resolved by the first
+                    //     event of each target, everything else is one independent event per thread.
+                    const uint32_t ybit = 1u << (y & 31);
+                    const int yw = (int)(y >> 5);
+                    if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) atomicOr(&M.dupm[yw], ybit); }
                     __syncthreads();
+                    const bool isdup = ev && (M.dupm[yw] & ybit);
+                    const unsigned dm = __ballot_sync(FULL, isdup);
+                    if (lane == 0) s_wdup[wid] = __popc(dm);
+                    __syncthreads();
+                    int dpos = 0, dtot = 0;
+                    for (int w = 0; w < NW; ++w) { const int c = s_wdup[w]; dtot += c; if (w < wid) dpos += c; }
+                    if (isdup) { dpos += __popc(dm & ((1u << lane) - 1u)); M.D[dpos] = (uint16_t)tid; }
+                    if (dtot) __syncthreads();
                     if (ev) {
                         bool leader = true;
-                        const bool shared = M.slot[slot] > 1;
-                        if (shared) for (int e2 = 0; e2 < tid; ++e2) if (M.Y[e2] == y) { leader = false; break; }
+                        if (isdup) for (int d = 0; d < dpos; ++d) if (M.Y[M.D[d]] == y) { leader = false; break; }
                         if (leader) {
-                            uint32_t sy = M.status[y];
+                            const uint32_t sy = M.status[y];
                             int rem = budget_of_s(M, key, y, day, sy);                                   // :811
                             bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;                     // :822
                             int xh_inf = -1;
-                            // own event first, then (rarely) the later events on the same target, in event order
-                            for (int e2 = tid; e2 < Ev; ++e2) {
-                                if (e2 != tid) { if (!shared) break; if (M.Y[e2] != y) continue; }
-                                if (rem == 0) break;                                                      // :812
+                            if (rem > 0) {                                                               // :812
                                 rem -= 1;                                                                 // :813
-                                const int q2 = M.Q[e2];
-                                if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }   // :823-827
+                                if (sus && bern(w1, s_bthr[q])) { sus = false; xh_inf = s_xh[q]; }       // :823-827
+                            }
+                            if (isdup) {
+                                for (int d = dpos + 1; d < dtot && rem > 0; ++d) {
+                                    const int e2 = M.D[d];
+                                    if (M.Y[e2] != y) continue;
+                                    rem -= 1;
+                                    const int q2 = M.Q[e2];
+                                    if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }
+                                }
                             }
                             uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
                             if (xh_inf >= 0) {
@@ -369,7 +390,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         }
                     }
                     __syncthreads();
-                    if (tid < Etot && M.Y[tid] != 0xFFFFFFFFu) M.slot[M.Y[tid] & (FUSED_SLOTS - 1)] = 0;
+                    if (ev) { M.touch[yw] = 0; M.dupm[yw] = 0; }
                     if (tid == 0) s_cursor = s_cand[cut - 1] + 1;
                     __syncthreads();
                 }
@@ -457,7 +478,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (bad) atomicOr(&S.err[r], ERR_SICKFROM);
         __syncthreads();
         if (tid < 4) S.infectors[r * 4 + tid] = s_infectors[tid];
-        if (tid == 0) { S.totalmet[r] = 0; S.totalinf[r] = 0; }
+        // diagnostics of the fused path: kilo-cycles spent on this replicate and dyntrans batches issued
+        if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; }
         if (hm && tma_ok && tid == 0) bulk_store_wait_all();
     }
 }

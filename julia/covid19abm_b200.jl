@@ -1,0 +1,108 @@
+# covid19abm_b200.jl — drop-in for covid19abm.jl's `ModelParameters` / `main(ip)` / `runsim(simnum, ip)` over
+# libcabm_b200.so (include/cabm.h). UNVERIFIED: Julia is not installed in the build image or on the GPU box;
+# the same C ABI is exercised through Python ctypes in tests/. Field order and defaults follow
+# /root/reference/src/covid19abm.jl:31-55.
+module covid19abm_b200
+
+using Parameters
+
+const LIB = get(ENV, "CABM_LIB", joinpath(@__DIR__, "..", "covid19abm.jl_b200", "libcabm_b200.so"))
+
+@enum HEALTH SUS LAT PRE ASYMP MILD MISO INF IISO HOS ICU REC DED UNDEF      # :5
+
+@with_kw mutable struct ModelParameters @deftype Float64                       # :31-55
+    β = 0.0
+    frelasymp::Float64 = 0.11
+    seasonal::Bool = false
+    popsize::Int64 = 10000
+    prov::Symbol = :newyork
+    calibration::Bool = false
+    modeltime::Int64 = 300
+    initialinf::Int64 = 1
+    initialhi::Int64 = 0
+    asymp_props::NTuple{5, Float64} = (0.25, 0.25, 0.14, 0.07, 0.07)
+    mild_props::NTuple{5, Float64} = (0.95, 0.9, 0.85, 0.6, 0.2)
+    τmild::Int64 = 0
+    fmild::Float64 = 0.0
+    fsevere::Float64 = 0.0
+    tpreiso::Int64 = 0
+    fpreiso::Float64 = 0.0
+    quar_grp::Int8 = 5
+    quar_grp_frac::Float64 = 0.0
+    ctstrat::Int8 = 0
+    fctcapture::Float16 = 0.0
+    fcontactst::Float16 = 0.0
+    cdaysback::Int8 = 0
+    strat3qdays::Int8 = 0
+end
+
+# struct cabm_params (include/cabm.h) — isbits, same layout as the C struct (192 bytes)
+struct CabmParams
+    beta::Cdouble; frelasymp::Cdouble
+    seasonal::Int32; popsize::Int32; prov_id::Int32; calibration::Int32; modeltime::Int32
+    initialinf::Int32; initialhi::Int32; tau_mild::Int32
+    asymp_props::NTuple{5, Cdouble}; mild_props::NTuple{5, Cdouble}
+    fmild::Cdouble; fsevere::Cdouble; fpreiso::Cdouble; quar_grp_frac::Cdouble
+    tpreiso::Int32; quar_grp::Int32; ctstrat::Int32; cdaysback::Int32; strat3qdays::Int32
+    fctcapture::Cfloat; fcontactst::Cfloat; _pad::Int32
+end
+
+const PROVINCES = (:alberta, :bc, :canada, :manitoba, :newbruns, :newfdland, :nwterrito, :novasco,
+                   :nunavut, :ontario, :pei, :quebec, :saskat, :yukon, :newyork)               # :319-333
+
+function to_c(ip::ModelParameters)
+    pid = findfirst(==(ip.prov), PROVINCES)
+    CabmParams(ip.β, ip.frelasymp, ip.seasonal, ip.popsize, pid === nothing ? -1 : pid - 1, ip.calibration,
+               ip.modeltime, ip.initialinf, ip.initialhi, ip.τmild, ip.asymp_props, ip.mild_props, ip.fmild,
+               ip.fsevere, ip.fpreiso, ip.quar_grp_frac, ip.tpreiso, ip.quar_grp, ip.ctstrat, ip.cdaysback,
+               ip.strat3qdays, Float32(ip.fctcapture), Float32(ip.fcontactst), 0)
+end
+
+function check(h, rc)
+    rc == 0 && return
+    error(unsafe_string(ccall((:cabm_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))   # the reference's error("...") text
+end
+
+const CURRENT_SEED = Ref{UInt64}(0)
+seed!(s) = (CURRENT_SEED[] = UInt64(s))            # stands in for Random.seed!(simnum*726) :78
+
+"main(ip) :104-142 — returns Matrix{Int16}(popsize, modeltime)"
+function main(ip::ModelParameters; device = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:cabm_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint), h, device, 1, ip.popsize, ip.modeltime, 1)
+    rc == 0 || error(unsafe_string(ccall((:cabm_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    try
+        p = Ref(to_c(ip)); seeds = UInt64[CURRENT_SEED[]]
+        check(h[], ccall((:cabm_configure, LIB), Cint, (Ptr{Cvoid}, Ref{CabmParams}, Cint, Ptr{Int32}, Cint, Ptr{UInt64}, Cint),
+                         h[], p, 1, C_NULL, 1, seeds, 0))
+        check(h[], ccall((:cabm_run, LIB), Cint, (Ptr{Cvoid},), h[]))
+        hmatrix = Matrix{Int16}(undef, ip.popsize, ip.modeltime)          # column-major: one day per column (:111,:221)
+        check(h[], ccall((:cabm_get_hmatrix, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int16}), h[], 0, hmatrix))
+        return hmatrix
+    finally
+        ccall((:cabm_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+end
+
+"pmap(x -> runsim(x, ip), 1:nsims) (scripts/local_run.jl:28-30) as one device run: curves [12, T, 6, nsims]"
+function run_ensemble(ip::ModelParameters, nsims::Integer; device = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:cabm_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint), h, device, nsims, ip.popsize, ip.modeltime, 0)
+    rc == 0 || error(unsafe_string(ccall((:cabm_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    try
+        p = Ref(to_c(ip)); seeds = UInt64[726 * x for x in 1:nsims]                               # :78
+        check(h[], ccall((:cabm_configure, LIB), Cint, (Ptr{Cvoid}, Ref{CabmParams}, Cint, Ptr{Int32}, Cint, Ptr{UInt64}, Cint),
+                         h[], p, 1, C_NULL, nsims, seeds, 0))
+        check(h[], ccall((:cabm_run, LIB), Cint, (Ptr{Cvoid},), h[]))
+        inc = Array{Int32}(undef, 12, ip.modeltime, 6, nsims); prev = similar(inc)                # C order [R][6][T][12]
+        check(h[], ccall((:cabm_get_curves, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), h[], inc, prev))
+        infectors = Matrix{Int64}(undef, 4, nsims); tiso = Vector{Int64}(undef, nsims)
+        check(h[], ccall((:cabm_get_scalars, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{UInt32}), h[], infectors, tiso, C_NULL, C_NULL))
+        return (inc = inc, prev = prev, infectors = infectors, totalisolated = tiso)
+    finally
+        ccall((:cabm_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+end
+
+export ModelParameters, HEALTH, main, run_ensemble
+end

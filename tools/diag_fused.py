@@ -1,0 +1,16 @@
+import sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import numpy as np, covid19abm_b200 as cv
+from bench import CFG, seeds_for
+ip = cv.ModelParameters(**CFG)
+pop = cv.Population(1000, 10000, 500, store_hmatrix=False)
+pop.configure(ip, seeds_for(0,0,1000)); pop.run(); pop.run()
+print("ms", pop.last_run_ms)
+met = np.zeros(1000, np.int32); inf = np.zeros(1000, np.int32)
+pop._chk(pop.L.cabm_get_dyntrans_counters(pop.h, met.ctypes.data, inf.ctypes.data))
+inc, prev = pop.curves()
+attack = 1 - prev[:,0,-1,0]/10000
+order = np.argsort(-met)
+print("kcycles sum", met.sum(), "max", met.max(), "mean", met.mean())
+for r in order[:12]: print(r, "kcyc", met[r], "ms", met[r]*1024/1.965e6, "rounds", inf[r], "attack", attack[r], "peak inf", prev[r,0,:,2:8].sum(axis=1).max(), "cyc/round", met[r]*1024/max(inf[r],1))
+print("takeoff count", (attack>0.1).sum(), "mean attack", attack.mean())
+for r in order[500:503]: print(r, "kcyc", met[r], "rounds", inf[r], "attack", attack[r])
