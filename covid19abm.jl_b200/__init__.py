@@ -145,6 +145,7 @@ def lib():
     L.cabm_launch_count.argtypes = [vp]; L.cabm_launch_count.restype = i64
     L.cabm_set_profiling.argtypes = [vp, i32]
     L.cabm_set_path.argtypes = [vp, i32]
+    L.cabm_get_debug.argtypes = [vp, vp]
     L.cabm_get_last_path.argtypes = [vp]
     L.cabm_get_profile.argtypes = [vp, vp, vp]
     L.cabm_step_initialize.argtypes = [vp]
@@ -461,3 +462,48 @@ def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_
         if own:
             pop.close()
     return out
+
+
+# ------------------------------------------------------------------ multi-GPU: replicate sharding
+def shard_indices(nsims, rank, world):
+    """Replicate r runs on rank r mod world (interleaved, so a β sweep spreads evenly): no hot-path traffic."""
+    return list(range(rank, nsims, world))
+
+
+def gather_ensemble(local, nsims, rank, world, dist=None, device="cpu", keys=("inc", "prev", "infectors", "totalisolated", "lat_inc_sum", "err")):
+    """The path's single collective: end-of-run gather of the per-replicate summaries (pmap's implicit gather,
+    scripts/local_run.jl:28-30,40-45) over torch.distributed (NCCL on GPUs, gloo in the CPU tests). `local[k]` holds this
+    rank's replicates in shard order; every rank returns the full arrays in replicate order."""
+    if world == 1 or dist is None:
+        return {k: np.asarray(local[k]) for k in keys if k in local}
+    import torch
+    nmax = (nsims + world - 1) // world
+    out = {}
+    for k in keys:
+        if k not in local:
+            continue
+        a = np.ascontiguousarray(local[k])
+        if a.dtype == np.uint32:
+            a = a.astype(np.int64)
+        pad = np.zeros((nmax,) + a.shape[1:], dtype=a.dtype)
+        pad[:a.shape[0]] = a
+        t = torch.from_numpy(pad).to(device)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        full = np.zeros((nsims,) + a.shape[1:], dtype=a.dtype)
+        for rk in range(world):
+            idx = shard_indices(nsims, rk, world)
+            full[idx] = parts[rk].cpu().numpy()[:len(idx)]
+        out[k] = full
+    return out
+
+
+def run_ensemble_sharded(ip, nsims, rank, world, dist=None, device_index=0, seeds=None, pset_of_rep=None, **kw):
+    """run_ensemble over `world` processes, one GPU each: this rank runs replicates rank, rank+world, ... and the
+    summaries are gathered once at the end."""
+    if seeds is None:
+        seeds = [726 * (i + 1) for i in range(nsims)]
+    idx = shard_indices(nsims, rank, world)
+    loc = run_ensemble(ip, len(idx), seeds=[seeds[i] for i in idx],
+                       pset_of_rep=None if pset_of_rep is None else [pset_of_rep[i] for i in idx], device=device_index, **kw)
+    return gather_ensemble(loc, nsims, rank, world, dist=dist, device=f"cuda:{device_index}" if dist is not None and dist.get_backend() == "nccl" else "cpu")

@@ -81,6 +81,7 @@ static ConstTables make_const_tables() {
         c.mh_hos_thr[g] = bernoulli_threshold(mh_hos[g]);
         c.mh_icu_thr[g] = bernoulli_threshold(2 * mh_hos[g]);                           // :586
     }
+    for (int g = 0; g < 5; ++g) for (int q = 0; q < 5; ++q) c.cm[g][q] = CONTACT_MATRIX[g][q];
     c.ct3_lat_thr = bernoulli_threshold(0.05); c.ct3_pre_thr = bernoulli_threshold(0.95); c.ct3_asymp_thr = bernoulli_threshold(0.70);
     return c;
 }
@@ -117,7 +118,7 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8);
     DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);
     DA(S.totalmet, (size_t)h->R); DA(S.totalinf, (size_t)h->R);
-    DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R);
+    DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R); DA(S.dbg, (size_t)h->R * 8);
     if (S.store_hm) DA(S.hm, (size_t)h->R * h->T * h->N);
     DA(h->d_scratch, (size_t)4 * h->N);
     DA(h->d_work, 4);
@@ -373,6 +374,12 @@ extern "C" int cabm_last_run_ms(cabm_handle *h, float *ms) {
     return CABM_OK;
 }
 extern "C" int64_t cabm_launch_count(const cabm_handle *h) { return h ? h->launches : 0; }
+extern "C" int cabm_get_debug(cabm_handle *h, int64_t *out) {
+    if (!h || !out) return CABM_E_ARG;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(out, h->S.dbg, (size_t)h->n_rep * 64, cudaMemcpyDeviceToHost));
+    return CABM_OK;
+}
 extern "C" int cabm_get_day(const cabm_handle *h) { return h ? h->day : -1; }
 
 extern "C" int cabm_step_initialize(cabm_handle *h) {

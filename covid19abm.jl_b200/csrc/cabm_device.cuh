@@ -59,6 +59,7 @@ struct ConstTables {
     int lat_base, pre_base, asy_base, inf_base, psi_base, mu_base;
     int nb_len[5];
     double hlo[5], hspan[5], clo[5], cspan[5];                 // move_to_inf :535-536
+    double cm[5][5];                                           // contact_matrix :838-848
     unsigned long long mh_inf_thr[5];                          // :537
     unsigned long long mh_hos_thr[5], mh_icu_thr[5];           // :585-586
     unsigned long long ct3_lat_thr, ct3_pre_thr, ct3_asymp_thr; // :741
@@ -76,6 +77,7 @@ struct Dev {
     uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;
     int *inc, *prev;                         // [R][6][T][12]
     long long *infectors, *latsum;           // [R][4], [R]
+    long long *dbg;                          // [R][8] per-phase cycle counts of the fused kernel (diagnostics)
     uint8_t *hm;                             // [R][T][N] health codes (widened to Int16 by cabm_get_hmatrix)
     const DevPset *psets; const unsigned long long *beta_thr;    // [P], [P][T][4]
     const uint32_t *nb_thr; const uint8_t *nb_guide;             // [5][256], [5][256]

@@ -23,11 +23,13 @@ namespace cabm {
 
 constexpr int FUSED_NT = 512;          // threads per CTA = max events per batch
 constexpr int FUSED_NCAND = 32;        // infectors per batch
+constexpr int FUSED_LCAP = 512;        // infectors listed per pass (more are handled in further passes)
 
 struct FusedSmem {
     uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
     uint32_t *nb_thr; uint8_t *nb_guide;
     uint32_t *Y, *W1; uint8_t *Q; uint32_t *touch, *dupm; uint16_t *D;
+    uint16_t *list; uint8_t *lcnt;       // the day's ordered infectious agents and their contact budgets
     int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
 };
 
@@ -41,6 +43,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int Np) {
     b += FUSED_NT * 4 * 2 + FUSED_NT;    // Y (= cnt), W1, Q
     b += (size_t)(Np / 32) * 4 * 2;      // touch, dupm bitmasks
     b += FUSED_NT * 2;                   // D (compacted duplicate events)
+    b += FUSED_LCAP * 3;                 // list, lcnt
     return (b + 15) / 16 * 16 + 64;
 }
 
@@ -67,6 +70,7 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); }   // bound the queue on idle days
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -88,21 +92,30 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         M.touch = (uint32_t *)p; p += (size_t)nwords * 4;
         M.dupm = (uint32_t *)p; p += (size_t)nwords * 4;
         M.D = (uint16_t *)p; p += NT * 2;
+        M.list = (uint16_t *)p; p += FUSED_LCAP * 2;
         M.nb_guide = (uint8_t *)p; p += 5 * 256;
         M.Q = (uint8_t *)p; p += NT;
+        M.lcnt = (uint8_t *)p; p += FUSED_LCAP;
     }
     __shared__ int s_r, s_off[8], s_wcnt[FUSED_NT / 32][5], s_base[5], s_total[5];
     __shared__ int s_sel_tid, s_sel_k, s_Ltot, s_ninf;
-    __shared__ int s_inc[60], s_out[60];
+    __shared__ int s_io[2][2][60];           // [day parity][entries | exits][(group, state)] — curve deltas of one day
+    __shared__ uint32_t s_tlat[4], s_tpre[4], s_tasy[40], s_tinf[40];
+    __shared__ unsigned long long s_beta[4];
+    __shared__ int s_nf[2], s_wsum[FUSED_NT / 32], s_g0[2][60];
     __shared__ int s_infectors[4];
     // dyntrans batch
-    __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_ncand, s_nb, s_cut, s_cursor;
+    __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_nb, s_cut;
     __shared__ unsigned long long s_gp[FUSED_NCAND], s_bthr[FUSED_NCAND];
     __shared__ uint8_t s_xh[FUSED_NCAND];
     __shared__ int s_wdup[FUSED_NT / 32];
 
     for (int k = tid; k < 5 * 256; k += NT) { M.nb_thr[k] = S.nb_thr[k]; M.nb_guide[k] = S.nb_guide[k]; }
     for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }
+    if (tid < 4) { s_tlat[tid] = c_tab.lat_thr[tid]; s_tpre[tid] = c_tab.pre_thr[tid]; }
+    if (tid < 40) { s_tasy[tid] = c_tab.asy_thr[tid]; s_tinf[tid] = c_tab.inf_thr[tid]; }
+    int *const s_inc = s_io[0][0], *const s_out = s_io[0][1];   // first-column phase uses parity 0
+    __syncthreads();
     const bool tma_ok = S.store_hm && (N % 16 == 0);     // cp.async.bulk needs 16-byte size and alignment
 
     for (;;) {
@@ -112,6 +125,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         const int r = s_r;
         if (r >= S.R) break;
         const long long t_start = clock64();
+        long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = t_start;   // per-phase cycles seen by thread 0 (diagnostics)
+#define PHASE(k) do { const long long t_now_ = clock64(); t_ph[k] += t_now_ - t_last; t_last = t_now_; } while (0)
         int n_rounds = 0;
         const DevPset &P = S.psets[S.pset_of[r]];
         const uint2 key = S.key[r];
@@ -129,10 +144,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 int ag0 = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ag0 += ((unsigned long long)wa.x >= P.age_thr[k]);
-                int latents = table_draw(wa.y, c_tab.lat_base, c_tab.lat_thr, c_tab.lat_len);
-                const int pres = table_draw(wa.z, c_tab.pre_base, c_tab.pre_thr, c_tab.pre_len);
-                const int asymps = table_draw(wa.w, c_tab.asy_base, c_tab.asy_thr, c_tab.asy_len);
-                const int infs = table_draw(wb.x, c_tab.inf_base, c_tab.inf_thr, c_tab.inf_len);
+                int latents = table_draw(wa.y, c_tab.lat_base, s_tlat, c_tab.lat_len);
+                const int pres = table_draw(wa.z, c_tab.pre_base, s_tpre, c_tab.pre_len);
+                const int asymps = table_draw(wa.w, c_tab.asy_base, s_tasy, c_tab.asy_len);
+                const int infs = table_draw(wb.x, c_tab.inf_base, s_tinf, c_tab.inf_len);
                 latents -= pres;
                 d4 = (uint32_t)latents | ((uint32_t)asymps << 8) | ((uint32_t)pres << 16) | ((uint32_t)infs << 24);
                 const bool quar = bern(wb.y, P.quar_thr) && ag0 == P.quar_grp0;
@@ -146,7 +161,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             S.tracestart[a] = -1; S.traceend[a] = -1; S.tracedxp[a] = 0; S.ct_head[a] = CT_NONE;
         }
         for (int k = tid; k < nwords; k += NT) M.inf[k] = 0;
-        if (tid < 60) { s_inc[tid] = 0; s_out[tid] = 0; }
+        if (tid < 240) (&s_io[0][0][0])[tid] = 0;
         if (tid < 5) s_total[tid] = 0;
         if (tid < 4) s_infectors[tid] = 0;
         if (tid == 0) s_ninf = 0;
@@ -238,7 +253,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             if (h != SUS) { atomicAdd(&s_inc[st_ag(st) * 12 + h], 1); atomicAdd(&s_out[st_ag(st) * 12 + SUS], 1); }
         }
         __syncthreads();
-        int run = 0;                              // running prevalence of (group, state) = (tid/12, tid%12), tid < 60; group 0 in tid 60..71
+        int run = 0;                              // running prevalence of (group, state) = (tid/12, tid%12), tid < 60; group 0 in tid 64..75
         if (tid < 60) {
             const int g = tid / 12, s = tid % 12;
             run = s_inc[tid] + (s == SUS ? (s_off[g + 1] - s_off[g]) - s_out[tid] : 0);
@@ -248,8 +263,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         }
         __syncthreads();
         long long latsum = 0;
-        if (tid >= 60 && tid < 72) {
-            const int s = tid - 60;
+        int g0_in = 0;
+        if (tid >= 64 && tid < 76) {
+            const int s = tid - 64;
             for (int g = 0; g < 5; ++g) run += M.cnt[g * 12 + s];
             const size_t b = (((size_t)r * 6 + 0) * (size_t)T + 0) * 12 + s;
             S.inc[b] = run; S.prev[b] = run;
@@ -263,204 +279,252 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         }
         __syncthreads();
 
+        PHASE(0);
         // ============================================================ the day loop :131-140
+        // s_nextfire = earliest expiry day of any agent. A day with nobody infectious and nothing expiring changes no
+        // state: it only repeats the column and the prevalence row, without a single barrier.
+        if (tid < 2) s_nf[tid] = 32767;
+        int nextfire = 0, act = 0;                                             // uniform registers
+        __syncthreads();
         for (int day = 1; day <= T; ++day) {
-            // -------------------------------------------------------- dyntrans(st) :790-834
-            if (s_ninf > 0) {
-                if (tid == 0) s_cursor = 0;
-                __syncthreads();
-                for (;;) {
-                    // (a) warp 0: next <=32 infectious agents at or after the cursor, in ascending order, with their
-                    //     contact budget (:802) and its split over the age groups (:804)
-                    if (wid == 0) {
-                        int found = 0;
-                        const int cw = s_cursor >> 5, cb = s_cursor & 31;
-                        for (int w0 = cw; w0 < nwords && found < FUSED_NCAND; w0 += 32) {
-                            uint32_t m = (w0 + lane < nwords) ? M.inf[w0 + lane] : 0u;
-                            if (w0 + lane == cw) m &= ~((1u << cb) - 1u);
+            const bool active = s_ninf > 0 || day >= nextfire;                 // uniform: s_ninf only changes between S1 and S2
+            if (active) {
+                // ---------------------------------------------------- dyntrans(st) :790-834
+                if (s_ninf > 0) {
+                    if (tid < 4) s_beta[tid] = beta[(size_t)(day - 1) * 4 + tid];              // _get_betavalue :756-769 for today
+                    int cursor = 0;                                                            // first agent index not yet listed
+                    for (;;) {
+                        // ordered list of (up to FUSED_LCAP) infectious agents at or after `cursor` (:794), built by the whole CTA
+                        int lbase = 0, w0 = cursor >> 5;
+                        for (; w0 < nwords && lbase < FUSED_LCAP; w0 += NT) {
+                            const int wi = w0 + tid;
+                            uint32_t m = (wi < nwords) ? M.inf[wi] : 0u;
+                            if (wi == (cursor >> 5)) m &= ~((1u << (cursor & 31)) - 1u);
                             const int c = __popc(m);
                             int incl = c;
                             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                            int pos = found + incl - c;
-                            while (m && pos < FUSED_NCAND) { const int b = __ffs(m) - 1; m &= m - 1; s_cand[pos++] = ((w0 + lane) << 5) + b; }
-                            found += __shfl_sync(FULL, incl, 31);
+                            if (lane == 31) s_wsum[wid] = incl;
+                            __syncthreads();
+                            int pos = lbase + incl - c, tot = 0;
+                            for (int w = 0; w < NW; ++w) { const int v = s_wsum[w]; tot += v; if (w < wid) pos += v; }
+                            while (m && pos < FUSED_LCAP) { const int b = __ffs(m) - 1; m &= m - 1; M.list[pos++] = (uint16_t)((wi << 5) + b); }
+                            lbase += tot;
+                            __syncthreads();
                         }
-                        const int ncand = min(found, FUSED_NCAND);
-                        __syncwarp();
-                        int E = 0;
-                        if (lane < ncand) {
-                            const int x = s_cand[lane];
-                            const uint32_t sx = M.status[x];
-                            const int cnts = budget_of_s(M, key, x, day, sx);
-                            const unsigned long long gp = __ldg(&S.gpw[st_ag(sx) * 256 + cnts]);
-                            E = (int)(gp & 0xFF) + (int)((gp >> 8) & 0xFF) + (int)((gp >> 16) & 0xFF) + (int)((gp >> 24) & 0xFF) + (int)((gp >> 32) & 0xFF);
-                            s_gp[lane] = gp;
-                            s_xh[lane] = (uint8_t)st_health(sx);
-                            s_bthr[lane] = beta[(size_t)(day - 1) * 4 + beta_class(st_health(sx))];   // :800
-                        }
-                        int incl = E;
-                        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                        s_pref[lane + 1] = incl;
-                        const unsigned fits = __ballot_sync(FULL, lane < ncand && incl <= NT);
-                        if (lane == 0) {
-                            s_pref[0] = 0;
-                            int nb = 0;
-                            while (nb < ncand && ((fits >> nb) & 1)) ++nb;      // prefix of candidates whose events fit (E <= 260 < NT: nb >= 1)
-                            s_ncand = ncand; s_nb = nb; s_cut = nb;
-                        }
-                    }
-                    __syncthreads();
-                    const int nb = s_nb;
-                    if (s_ncand == 0) break;
-                    ++n_rounds;
-                    const int Etot = s_pref[nb];
-                    // (b) one contact event per thread: target draw (:807) and transmission word (:823)
-                    uint32_t y = 0, w1 = 0; int q = 0; bool ev = tid < Etot;
-                    if (ev) {
-                        int lo = 0, hi = nb - 1;                               // last q with pref[q] <= tid
-                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= tid) lo = mid; else hi = mid - 1; }
-                        q = lo;
-                        const int e = tid - s_pref[q];
-                        const unsigned long long gp = s_gp[q];
-                        const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF), p4 = p3 + (int)((gp >> 24) & 0xFF);
-                        const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
-                        const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
-                        const int go = s_off[g], len = s_off[g + 1] - go;
-                        const int x = s_cand[q];
-                        if (len == 0) { atomicOr(&S.err[r], ERR_EMPTY_GROUP); ev = false; }
-                        else {
-                            const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
-                            y = M.grp[go + below(w.x, len)]; w1 = w.y;
-                            // an infector later in this batch that gets contacted must re-read its budget: cut the batch there
-                            if ((int)y > x && (int)y <= s_cand[nb - 1] && ((M.inf[y >> 5] >> (y & 31)) & 1u)) {
-                                int a = q + 1, b = nb - 1;
-                                while (a < b) { const int mid = (a + b) >> 1; if (s_cand[mid] < (int)y) a = mid + 1; else b = mid; }
-                                atomicMin(&s_cut, a);
-                            }
-                        }
-                    }
-                    M.Y[tid] = ev ? y : 0xFFFFFFFFu; M.W1[tid] = w1; M.Q[tid] = (uint8_t)q;
-                    __syncthreads();
-                    const int cut = s_cut;
-                    const int Ev = s_pref[cut];                                // events of infectors [0, cut) are final
-                    ev = ev && tid < Ev;
-                    // (c) events that share a target must be applied in event order (:809-830). Exact detection with two
-                    //     agent bitmasks; the (few) duplicate events are compacted in event order and resolved by the first
-                    //     event of each target, everything else is one independent event per thread.
-                    const uint32_t ybit = 1u << (y & 31);
-                    const int yw = (int)(y >> 5);
-                    if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) atomicOr(&M.dupm[yw], ybit); }
-                    __syncthreads();
-                    const bool isdup = ev && (M.dupm[yw] & ybit);
-                    const unsigned dm = __ballot_sync(FULL, isdup);
-                    if (lane == 0) s_wdup[wid] = __popc(dm);
-                    __syncthreads();
-                    int dpos = 0, dtot = 0;
-                    for (int w = 0; w < NW; ++w) { const int c = s_wdup[w]; dtot += c; if (w < wid) dpos += c; }
-                    if (isdup) { dpos += __popc(dm & ((1u << lane) - 1u)); M.D[dpos] = (uint16_t)tid; }
-                    if (dtot) __syncthreads();
-                    if (ev) {
-                        bool leader = true;
-                        if (isdup) for (int d = 0; d < dpos; ++d) if (M.Y[M.D[d]] == y) { leader = false; break; }
-                        if (leader) {
-                            const uint32_t sy = M.status[y];
-                            int rem = budget_of_s(M, key, y, day, sy);                                   // :811
-                            bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;                     // :822
-                            int xh_inf = -1;
-                            if (rem > 0) {                                                               // :812
-                                rem -= 1;                                                                 // :813
-                                if (sus && bern(w1, s_bthr[q])) { sus = false; xh_inf = s_xh[q]; }       // :823-827
-                            }
-                            if (isdup) {
-                                for (int d = dpos + 1; d < dtot && rem > 0; ++d) {
-                                    const int e2 = M.D[d];
-                                    if (M.Y[e2] != y) continue;
-                                    rem -= 1;
-                                    const int q2 = M.Q[e2];
-                                    if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }
+                        const int nlist = min(lbase, FUSED_LCAP);
+                        PHASE(1);
+                        if (nlist == 0) break;
+                        // the day's contact budget of every listed infector (:802), drawn once; a later hit by an earlier
+                        // infector shows up as tag == day in its status word and overrides this value
+                        if (tid < nlist) { const int x = M.list[tid]; M.lcnt[tid] = (uint8_t)budget_of_s(M, key, x, day, M.status[x]); }
+                        __syncthreads();
+                        PHASE(2);
+                        int lpos = 0;
+                        while (lpos < nlist) {
+                            ++n_rounds;
+                            // (a) warp 0: the next <= 32 infectors, their budget split over the age groups (:804), event prefix
+                            if (wid == 0) {
+                                const int ncand = min(FUSED_NCAND, nlist - lpos);
+                                int E = 0;
+                                if (lane < ncand) {
+                                    const int x = M.list[lpos + lane];
+                                    const uint32_t sx = M.status[x];
+                                    const int cnts = st_tag(sx) == day ? st_rem(sx) : (int)M.lcnt[lpos + lane];
+                                    unsigned long long gp = 0;                                  // round.(cm[ag]*cnts), half-to-even
+#pragma unroll
+                                    for (int g = 0; g < 5; ++g) gp |= (unsigned long long)(unsigned)__double2int_rn(__dmul_rn(c_tab.cm[st_ag(sx)][g], (double)cnts)) << (8 * g);
+                                    E = (int)(gp & 0xFF) + (int)((gp >> 8) & 0xFF) + (int)((gp >> 16) & 0xFF) + (int)((gp >> 24) & 0xFF) + (int)((gp >> 32) & 0xFF);
+                                    s_cand[lane] = x; s_gp[lane] = gp;
+                                    s_xh[lane] = (uint8_t)st_health(sx);
+                                    s_bthr[lane] = s_beta[beta_class(st_health(sx))];         // :800
+                                }
+                                int incl = E;
+                                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                                s_pref[lane + 1] = incl;
+                                const unsigned fits = __ballot_sync(FULL, lane < ncand && incl <= NT);
+                                if (lane == 0) {
+                                    s_pref[0] = 0;
+                                    const int nb = fits == FULL ? ncand : min(ncand, __ffs(~fits) - 1);   // candidates whose events fit (E <= 260 < NT: nb >= 1)
+                                    s_nb = nb; s_cut = nb;
                                 }
                             }
-                            uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
-                            if (xh_inf >= 0) {
-                                ns = st_set_swap(ns, LAT);
-                                S.sickfrom[rb + y] = (uint8_t)xh_inf;
-                                M.expday[y] = (int16_t)day;                    // y.exp = y.tis :826 — fires in today's time_update
+                            __syncthreads();                                                   // B1
+                            const int nb = s_nb, Etot = s_pref[nb];
+                            // (b) one contact event per thread: target draw (:807), transmission word (:823); mark the target
+                            uint32_t y = 0, w1 = 0; int q = 0; bool ev = tid < Etot;
+                            if (ev) {
+                                int lo = 0, hi = nb - 1;                               // last q with pref[q] <= tid
+                                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= tid) lo = mid; else hi = mid - 1; }
+                                q = lo;
+                                const int e = tid - s_pref[q];
+                                const unsigned long long gp = s_gp[q];
+                                const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF), p4 = p3 + (int)((gp >> 24) & 0xFF);
+                                const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
+                                const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
+                                const int go = s_off[g], len = s_off[g + 1] - go;
+                                const int x = s_cand[q];
+                                if (len == 0) { atomicOr(&S.err[r], ERR_EMPTY_GROUP); ev = false; }
+                                else {
+                                    const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                                    y = M.grp[go + below(w.x, len)]; w1 = w.y;
+                                    // an infector later in this batch that gets contacted must re-read its budget: cut the batch there
+                                    if ((int)y > x && (int)y <= s_cand[nb - 1] && ((M.inf[y >> 5] >> (y & 31)) & 1u)) {
+                                        int a = q + 1, b = nb - 1;
+                                        while (a < b) { const int mid = (a + b) >> 1; if (s_cand[mid] < (int)y) a = mid + 1; else b = mid; }
+                                        atomicMin(&s_cut, a);
+                                    }
+                                }
                             }
-                            M.status[y] = ns;
+                            M.Y[tid] = ev ? y : 0xFFFFFFFFu; M.W1[tid] = w1; M.Q[tid] = (uint8_t)q;
+                            const uint32_t ybit = 1u << (y & 31);
+                            const int yw = (int)(y >> 5);
+                            // targets hit more than once (by any event of the batch, cut or not) take the ordered path below
+                            if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) atomicOr(&M.dupm[yw], ybit); }
+                            __syncthreads();                                                   // B2
+                            const int cut = s_cut;
+                            const int Ev = s_pref[cut];                                // events of infectors [0, cut) are final
+                            const bool marked = ev;
+                            ev = ev && tid < Ev;
+                            const bool isdup = ev && (M.dupm[yw] & ybit);
+                            // (c) events sharing a target are applied in event order (:809-830) by the first event of the target,
+                            //     over the compacted list of such events; every other event is independent
+                            int dpos = 0, dtot = 0;
+                            if (__syncthreads_or(isdup)) {                                     // B3
+                                const unsigned dm = __ballot_sync(FULL, isdup);
+                                if (lane == 0) s_wdup[wid] = __popc(dm);
+                                __syncthreads();
+                                for (int w = 0; w < NW; ++w) { const int c = s_wdup[w]; dtot += c; if (w < wid) dpos += c; }
+                                if (isdup) { dpos += __popc(dm & ((1u << lane) - 1u)); M.D[dpos] = (uint16_t)tid; }
+                                __syncthreads();
+                            }
+                            if (ev) {
+                                bool leader = true;
+                                if (isdup) for (int d = 0; d < dpos; ++d) if (M.Y[M.D[d]] == y) { leader = false; break; }
+                                if (leader) {
+                                    const uint32_t sy = M.status[y];
+                                    int rem = budget_of_s(M, key, y, day, sy);                           // :811
+                                    bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;             // :822
+                                    int xh_inf = -1;
+                                    if (rem > 0) {                                                       // :812
+                                        rem -= 1;                                                         // :813
+                                        if (sus && bern(w1, s_bthr[q])) { sus = false; xh_inf = s_xh[q]; }   // :823-827
+                                    }
+                                    if (isdup) {
+                                        for (int d = dpos + 1; d < dtot && rem > 0; ++d) {
+                                            const int e2 = M.D[d];
+                                            if (M.Y[e2] != y) continue;
+                                            rem -= 1;
+                                            const int q2 = M.Q[e2];
+                                            if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }
+                                        }
+                                    }
+                                    uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
+                                    if (xh_inf >= 0) {
+                                        ns = st_set_swap(ns, LAT);
+                                        S.sickfrom[rb + y] = (uint8_t)xh_inf;
+                                        M.expday[y] = (int16_t)day;                // y.exp = y.tis :826 — fires in today's time_update
+                                    }
+                                    M.status[y] = ns;
+                                }
+                            }
+                            __syncthreads();                                                   // B5: status writes visible to the next batch
+                            if (marked) { M.touch[yw] = 0; M.dupm[yw] = 0; }                   // next marking is after the next B1
+                            lpos += cut;
                         }
+                        PHASE(3);
+                        if (w0 >= nwords && lbase <= FUSED_LCAP) break;                        // the list held every infectious agent
+                        cursor = (int)M.list[FUSED_LCAP - 1] + 1;
+                        __syncthreads();
                     }
-                    __syncthreads();
-                    if (ev) { M.touch[yw] = 0; M.dupm[yw] = 0; }
-                    if (tid == 0) s_cursor = s_cand[cut - 1] + 1;
-                    __syncthreads();
                 }
-            }
-            __syncthreads();
 
-            // -------------------------------------------------------- time_update() :399-428
-            if (hm && tma_ok && tid == 0) bulk_store_wait_read();              // previous column has left shared memory
-            __syncthreads();
-            for (int i0 = tid * 8; i0 < N; i0 += NT * 8) {
-                union { uint4 v; int16_t e[8]; } ex;
-                ex.v = *reinterpret_cast<const uint4 *>(M.expday + i0);
-                unsigned fire = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) fire |= (unsigned)((int)ex.e[k] <= day) << k;
+                // ---------------------------------------------------- time_update() :399-428
+                if (hm && tma_ok && tid == 0) bulk_store_wait_read();          // earlier columns have left shared memory
+                __syncthreads();                                               // S1: dyntrans writes visible; col reusable
+                if (tid == 0) s_nf[(act + 1) & 1] = 32767;                     // buffer of the next active day (last read after the previous S2)
                 if (day == 1) {                                                // seeds isolated by fpreiso: resync isob (see k_time_update)
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { const uint32_t st = M.status[i0 + k]; fire |= (((st >> 19) ^ (st >> 20)) & 1u) << k; }
+                    for (int i = tid; i < N; i += NT) { const uint32_t st = M.status[i]; if (((st >> 19) ^ (st >> 20)) & 1u) M.status[i] = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB); }
                 }
-                while (fire) {
-                    const int k = __ffs(fire) - 1; fire &= fire - 1;
-                    const int i = i0 + k;
-                    if (i >= N) break;
-                    uint32_t st = M.status[i];
-                    if ((int)ex.e[k] <= day) {
-                        const Tr t = transition_core(S, P, r, i, day, st, key, st_swap(st), false);
-                        st = t.st;
-                        M.expday[i] = (int16_t)t.expday;
-                        if (t.newh != t.oldh) {
-                            M.col[i] = (uint8_t)t.newh;
-                            if (day < T) { atomicAdd(&s_inc[st_ag(st) * 12 + t.newh], 1); atomicAdd(&s_out[st_ag(st) * 12 + t.oldh], 1); }
-                            if (is_infectious(t.newh) != is_infectious(t.oldh)) {
-                                atomicXor(&M.inf[i >> 5], 1u << (i & 31));
-                                atomicAdd(&s_ninf, is_infectious(t.newh) ? 1 : -1);
+                const uint32_t dd = (uint32_t)day * 0x10001u;
+                uint32_t mn = 0x7FFF7FFFu;                                     // running min of the expiry days that stay (2 x i16)
+                for (int i0 = tid * 8; i0 < N; i0 += NT * 8) {
+                    uint4 ex = *reinterpret_cast<const uint4 *>(M.expday + i0);
+                    const uint32_t m0 = __vcmples2(ex.x, dd), m1 = __vcmples2(ex.y, dd), m2 = __vcmples2(ex.z, dd), m3 = __vcmples2(ex.w, dd);
+                    if (m0 | m1 | m2 | m3) {                                   // somebody in these 8 expires today (:405)
+                        unsigned fire = (m0 & 1u) | ((m0 >> 15) & 2u) | ((m1 & 1u) << 2) | ((m1 >> 13) & 8u) | ((m2 & 1u) << 4) | ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u);
+                        while (fire) {
+                            const int k = __ffs(fire) - 1; fire &= fire - 1;
+                            const int i = i0 + k;
+                            if (i >= N) break;
+                            const uint32_t st = M.status[i];
+                            const Tr t = transition_core(S, P, r, i, day, st, key, st_swap(st), false);
+                            M.status[i] = t.st;
+                            M.expday[i] = (int16_t)t.expday;
+                            if (t.newh != t.oldh) {
+                                M.col[i] = (uint8_t)t.newh;
+                                atomicAdd(&s_io[day & 1][0][st_ag(st) * 12 + t.newh], 1); atomicAdd(&s_io[day & 1][1][st_ag(st) * 12 + t.oldh], 1);
+                                if (is_infectious(t.newh) != is_infectious(t.oldh)) {
+                                    atomicXor(&M.inf[i >> 5], 1u << (i & 31));
+                                    atomicAdd(&s_ninf, is_infectious(t.newh) ? 1 : -1);
+                                }
                             }
                         }
+                        ex = *reinterpret_cast<const uint4 *>(M.expday + i0);  // with the new expiry days
                     }
-                    st = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);
-                    M.status[i] = st;
+                    mn = __vmins2(mn, __vmins2(__vmins2(ex.x, ex.y), __vmins2(ex.z, ex.w)));
                 }
+                {
+                    int v = min((int)(short)(mn & 0xFFFF), (int)(short)(mn >> 16));
+                    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+                    if (lane == 0) atomicMin(&s_nf[act & 1], v);
+                }
+                if (hm && tma_ok) bulk_store_g2s_fence();
+                __syncthreads();                                               // S2
+                nextfire = s_nf[act & 1]; ++act;
+                PHASE(4);
             }
-            __syncthreads();
             // -------------------------------------------------------- column st+1 (:136 of the next day) and its curves
             if (day < T) {
+                // threads 0..59 own one (age group, state) pair each and keep its running prevalence in a register;
+                // threads 64..75 own group 0 ("all" = the sum over the five groups, :91-97). Idle days repeat the values.
+                int in = 0;
+                if (active && tid < 60) {
+                    in = s_io[day & 1][0][tid];
+                    run += in - s_io[day & 1][1][tid];
+                    s_io[day & 1][0][tid] = 0; s_io[day & 1][1][tid] = 0;        // next touched by the atomics after a later S1
+                    s_g0[0][tid] = in; s_g0[1][tid] = run;
+                }
+                if (active && tid < 128) {                                     // warps 0-3, warp-uniform and convergent
+                    __syncwarp();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
                 if (tid < 60) {
-                    const int g = tid / 12, s = tid % 12, in = s_inc[tid];
-                    run += in - s_out[tid];
+                    const int g = tid / 12, s = tid % 12;
                     const size_t b = (((size_t)r * 6 + (g + 1)) * (size_t)T + (size_t)day) * 12 + s;
                     S.inc[b] = in; S.prev[b] = run;
-                } else if (tid < 72) {
-                    const int s = tid - 60;
-                    int in = 0, out = 0;
-                    for (int g = 0; g < 5; ++g) { in += s_inc[g * 12 + s]; out += s_out[g * 12 + s]; }
-                    run += in - out;
+                } else if (tid >= 64 && tid < 76) {
+                    const int s = tid - 64;
+                    g0_in = 0;
+                    if (active) {
+                        int pv = 0;
+                        for (int g = 0; g < 5; ++g) { g0_in += s_g0[0][g * 12 + s]; pv += s_g0[1][g * 12 + s]; }
+                        run = pv;
+                    }
                     const size_t b = (((size_t)r * 6 + 0) * (size_t)T + (size_t)day) * 12 + s;
-                    S.inc[b] = in; S.prev[b] = run;
-                    if (s == LAT) latsum += in;
+                    S.inc[b] = g0_in; S.prev[b] = run;
+                    if (s == LAT) latsum += g0_in;
                 }
                 if (hm) {
-                    if (tma_ok) { bulk_store_g2s_fence(); __syncthreads(); if (tid == 0) bulk_store(hm + (size_t)day * N, M.col, (uint32_t)N); }
+                    if (tma_ok) { if (tid == 0) { bulk_store_wait_read_n(); bulk_store(hm + (size_t)day * N, M.col, (uint32_t)N); } }
                     else for (int i = tid; i < N; i += NT) hm[(size_t)day * N + i] = M.col[i];
                 }
-                __syncthreads();
-                if (tid < 60) { s_inc[tid] = 0; s_out[tid] = 0; }
             }
+            PHASE(5);
         }
         __syncthreads();
 
         // ------------------------------------------------------------ final state back to HBM, _count_infectors :295-313
-        if (tid == 60 + LAT) S.latsum[r] = latsum;
+        if (tid == 64 + LAT) S.latsum[r] = latsum;
         int l[4] = {0, 0, 0, 0};
         bool bad = false;
         for (int i = tid; i < Np; i += NT) {
@@ -479,7 +543,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         __syncthreads();
         if (tid < 4) S.infectors[r * 4 + tid] = s_infectors[tid];
         // diagnostics of the fused path: kilo-cycles spent on this replicate and dyntrans batches issued
-        if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; }
+        PHASE(6);
+        if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; for (int k = 0; k < 8; ++k) S.dbg[(size_t)r * 8 + k] = t_ph[k]; }
+#undef PHASE
         if (hm && tma_ok && tid == 0) bulk_store_wait_all();
     }
 }

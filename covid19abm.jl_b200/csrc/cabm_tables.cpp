@@ -89,7 +89,7 @@ static Table negbin(double mean, double sd) {
     return t;
 }
 
-static const double CM[5][5] = {   // contact_matrix :838-848
+const double CONTACT_MATRIX[5][5] = {   // contact_matrix :838-848
     {0.2287, 0.1839, 0.4219, 0.1116, 0.0539}, {0.0276, 0.5964, 0.2878, 0.0591, 0.0291},
     {0.0376, 0.1454, 0.6253, 0.1423, 0.0494}, {0.0242, 0.1094, 0.4867, 0.2723, 0.1074},
     {0.0207, 0.1083, 0.4071, 0.2193, 0.2446} };
@@ -105,7 +105,7 @@ const double PROV_AG[15][5] = {    // get_province_ag :317-337
     {0.064000, 0.163000, 0.448000, 0.181000, 0.144000} };
 
 void gpw_split(int ag, int cnts, int out[5]) {   // :804, Julia round = half-to-even = nearbyint
-    for (int g = 0; g < 5; ++g) out[g] = (int)std::nearbyint(CM[ag - 1][g] * (double)cnts);
+    for (int g = 0; g < 5; ++g) out[g] = (int)std::nearbyint(CONTACT_MATRIX[ag - 1][g] * (double)cnts);
 }
 
 const Tables &tables() {

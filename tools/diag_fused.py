@@ -14,3 +14,10 @@ print("kcycles sum", met.sum(), "max", met.max(), "mean", met.mean())
 for r in order[:12]: print(r, "kcyc", met[r], "ms", met[r]*1024/1.965e6, "rounds", inf[r], "attack", attack[r], "peak inf", prev[r,0,:,2:8].sum(axis=1).max(), "cyc/round", met[r]*1024/max(inf[r],1))
 print("takeoff count", (attack>0.1).sum(), "mean attack", attack.mean())
 for r in order[500:503]: print(r, "kcyc", met[r], "rounds", inf[r], "attack", attack[r])
+
+dbg = np.zeros((1000, 8), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
+names = ["setup","list","budgets","rounds","time_update","curves/idle","writeback","-"]
+big = attack > 0.1
+print("phase kcycles  take-off mean | extinct mean")
+for k in range(7): print(f"{names[k]:12s} {dbg[big,k].mean()/1e3:10.1f} | {dbg[~big,k].mean()/1e3:10.1f}")
+print("rounds take-off mean", inf[big].mean(), "extinct", inf[~big].mean())
