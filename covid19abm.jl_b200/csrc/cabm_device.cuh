@@ -77,7 +77,7 @@ struct Dev {
     uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;
     int *inc, *prev;                         // [R][6][T][12]
     long long *infectors, *latsum;           // [R][4], [R]
-    long long *dbg;                          // [R][8] per-phase cycle counts of the fused kernel (diagnostics)
+    long long *dbg;                          // [R][16] per-phase cycle counts of the fused kernel (diagnostics)
     uint8_t *hm;                             // [R][T][N] health codes (widened to Int16 by cabm_get_hmatrix)
     const DevPset *psets; const unsigned long long *beta_thr;    // [P], [P][T][4]
     const uint32_t *nb_thr; const uint8_t *nb_guide;             // [5][256], [5][256]

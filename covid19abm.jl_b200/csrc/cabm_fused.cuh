@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     __shared__ int s_io[2][2][60];           // [day parity][entries | exits][(group, state)] — curve deltas of one day
     __shared__ uint32_t s_tlat[4], s_tpre[4], s_tasy[40], s_tinf[40];
     __shared__ unsigned long long s_beta[4];
+    __shared__ DevPset s_P;                  // this replicate's parameter set (read on every transition)
+    __shared__ double s_cm[25];              // contact_matrix :838-848
     __shared__ int s_nf[2], s_wsum[FUSED_NT / 32], s_g0[2][60];
     __shared__ int s_infectors[4];
     // dyntrans batch
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }
     if (tid < 4) { s_tlat[tid] = c_tab.lat_thr[tid]; s_tpre[tid] = c_tab.pre_thr[tid]; }
     if (tid < 40) { s_tasy[tid] = c_tab.asy_thr[tid]; s_tinf[tid] = c_tab.inf_thr[tid]; }
+    if (tid < 25) s_cm[tid] = c_tab.cm[tid / 5][tid % 5];
     int *const s_inc = s_io[0][0], *const s_out = s_io[0][1];   // first-column phase uses parity 0
     __syncthreads();
     const bool tma_ok = S.store_hm && (N % 16 == 0);     // cp.async.bulk needs 16-byte size and alignment
@@ -125,10 +128,12 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         const int r = s_r;
         if (r >= S.R) break;
         const long long t_start = clock64();
-        long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = t_start;   // per-phase cycles seen by thread 0 (diagnostics)
+        long long t_ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = t_start;   // per-phase cycles seen by thread 0 (diagnostics)
 #define PHASE(k) do { const long long t_now_ = clock64(); t_ph[k] += t_now_ - t_last; t_last = t_now_; } while (0)
         int n_rounds = 0;
-        const DevPset &P = S.psets[S.pset_of[r]];
+        if (tid < (int)(sizeof(DevPset) / 4)) reinterpret_cast<uint32_t *>(&s_P)[tid] = reinterpret_cast<const uint32_t *>(&S.psets[S.pset_of[r]])[tid];
+        __syncthreads();
+        const DevPset &P = s_P;
         const uint2 key = S.key[r];
         const size_t rb = (size_t)r * Np;
         const unsigned long long *beta = S.beta_thr + (size_t)S.pset_of[r] * T * 4;
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     const int cnts = st_tag(sx) == day ? st_rem(sx) : (int)M.lcnt[lpos + lane];
                                     unsigned long long gp = 0;                                  // round.(cm[ag]*cnts), half-to-even
 #pragma unroll
-                                    for (int g = 0; g < 5; ++g) gp |= (unsigned long long)(unsigned)__double2int_rn(__dmul_rn(c_tab.cm[st_ag(sx)][g], (double)cnts)) << (8 * g);
+                                    for (int g = 0; g < 5; ++g) gp |= (unsigned long long)(unsigned)__double2int_rn(__dmul_rn(s_cm[st_ag(sx) * 5 + g], (double)cnts)) << (8 * g);
                                     E = (int)(gp & 0xFF) + (int)((gp >> 8) & 0xFF) + (int)((gp >> 16) & 0xFF) + (int)((gp >> 24) & 0xFF) + (int)((gp >> 32) & 0xFF);
                                     s_cand[lane] = x; s_gp[lane] = gp;
                                     s_xh[lane] = (uint8_t)st_health(sx);
@@ -349,6 +354,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 }
                             }
                             __syncthreads();                                                   // B1
+                            PHASE(8);
                             const int nb = s_nb, Etot = s_pref[nb];
                             // (b) one contact event per thread: target draw (:807), transmission word (:823); mark the target
                             uint32_t y = 0, w1 = 0; int q = 0; bool ev = tid < Etot;
@@ -381,6 +387,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             // targets hit more than once (by any event of the batch, cut or not) take the ordered path below
                             if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) atomicOr(&M.dupm[yw], ybit); }
                             __syncthreads();                                                   // B2
+                            PHASE(9);
                             const int cut = s_cut;
                             const int Ev = s_pref[cut];                                // events of infectors [0, cut) are final
                             const bool marked = ev;
@@ -397,6 +404,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 if (isdup) { dpos += __popc(dm & ((1u << lane) - 1u)); M.D[dpos] = (uint16_t)tid; }
                                 __syncthreads();
                             }
+                            PHASE(10);
                             if (ev) {
                                 bool leader = true;
                                 if (isdup) for (int d = 0; d < dpos; ++d) if (M.Y[M.D[d]] == y) { leader = false; break; }
@@ -428,6 +436,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 }
                             }
                             __syncthreads();                                                   // B5: status writes visible to the next batch
+                            PHASE(11);
                             if (marked) { M.touch[yw] = 0; M.dupm[yw] = 0; }                   // next marking is after the next B1
                             lpos += cut;
                         }
@@ -441,6 +450,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 // ---------------------------------------------------- time_update() :399-428
                 if (hm && tma_ok && tid == 0) bulk_store_wait_read();          // earlier columns have left shared memory
                 __syncthreads();                                               // S1: dyntrans writes visible; col reusable
+                PHASE(12);
                 if (tid == 0) s_nf[(act + 1) & 1] = 32767;                     // buffer of the next active day (last read after the previous S2)
                 if (day == 1) {                                                // seeds isolated by fpreiso: resync isob (see k_time_update)
                     for (int i = tid; i < N; i += NT) { const uint32_t st = M.status[i]; if (((st >> 19) ^ (st >> 20)) & 1u) M.status[i] = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB); }
@@ -544,7 +554,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid < 4) S.infectors[r * 4 + tid] = s_infectors[tid];
         // diagnostics of the fused path: kilo-cycles spent on this replicate and dyntrans batches issued
         PHASE(6);
-        if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; for (int k = 0; k < 8; ++k) S.dbg[(size_t)r * 8 + k] = t_ph[k]; }
+        if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; for (int k = 0; k < 16; ++k) S.dbg[(size_t)r * 16 + k] = t_ph[k]; }
 #undef PHASE
         if (hm && tma_ok && tid == 0) bulk_store_wait_all();
     }

@@ -112,8 +112,8 @@ int cabm_get_profile(cabm_handle *h, float *ms /*[CABM_N_KCLASS]*/, int32_t *lau
 enum { CABM_PATH_AUTO = 0, CABM_PATH_MULTIKERNEL = 1, CABM_PATH_FUSED = 2 };
 int cabm_set_path(cabm_handle *h, int path);
 int cabm_get_last_path(const cabm_handle *h);
-/* diagnostics of the fused path: per replicate, cycles thread 0 spent in 8 phases (setup, infector list, budgets,
- * dyntrans batches, time_update, curves/idle days, write-back, unused): int64 [n_rep][8] */
+/* diagnostics of the fused path: per replicate, cycles thread 0 spent in 16 phase slots (tools/diag_fused.py names them):
+ * int64 [n_rep][16] */
 int cabm_get_debug(cabm_handle *h, int64_t *out);
 /* number of kernel launches issued by this handle so far */
 int64_t cabm_launch_count(const cabm_handle *h);

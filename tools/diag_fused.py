@@ -15,9 +15,9 @@ for r in order[:12]: print(r, "kcyc", met[r], "ms", met[r]*1024/1.965e6, "rounds
 print("takeoff count", (attack>0.1).sum(), "mean attack", attack.mean())
 for r in order[500:503]: print(r, "kcyc", met[r], "rounds", inf[r], "attack", attack[r])
 
-dbg = np.zeros((1000, 8), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
-names = ["setup","list","budgets","rounds","time_update","curves/idle","writeback","-"]
+dbg = np.zeros((1000, 16), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
+names = ["setup","list","budgets","(rounds tail)","time_update after S1","curves/idle","writeback","-","round: warp0 cand ->B1","round: events ->B2","round: dup compaction ->B3","round: apply ->B5","dyntrans end -> S1"]
 big = attack > 0.1
 print("phase kcycles  take-off mean | extinct mean")
-for k in range(7): print(f"{names[k]:12s} {dbg[big,k].mean()/1e3:10.1f} | {dbg[~big,k].mean()/1e3:10.1f}")
-print("rounds take-off mean", inf[big].mean(), "extinct", inf[~big].mean())
+for k in range(13): print(f"{names[k]:28s} {dbg[big,k].mean()/1e3:10.1f} | {dbg[~big,k].mean()/1e3:10.1f}")
+print("rounds take-off mean", inf[big].mean(), "extinct", inf[~big].mean(), " active days?")
