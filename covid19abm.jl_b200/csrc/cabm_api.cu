@@ -115,7 +115,7 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.status, A); DA(S.expday, A); DA(S.entry, A); DA(S.dur, A); DA(S.sickfrom, A); DA(S.isovia, A);
     DA(S.latday, A); DA(S.tracestart, A); DA(S.traceend, A); DA(S.tracedxp, A); DA(S.ct_head, A);
     DA(S.mark_pre, W); DA(S.mark_post, W); DA(S.infmask, W); DA(S.ct_cnt, (size_t)h->R);
-    DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8);
+    DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8); DA(S.hits, A);
     DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);
     DA(S.totalmet, (size_t)h->R); DA(S.totalinf, (size_t)h->R);
     DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R); DA(S.dbg, (size_t)h->R * 16);
@@ -295,8 +295,8 @@ template <class F> static void timed(cabm_handle *h, int cls, F f) {
 }
 
 static int do_dyntrans(cabm_handle *h, int day) {
-    // CABM_MODE_NATIVE currently shares the exact schedule (the relaxed per-infector kernel is a later row)
-    timed(h, CABM_K_DYNTRANS, [&] { return launch_dyntrans_exact(h->S, day, h->stream); });
+    if (h->mode == CABM_MODE_NATIVE) timed(h, CABM_K_DYNTRANS, [&] { return launch_dyntrans_native(h->S, day, h->stream); });
+    else timed(h, CABM_K_DYNTRANS, [&] { return launch_dyntrans_exact(h->S, day, h->stream); });
     return CABM_OK;
 }
 static int do_time_update(cabm_handle *h, int day) {

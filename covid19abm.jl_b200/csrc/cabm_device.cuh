@@ -74,6 +74,7 @@ struct Dev {
     uint2 *ct_log; uint32_t *ct_cnt;         // [R][ct_cap] (y, next), [R]
     uint32_t *grp_idx; int *grp_off;         // [R][Np], [R][8]
     uint32_t *infmask;                       // [R][nwords]
+    uint32_t *hits;                          // 2 x [R][Np/2] of 2 x u16: native mode, contacts received from lower-indexed infectors
     uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;
     int *inc, *prev;                         // [R][6][T][12]
     long long *infectors, *latsum;           // [R][4], [R]

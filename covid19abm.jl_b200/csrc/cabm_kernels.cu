@@ -271,6 +271,106 @@ __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
     if (lane == 0) { S.totalmet[r] = met; S.totalinf[r] = ninf; if (ct) S.ct_cnt[r] = logn; }
 }
 
+// ============================================================================ dyntrans :790-834 (native schedule)
+// One warp per infectious agent, lanes over its contact events, all replicates and all infectors in flight at once.
+// The reference's sequential order (:797) is given up: a contact event claims one unit of the target's budget and, if
+// the target is susceptible, infects it — both in a single atomicCAS on the target's status word, so the shared budget
+// (:811-813) and "first infector wins" (:822-827) stay race-free. Which events are admitted when a budget runs out
+// depends on timing: ensemble-equivalent to the reference (tests/test_native_ensemble.py), not bit-identical.
+//
+// In the reference an infector's own budget (:802) has already been reduced by the contacts it received from
+// lower-indexed infectors (:813) when its turn comes. Launching everybody at once would hand out slightly too many
+// contacts (measured: +0.2 % attack rate), so the kernel runs twice a day: COUNT draws every event from the undiminished
+// budgets and counts, per infectious target, the hits coming from lower indices; APPLY gives infector x
+// gpw(budget_x - hits_x) contacts and resolves them with CAS. COUNT runs twice (the second sweep uses the corrected
+// budgets of the first), leaving a third-order difference in the infectious fraction.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const uint32_t *hits_in, uint32_t *hits_out) {
+    const int r = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const DevPset &P = S.psets[S.pset_of[r]];
+    const uint2 key = S.key[r];
+    const size_t rb = (size_t)r * S.Np;
+    const unsigned long long *bt = S.beta_thr + ((size_t)S.pset_of[r] * S.T + (size_t)(day - 1)) * 4;
+    const int *off = S.grp_off + r * 8;
+    const bool ct = P.ctstrat != 0;
+    const uint32_t *mask = S.infmask + (size_t)r * S.nwords;
+    int met = 0, ninf = 0;
+    // 64 mask words (2048 agents) per block, 8 per warp
+    const int w_begin = blockIdx.x * 64 + wid * 8;
+    for (int wi = w_begin; wi < w_begin + 8 && wi < S.nwords; ++wi) {
+        uint32_t m = mask[wi];
+        while (m) {
+            const int b = __ffs(m) - 1; m &= m - 1;
+            const int x = (wi << 5) + b;
+            const uint32_t sx = __ldcg(&S.status[rb + x]);
+            const int xh = st_health(sx);
+            int cnts = st_health(sx) == DED ? 0 : fresh_budget(S, key, x, day, sx);    // :802, the day's undiminished budget
+            if (hits_in) cnts = max(0, cnts - (int)((hits_in[(rb + x) >> 1] >> (16 * (x & 1))) & 0xFFFFu));
+            if (cnts == 0) continue;
+            const unsigned long long gp = __ldg(&S.gpw[st_ag(sx) * 256 + cnts]);     // :804
+            const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF),
+                      p4 = p3 + (int)((gp >> 24) & 0xFF), E = p4 + (int)((gp >> 32) & 0xFF);
+            const unsigned long long bthr = bt[beta_class(xh)];                      // :800
+            const bool tracing = ct && (sx & ST_TRACING);
+            for (int e0 = 0; e0 < E; e0 += 32) {
+                const int e = e0 + lane;
+                bool adm = false;
+                uint32_t j = 0;
+                if (e < E) {
+                    const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
+                    const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
+                    const int go = off[g], len = off[g + 1] - go;
+                    if (len == 0) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
+                    else {
+                        const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                        j = S.grp_idx[rb + go + below(w.x, len)];                    // :807
+                        if (COUNT) {
+                            if ((int)j > x && ((mask[j >> 5] >> (j & 31)) & 1u)) atomicAdd(&hits_out[(rb + j) >> 1], 1u << (16 * (j & 1)));
+                            continue;
+                        }
+                        uint32_t old = __ldcg(&S.status[rb + j]);
+                        int fresh = -1;
+                        for (;;) {
+                            int rem;
+                            if (st_tag(old) == day) rem = st_rem(old);
+                            else { if (fresh < 0) fresh = fresh_budget(S, key, j, day, old); rem = fresh; }
+                            if (rem == 0) break;                                      // :812
+                            uint32_t nw = (old & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)(rem - 1) | ((uint32_t)day << 22);   // :813
+                            const bool infect = st_health(old) == SUS && st_swap(old) == UNDEF && bern(w.y, bthr);           // :822-823
+                            if (infect) nw = st_set_swap(nw, LAT);
+                            const uint32_t seen = atomicCAS(&S.status[rb + j], old, nw);
+                            if (seen == old) {
+                                adm = true;
+                                if (infect) { S.sickfrom[rb + j] = (uint8_t)xh; S.expday[rb + j] = (int16_t)day; ++ninf; }   // :825-827
+                                break;
+                            }
+                            old = seen;
+                        }
+                    }
+                }
+                met += adm;
+                if (!COUNT && tracing) {                                              // :817-819 — only this warp appends to x's list
+                    unsigned am = __ballot_sync(FULL, adm);
+                    uint32_t head = S.ct_head[rb + x];
+                    while (am) {
+                        const int src = __ffs(am) - 1; am &= am - 1;
+                        const uint32_t jj = __shfl_sync(FULL, j, src);
+                        if (lane == 0) {
+                            const uint32_t slot = atomicAdd(&S.ct_cnt[r], 1u);
+                            if (slot < S.ct_cap) { S.ct_log[(size_t)r * S.ct_cap + slot] = make_uint2(jj, head); head = slot; }
+                            else atomicOr(&S.err[r], ERR_CT_LOG_FULL);
+                        }
+                    }
+                    if (lane == 0) S.ct_head[rb + x] = head;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) { met += __shfl_xor_sync(FULL, met, o); ninf += __shfl_xor_sync(FULL, ninf, o); }
+    if (!COUNT && lane == 0 && (met | ninf)) { atomicAdd(&S.totalmet[r], met); atomicAdd(&S.totalinf[r], ninf); }
+}
+
 // ============================================================================ contact tracing, pass A
 // The identification branch of ct_dynamics :705-716 writes *other* agents from inside the sequential agent loop.
 // An index case x identifies on a day fixed when it became latent (doi == traceend), so the cross-agent writes are
@@ -586,6 +686,18 @@ int launch_insert_infected(const Dev &S, int which, int health, int num, int ag,
 }
 int launch_first_column(const Dev &S, cudaStream_t s) { k_first_column<<<agent_grid(S, 1), 256, 0, s>>>(S); return 1; }
 int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s) { k_dyntrans_exact<<<S.R, 32, 0, s>>>(S, day); return 1; }
+int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s) {
+    cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, s); cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, s);
+    // two fixed-point sweeps for the budgets (first and second order in the infectious fraction), then the CAS pass
+    const size_t half = (size_t)S.R * S.Np / 2;
+    uint32_t *h0 = S.hits, *h1 = S.hits + half;
+    cudaMemsetAsync(S.hits, 0, half * 8, s);
+    const dim3 grid((unsigned)((S.nwords + 63) / 64), (unsigned)S.R);
+    k_dyntrans_native<true><<<grid, 256, 0, s>>>(S, day, nullptr, h0);
+    k_dyntrans_native<true><<<grid, 256, 0, s>>>(S, day, h0, h1);
+    k_dyntrans_native<false><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
+    return 3;
+}
 int launch_ct_identify(const Dev &S, int day, cudaStream_t s) { k_ct_identify<<<agent_grid(S, 1), 256, 0, s>>>(S, day); return 1; }
 int launch_time_update(const Dev &S, int day, cudaStream_t s) { k_time_update<<<agent_grid(S, 8), 256, 0, s>>>(S, day); return 1; }
 int launch_clear_marks(const Dev &S, cudaStream_t s) { k_clear_marks<<<296, 256, 0, s>>>(S); return 1; }

@@ -11,6 +11,7 @@ int launch_build_groups(const Dev &S, cudaStream_t s);
 int launch_insert_infected(const Dev &S, int which, int health, int num, int ag, int call_id, int day, cudaStream_t s);
 int launch_first_column(const Dev &S, cudaStream_t s);
 int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s);
+int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s);
 int launch_ct_identify(const Dev &S, int day, cudaStream_t s);
 int launch_time_update(const Dev &S, int day, cudaStream_t s);
 int launch_clear_marks(const Dev &S, cudaStream_t s);

@@ -1,0 +1,78 @@
+"""Native (relaxed-order) mode: ensemble equivalence with the sequential reference order (BASELINE.json north_star).
+
+The native dyntrans kernel resolves contact events with atomicCAS instead of the reference's ascending-infector order,
+so single trajectories may differ from the oracle; the ensemble must not: two-sample KS tests (p > 0.01) on attack
+rate, peak day and peak ICU, ensemble means within 3 standard errors of the difference, and the extinction fraction
+(single-seed runs are bimodal: SURVEY §8c). The oracle ensemble uses different seeds, so this is a statistical
+comparison of two independent samples, not a replay. A 2-SE criterion on independent samples raises a false alarm for
+~5 % of seed sets per statistic (and early-growth luck is shared by all scenarios run on one seed set), so the bound here
+is 3 SE; the north star's 2-SE requirement is checked in the much sharper paired form at the bottom of this file, where
+both schedules run the same seeds and the mean difference must stay below half a standard error of the ensemble."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from test_gpu_parity import to_oracle
+
+pytestmark = pytest.mark.gpu
+
+NREP, T, N = 600, 300, 10000
+
+
+def summary(prev):
+    """prev: [R][6][T][12] -> attack rate, peak day, peak ICU per replicate (group 0 = all agents)."""
+    tot = prev[:, 0]
+    attack = 1.0 - tot[:, -1, 0] / N
+    infectious = tot[:, :, 2:8].sum(axis=2)
+    return attack, infectious.argmax(axis=1).astype(np.float64), tot[:, :, 9].max(axis=1).astype(np.float64)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(β=0.05, prov="ontario", initialinf=3, modeltime=T),
+    dict(β=0.06, prov="ontario", initialinf=3, modeltime=T, fmild=0.5, τmild=1, fsevere=1.0, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3),
+], ids=["plain", "isolation+tracing"])
+def test_native_ensemble_matches_sequential_order(cv, O, kw):
+    ip = cv.ModelParameters(**kw)
+    g = cv.run_ensemble(ip, NREP, seeds=[726 * (i + 1) for i in range(NREP)], mode=cv.MODE_NATIVE, path="multikernel")
+    assert g["path"] == "multikernel" and (g["err"] == 0).all()
+    # the oracle takes the next NREP replicate ids of the same seeding rule (runsim :78): disjoint, independent samples
+    r = O.run_ensemble([to_oracle(O, ip)], [0] * NREP, [726 * (NREP + i + 1) for i in range(NREP)], nthreads=16)
+    ga, gd, gi = summary(g["prev"])
+    ra, rd, ri = summary(r["prev"])
+    # extinction fraction (attack < 2 %): binomial SE of the difference
+    ge, re_ = (ga < 0.02).mean(), (ra < 0.02).mean()
+    assert abs(ge - re_) < 3 * np.sqrt(ge * (1 - ge) / NREP + re_ * (1 - re_) / NREP) + 1e-9
+    big_g, big_r = ga >= 0.02, ra >= 0.02
+    for name, a, b in (("attack", ga[big_g], ra[big_r]), ("peak_day", gd[big_g], rd[big_r]), ("peak_icu", gi[big_g], ri[big_r]),
+                       ("attack_all", ga, ra)):
+        p = stats.ks_2samp(a, b).pvalue
+        assert p > 0.01, (name, p)
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) < 3 * se, (name, a.mean(), b.mean(), se)
+    # conservation: every column of the state matrix sums to N (SURVEY §8c v)
+    assert (g["prev"][:, 0].sum(axis=2) == N).all()
+    assert (g["prev"][:, 1:].sum(axis=1) == g["prev"][:, 0]).all()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(β=0.05, prov="ontario", initialinf=3, modeltime=200),
+    dict(β=0.0345, prov="ontario", initialinf=1, modeltime=300, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3),
+], ids=["plain", "configB"])
+def test_native_vs_exact_common_random_numbers(cv, kw):
+    """Same seeds through both schedules (common random numbers): the paired difference isolates any bias of the relaxed
+    order far below the ensemble's own standard error. Also: trajectories are identical until the first day on which an
+    exhausted budget or a contacted infector makes the order matter."""
+    ip = cv.ModelParameters(**kw)
+    R = 400
+    seeds = [726 * (i + 1) for i in range(R)]
+    a = cv.run_ensemble(ip, R, seeds=seeds, mode=cv.MODE_EXACT, path="multikernel", want_hmatrix=True)
+    b = cv.run_ensemble(ip, R, seeds=seeds, mode=cv.MODE_NATIVE, path="multikernel", want_hmatrix=True)
+    assert (b["err"] == 0).all()
+    assert (a["hmatrix"][:, :3] == b["hmatrix"][:, :3]).all()          # seeding and the first days agree bit for bit
+    xa = 1.0 - a["prev"][:, 0, -1, 0] / N
+    xb = 1.0 - b["prev"][:, 0, -1, 0] / N
+    assert ((xa < 0.02) == (xb < 0.02)).mean() > 0.97                   # same replicates go extinct
+    d = xb - xa
+    se_ens = xa.std(ddof=1) / np.sqrt(R)
+    assert abs(d.mean()) < 0.5 * se_ens, (d.mean(), se_ens)
+    assert (b["prev"][:, 0].sum(axis=2) == N).all()
