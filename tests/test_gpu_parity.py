@@ -159,3 +159,26 @@ def test_stepwise_fields_follow_oracle(cv, O):
                 assert (g == r).all(), (day, "time_update", f, np.nonzero(g != r)[0][:5])
         assert pop.totalisolated()[0] == sim.totalisolated
         sim.close()
+
+
+def test_large_population_bit_exact(cv, O):
+    """BASELINE config 5 ingredients beyond the reference's 10,000-agent limit (:113): 200,000 agents, 100 seeds, a
+    quarantined age group — exact schedule on the per-day kernels (the population does not fit shared memory)."""
+    ip = cv.ModelParameters(β=0.06, prov="ontario", popsize=200000, modeltime=40, initialinf=100, quar_grp_frac=0.5, quar_grp=5)
+    got = cv.run_ensemble(ip, 2, seeds=[726, 1452], want_hmatrix=True)
+    assert got["path"] == "multikernel"
+    ref = O.run_ensemble([to_oracle(O, ip)], [0, 0], [726, 1452], nthreads=2, want_hmatrix=True)
+    assert (got["err"] == 0).all()
+    assert (got["hmatrix"] == ref["hmatrix"]).all()
+    assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all()
+    assert (got["infectors"] == ref["infectors"]).all()
+
+
+def test_odd_population_sizes_bit_exact(cv, O):
+    """popsize not a multiple of 8/16/32 (ragged tails of the vector loads and of the TMA column store)."""
+    for n, path in ((9999, "fused"), (1003, "fused"), (1003, "multikernel"), (37, "fused")):
+        ip = cv.ModelParameters(β=0.3, prov="ontario", popsize=n, modeltime=60, initialinf=3, fmild=0.4, τmild=1, fsevere=0.6)
+        got = cv.run_ensemble(ip, 3, seeds=[5, 6, 7], want_hmatrix=True, path=path)
+        ref = O.run_ensemble([to_oracle(O, ip)], [0, 0, 0], [5, 6, 7], nthreads=3, want_hmatrix=True)
+        assert (got["hmatrix"] == ref["hmatrix"]).all(), (n, path)
+        assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all(), (n, path)
