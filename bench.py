@@ -83,7 +83,7 @@ def cpu_sample(nrep, threads):
     return nrep * N_AGENTS * T_DAYS / dt, dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's CPU implementation of the path. Julia is absent from the image, so this is
     the oracle port (kind "port"), all host threads, each step a bounded sample of the same workload."""
     if rank != 0:
@@ -104,7 +104,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{nrep} replicates per step, one per thread"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -122,8 +122,16 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # the contract is ONE JSON line on stdout: libraries (NCCL's version banner, torchrun) also write there, so everything
+    # else goes to stderr and the line is written to the saved descriptor at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import numpy as np
@@ -229,8 +237,8 @@ def main():
                             "At the reference-width figure of SURVEY 8(d) (14 B/agent-day) the same launch would read "
                             f"{round(14 * R * N_AGENTS * T_DAYS / (ms / n * 1e-3) / 1e9, 1)} GB/s"}
     else:
-        # algorithmic bytes per agent-day of k_time_update in the HBM layout: status 4 r + expday 2 r + hmatrix 1 w
-        tu_bytes = (6 + (0 if args.no_hmatrix else 1)) * R * N_AGENTS
+        # algorithmic bytes per agent-day of k_time_update in the HBM layout: expday 2 r + previous column 1 r + next column 1 w
+        tu_bytes = (2 + (0 if args.no_hmatrix else 2)) * R * N_AGENTS
         dom = max(("dyntrans", "time_update"), key=lambda k: prof[k][0])
         tu_ms, tu_n = prof["time_update"]
         tu_gbs = tu_bytes / (tu_ms / tu_n * 1e-3) / 1e9 if tu_n else 0.0
@@ -262,7 +270,7 @@ def main():
                         "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] int32 x2 and per-replicate scalars (runsim :77-101), pinned host buffers"},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     pop.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -16,7 +16,7 @@ static_assert((int)CABM_UNDEF == (int)UNDEF && (int)CABM_DED == (int)DED, "HEALT
 
 struct cabm_handle {
     int device = 0, R = 0, N = 0, Np = 0, T = 0, flags = 0;
-    int n_rep = 0, n_psets = 0, mode = 0, day = 1, any_ct = 0, configured = 0;
+    int n_rep = 0, n_psets = 0, mode = 0, day = 1, any_ct = 0, all_ct = 0, configured = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Dev S{};
@@ -197,7 +197,7 @@ extern "C" int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_ps
     CU(cudaSetDevice(h->device));
     std::vector<DevPset> dp(n_psets);
     std::vector<unsigned long long> beta((size_t)n_psets * h->T * 4);
-    int any_ct = 0;
+    int any_ct = 0, all_ct = 1;
     for (int q = 0; q < n_psets; ++q) {
         const cabm_params &p = psets[q];
         if (p.popsize == 0) return fail(h, CABM_E_PARAM, "no population size given");                       // :164
@@ -219,6 +219,7 @@ extern "C" int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_ps
         d.initialinf = p.initialinf; d.initialhi = p.initialhi;
         d.qdays = p.ctstrat == 1 ? 14 : p.ctstrat == 3 ? p.strat3qdays : 0;                                  // :650-655
         any_ct |= p.ctstrat != 0;
+        all_ct &= p.ctstrat != 0;
         // init_betas :191-202 and _get_betavalue :756-769
         std::vector<double> seas;
         if (p.seasonal) td_seasonality(h->T, seas);
@@ -258,7 +259,7 @@ extern "C" int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_ps
         h->S.ct_cap = (uint32_t)cap;
     }
     h->S.psets = h->d_psets; h->S.beta_thr = h->d_beta; h->S.P = n_psets;
-    h->n_rep = n_rep; h->n_psets = n_psets; h->mode = mode; h->any_ct = any_ct; h->configured = 1; h->day = 1; h->ran = false;
+    h->n_rep = n_rep; h->n_psets = n_psets; h->mode = mode; h->any_ct = any_ct; h->all_ct = all_ct; h->configured = 1; h->day = 1; h->ran = false;
     h->S.R = n_rep;
     return CABM_OK;
 }
@@ -301,7 +302,7 @@ static int do_dyntrans(cabm_handle *h, int day) {
 }
 static int do_time_update(cabm_handle *h, int day) {
     if (h->any_ct) timed(h, CABM_K_CT_IDENTIFY, [&] { return launch_ct_identify(h->S, day, h->stream); });
-    timed(h, CABM_K_TIME_UPDATE, [&] { return launch_time_update(h->S, day, h->stream); });
+    timed(h, CABM_K_TIME_UPDATE, [&] { return launch_time_update(h->S, day, h->any_ct != 0, h->all_ct != 0, h->stream); });
     return CABM_OK;
 }
 

@@ -457,15 +457,73 @@ __device__ inline uint32_t agent_update_ct(const Dev &S, const DevPset &P, int r
 }
 
 // ============================================================================ time_update :399-428 (+ snapshot :218-223)
-// Thread per 8 consecutive agents: 128-bit loads of the expiry days and status words, 128-bit store of the next
-// hmatrix column. tis/doi are not stored (absolute days), and the next-day contact count (:425) is drawn lazily by
-// dyntrans, so an agent-day costs one compare unless the agent's state expires (or tracing is on).
-__global__ void __launch_bounds__(256) k_time_update(Dev S, int day) {
+// The per-agent streaming kernel. tis/doi are not stored (absolute days) and the next-day contact count (:425) is drawn
+// lazily by dyntrans, so an agent-day is one 16-bit compare of its expiry day; the next hmatrix column is the previous
+// one with the (rare) transitions patched in. Thread per 16 consecutive agents: two 128-bit loads of expiry days, one
+// 128-bit load and one 128-bit store of column bytes = 4 B per agent-day (2 B without the state matrix). The status
+// word, durations etc. are touched only by agents whose state expires. Replicates with contact tracing take the
+// per-agent path below (k_time_update_ct).
+__device__ __noinline__ uint32_t time_update_fire(const Dev &S, int r, int i, int day) {
+    const size_t a = (size_t)r * S.Np + i;
+    const uint32_t st = S.status[a];
+    const uint32_t ns = transition(S, S.psets[S.pset_of[r]], r, i, day, st, S.key[r], st_swap(st), false, true);
+    S.status[a] = ns;
+    return (uint32_t)st_health(ns);
+}
+
+__global__ void __launch_bounds__(256) k_time_update(const __grid_constant__ Dev S, int day, int mixed) {
+    const int r = blockIdx.y;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= S.N) return;
+    if (mixed && S.psets[S.pset_of[r]].ctstrat != 0) return;         // mixed ensembles: tracing replicates go to k_time_update_ct
+    const size_t a0 = (size_t)r * S.Np + i0;
+    const uint4 e0 = *reinterpret_cast<const uint4 *>(S.expday + a0), e1 = *reinterpret_cast<const uint4 *>(S.expday + a0 + 8);
+    const uint32_t dd = (uint32_t)day * 0x10001u;
+    const uint32_t m[8] = {__vcmples2(e0.x, dd), __vcmples2(e0.y, dd), __vcmples2(e0.z, dd), __vcmples2(e0.w, dd),
+                           __vcmples2(e1.x, dd), __vcmples2(e1.y, dd), __vcmples2(e1.z, dd), __vcmples2(e1.w, dd)};
+    const bool any = (m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7]) != 0;   // somebody expires today (:405)
+    const bool hm_on = S.store_hm && day < S.T;                      // column st+1 = state at the start of the next day
+    const bool vec = (S.N & 15) == 0;
+    union { uint4 v; uint8_t b[16]; } col;
+    col.v = make_uint4(0, 0, 0, 0);
+    uint8_t *cur = nullptr;
+    if (hm_on) {
+        const uint8_t *prv = S.hm + ((size_t)r * S.T + (size_t)(day - 1)) * S.N + i0;
+        cur = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
+        if (vec) col.v = *reinterpret_cast<const uint4 *>(prv);
+        else for (int k = 0; k < 16 && i0 + k < S.N; ++k) col.b[k] = prv[k];
+    }
+    if (any) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const bool f = (m[k >> 1] >> ((k & 1) * 16)) & 1u;
+            if (f && i0 + k < S.N) col.b[k] = (uint8_t)time_update_fire(S, r, i0 + k, day);
+        }
+    }
+    if (hm_on) {
+        if (vec) *reinterpret_cast<uint4 *>(cur) = col.v;
+        else for (int k = 0; k < 16 && i0 + k < S.N; ++k) cur[k] = col.b[k];
+    }
+}
+
+// Seeds isolated through fpreiso at seeding keep the day-1 contact budget that initialize drew for them (:186): their
+// isob trails iso until the end of the first update. One pass after time_update(1).
+__global__ void __launch_bounds__(256) k_resync_isob(Dev S) {
+    const size_t n = (size_t)S.R * S.Np;
+    for (size_t a = blockIdx.x * (size_t)blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t st = S.status[a];
+        if (((st >> 19) ^ (st >> 20)) & 1u) S.status[a] = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);
+    }
+}
+
+// time_update for replicates with contact tracing: thread per 8 agents, every agent runs ct_dynamics (:422).
+__global__ void __launch_bounds__(256) k_time_update_ct(Dev S, int day) {
     const int r = blockIdx.y;
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (i0 >= S.N) return;
-    const size_t a0 = (size_t)r * S.Np + i0;
     const DevPset &P = S.psets[S.pset_of[r]];
+    if (P.ctstrat == 0) return;
+    const size_t a0 = (size_t)r * S.Np + i0;
     union { uint4 v; int16_t e[8]; } ex;
     union { uint4 v[2]; uint32_t s[8]; } st;
     ex.v = *reinterpret_cast<const uint4 *>(S.expday + a0);
@@ -474,34 +532,17 @@ __global__ void __launch_bounds__(256) k_time_update(Dev S, int day) {
     unsigned fire = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) fire |= (unsigned)((int)ex.e[k] <= day && i0 + k < S.N) << k;
-    if (P.ctstrat != 0) {
-        const uint2 key = S.key[r];
-        const size_t wi = (size_t)r * S.nwords + (i0 >> 5);
-        const unsigned sh = i0 & 31;
-        const unsigned pre = (S.mark_pre[wi] >> sh) & 0xFF, post = (S.mark_post[wi] >> sh) & 0xFF;
-        if (pre) atomicAnd(&S.mark_pre[wi], ~(0xFFu << sh));          // marks are consumed by this update
-        if (post) atomicAnd(&S.mark_post[wi], ~(0xFFu << sh));
-        for (int k = 0; k < 8 && i0 + k < S.N; ++k) {
-            const uint32_t ns = agent_update_ct(S, P, r, i0 + k, day, key, st.s[k], (fire >> k) & 1, (pre >> k) & 1, (post >> k) & 1);
-            if (ns != st.s[k]) { st.s[k] = ns; S.status[a0 + k] = ns; }
-        }
-    } else {
-        // isob trails iso only for agents isolated by seeding (their day-1 budget predates it, :186): resync
-        unsigned stale = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) stale |= (((st.s[k] >> 19) ^ (st.s[k] >> 20)) & 1u) << k;
-        if (fire | stale) {
-            const uint2 key = S.key[r];
-            for (int k = 0; k < 8; ++k) {
-                if (!(((fire | stale) >> k) & 1)) continue;
-                uint32_t ns = st.s[k];
-                if ((fire >> k) & 1) ns = transition(S, P, r, i0 + k, day, ns, key, st_swap(ns), false, true);
-                ns = (ns & ST_ISO) ? (ns | ST_ISOB) : (ns & ~ST_ISOB);
-                st.s[k] = ns; S.status[a0 + k] = ns;
-            }
-        }
+    const uint2 key = S.key[r];
+    const size_t wi = (size_t)r * S.nwords + (i0 >> 5);
+    const unsigned sh = i0 & 31;
+    const unsigned pre = (S.mark_pre[wi] >> sh) & 0xFF, post = (S.mark_post[wi] >> sh) & 0xFF;
+    if (pre) atomicAnd(&S.mark_pre[wi], ~(0xFFu << sh));          // marks are consumed by this update
+    if (post) atomicAnd(&S.mark_post[wi], ~(0xFFu << sh));
+    for (int k = 0; k < 8 && i0 + k < S.N; ++k) {
+        const uint32_t ns = agent_update_ct(S, P, r, i0 + k, day, key, st.s[k], (fire >> k) & 1, (pre >> k) & 1, (post >> k) & 1);
+        if (ns != st.s[k]) { st.s[k] = ns; S.status[a0 + k] = ns; }
     }
-    if (S.store_hm && day < S.T) {                            // column st+1 = state at the start of the next day
+    if (S.store_hm && day < S.T) {
         uint8_t *col = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
         if ((S.N & 7) == 0) {
             union { uint2 v; uint8_t h[8]; } o;
@@ -699,7 +740,13 @@ int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s) {
     return 3;
 }
 int launch_ct_identify(const Dev &S, int day, cudaStream_t s) { k_ct_identify<<<agent_grid(S, 1), 256, 0, s>>>(S, day); return 1; }
-int launch_time_update(const Dev &S, int day, cudaStream_t s) { k_time_update<<<agent_grid(S, 8), 256, 0, s>>>(S, day); return 1; }
+int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStream_t s) {
+    int n = 0;
+    if (!all_ct) { k_time_update<<<agent_grid(S, 16), 256, 0, s>>>(S, day, any_ct ? 1 : 0); ++n; }
+    if (any_ct) { k_time_update_ct<<<agent_grid(S, 8), 256, 0, s>>>(S, day); ++n; }
+    if (day == 1 && !all_ct) { k_resync_isob<<<148 * 8, 256, 0, s>>>(S); ++n; }
+    return n;
+}
 int launch_clear_marks(const Dev &S, cudaStream_t s) { k_clear_marks<<<296, 256, 0, s>>>(S); return 1; }
 int launch_curves_finalize(const Dev &S, cudaStream_t s) { k_curves_finalize<<<S.R, 64, 0, s>>>(S); return 1; }
 int launch_count_infectors(const Dev &S, cudaStream_t s) { k_count_infectors<<<S.R, 256, 0, s>>>(S); return 1; }

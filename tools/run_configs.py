@@ -37,7 +37,9 @@ def run(name, ip, nrep, pof=None, mode=cv.MODE_EXACT, path="auto", store_hm=Fals
         out["kernels"] = {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in pr.items() if v[1]}
         if pr["time_update"][1]:
             ct = any(p.ctstrat for p in (ip if isinstance(ip, list) else [ip]))
-            bpd = (6 + (1 if store_hm else 0)) + (9 if ct else 0)
+            # k_time_update: expday 2 r (+ previous column 1 r + next column 1 w); k_time_update_ct: status 4 + expday 2 + latday/tracestart/
+            # traceend/tracedxp 8 + isovia 1 r (+ column 1 w)
+            bpd = (15 + (1 if store_hm else 0)) if ct else (2 + (2 if store_hm else 0))
             tu = pr["time_update"]
             gbs = bpd * nrep * first.popsize / (tu[0] / tu[1] * 1e-3) / 1e9
             out["time_update_roofline"] = {"bytes_per_agent_day": bpd, "achieved_GBps": round(gbs, 1), "frac_of_measured_hbm_peak": round(gbs / peak, 4)}
