@@ -161,7 +161,7 @@ def main():
     pop = cv.Population(R, N_AGENTS, T_DAYS, store_hmatrix=not args.no_hmatrix, device=local)
     pop.set_path(args.path)
     shape = (R, 6, T_DAYS, 12)
-    pin_inc, pin_prev = cv.PinnedArray(shape, np.int32), cv.PinnedArray(shape, np.int32)
+    pin_inc, pin_prev = cv.PinnedArray(shape, np.int16), cv.PinnedArray(shape, np.int16)   # counts <= popsize = 10000 fit Int16
     units = R * N_AGENTS * T_DAYS                      # agent-days per step per GPU
 
     for w in range(args.warmup):
@@ -197,7 +197,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     h2d = R * 8 + R * 4 + 280 + 4 * T_DAYS * 8
-    d2h = 2 * int(np.prod(shape)) * 4 + R * (32 + 8 + 8 + 4)
+    d2h = 2 * int(np.prod(shape)) * 2 + R * (32 + 8 + 8 + 4)
     assert (sc["err"] == 0).all()
 
     # ---- end-of-run gather of the summary curves (the path's only collective): mean prevalence per day/state
@@ -230,8 +230,12 @@ def main():
         alg_bytes = hm_b + R * N_AGENTS * 26 + 2 * R * 6 * T_DAYS * 12 * 4
         ms, n = prof["fused"]
         gbs = alg_bytes / (ms / n * 1e-3) / 1e9
+        traffic = None                                     # dram__bytes_read+write per launch from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r01_fused_traffic.json")
+        if os.path.exists(tpath) and R == 1000 and not args.no_hmatrix:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         roofline = {"kernel": "k_sim_fused", "bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(gbs / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_launch": alg_bytes, "bytes_per_agent_day": round(alg_bytes / (R * N_AGENTS * T_DAYS), 3),
                     "note": "algorithmic bytes = u8 state matrix + per-agent HBM fields + curves; agent state itself never leaves shared memory. "
                             "At the reference-width figure of SURVEY 8(d) (14 B/agent-day) the same launch would read "
@@ -267,7 +271,7 @@ def main():
                            "l2": "inputs larger than L2: 0.3 GB of agent state + 5 GB state matrix + 0.3 GB curves written per step, rebuilt every step",
                            "wall_ms_per_step": wall_ms / args.steps, "attack_rate_mean": attack},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] int32 x2 and per-replicate scalars (runsim :77-101), pinned host buffers"},
+                        "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] Int16 x2 (narrowed on device) and per-replicate scalars (runsim :77-101), pinned host buffers"},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
                 "cpu_baseline": cpu}
         emit(line)

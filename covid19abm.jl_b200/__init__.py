@@ -155,6 +155,7 @@ def lib():
     L.cabm_get_dyntrans_counters.argtypes = [vp, vp, vp]
     L.cabm_get_hmatrix.argtypes = [vp, i32, vp]; L.cabm_get_hmatrix_all.argtypes = [vp, vp]
     L.cabm_get_curves.argtypes = [vp, vp, vp]
+    L.cabm_get_curves_i16.argtypes = [vp, vp, vp]
     L.cabm_get_scalars.argtypes = [vp, vp, vp, vp, vp]
     L.cabm_get_field.argtypes = [vp, i32, i32, vp]
     L.cabm_set_field.argtypes = [vp, i32, i32, i32, C.c_int32]
@@ -326,11 +327,15 @@ class Population:
         self._chk(self.L.cabm_get_hmatrix_all(self.h, out.ctypes.data))
         return out
 
-    def curves(self, inc=None, prev=None):
+    def curves(self, inc=None, prev=None, dtype=np.int32):
+        """(inc, prev) [n_rep][6][T][12]; dtype int32, or int16 (narrowed on the device, popsize <= 32767)."""
         shape = (self.n_rep, 6, self.T, 12)
-        inc = np.zeros(shape, dtype=np.int32) if inc is None else inc
-        prev = np.zeros(shape, dtype=np.int32) if prev is None else prev
-        self._chk(self.L.cabm_get_curves(self.h, inc.ctypes.data, prev.ctypes.data))
+        inc = np.zeros(shape, dtype=dtype) if inc is None else inc
+        prev = np.zeros(shape, dtype=dtype) if prev is None else prev
+        if inc.dtype == np.int16:
+            self._chk(self.L.cabm_get_curves_i16(self.h, inc.ctypes.data, prev.ctypes.data))
+        else:
+            self._chk(self.L.cabm_get_curves(self.h, inc.ctypes.data, prev.ctypes.data))
         return inc, prev
 
     def scalars(self):

@@ -28,6 +28,7 @@ struct cabm_handle {
     int n_sm = 148, path = CABM_PATH_AUTO, last_path = 0;
     int64_t launches = 0;
     bool ran = false;
+    bool poked = false;                // state was edited through cabm_set_field: pass A falls back to the full scan
     // optional per-kernel-class timing (cabm_set_profiling): events around every launch of the next cabm_run
     int profiling = 0;
     std::vector<cudaEvent_t> pev; std::vector<int> pcls; size_t pev_used = 0;
@@ -168,6 +169,8 @@ extern "C" void cabm_destroy(cabm_handle *h) {
     if (h->d_psets) cudaFree(h->d_psets);
     if (h->d_beta) cudaFree(h->d_beta);
     if (h->S.ct_log) cudaFree(h->S.ct_log);
+    if (h->S.ident_list) cudaFree(h->S.ident_list);
+    if (h->S.ident_cnt) cudaFree(h->S.ident_cnt);
     if (h->d_stage) cudaFree(h->d_stage);
     for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -257,6 +260,8 @@ extern "C" int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_ps
         if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
         CU(cudaMalloc((void **)&h->S.ct_log, sizeof(uint2) * cap * h->R));
         h->S.ct_cap = (uint32_t)cap;
+        CU(cudaMalloc((void **)&h->S.ident_list, sizeof(uint32_t) * 2 * (size_t)h->R * h->Np));
+        CU(cudaMalloc((void **)&h->S.ident_cnt, sizeof(uint32_t) * 2 * (size_t)h->R));
     }
     h->S.psets = h->d_psets; h->S.beta_thr = h->d_beta; h->S.P = n_psets;
     h->n_rep = n_rep; h->n_psets = n_psets; h->mode = mode; h->any_ct = any_ct; h->all_ct = all_ct; h->configured = 1; h->day = 1; h->ran = false;
@@ -277,6 +282,8 @@ static int reset_state(cabm_handle *h) {
     const size_t W = (size_t)S.R * S.nwords, C = (size_t)S.R * 6 * S.T * 12;
     CU(cudaMemsetAsync(S.mark_pre, 0, W * 4, h->stream)); CU(cudaMemsetAsync(S.mark_post, 0, W * 4, h->stream));
     CU(cudaMemsetAsync(S.infmask, 0, W * 4, h->stream)); CU(cudaMemsetAsync(S.ct_cnt, 0, (size_t)S.R * 4, h->stream));
+    if (S.ident_cnt) CU(cudaMemsetAsync(S.ident_cnt, 0, (size_t)S.R * 8, h->stream));
+    h->poked = false;
     CU(cudaMemsetAsync(S.err, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totiso, 0, (size_t)S.R * 8, h->stream));
     CU(cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, h->stream));
     CU(cudaMemsetAsync(S.inc, 0, C * 4, h->stream)); CU(cudaMemsetAsync(S.prev, 0, C * 4, h->stream));
@@ -301,7 +308,7 @@ static int do_dyntrans(cabm_handle *h, int day) {
     return CABM_OK;
 }
 static int do_time_update(cabm_handle *h, int day) {
-    if (h->any_ct) timed(h, CABM_K_CT_IDENTIFY, [&] { return launch_ct_identify(h->S, day, h->stream); });
+    if (h->any_ct) timed(h, CABM_K_CT_IDENTIFY, [&] { return launch_ct_identify(h->S, day, h->poked, h->stream); });
     timed(h, CABM_K_TIME_UPDATE, [&] { return launch_time_update(h->S, day, h->any_ct != 0, h->all_ct != 0, h->stream); });
     return CABM_OK;
 }
@@ -431,7 +438,9 @@ extern "C" int cabm_get_dyntrans_counters(cabm_handle *h, int32_t *totalmet, int
 // hmatrix is kept as one byte per element on the device and leaves as Int16 (:111): widen through a staging buffer
 static int copy_hmatrix(cabm_handle *h, size_t first_elem, size_t n_elem, int16_t *out) {
     const size_t chunk = (size_t)32 << 20;
-    if (!h->d_stage) {
+    if (!h->d_stage || h->stage_elems < (size_t)h->T * h->N) {
+        if (h->d_stage) cudaFree(h->d_stage);
+        h->d_stage = nullptr;
         h->stage_elems = n_elem < chunk ? n_elem : chunk;
         if (h->stage_elems < (size_t)h->T * h->N) h->stage_elems = (size_t)h->T * h->N;
         CU(cudaMalloc((void **)&h->d_stage, h->stage_elems * 2));
@@ -466,6 +475,24 @@ extern "C" int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev) {
     CU(cudaStreamSynchronize(h->stream));
     return CABM_OK;
 }
+extern "C" int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) {
+    int rc = need_config(h); if (rc) return rc;
+    if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");
+    if (h->N > 32767) return fail(h, CABM_E_ARG, "cabm_get_curves_i16 needs popsize <= 32767");
+    if (!inc || !prev) return fail(h, CABM_E_ARG, "cabm_get_curves_i16: bad argument");
+    const size_t n = (size_t)h->n_rep * 6 * h->T * 12;
+    if (h->stage_elems < 2 * n) {
+        if (h->d_stage) cudaFree(h->d_stage);
+        h->d_stage = nullptr; h->stage_elems = 0;
+        CU(cudaMalloc((void **)&h->d_stage, 2 * n * 2));
+        h->stage_elems = 2 * n;
+    }
+    h->launches += launch_narrow(h->S.inc, h->S.prev, h->d_stage, n, h->stream);
+    CU(cudaMemcpyAsync(inc, h->d_stage, n * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(prev, h->d_stage + n, n * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CABM_OK;
+}
 extern "C" int cabm_get_scalars(cabm_handle *h, int64_t *infectors, int64_t *totalisolated, int64_t *lat_inc_sum, uint32_t *err) {
     int rc = need_config(h); if (rc) return rc;
     if ((infectors || lat_inc_sum) && !h->ran) return fail(h, CABM_E_STATE, "infectors/lat_inc_sum exist after cabm_run");
@@ -491,6 +518,7 @@ extern "C" int cabm_set_field(cabm_handle *h, int field, int replicate, int agen
     int rc = need_config(h); if (rc) return rc;
     if (field < 0 || field > CABM_F_TRACEDXP || field == CABM_F_AG || field == CABM_F_DUR || replicate < 0 || replicate >= h->n_rep || agent < 0 || agent >= h->N)
         return fail(h, CABM_E_ARG, "cabm_set_field: bad argument");
+    h->poked = true;
     h->launches += launch_poke(h->S, field, replicate, agent, h->day, value, h->stream);
     CU(cudaStreamSynchronize(h->stream));
     return CABM_OK;

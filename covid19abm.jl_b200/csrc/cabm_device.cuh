@@ -72,6 +72,7 @@ struct Dev {
     int16_t *latday, *tracestart, *traceend, *tracedxp; uint32_t *ct_head;
     uint32_t *mark_pre, *mark_post;          // [R][nwords] bitmasks
     uint2 *ct_log; uint32_t *ct_cnt;         // [R][ct_cap] (y, next), [R]
+    uint32_t *ident_list, *ident_cnt;        // [R][2][Np], [R][2]: agents whose identification day is today / tomorrow
     uint32_t *grp_idx; int *grp_off;         // [R][Np], [R][8]
     uint32_t *infmask;                       // [R][nwords]
     uint32_t *hits;                          // 2 x [R][Np/2] of 2 x u16: native mode, contacts received from lower-indexed infectors

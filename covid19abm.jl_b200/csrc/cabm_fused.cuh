@@ -21,9 +21,9 @@
 
 namespace cabm {
 
-constexpr int FUSED_NT = 512;          // threads per CTA = max events per batch
+constexpr int FUSED_NT = 256;          // threads per CTA = max events per batch
 constexpr int FUSED_NCAND = 32;        // infectors per batch
-constexpr int FUSED_LCAP = 512;        // infectors listed per pass (more are handled in further passes)
+constexpr int FUSED_LCAP = 256;        // infectors listed per pass (more are handled in further passes)
 
 struct FusedSmem {
     uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;

@@ -376,13 +376,8 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
 // An index case x identifies on a day fixed when it became latent (doi == traceend), so the cross-agent writes are
 // hoisted: this kernel draws Bernoulli(fcontactst) once per distinct traced contact y (:709-713) and leaves a mark —
 // "pre" if y > x (y sees the isolation in its own update today), "post" if y < x (y was already updated today).
-__global__ void __launch_bounds__(256) k_ct_identify(Dev S, int day) {
-    const int r = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
-    const DevPset &P = S.psets[S.pset_of[r]];
-    if (P.ctstrat == 0 || x >= S.N) return;
+__device__ inline void ct_identify_one(const Dev &S, const DevPset &P, int r, int x, int day) {
     const size_t a = (size_t)r * S.Np + x;
-    const int te = S.traceend[a];
-    if (te < 0 || day - (int)S.latday[a] != te) return;
     const uint2 key = S.key[r];
     const uint2 *log = S.ct_log + (size_t)r * S.ct_cap;
     const uint32_t head = S.ct_head[a];
@@ -397,6 +392,31 @@ __global__ void __launch_bounds__(256) k_ct_identify(Dev S, int day) {
         if (y > (uint32_t)x) atomicOr(&S.mark_pre[(size_t)r * S.nwords + (y >> 5)], 1u << (y & 31));
         else if (y < (uint32_t)x) atomicOr(&S.mark_post[(size_t)r * S.nwords + (y >> 5)], 1u << (y & 31));
     }
+}
+
+// scan variant: every agent checks whether today is its identification day (used after state was poked by hand)
+__global__ void __launch_bounds__(256) k_ct_identify(Dev S, int day) {
+    const int r = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+    const DevPset &P = S.psets[S.pset_of[r]];
+    if (P.ctstrat == 0 || x >= S.N) return;
+    const size_t a = (size_t)r * S.Np + x;
+    const int te = S.traceend[a];
+    if (te < 0 || day - (int)S.latday[a] != te) return;
+    ct_identify_one(S, P, r, x, day);
+}
+
+// list variant: yesterday's update queued the agents whose identification day is today (agent_update_ct), so the work is
+// proportional to the number of index cases instead of the population. CTA per replicate.
+__global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
+    const int r = blockIdx.x;
+    const DevPset &P = S.psets[S.pset_of[r]];
+    if (P.ctstrat == 0) return;
+    uint32_t *cnt = &S.ident_cnt[r * 2 + (day & 1)];
+    const uint32_t n = *cnt;
+    const uint32_t *list = S.ident_list + ((size_t)r * 2 + (day & 1)) * S.Np;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) ct_identify_one(S, P, r, (int)list[k], day);
+    __syncthreads();
+    if (threadIdx.x == 0) *cnt = 0;
 }
 
 // ct_dynamics :658-752 for one agent, with the hoisted marks applied where the sequential loop would have.
@@ -453,6 +473,10 @@ __device__ inline uint32_t agent_update_ct(const Dev &S, const DevPset &P, int r
     st = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);                    // the iso that :778 sees
     if (post) st = isolate_ct(st);
     if (txp != txp0) S.tracedxp[a] = (int16_t)txp;
+    if (te >= 0 && day + 1 - (int)S.latday[a] == te) {                         // identifies tomorrow (:705): queue for pass A
+        const uint32_t slot = atomicAdd(&S.ident_cnt[r * 2 + ((day + 1) & 1)], 1u);
+        S.ident_list[((size_t)r * 2 + ((day + 1) & 1)) * S.Np + slot] = (uint32_t)i;
+    }
     return st;
 }
 
@@ -567,6 +591,17 @@ __global__ void k_widen_u8_i16(const uint8_t *src, int16_t *dst, size_t n) {
         } else {
             for (size_t k = i; k < n && k < i + 16; ++k) dst[k] = src[k];
         }
+    }
+}
+
+// curves leave as Int16 when every count fits (popsize <= 32767): halves the device->host bytes of an ensemble
+__global__ void k_narrow_i32_i16(const int *a, const int *b, int16_t *out, size_t n) {
+    for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; i < 2 * n; i += (size_t)gridDim.x * blockDim.x * 4) {
+        const int *src = i < n ? a + i : b + (i - n);          // n is a multiple of 4 (12 states per row)
+        const int4 v = *reinterpret_cast<const int4 *>(src);
+        union { uint2 u; int16_t h[4]; } o;
+        o.h[0] = (int16_t)v.x; o.h[1] = (int16_t)v.y; o.h[2] = (int16_t)v.z; o.h[3] = (int16_t)v.w;
+        *reinterpret_cast<uint2 *>(out + i) = o.u;
     }
 }
 
@@ -739,7 +774,11 @@ int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s) {
     k_dyntrans_native<false><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
     return 3;
 }
-int launch_ct_identify(const Dev &S, int day, cudaStream_t s) { k_ct_identify<<<agent_grid(S, 1), 256, 0, s>>>(S, day); return 1; }
+int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s) {
+    if (scan) k_ct_identify<<<agent_grid(S, 1), 256, 0, s>>>(S, day);
+    else k_ct_identify_list<<<S.R, 128, 0, s>>>(S, day);
+    return 1;
+}
 int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStream_t s) {
     int n = 0;
     if (!all_ct) { k_time_update<<<agent_grid(S, 16), 256, 0, s>>>(S, day, any_ct ? 1 : 0); ++n; }
@@ -756,6 +795,9 @@ int launch_reduce_hmatrix(const int16_t *hm, const int *ags, int M, int N, int T
 int launch_widen(const uint8_t *src, int16_t *dst, size_t n, cudaStream_t s) {
     size_t blocks = (n / 16 + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
     k_widen_u8_i16<<<(unsigned)blocks, 256, 0, s>>>(src, dst, n); return 1;
+}
+int launch_narrow(const int *a, const int *b, int16_t *out, size_t n, cudaStream_t s) {
+    k_narrow_i32_i16<<<148 * 8, 256, 0, s>>>(a, b, out, n); return 1;
 }
 int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s) { k_peek<<<(S.N + 255) / 256, 256, 0, s>>>(S, field, r, day, out); return 1; }
 int launch_poke(const Dev &S, int field, int r, int i, int day, int value, cudaStream_t s) { k_poke<<<1, 1, 0, s>>>(S, field, r, i, day, value); return 1; }

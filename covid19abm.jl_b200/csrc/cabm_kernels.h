@@ -12,7 +12,7 @@ int launch_insert_infected(const Dev &S, int which, int health, int num, int ag,
 int launch_first_column(const Dev &S, cudaStream_t s);
 int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s);
 int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s);
-int launch_ct_identify(const Dev &S, int day, cudaStream_t s);
+int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s);
 int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStream_t s);
 int launch_clear_marks(const Dev &S, cudaStream_t s);
 int launch_curves_finalize(const Dev &S, cudaStream_t s);
@@ -21,6 +21,7 @@ int launch_reduce_hmatrix(const int16_t *hm, const int *ags, int M, int N, int T
 int launch_widen(const uint8_t *src, int16_t *dst, size_t n, cudaStream_t s);
 int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, cudaStream_t s);
 size_t fused_smem_bytes_host(int Np);
+int launch_narrow(const int *a, const int *b, int16_t *out, size_t n, cudaStream_t s);
 int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s);
 int launch_poke(const Dev &S, int field, int r, int i, int day, int value, cudaStream_t s);
 

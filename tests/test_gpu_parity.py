@@ -182,3 +182,13 @@ def test_odd_population_sizes_bit_exact(cv, O):
         ref = O.run_ensemble([to_oracle(O, ip)], [0, 0, 0], [5, 6, 7], nthreads=3, want_hmatrix=True)
         assert (got["hmatrix"] == ref["hmatrix"]).all(), (n, path)
         assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all(), (n, path)
+
+
+def test_int16_curves_equal_int32(cv):
+    ip = cv.ModelParameters(β=0.2, prov="ontario", modeltime=80, initialinf=5)
+    with cv.Population(8, ip.popsize, ip.modeltime) as pop:
+        pop.configure(ip, [11 * (i + 1) for i in range(8)])
+        pop.run()
+        a, b = pop.curves()
+        c, d = pop.curves(dtype=np.int16)
+        assert c.dtype == np.int16 and (a == c).all() and (b == d).all() and a.sum() > 0
