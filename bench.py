@@ -126,6 +126,7 @@ def main():
     # else goes to stderr and the line is written to the saved descriptor at the end
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    os.environ["NCCL_DEBUG"] = "WARN"          # the pool sets VERSION, whose banner would land on stdout
 
     def emit(line):
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
