@@ -156,6 +156,7 @@ def lib():
     L.cabm_get_hmatrix.argtypes = [vp, i32, vp]; L.cabm_get_hmatrix_all.argtypes = [vp, vp]
     L.cabm_get_curves.argtypes = [vp, vp, vp]
     L.cabm_get_curves_i16.argtypes = [vp, vp, vp]
+    L.cabm_get_mean_curves.argtypes = [vp, vp, vp]
     L.cabm_get_scalars.argtypes = [vp, vp, vp, vp, vp]
     L.cabm_get_field.argtypes = [vp, i32, i32, vp]
     L.cabm_set_field.argtypes = [vp, i32, i32, i32, C.c_int32]
@@ -337,6 +338,13 @@ class Population:
         else:
             self._chk(self.L.cabm_get_curves(self.h, inc.ctypes.data, prev.ctypes.data))
         return inc, prev
+
+    def mean_curves(self):
+        """compute_yearly_average (scripts/local_run.jl:75-103) on the device: (inc_mean, prev_mean) [6][T][12] float64."""
+        a = np.zeros((6, self.T, 12), dtype=np.float64)
+        b = np.zeros((6, self.T, 12), dtype=np.float64)
+        self._chk(self.L.cabm_get_mean_curves(self.h, a.ctypes.data, b.ctypes.data))
+        return a, b
 
     def scalars(self):
         inf = np.zeros((self.n_rep, 4), dtype=np.int64)

@@ -493,6 +493,21 @@ extern "C" int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) 
     CU(cudaStreamSynchronize(h->stream));
     return CABM_OK;
 }
+extern "C" int cabm_get_mean_curves(cabm_handle *h, double *inc_mean, double *prev_mean) {
+    int rc = need_config(h); if (rc) return rc;
+    if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");
+    if (!inc_mean || !prev_mean) return fail(h, CABM_E_ARG, "cabm_get_mean_curves: bad argument");
+    const size_t per_rep = (size_t)6 * h->T * 12;
+    double *d = nullptr;
+    CU(cudaMalloc((void **)&d, per_rep * 2 * sizeof(double)));
+    h->launches += launch_mean_curves(h->S.inc, h->S.prev, d, d + per_rep, h->n_rep, per_rep, h->stream);
+    cudaError_t e = cudaMemcpyAsync(inc_mean, d, per_rep * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(prev_mean, d + per_rep, per_rep * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, CABM_E_CUDA, cudaGetErrorString(e));
+    return CABM_OK;
+}
 extern "C" int cabm_get_scalars(cabm_handle *h, int64_t *infectors, int64_t *totalisolated, int64_t *lat_inc_sum, uint32_t *err) {
     int rc = need_config(h); if (rc) return rc;
     if ((infectors || lat_inc_sum) && !h->ran) return fail(h, CABM_E_STATE, "infectors/lat_inc_sum exist after cabm_run");

@@ -29,7 +29,7 @@ struct FusedSmem {
     uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
     uint32_t *nb_thr; uint8_t *nb_guide;
     uint32_t *Y, *W1; uint8_t *Q; uint32_t *touch, *dupm; uint16_t *D;
-    uint16_t *list; uint8_t *lcnt;       // the day's ordered infectious agents and their contact budgets
+    uint16_t *list; uint8_t *lcnt, *lE;  // the day's ordered infectious agents, their contact budgets and event counts
     int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
 };
 
@@ -43,7 +43,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int Np) {
     b += FUSED_NT * 4 * 2 + FUSED_NT;    // Y (= cnt), W1, Q
     b += (size_t)(Np / 32) * 4 * 2;      // touch, dupm bitmasks
     b += FUSED_NT * 2;                   // D (compacted duplicate events)
-    b += FUSED_LCAP * 3;                 // list, lcnt
+    b += FUSED_LCAP * 4;                 // list, lcnt, lE
     return (b + 15) / 16 * 16 + 64;
 }
 
@@ -61,6 +61,17 @@ __device__ __forceinline__ int fresh_budget_s(const FusedSmem &M, uint2 key, uin
 }
 __device__ __forceinline__ int budget_of_s(const FusedSmem &M, uint2 key, uint32_t i, int day, uint32_t st) {
     return st_tag(st) == day ? st_rem(st) : fresh_budget_s(M, key, i, (uint32_t)day, st);
+}
+
+// gpw = Int.(round.(cm[ag]*cnts)) :804 (half-to-even) packed as five bytes; cm row in shared memory
+__device__ __forceinline__ unsigned long long gpw_pack(const double *cm_row, int cnts) {
+    unsigned long long gp = 0;
+#pragma unroll
+    for (int g = 0; g < 5; ++g) gp |= (unsigned long long)(unsigned)__double2int_rn(__dmul_rn(cm_row[g], (double)cnts)) << (8 * g);
+    return gp;
+}
+__device__ __forceinline__ int gpw_sum(unsigned long long gp) {
+    return (int)(gp & 0xFF) + (int)((gp >> 8) & 0xFF) + (int)((gp >> 16) & 0xFF) + (int)((gp >> 24) & 0xFF) + (int)((gp >> 32) & 0xFF);
 }
 
 // TMA bulk store of one hmatrix column from shared memory (UBLKCP in SASS)
@@ -96,6 +107,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         M.nb_guide = (uint8_t *)p; p += 5 * 256;
         M.Q = (uint8_t *)p; p += NT;
         M.lcnt = (uint8_t *)p; p += FUSED_LCAP;
+        M.lE = (uint8_t *)p; p += FUSED_LCAP;
     }
     __shared__ int s_r, s_off[8], s_wcnt[FUSED_NT / 32][5], s_base[5], s_total[5];
     __shared__ int s_sel_tid, s_sel_k, s_Ltot, s_ninf;
@@ -108,7 +120,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     __shared__ int s_infectors[4];
     // dyntrans batch
     __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_nb, s_cut;
-    __shared__ unsigned long long s_gp[FUSED_NCAND], s_bthr[FUSED_NCAND];
+    __shared__ unsigned long long s_bthr[FUSED_NCAND];
+    __shared__ uint8_t s_ccnt[FUSED_NCAND], s_cag[FUSED_NCAND];
     __shared__ uint8_t s_xh[FUSED_NCAND];
     __shared__ int s_wdup[FUSED_NT / 32];
 
@@ -321,7 +334,13 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         if (nlist == 0) break;
                         // the day's contact budget of every listed infector (:802), drawn once; a later hit by an earlier
                         // infector shows up as tag == day in its status word and overrides this value
-                        if (tid < nlist) { const int x = M.list[tid]; M.lcnt[tid] = (uint8_t)budget_of_s(M, key, x, day, M.status[x]); }
+                        if (tid < nlist) {
+                            const int x = M.list[tid];
+                            const uint32_t sx = M.status[x];
+                            const int cnts = budget_of_s(M, key, x, day, sx);
+                            M.lcnt[tid] = (uint8_t)cnts;
+                            M.lE[tid] = (uint8_t)gpw_sum(gpw_pack(s_cm + st_ag(sx) * 5, cnts));
+                        }
                         __syncthreads();
                         PHASE(2);
                         int lpos = 0;
@@ -334,12 +353,13 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 if (lane < ncand) {
                                     const int x = M.list[lpos + lane];
                                     const uint32_t sx = M.status[x];
-                                    const int cnts = st_tag(sx) == day ? st_rem(sx) : (int)M.lcnt[lpos + lane];
-                                    unsigned long long gp = 0;                                  // round.(cm[ag]*cnts), half-to-even
-#pragma unroll
-                                    for (int g = 0; g < 5; ++g) gp |= (unsigned long long)(unsigned)__double2int_rn(__dmul_rn(s_cm[st_ag(sx) * 5 + g], (double)cnts)) << (8 * g);
-                                    E = (int)(gp & 0xFF) + (int)((gp >> 8) & 0xFF) + (int)((gp >> 16) & 0xFF) + (int)((gp >> 24) & 0xFF) + (int)((gp >> 32) & 0xFF);
-                                    s_cand[lane] = x; s_gp[lane] = gp;
+                                    int cnts = (int)M.lcnt[lpos + lane];
+                                    E = (int)M.lE[lpos + lane];
+                                    if (st_tag(sx) == day) {                                    // contacted earlier today: budget changed (:813)
+                                        cnts = st_rem(sx);
+                                        E = gpw_sum(gpw_pack(s_cm + st_ag(sx) * 5, cnts));
+                                    }
+                                    s_cand[lane] = x; s_ccnt[lane] = (uint8_t)cnts; s_cag[lane] = (uint8_t)st_ag(sx);
                                     s_xh[lane] = (uint8_t)st_health(sx);
                                     s_bthr[lane] = s_beta[beta_class(st_health(sx))];         // :800
                                 }
@@ -357,13 +377,13 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             PHASE(8);
                             const int nb = s_nb, Etot = s_pref[nb];
                             // (b) one contact event per thread: target draw (:807), transmission word (:823); mark the target
-                            uint32_t y = 0, w1 = 0; int q = 0; bool ev = tid < Etot;
+                            uint32_t y = 0, w1 = 0, sy = 0; int q = 0, remy = 0; bool ev = tid < Etot;
                             if (ev) {
                                 int lo = 0, hi = nb - 1;                               // last q with pref[q] <= tid
                                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= tid) lo = mid; else hi = mid - 1; }
                                 q = lo;
                                 const int e = tid - s_pref[q];
-                                const unsigned long long gp = s_gp[q];
+                                const unsigned long long gp = gpw_pack(s_cm + s_cag[q] * 5, s_ccnt[q]);   // round.(cm[ag]*cnts) :804
                                 const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF), p4 = p3 + (int)((gp >> 24) & 0xFF);
                                 const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
                                 const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
@@ -373,6 +393,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 else {
                                     const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
                                     y = M.grp[go + below(w.x, len)]; w1 = w.y;
+                                    sy = M.status[y];                              // stable until the apply phase of this batch
+                                    remy = budget_of_s(M, key, y, day, sy);        // :811, the target's budget (lazy draw on first touch)
                                     // an infector later in this batch that gets contacted must re-read its budget: cut the batch there
                                     if ((int)y > x && (int)y <= s_cand[nb - 1] && ((M.inf[y >> 5] >> (y & 31)) & 1u)) {
                                         int a = q + 1, b = nb - 1;
@@ -409,8 +431,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 bool leader = true;
                                 if (isdup) for (int d = 0; d < dpos; ++d) if (M.Y[M.D[d]] == y) { leader = false; break; }
                                 if (leader) {
-                                    const uint32_t sy = M.status[y];
-                                    int rem = budget_of_s(M, key, y, day, sy);                           // :811
+                                    int rem = remy;
                                     bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;             // :822
                                     int xh_inf = -1;
                                     if (rem > 0) {                                                       // :812

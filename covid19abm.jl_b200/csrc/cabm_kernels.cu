@@ -605,6 +605,15 @@ __global__ void k_narrow_i32_i16(const int *a, const int *b, int16_t *out, size_
     }
 }
 
+// compute_yearly_average (scripts/local_run.jl:75-103): mean over the replicates of every curve entry, per day
+__global__ void k_mean_curves(const int *inc, const int *prev, double *minc, double *mprev, int R, size_t per_rep) {
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= per_rep) return;
+    long long a = 0, b = 0;
+    for (int r = 0; r < R; ++r) { a += inc[(size_t)r * per_rep + e]; b += prev[(size_t)r * per_rep + e]; }
+    minc[e] = (double)a / (double)R; mprev[e] = (double)b / (double)R;
+}
+
 // clears the pass-A marks after time_update consumed them
 __global__ void k_clear_marks(Dev S) {
     const size_t n = (size_t)S.R * S.nwords;
@@ -798,6 +807,9 @@ int launch_widen(const uint8_t *src, int16_t *dst, size_t n, cudaStream_t s) {
 }
 int launch_narrow(const int *a, const int *b, int16_t *out, size_t n, cudaStream_t s) {
     k_narrow_i32_i16<<<148 * 8, 256, 0, s>>>(a, b, out, n); return 1;
+}
+int launch_mean_curves(const int *inc, const int *prev, double *minc, double *mprev, int R, size_t per_rep, cudaStream_t s) {
+    k_mean_curves<<<(unsigned)((per_rep + 255) / 256), 256, 0, s>>>(inc, prev, minc, mprev, R, per_rep); return 1;
 }
 int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s) { k_peek<<<(S.N + 255) / 256, 256, 0, s>>>(S, field, r, day, out); return 1; }
 int launch_poke(const Dev &S, int field, int r, int i, int day, int value, cudaStream_t s) { k_poke<<<1, 1, 0, s>>>(S, field, r, i, day, value); return 1; }

@@ -11,3 +11,6 @@ _mod = importlib.util.module_from_spec(_spec)
 sys.modules["covid19abm_jl_b200"] = _mod
 _spec.loader.exec_module(_mod)
 globals().update({k: v for k, v in vars(_mod).items() if not k.startswith("__")})
+
+import importlib as _il
+local_run = _il.import_module("covid19abm_jl_b200.local_run")     # scripts/local_run.jl mirror (run, calibrate, ...)

@@ -139,6 +139,9 @@ int cabm_get_hmatrix_all(cabm_handle *h, int16_t *out);
 int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev);
 /* the same curves narrowed to Int16 on the device (every count <= popsize <= 32767): half the device->host bytes */
 int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev);
+/* compute_yearly_average (scripts/local_run.jl:75-103): the mean over all replicates of every curve entry, reduced on the
+ * device: inc_mean and prev_mean are double [6][modeltime][12] */
+int cabm_get_mean_curves(cabm_handle *h, double *inc_mean, double *prev_mean);
 /* infectors = _count_infectors() :295-313 [n_rep][4]; totalisolated = ct_data.totalisolated :61,649 [n_rep];
  * lat_inc_sum = sum(_get_column_incidence(h, LAT)) (scripts/local_run.jl:143) [n_rep]; err = CABM_ERR_* bits.
  * Any pointer may be NULL. */

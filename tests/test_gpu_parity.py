@@ -192,3 +192,28 @@ def test_int16_curves_equal_int32(cv):
         a, b = pop.curves()
         c, d = pop.curves(dtype=np.int16)
         assert c.dtype == np.int16 and (a == c).all() and (b == d).all() and a.sum() > 0
+
+
+def test_local_run_outputs(cv, O, tmp_path):
+    """scripts/local_run.jl mirror: run() writes the .dat files from device-reduced curves; compute_yearly_average is the
+    device-side ensemble mean; _calibrate is the mean LAT-incidence sum (the author's R0 estimate, :135-147)."""
+    ip = cv.ModelParameters(β=0.1, prov="ontario", modeltime=60, initialinf=2)
+    nsims = 6
+    dfs = cv.local_run.run(ip, nsims, str(tmp_path), True)
+    ref = O.run_ensemble([to_oracle(O, ip)], [0] * nsims, [726 * x for x in range(1, nsims + 1)], nthreads=4)
+    assert (dfs["all"]["LAT_INC"].reshape(nsims, 60) == ref["inc"][:, 0, :, 1]).all()
+    tl = np.genfromtxt(tmp_path / "timelevel_all.dat", delimiter=",", names=True)
+    assert np.allclose(tl["lat_inc"], ref["inc"][:, 0, :, 1].mean(axis=0)) and np.allclose(tl["sus_prev"], ref["prev"][:, 0, :, 0].mean(axis=0))
+    sl = np.genfromtxt(tmp_path / "simlevel_icu_prev_all.dat", delimiter=",", skip_header=1)
+    assert sl.shape == (60, nsims + 1) and (sl[:, 1:].T == ref["prev"][:, 0, :, 9]).all()
+    inf = np.loadtxt(tmp_path / "infectors.dat")
+    assert (inf == ref["infectors"]).all()
+    for f in ("ctnumbers.dat", "secondarys_all.dat", "simlevel_lat_inc_all.dat", "simlevel_ded_prev_all.dat"):
+        assert (tmp_path / f).exists()
+    cal = cv.ModelParameters(β=0.05, prov="ontario", modeltime=50, calibration=True)
+    m, sd = cv.local_run._calibrate(64, cal)
+    rc = O.run_ensemble([to_oracle(O, cal)], [0] * 64, [726 * x for x in range(1, 65)], nthreads=8)
+    v = rc["inc"][:, 0, :, 1].sum(axis=1).astype(float)
+    assert m == v.mean() and abs(sd - v.std(ddof=1)) < 1e-12
+    a, b, betas, ros = cv.local_run.calibrate_regression(betas=[0.03, 0.05, 0.07], nsims=200, prov="newyork")
+    assert 30 < b < 60 and abs(a) < 0.6        # the author's fit: R0 = 46.1761 beta - 0.00285 (scripts/local_run.jl:174)
