@@ -254,11 +254,11 @@ extern "C" int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_ps
     CU(cudaMemcpy(h->S.key, keys.data(), sizeof(uint2) * n_rep, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->S.pset_of, pof.data(), sizeof(int) * n_rep, cudaMemcpyHostToDevice));
     if (any_ct && !h->S.ct_log) {
-        // contact log: (target, next) per traced contact. 64 entries per agent covers a full epidemic with
-        // cdaysback of a few days (mean ~13 contacts/day for the ~half of infections that are captured).
-        size_t cap = (size_t)64 * h->N;
+        // contact log: one chunk [next, count, targets...] per (traced agent, day). 128 words per agent cover a full epidemic
+        // with cdaysback of a few days (mean ~13 contacts/day for the ~half of infections that are captured).
+        size_t cap = (size_t)128 * h->N;                    // 32-bit words per replicate
         if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
-        CU(cudaMalloc((void **)&h->S.ct_log, sizeof(uint2) * cap * h->R));
+        CU(cudaMalloc((void **)&h->S.ct_log, sizeof(uint32_t) * cap * h->R));
         h->S.ct_cap = (uint32_t)cap;
         CU(cudaMalloc((void **)&h->S.ident_list, sizeof(uint32_t) * 2 * (size_t)h->R * h->Np));
         CU(cudaMalloc((void **)&h->S.ident_cnt, sizeof(uint32_t) * 2 * (size_t)h->R));

@@ -13,7 +13,7 @@
 //   entry   i16  : day of entry to the current state (tis = updates_done - entry)
 //   dur     u32  : 4 x u8 (latents, asymps, pres, infs) :18
 //   sickfrom/isovia u8, latday i16 (doi = updates_done - latday :19), tracestart/traceend/tracedxp i16,
-//   ct_head u32 -> per-replicate contact log (linked list replacing the Bool[10000] of :25).
+//   ct_head u32 -> newest chunk of the agent in the per-replicate contact log (replaces the Bool[10000] of :25).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -71,7 +71,7 @@ struct Dev {
     uint32_t *status; int16_t *expday; int16_t *entry; uint32_t *dur; uint8_t *sickfrom; uint8_t *isovia;
     int16_t *latday, *tracestart, *traceend, *tracedxp; uint32_t *ct_head;
     uint32_t *mark_pre, *mark_post;          // [R][nwords] bitmasks
-    uint2 *ct_log; uint32_t *ct_cnt;         // [R][ct_cap] (y, next), [R]
+    uint32_t *ct_log; uint32_t *ct_cnt;      // [R][ct_cap] words: chunks [next chunk, count, targets...] per (traced agent, day); [R] words used
     uint32_t *ident_list, *ident_cnt;        // [R][2][Np], [R][2]: agents whose identification day is today / tomorrow
     uint32_t *grp_idx; int *grp_off;         // [R][Np], [R][8]
     uint32_t *infmask;                       // [R][nwords]

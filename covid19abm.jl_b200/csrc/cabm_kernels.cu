@@ -211,8 +211,13 @@ __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
                 const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF),
                           p4 = p3 + (int)((gp >> 24) & 0xFF), E = p4 + (int)((gp >> 32) & 0xFF);
                 const unsigned long long bthr = bt[beta_class(xh)];                      // :800
-                const bool tracing = ct && (sx & ST_TRACING);
-                uint32_t head = tracing ? S.ct_head[rb + x] : CT_NONE;
+                bool tracing = ct && (sx & ST_TRACING);
+                // contacts x makes while traced (:817-819) go to one chunk per (agent, day): [next chunk, count, targets...]
+                uint32_t cbase = 0, ccount = 0;
+                if (tracing) {
+                    if (logn + 2u + (uint32_t)E <= S.ct_cap) { cbase = logn; logn += 2u + (uint32_t)E; }
+                    else { if (lane == 0) atomicOr(&S.err[r], ERR_CT_LOG_FULL); tracing = false; }
+                }
                 for (int e0 = 0; e0 < E; e0 += 32) {
                     const int e = e0 + lane;
                     bool act = e < E;
@@ -251,19 +256,19 @@ __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
                     }
                     met += adm;
                     if (tracing && admm) {                                                // :817-819
-                        unsigned am = admm;
-                        while (am) {
-                            const int src = __ffs(am) - 1; am &= am - 1;
-                            const uint32_t jj = __shfl_sync(FULL, j, src);
-                            if (lane == 0) {
-                                if (logn < S.ct_cap) { S.ct_log[(size_t)r * S.ct_cap + logn] = make_uint2(jj, head); head = logn; ++logn; }
-                                else atomicOr(&S.err[r], ERR_CT_LOG_FULL);
-                            }
-                        }
+                        if (adm) S.ct_log[(size_t)r * S.ct_cap + cbase + 2u + ccount + (uint32_t)__popc(admm & lt)] = j;
+                        ccount += (uint32_t)__popc(admm);
                     }
                     __syncwarp();
                 }
-                if (tracing && lane == 0) S.ct_head[rb + x] = head;
+                if (tracing) {
+                    if (ccount == 0) logn = cbase;                                        // nothing admitted: give the chunk back
+                    else if (lane == 0) {
+                        uint32_t *c = S.ct_log + (size_t)r * S.ct_cap + cbase;
+                        c[0] = S.ct_head[rb + x]; c[1] = ccount;
+                        S.ct_head[rb + x] = cbase;
+                    }
+                }
             }
         }
     }
@@ -312,6 +317,8 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
                       p4 = p3 + (int)((gp >> 24) & 0xFF), E = p4 + (int)((gp >> 32) & 0xFF);
             const unsigned long long bthr = bt[beta_class(xh)];                      // :800
             const bool tracing = ct && (sx & ST_TRACING);
+            uint32_t cbase = 0, ccount = 0;
+            bool cfull = false;
             for (int e0 = 0; e0 < E; e0 += 32) {
                 const int e = e0 + lane;
                 bool adm = false;
@@ -349,21 +356,24 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
                     }
                 }
                 met += adm;
-                if (!COUNT && tracing) {                                              // :817-819 — only this warp appends to x's list
-                    unsigned am = __ballot_sync(FULL, adm);
-                    uint32_t head = S.ct_head[rb + x];
-                    while (am) {
-                        const int src = __ffs(am) - 1; am &= am - 1;
-                        const uint32_t jj = __shfl_sync(FULL, j, src);
-                        if (lane == 0) {
-                            const uint32_t slot = atomicAdd(&S.ct_cnt[r], 1u);
-                            if (slot < S.ct_cap) { S.ct_log[(size_t)r * S.ct_cap + slot] = make_uint2(jj, head); head = slot; }
-                            else atomicOr(&S.err[r], ERR_CT_LOG_FULL);
-                        }
+                if (!COUNT && tracing) {                                              // :817-819 — only this warp appends to x's chunk
+                    const unsigned am = __ballot_sync(FULL, adm);
+                    if (e0 == 0) {                                                        // reserve [next, count, E targets] once per (agent, day)
+                        uint32_t b0 = 0;
+                        if (lane == 0) b0 = atomicAdd(&S.ct_cnt[r], 2u + (uint32_t)E);
+                        cbase = __shfl_sync(FULL, b0, 0);
+                        if (cbase + 2u + (uint32_t)E > S.ct_cap) { if (lane == 0) atomicOr(&S.err[r], ERR_CT_LOG_FULL); cfull = true; }
                     }
-                    if (lane == 0) S.ct_head[rb + x] = head;
-                    __syncwarp();
+                    if (!cfull) {
+                        if (adm) S.ct_log[(size_t)r * S.ct_cap + cbase + 2u + ccount + (uint32_t)__popc(am & ((1u << lane) - 1u))] = j;
+                        ccount += (uint32_t)__popc(am);
+                    }
                 }
+            }
+            if (!COUNT && tracing && !cfull && ccount > 0 && lane == 0) {
+                uint32_t *c = S.ct_log + (size_t)r * S.ct_cap + cbase;
+                c[0] = S.ct_head[rb + x]; c[1] = ccount;
+                S.ct_head[rb + x] = cbase;
             }
         }
     }
@@ -376,45 +386,78 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
 // An index case x identifies on a day fixed when it became latent (doi == traceend), so the cross-agent writes are
 // hoisted: this kernel draws Bernoulli(fcontactst) once per distinct traced contact y (:709-713) and leaves a mark —
 // "pre" if y > x (y sees the isolation in its own update today), "post" if y < x (y was already updated today).
-__device__ inline void ct_identify_one(const Dev &S, const DevPset &P, int r, int x, int day) {
+// One index case, handled by a whole warp: gather its traced contacts (chunks are contiguous, so the reads coalesce),
+// drop repeats (the reference's contact set is a Bool vector, :25) and draw Bernoulli(fcontactst) per distinct contact.
+constexpr int CT_GATHER = 512;          // contacts gathered in shared memory per warp; longer sets take the slow path
+__device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, int x, int day, uint32_t *buf) {
+    const int lane = threadIdx.x & 31;
     const size_t a = (size_t)r * S.Np + x;
     const uint2 key = S.key[r];
-    const uint2 *log = S.ct_log + (size_t)r * S.ct_cap;
+    const uint32_t *log = S.ct_log + (size_t)r * S.ct_cap;
     const uint32_t head = S.ct_head[a];
-    for (uint32_t e = head; e != CT_NONE; e = log[e].y) {
-        const uint32_t y = log[e].x;
-        bool dup = false;                                     // the reference's contact set is a Bool vector (:25)
-        for (uint32_t f = head; f != e; f = log[f].y) if (log[f].x == y) { dup = true; break; }
-        if (dup) continue;
+    int n = 0;
+    for (uint32_t c = head; c != CT_NONE; c = log[c]) n += (int)log[c + 1];
+    auto contact = [&](uint32_t y) {
         const uint4 w = philox(x, day, S_CTCON, y, key);
-        if (!bern(w.x, P.fcontact_thr)) continue;             // :711
+        if (!bern(w.x, P.fcontact_thr)) return;               // :711
         atomicAdd(&S.totiso[r], 1ull);                        // :649
         if (y > (uint32_t)x) atomicOr(&S.mark_pre[(size_t)r * S.nwords + (y >> 5)], 1u << (y & 31));
         else if (y < (uint32_t)x) atomicOr(&S.mark_post[(size_t)r * S.nwords + (y >> 5)], 1u << (y & 31));
+    };
+    if (n <= CT_GATHER) {
+        int o = 0;
+        for (uint32_t c = head; c != CT_NONE; c = log[c]) {
+            const int cnt = (int)log[c + 1];
+            for (int k = lane; k < cnt; k += 32) buf[o + k] = log[c + 2 + k];
+            o += cnt;
+        }
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) {
+            const uint32_t y = buf[k];
+            bool dup = false;
+            for (int q = 0; q < k; ++q) if (buf[q] == y) { dup = true; break; }
+            if (!dup) contact(y);
+        }
+        __syncwarp();
+    } else if (lane == 0) {                                   // very long contact sets: one lane, quadratic walk
+        for (uint32_t c = head; c != CT_NONE; c = log[c]) {
+            for (uint32_t k = 0; k < log[c + 1]; ++k) {
+                const uint32_t y = log[c + 2 + k];
+                bool dup = false;
+                for (uint32_t c2 = head; c2 != CT_NONE && !dup; c2 = log[c2]) {
+                    const uint32_t lim = c2 == c ? k : log[c2 + 1];
+                    for (uint32_t k2 = 0; k2 < lim; ++k2) if (log[c2 + 2 + k2] == y) { dup = true; break; }
+                    if (c2 == c) break;
+                }
+                if (!dup) contact(y);
+            }
+        }
     }
 }
 
-// scan variant: every agent checks whether today is its identification day (used after state was poked by hand)
-__global__ void __launch_bounds__(256) k_ct_identify(Dev S, int day) {
+// scan variant (after state was poked by hand): every agent checks whether today is its identification day and queues itself
+__global__ void __launch_bounds__(256) k_ct_scan_identifiers(Dev S, int day) {
     const int r = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
     const DevPset &P = S.psets[S.pset_of[r]];
     if (P.ctstrat == 0 || x >= S.N) return;
     const size_t a = (size_t)r * S.Np + x;
     const int te = S.traceend[a];
     if (te < 0 || day - (int)S.latday[a] != te) return;
-    ct_identify_one(S, P, r, x, day);
+    const uint32_t slot = atomicAdd(&S.ident_cnt[r * 2 + (day & 1)], 1u);
+    S.ident_list[((size_t)r * 2 + (day & 1)) * S.Np + slot] = (uint32_t)x;
 }
 
-// list variant: yesterday's update queued the agents whose identification day is today (agent_update_ct), so the work is
-// proportional to the number of index cases instead of the population. CTA per replicate.
+// Pass A over the queued index cases of today (queued by yesterday's agent_update_ct, or by the scan above): the work is
+// proportional to the number of index cases, not to the population. CTA per replicate, warp per index case.
 __global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
-    const int r = blockIdx.x;
+    __shared__ uint32_t buf[4][CT_GATHER];
+    const int r = blockIdx.x, wid = threadIdx.x >> 5;
     const DevPset &P = S.psets[S.pset_of[r]];
     if (P.ctstrat == 0) return;
     uint32_t *cnt = &S.ident_cnt[r * 2 + (day & 1)];
     const uint32_t n = *cnt;
     const uint32_t *list = S.ident_list + ((size_t)r * 2 + (day & 1)) * S.Np;
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) ct_identify_one(S, P, r, (int)list[k], day);
+    for (uint32_t k = wid; k < n; k += 4) ct_identify_warp(S, P, r, (int)list[k], day, buf[wid]);
     __syncthreads();
     if (threadIdx.x == 0) *cnt = 0;
 }
@@ -721,12 +764,19 @@ __global__ void __launch_bounds__(256) k_peek(Dev S, int field, int r, int day, 
     case 13: v = S.traceend[a]; break;
     case 14: v = S.tracedxp[a]; break;
     case 15: {
-        const uint2 *log = S.ct_log + (size_t)r * S.ct_cap;
+        const uint32_t *log = S.ct_log + (size_t)r * S.ct_cap;
         const uint32_t head = S.ct_head[a];
-        for (uint32_t e = head; e != CT_NONE; e = log[e].y) {
-            bool dup = false;
-            for (uint32_t f = head; f != e; f = log[f].y) if (log[f].x == log[e].x) { dup = true; break; }
-            v += !dup;
+        for (uint32_t c = head; c != CT_NONE; c = log[c]) {
+            for (uint32_t k = 0; k < log[c + 1]; ++k) {
+                const uint32_t y = log[c + 2 + k];
+                bool dup = false;
+                for (uint32_t c2 = head; c2 != CT_NONE && !dup; c2 = log[c2]) {
+                    const uint32_t lim = c2 == c ? k : log[c2 + 1];
+                    for (uint32_t k2 = 0; k2 < lim; ++k2) if (log[c2 + 2 + k2] == y) { dup = true; break; }
+                    if (c2 == c) break;
+                }
+                v += !dup;
+            }
         }
         break; }
     }
@@ -784,9 +834,13 @@ int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s) {
     return 3;
 }
 int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s) {
-    if (scan) k_ct_identify<<<agent_grid(S, 1), 256, 0, s>>>(S, day);
-    else k_ct_identify_list<<<S.R, 128, 0, s>>>(S, day);
-    return 1;
+    int n = 1;
+    if (scan) {        // the queue may be stale: rebuild today's from the agent fields
+        cudaMemsetAsync(S.ident_cnt, 0, (size_t)S.R * 8, s);
+        k_ct_scan_identifiers<<<agent_grid(S, 1), 256, 0, s>>>(S, day); ++n;
+    }
+    k_ct_identify_list<<<S.R, 128, 0, s>>>(S, day);
+    return n;
 }
 int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStream_t s) {
     int n = 0;
