@@ -113,8 +113,8 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     S.ct_cap = 0;
     const size_t A = (size_t)h->R * h->Np, W = (size_t)h->R * S.nwords, C = (size_t)h->R * 6 * h->T * 12;
 #define DA(ptr, count) if ((e = dalloc(h, &(ptr), (count))) != cudaSuccess) return bail(e, #ptr)
-    DA(S.status, A); DA(S.expday, A); DA(S.entry, A); DA(S.dur, A); DA(S.sickfrom, A); DA(S.isovia, A);
-    DA(S.latday, A); DA(S.tracestart, A); DA(S.traceend, A); DA(S.tracedxp, A); DA(S.ct_head, A);
+    DA(S.status, A); DA(S.expday, A); DA(S.texp, A); DA(S.entry, A); DA(S.dur, A); DA(S.sickfrom, A); DA(S.isovia, A);
+    DA(S.latday, A); DA(S.tracestart, A); DA(S.traceend, A); DA(S.txpday, A); DA(S.ct_head, A);
     DA(S.mark_pre, W); DA(S.mark_post, W); DA(S.infmask, W); DA(S.ct_cnt, (size_t)h->R);
     DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8); DA(S.hits, A);
     DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);

@@ -9,10 +9,12 @@
 //                    nextday_meetcnt (:13,:786) is a pure function of the keyed draw, so it is evaluated
 //                    lazily for infectors and their targets instead of once per agent-day (:425,:781);
 //                  - isob is `iso` as of the agent's own last update step (the value :778 used).
-//   expday  i16  : absolute day on which tis >= exp (:405) becomes true   (replaces tis/exp :16-17)
+//   expday  i16  : the agent's next event day = the scan key of time_update: min of texp and the contact-tracing days below
+//   texp    i16  : absolute day on which tis >= exp (:405) becomes true   (replaces tis/exp :16-17)
 //   entry   i16  : day of entry to the current state (tis = updates_done - entry)
 //   dur     u32  : 4 x u8 (latents, asymps, pres, infs) :18
-//   sickfrom/isovia u8, latday i16 (doi = updates_done - latday :19), tracestart/traceend/tracedxp i16,
+//   sickfrom/isovia u8, latday i16 (doi = updates_done - latday :19), tracestart/traceend i16 (:23-24, relative to latday),
+//   txpday i16 (absolute day on which tracedxp :26 reaches 0; 0 = no countdown),
 //   ct_head u32 -> newest chunk of the agent in the per-replicate contact log (replaces the Bool[10000] of :25).
 #pragma once
 #include <cstdint>
@@ -68,8 +70,8 @@ struct ConstTables {
 struct Dev {
     int R, N, Np, T, P, store_hm, nwords;
     uint32_t ct_cap;
-    uint32_t *status; int16_t *expday; int16_t *entry; uint32_t *dur; uint8_t *sickfrom; uint8_t *isovia;
-    int16_t *latday, *tracestart, *traceend, *tracedxp; uint32_t *ct_head;
+    uint32_t *status; int16_t *expday; int16_t *texp; int16_t *entry; uint32_t *dur; uint8_t *sickfrom; uint8_t *isovia;
+    int16_t *latday, *tracestart, *traceend, *txpday; uint32_t *ct_head;
     uint32_t *mark_pre, *mark_post;          // [R][nwords] bitmasks
     uint32_t *ct_log; uint32_t *ct_cnt;      // [R][ct_cap] words: chunks [next chunk, count, targets...] per (traced agent, day); [R] words used
     uint32_t *ident_list, *ident_cnt;        // [R][2][Np], [R][2]: agents whose identification day is today / tomorrow
@@ -212,13 +214,20 @@ __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int 
     return Tr{st, day + exp, oldh, newh};
 }
 
-// HBM-resident variant used by the per-day kernels: stores expday, flips the infectious bitmask, counts the curves.
-__device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
-                                      int target, bool seed_simple_inf, bool count_curves) {
+// HBM-resident variants used by the per-day kernels: flip the infectious bitmask, count the curves (transition_hbm) and
+// store the expiry day both as texp and as the scan key (transition).
+__device__ inline Tr transition_hbm(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
+                                    int target, bool seed_simple_inf, bool count_curves) {
     const Tr t = transition_core(S, P, r, i, day, st, key, target, seed_simple_inf);
-    S.expday[(size_t)r * S.Np + i] = (int16_t)t.expday;
     if (is_infectious(t.newh) != is_infectious(t.oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
     if (count_curves) curve_move(S, r, st_ag(st), day, t.oldh, t.newh);
+    return t;
+}
+__device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
+                                      int target, bool seed_simple_inf, bool count_curves) {
+    const Tr t = transition_hbm(S, P, r, i, day, st, key, target, seed_simple_inf, count_curves);
+    S.texp[(size_t)r * S.Np + i] = (int16_t)t.expday;
+    S.expday[(size_t)r * S.Np + i] = (int16_t)t.expday;
     return t.st;
 }
 

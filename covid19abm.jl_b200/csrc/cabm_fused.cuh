@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             M.expday[i] = (i < N) ? (int16_t)999 : (int16_t)32767;
             M.col[i] = SUS;
             S.dur[a] = d4; S.isovia[a] = via; S.entry[a] = 0; S.sickfrom[a] = UNDEF; S.latday[a] = -999;
-            S.tracestart[a] = -1; S.traceend[a] = -1; S.tracedxp[a] = 0; S.ct_head[a] = CT_NONE;
+            S.tracestart[a] = -1; S.traceend[a] = -1; S.txpday[a] = 0; S.ct_head[a] = CT_NONE;
         }
         for (int k = tid; k < nwords; k += NT) M.inf[k] = 0;
         if (tid < 240) (&s_io[0][0][0])[tid] = 0;
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         for (int i = tid; i < Np; i += NT) {
             const uint32_t st = M.status[i];
             S.status[rb + i] = st;
-            S.expday[rb + i] = M.expday[i];
+            S.expday[rb + i] = M.expday[i]; S.texp[rb + i] = M.expday[i];
             if (i < N && st_health(st) != SUS) {
                 const int f = S.sickfrom[rb + i];
                 if (f == PRE) l[0]++; else if (f == ASYMP) l[1]++; else if (f == MILD || f == MISO) l[2]++;

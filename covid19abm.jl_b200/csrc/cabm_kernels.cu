@@ -38,11 +38,11 @@ __global__ void __launch_bounds__(256) k_initialize(Dev S) {
     }
     S.status[a] = st;
     S.dur[a] = d4;
-    S.expday[a] = (i < S.N) ? (int16_t)999 : (int16_t)32767;                             // :179
+    S.expday[a] = S.texp[a] = (i < S.N) ? (int16_t)999 : (int16_t)32767;                 // :179
     S.entry[a] = 0;
     S.sickfrom[a] = UNDEF;
     S.latday[a] = -999;                                                                   // doi = 999 (:19)
-    S.tracestart[a] = -1; S.traceend[a] = -1; S.tracedxp[a] = 0;
+    S.tracestart[a] = -1; S.traceend[a] = -1; S.txpday[a] = 0;
     S.ct_head[a] = CT_NONE;
 }
 
@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(256) k_insert_infected(Dev S, int which, int h
                 if (k-- > 0) continue;
                 uint32_t ns = transition(S, P, r, i, day, st, key, health, /*seed_simple_inf=*/true, /*count_curves=*/false);
                 if (health == LAT) {                                                     // x.tis = x.exp :383
-                    const int ex = (int)S.expday[rb + i] - day;
-                    S.entry[rb + i] = (int16_t)(day - ex); S.expday[rb + i] = (int16_t)day;
+                    const int ex = (int)S.texp[rb + i] - day;
+                    S.entry[rb + i] = (int16_t)(day - ex); S.texp[rb + i] = S.expday[rb + i] = (int16_t)day;
                 }
                 // the contact budget already drawn for the coming day (:186 / :425) used the agent's old `iso`
                 ns = (ns & ~ST_ISOB) | (st & ST_ISOB);
@@ -462,93 +462,131 @@ __global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
     if (threadIdx.x == 0) *cnt = 0;
 }
 
-// ct_dynamics :658-752 for one agent, with the hoisted marks applied where the sequential loop would have.
-__device__ inline uint32_t agent_update_ct(const Dev &S, const DevPset &P, int r, int i, int day, uint2 key,
-                                           uint32_t st, bool fire, bool pre, bool post) {
+// ============================================================================ time_update :399-428 (+ snapshot :218-223)
+// The per-agent streaming kernel. tis/doi/tracedxp are not stored as counters (absolute days) and the next-day contact
+// count (:425) is drawn lazily by dyntrans, so an agent-day is one 16-bit compare of the agent's next event day; the next
+// hmatrix column is the previous one with the (rare) changes patched in. Thread per 16 consecutive agents: two 128-bit
+// loads of event days, one 128-bit load and one 128-bit store of column bytes = 4 B per agent-day (2 B without the state
+// matrix; replicates with contact tracing also read their two mark bitmasks, 0.25 B). Everything else — the status word,
+// durations, the tracing fields — is touched only by agents that have an event today (agent_event).
+//
+// agent_event: time_update's body for one agent whose next event day has come (:403-425), in the reference's order:
+// [pre mark] -> state transition if expired (:405-420) -> ct_dynamics (:658-752: window set-up, tracing on,
+// identification, quarantine expiry) -> isob := iso (the value :778 sees) -> [post mark]; then the next event day.
+// The marks are the hoisted cross-agent writes of :705-716 (k_ct_identify_list). Quarantine countdown (:718-750):
+// tracedxp == txpday - day after today's update.
+__device__ __noinline__ uint32_t agent_event(const Dev &S, int r, int i, int day, bool pre, bool post) {
     const size_t a = (size_t)r * S.Np + i;
-    int txp = S.tracedxp[a];
-    const int txp0 = txp;
-    auto isolate_ct = [&](uint32_t s) {                       // apply_ct_strategy :647-656
-        if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
-        txp = P.qdays;
-        return s | ST_ISO;
-    };
-    if (pre) st = isolate_ct(st);
-    if (fire) st = transition(S, P, r, i, day, st, key, st_swap(st), false, true);
-    const int doi = day - (int)S.latday[a];
-    int ts = S.tracestart[a], te = S.traceend[a];
-    if (st_health(st) == LAT && st_swap(st) != ASYMP && doi == 0) {          // :678
-        const uint4 w = philox(i, day, S_CTWIN, 0, key);
-        if (bern(w.x, P.fctcap_thr)) {
-            const uint32_t d4 = S.dur[a];
-            const int tid = 1 + below(w.y, (int)(d4 >> 24));                  // :680
-            const int delta = (int)(d4 & 0xFF) + (int)((d4 >> 16) & 0xFF) + tid;
-            const int q = delta - P.cdaysback;
-            ts = q > 0 ? q : 0; te = delta;
-            S.tracestart[a] = (int16_t)ts; S.traceend[a] = (int16_t)te;
-            st &= ~ST_TRACING;
-            S.ct_head[a] = CT_NONE;                                            // :687
+    const DevPset &P = S.psets[S.pset_of[r]];
+    const uint2 key = S.key[r];
+    uint32_t st = S.status[a];
+    const uint32_t st0 = st;
+    int texp = S.texp[a];
+    const bool ct = P.ctstrat != 0;
+    int txp = 0, txp0 = 0;
+    if (ct) {
+        txp = txp0 = S.txpday[a];
+        if (pre) {                                             // apply_ct_strategy :647-656 by an index case with a lower index
+            st |= ST_ISO;
+            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            txp = P.qdays > 0 ? day + P.qdays - 1 : 0;         // counted down once more in this same update
         }
     }
-    if (doi >= ts && doi < te) st |= ST_TRACING;                              // :699-701
-    if (doi == te) {                                                          // :705-716 (contacts were handled in pass A)
-        st &= ~ST_TRACING;
-        st = isolate_ct(st);
-        atomicAdd(&S.totiso[r], 1ull);
-        S.ct_head[a] = CT_NONE;
+    if (texp <= day || (st_health(st) == SUS && st_swap(st) == LAT)) {      // :405 (an infection today set exp = tis :826)
+        const Tr t = transition_hbm(S, P, r, i, day, st, key, st_swap(st), false, true);
+        st = t.st; texp = t.expday;
+        S.texp[a] = (int16_t)texp;
     }
-    if (txp > 0) {                                                            // :718-750
-        if (!(st & ST_ISO)) atomicOr(&S.err[r], ERR_TRACED_NOT_ISO);
-        txp -= 1;
-        if (txp == 0) {
-            st &= ~ST_ISO;
-            S.isovia[a] = VIA_NULL;
-            if (P.ctstrat == 3) {
-                const uint4 w = philox(i, day, S_CT3, 0, key);
-                const int h = st_health(st);
-                if ((h == LAT && bern(w.x, c_tab.ct3_lat_thr)) || (h == PRE && bern(w.x, c_tab.ct3_pre_thr)) ||
-                    (h == ASYMP && bern(w.x, c_tab.ct3_asymp_thr)) || h == MILD || h == INF || h == MISO || h == IISO) {
-                    st |= ST_ISO; S.isovia[a] = VIA_CT; txp = 14;
+    int ne = texp;
+    if (ct) {
+        const int latday = S.latday[a], doi = day - latday;
+        int ts = S.tracestart[a], te = S.traceend[a];
+        if (st_health(st) == LAT && st_swap(st) != ASYMP && doi == 0) {      // :678
+            const uint4 w = philox(i, day, S_CTWIN, 0, key);
+            if (bern(w.x, P.fctcap_thr)) {
+                const uint32_t d4 = S.dur[a];
+                const int tid = 1 + below(w.y, (int)(d4 >> 24));              // :680
+                const int delta = (int)(d4 & 0xFF) + (int)((d4 >> 16) & 0xFF) + tid;
+                const int q = delta - P.cdaysback;
+                ts = q > 0 ? q : 0; te = delta;
+                S.tracestart[a] = (int16_t)ts; S.traceend[a] = (int16_t)te;
+                st &= ~ST_TRACING;
+                S.ct_head[a] = CT_NONE;                                        // :687
+            }
+        }
+        if (doi >= ts && doi < te) st |= ST_TRACING;                          // :699-701
+        if (doi == te) {                                                      // :705-716 (contacts were handled in pass A)
+            st &= ~ST_TRACING;
+            st |= ST_ISO;
+            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            txp = P.qdays > 0 ? day + P.qdays - 1 : 0;
+            atomicAdd(&S.totiso[r], 1ull);
+            S.ct_head[a] = CT_NONE;
+        }
+        if (txp != 0 && txp >= day) {                                         // :718 tracedxp > 0
+            if (!(st & ST_ISO)) atomicOr(&S.err[r], ERR_TRACED_NOT_ISO);
+            if (txp == day) {                                                 // :734 the countdown ends today
+                st &= ~ST_ISO;
+                S.isovia[a] = VIA_NULL;
+                txp = 0;
+                if (P.ctstrat == 3) {
+                    const uint4 w = philox(i, day, S_CT3, 0, key);
+                    const int h = st_health(st);
+                    if ((h == LAT && bern(w.x, c_tab.ct3_lat_thr)) || (h == PRE && bern(w.x, c_tab.ct3_pre_thr)) ||
+                        (h == ASYMP && bern(w.x, c_tab.ct3_asymp_thr)) || h == MILD || h == INF || h == MISO || h == IISO) {
+                        st |= ST_ISO; S.isovia[a] = VIA_CT; txp = day + 14;
+                    }
                 }
             }
         }
     }
-    st = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);                    // the iso that :778 sees
-    if (post) st = isolate_ct(st);
-    if (txp != txp0) S.tracedxp[a] = (int16_t)txp;
-    if (te >= 0 && day + 1 - (int)S.latday[a] == te) {                         // identifies tomorrow (:705): queue for pass A
-        const uint32_t slot = atomicAdd(&S.ident_cnt[r * 2 + ((day + 1) & 1)], 1u);
-        S.ident_list[((size_t)r * 2 + ((day + 1) & 1)) * S.Np + slot] = (uint32_t)i;
+    st = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);
+    if (ct) {
+        if (post) {                                            // apply_ct_strategy by an index case with a higher index: after this agent's own step
+            st |= ST_ISO;
+            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            txp = P.qdays > 0 ? day + P.qdays : 0;
+        }
+        if (txp != txp0) S.txpday[a] = (int16_t)txp;
+        // next event: state expiry, tracing on, the eve of identification (to queue for pass A), identification, end of quarantine
+        const int te = S.traceend[a];
+        if (te >= 0) {
+            const int latday = S.latday[a], ts = S.tracestart[a], idd = latday + te, tron = latday + ts;
+            if (ts < te && tron > day) ne = min(ne, tron);
+            if (idd - 1 > day) ne = min(ne, idd - 1);
+            if (idd > day) ne = min(ne, idd);
+            if (idd == day + 1) {                              // identifies tomorrow (:705): queue for pass A
+                const uint32_t slot = atomicAdd(&S.ident_cnt[r * 2 + ((day + 1) & 1)], 1u);
+                S.ident_list[((size_t)r * 2 + ((day + 1) & 1)) * S.Np + slot] = (uint32_t)i;
+            }
+        }
+        if (txp > day) ne = min(ne, txp);
+        // a post mark isolates after the budget draw of today (:778 saw the old iso): tomorrow's own step must see the new one
+        if (((st >> 19) ^ (st >> 20)) & 1u) ne = min(ne, day + 1);
     }
-    return st;
+    S.expday[a] = (int16_t)ne;
+    if (st != st0) S.status[a] = st;
+    return (uint32_t)st_health(st);
 }
 
-// ============================================================================ time_update :399-428 (+ snapshot :218-223)
-// The per-agent streaming kernel. tis/doi are not stored (absolute days) and the next-day contact count (:425) is drawn
-// lazily by dyntrans, so an agent-day is one 16-bit compare of its expiry day; the next hmatrix column is the previous
-// one with the (rare) transitions patched in. Thread per 16 consecutive agents: two 128-bit loads of expiry days, one
-// 128-bit load and one 128-bit store of column bytes = 4 B per agent-day (2 B without the state matrix). The status
-// word, durations etc. are touched only by agents whose state expires. Replicates with contact tracing take the
-// per-agent path below (k_time_update_ct).
-__device__ __noinline__ uint32_t time_update_fire(const Dev &S, int r, int i, int day) {
-    const size_t a = (size_t)r * S.Np + i;
-    const uint32_t st = S.status[a];
-    const uint32_t ns = transition(S, S.psets[S.pset_of[r]], r, i, day, st, S.key[r], st_swap(st), false, true);
-    S.status[a] = ns;
-    return (uint32_t)st_health(ns);
-}
-
-__global__ void __launch_bounds__(256) k_time_update(const __grid_constant__ Dev S, int day, int mixed) {
+__global__ void __launch_bounds__(256) k_time_update(const __grid_constant__ Dev S, int day, int any_ct) {
     const int r = blockIdx.y;
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (i0 >= S.N) return;
-    if (mixed && S.psets[S.pset_of[r]].ctstrat != 0) return;         // mixed ensembles: tracing replicates go to k_time_update_ct
     const size_t a0 = (size_t)r * S.Np + i0;
     const uint4 e0 = *reinterpret_cast<const uint4 *>(S.expday + a0), e1 = *reinterpret_cast<const uint4 *>(S.expday + a0 + 8);
+    unsigned pre = 0, post = 0;
+    if (any_ct) {                                                    // marks left by today's index cases (pass A)
+        const size_t wi = (size_t)r * S.nwords + (i0 >> 5);
+        const unsigned sh = i0 & 31;
+        pre = (S.mark_pre[wi] >> sh) & 0xFFFFu; post = (S.mark_post[wi] >> sh) & 0xFFFFu;
+        if (pre) atomicAnd(&S.mark_pre[wi], ~(0xFFFFu << sh));       // consumed by this update
+        if (post) atomicAnd(&S.mark_post[wi], ~(0xFFFFu << sh));
+    }
     const uint32_t dd = (uint32_t)day * 0x10001u;
     const uint32_t m[8] = {__vcmples2(e0.x, dd), __vcmples2(e0.y, dd), __vcmples2(e0.z, dd), __vcmples2(e0.w, dd),
                            __vcmples2(e1.x, dd), __vcmples2(e1.y, dd), __vcmples2(e1.z, dd), __vcmples2(e1.w, dd)};
-    const bool any = (m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7]) != 0;   // somebody expires today (:405)
+    const bool any = ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7]) | pre | post) != 0;   // somebody has an event today
     const bool hm_on = S.store_hm && day < S.T;                      // column st+1 = state at the start of the next day
     const bool vec = (S.N & 15) == 0;
     union { uint4 v; uint8_t b[16]; } col;
@@ -563,8 +601,8 @@ __global__ void __launch_bounds__(256) k_time_update(const __grid_constant__ Dev
     if (any) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const bool f = (m[k >> 1] >> ((k & 1) * 16)) & 1u;
-            if (f && i0 + k < S.N) col.b[k] = (uint8_t)time_update_fire(S, r, i0 + k, day);
+            const bool f = ((m[k >> 1] >> ((k & 1) * 16)) | (pre >> k) | (post >> k)) & 1u;
+            if (f && i0 + k < S.N) col.b[k] = (uint8_t)agent_event(S, r, i0 + k, day, (pre >> k) & 1u, (post >> k) & 1u);
         }
     }
     if (hm_on) {
@@ -580,45 +618,6 @@ __global__ void __launch_bounds__(256) k_resync_isob(Dev S) {
     for (size_t a = blockIdx.x * (size_t)blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x) {
         const uint32_t st = S.status[a];
         if (((st >> 19) ^ (st >> 20)) & 1u) S.status[a] = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);
-    }
-}
-
-// time_update for replicates with contact tracing: thread per 8 agents, every agent runs ct_dynamics (:422).
-__global__ void __launch_bounds__(256) k_time_update_ct(Dev S, int day) {
-    const int r = blockIdx.y;
-    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    if (i0 >= S.N) return;
-    const DevPset &P = S.psets[S.pset_of[r]];
-    if (P.ctstrat == 0) return;
-    const size_t a0 = (size_t)r * S.Np + i0;
-    union { uint4 v; int16_t e[8]; } ex;
-    union { uint4 v[2]; uint32_t s[8]; } st;
-    ex.v = *reinterpret_cast<const uint4 *>(S.expday + a0);
-    st.v[0] = *reinterpret_cast<const uint4 *>(S.status + a0);
-    st.v[1] = *reinterpret_cast<const uint4 *>(S.status + a0 + 4);
-    unsigned fire = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) fire |= (unsigned)((int)ex.e[k] <= day && i0 + k < S.N) << k;
-    const uint2 key = S.key[r];
-    const size_t wi = (size_t)r * S.nwords + (i0 >> 5);
-    const unsigned sh = i0 & 31;
-    const unsigned pre = (S.mark_pre[wi] >> sh) & 0xFF, post = (S.mark_post[wi] >> sh) & 0xFF;
-    if (pre) atomicAnd(&S.mark_pre[wi], ~(0xFFu << sh));          // marks are consumed by this update
-    if (post) atomicAnd(&S.mark_post[wi], ~(0xFFu << sh));
-    for (int k = 0; k < 8 && i0 + k < S.N; ++k) {
-        const uint32_t ns = agent_update_ct(S, P, r, i0 + k, day, key, st.s[k], (fire >> k) & 1, (pre >> k) & 1, (post >> k) & 1);
-        if (ns != st.s[k]) { st.s[k] = ns; S.status[a0 + k] = ns; }
-    }
-    if (S.store_hm && day < S.T) {
-        uint8_t *col = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
-        if ((S.N & 7) == 0) {
-            union { uint2 v; uint8_t h[8]; } o;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o.h[k] = (uint8_t)st_health(st.s[k]);
-            *reinterpret_cast<uint2 *>(col) = o.v;
-        } else {
-            for (int k = 0; k < 8 && i0 + k < S.N; ++k) col[k] = (uint8_t)st_health(st.s[k]);
-        }
     }
 }
 
@@ -754,7 +753,7 @@ __global__ void __launch_bounds__(256) k_peek(Dev S, int field, int r, int day, 
     case 3: v = budget_of(S, S.key[r], i, day, st); break;
     case 4: v = st_ag(st) + 1; break;
     case 5: v = tis; break;
-    case 6: v = (st_health(st) == SUS && st_swap(st) == LAT) ? tis : (int)S.expday[a] - (int)S.entry[a]; break;
+    case 6: v = (st_health(st) == SUS && st_swap(st) == LAT) ? tis : (int)S.texp[a] - (int)S.entry[a]; break;
     case 7: { const uint32_t d4 = S.dur[a]; out[4 * i] = d4 & 0xFF; out[4 * i + 1] = (d4 >> 8) & 0xFF; out[4 * i + 2] = (d4 >> 16) & 0xFF; out[4 * i + 3] = d4 >> 24; return; }
     case 8: v = done - S.latday[a]; break;
     case 9: v = (st & ST_ISO) ? 1 : 0; break;
@@ -762,7 +761,7 @@ __global__ void __launch_bounds__(256) k_peek(Dev S, int field, int r, int day, 
     case 11: v = (st & ST_TRACING) ? 1 : 0; break;
     case 12: v = S.tracestart[a]; break;
     case 13: v = S.traceend[a]; break;
-    case 14: v = S.tracedxp[a]; break;
+    case 14: { const int t = S.txpday[a]; v = (t != 0 && t > done) ? t - done : 0; break; }      // tracedxp :26
     case 15: {
         const uint32_t *log = S.ct_log + (size_t)r * S.ct_cap;
         const uint32_t head = S.ct_head[a];
@@ -795,18 +794,19 @@ __global__ void k_poke(Dev S, int field, int r, int i, int day, int value) {
     case 1: st = st_set_swap(st, value); break;
     case 2: S.sickfrom[a] = (uint8_t)value; break;
     case 3: st = (st & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)(value & 0xFF) | ((uint32_t)day << 22); break;
-    case 5: { const int exp = (int)S.expday[a] - (int)S.entry[a]; S.entry[a] = (int16_t)(done - value); S.expday[a] = (int16_t)(done - value + exp); break; }
-    case 6: S.expday[a] = (int16_t)((int)S.entry[a] + value); break;
+    case 5: { const int exp = (int)S.texp[a] - (int)S.entry[a]; S.entry[a] = (int16_t)(done - value); S.texp[a] = (int16_t)(done - value + exp); break; }
+    case 6: S.texp[a] = (int16_t)((int)S.entry[a] + value); break;
     case 8: S.latday[a] = (int16_t)(done - value); break;
     case 9: st = value ? (st | ST_ISO | ST_ISOB) : (st & ~(ST_ISO | ST_ISOB)); break;
     case 10: S.isovia[a] = (uint8_t)value; break;
     case 11: st = value ? (st | ST_TRACING) : (st & ~ST_TRACING); break;
     case 12: S.tracestart[a] = (int16_t)value; break;
     case 13: S.traceend[a] = (int16_t)value; break;
-    case 14: S.tracedxp[a] = (int16_t)value; break;
+    case 14: S.txpday[a] = (int16_t)(value > 0 ? done + value : 0); break;
     default: break;
     }
     S.status[a] = st;
+    S.expday[a] = 0;      // wake the agent at the next update: agent_event recomputes its next event day from the edited fields
 }
 
 // ============================================================================ launchers
@@ -843,10 +843,10 @@ int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s) {
     return n;
 }
 int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStream_t s) {
-    int n = 0;
-    if (!all_ct) { k_time_update<<<agent_grid(S, 16), 256, 0, s>>>(S, day, any_ct ? 1 : 0); ++n; }
-    if (any_ct) { k_time_update_ct<<<agent_grid(S, 8), 256, 0, s>>>(S, day); ++n; }
-    if (day == 1 && !all_ct) { k_resync_isob<<<148 * 8, 256, 0, s>>>(S); ++n; }
+    (void)all_ct;
+    int n = 1;
+    k_time_update<<<agent_grid(S, 16), 256, 0, s>>>(S, day, any_ct ? 1 : 0);
+    if (day == 1) { k_resync_isob<<<148 * 8, 256, 0, s>>>(S); ++n; }
     return n;
 }
 int launch_clear_marks(const Dev &S, cudaStream_t s) { k_clear_marks<<<296, 256, 0, s>>>(S); return 1; }
