@@ -320,10 +320,10 @@ extern "C" int cabm_run(cabm_handle *h) {
     CU(cudaEventRecord(h->ev0, h->stream));
     if ((rc = reset_state(h))) return rc;
     // The fused kernel keeps a replicate's hot state in shared memory: usable when it fits two CTAs per SM budget
-    // (popsize <= ~21k agents), with the exact schedule and no contact tracing; otherwise one kernel per phase per day.
-    const bool fused_ok = !h->any_ct && h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 226 * 1024;
+    // (popsize <= ~21k agents) with the exact schedule; otherwise one kernel per phase per day.
+    const bool fused_ok = h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 226 * 1024;
     const bool use_fused = h->path == CABM_PATH_FUSED ? fused_ok : (h->path == CABM_PATH_AUTO && fused_ok);
-    if (h->path == CABM_PATH_FUSED && !fused_ok) return fail(h, CABM_E_STATE, "fused path needs ctstrat == 0, exact mode and a population that fits shared memory");
+    if (h->path == CABM_PATH_FUSED && !fused_ok) return fail(h, CABM_E_STATE, "fused path needs the exact schedule and a population that fits shared memory");
     h->last_path = use_fused ? CABM_PATH_FUSED : CABM_PATH_MULTIKERNEL;
     if (use_fused) {
         timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->stream); });            // :104-142 in one launch

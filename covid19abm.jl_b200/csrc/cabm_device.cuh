@@ -231,6 +231,100 @@ __device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int
     return t.st;
 }
 
+// time_update's body for one agent that has an event today (see k_time_update in cabm_kernels.cu for the ordering notes).
+// Takes and returns the status word and the state-expiry day; touches the HBM-resident tracing fields directly; the caller
+// stores status / texp / next event day and does the infectious-set and curve accounting from (oldh, newh).
+struct Ev { uint32_t st; int texp, ne, oldh, newh; };
+
+__device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int i, int day, uint2 key, uint32_t st, int texp,
+                                      bool pre, bool post, uint32_t *queue_cnt /* tomorrow's index cases */, uint32_t *queue) {
+    const size_t a = (size_t)r * S.Np + i;
+    int oldh = st_health(st), newh = oldh;
+    const bool ct = P.ctstrat != 0;
+    int txp = 0, txp0 = 0;
+    if (ct) {
+        txp = txp0 = S.txpday[a];
+        if (pre) {                                             // apply_ct_strategy :647-656 by an index case with a lower index
+            st |= ST_ISO;
+            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            txp = P.qdays > 0 ? day + P.qdays - 1 : 0;         // counted down once more in this same update
+        }
+    }
+    if (texp <= day || (st_health(st) == SUS && st_swap(st) == LAT)) {      // :405 (an infection today set exp = tis :826)
+        const Tr t = transition_core(S, P, r, i, day, st, key, st_swap(st), false);
+        st = t.st; texp = t.expday; oldh = t.oldh; newh = t.newh;
+    }
+    int ne = texp;
+    if (ct) {
+        const int latday = S.latday[a], doi = day - latday;
+        int ts = S.tracestart[a], te = S.traceend[a];
+        if (st_health(st) == LAT && st_swap(st) != ASYMP && doi == 0) {      // :678
+            const uint4 w = philox(i, day, S_CTWIN, 0, key);
+            if (bern(w.x, P.fctcap_thr)) {
+                const uint32_t d4 = S.dur[a];
+                const int tid = 1 + below(w.y, (int)(d4 >> 24));              // :680
+                const int delta = (int)(d4 & 0xFF) + (int)((d4 >> 16) & 0xFF) + tid;
+                const int q = delta - P.cdaysback;
+                ts = q > 0 ? q : 0; te = delta;
+                S.tracestart[a] = (int16_t)ts; S.traceend[a] = (int16_t)te;
+                st &= ~ST_TRACING;
+                S.ct_head[a] = CT_NONE;                                        // :687
+            }
+        }
+        if (doi >= ts && doi < te) st |= ST_TRACING;                          // :699-701
+        if (doi == te) {                                                      // :705-716 (contacts were handled in pass A)
+            st &= ~ST_TRACING;
+            st |= ST_ISO;
+            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            txp = P.qdays > 0 ? day + P.qdays - 1 : 0;
+            atomicAdd(&S.totiso[r], 1ull);
+            S.ct_head[a] = CT_NONE;
+        }
+        if (txp != 0 && txp >= day) {                                         // :718 tracedxp > 0
+            if (!(st & ST_ISO)) atomicOr(&S.err[r], ERR_TRACED_NOT_ISO);
+            if (txp == day) {                                                 // :734 the countdown ends today
+                st &= ~ST_ISO;
+                S.isovia[a] = VIA_NULL;
+                txp = 0;
+                if (P.ctstrat == 3) {
+                    const uint4 w = philox(i, day, S_CT3, 0, key);
+                    const int h = st_health(st);
+                    if ((h == LAT && bern(w.x, c_tab.ct3_lat_thr)) || (h == PRE && bern(w.x, c_tab.ct3_pre_thr)) ||
+                        (h == ASYMP && bern(w.x, c_tab.ct3_asymp_thr)) || h == MILD || h == INF || h == MISO || h == IISO) {
+                        st |= ST_ISO; S.isovia[a] = VIA_CT; txp = day + 14;
+                    }
+                }
+            }
+        }
+    }
+    st = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);
+    if (ct) {
+        if (post) {                                            // apply_ct_strategy by an index case with a higher index: after this agent's own step
+            st |= ST_ISO;
+            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            txp = P.qdays > 0 ? day + P.qdays : 0;
+        }
+        if (txp != txp0) S.txpday[a] = (int16_t)txp;
+        // next event: state expiry, tracing on, the eve of identification (to queue for pass A), identification, end of quarantine
+        const int te = S.traceend[a];
+        if (te >= 0) {
+            const int latday = S.latday[a], ts = S.tracestart[a], idd = latday + te, tron = latday + ts;
+            if (ts < te && tron > day) ne = min(ne, tron);
+            if (idd - 1 > day) ne = min(ne, idd - 1);
+            if (idd > day) ne = min(ne, idd);
+            if (idd == day + 1) {                              // identifies tomorrow (:705): queue for pass A
+                const uint32_t slot = atomicAdd(queue_cnt, 1u);
+                queue[slot] = (uint32_t)i;
+            }
+        }
+        if (txp > day) ne = min(ne, txp);
+        // a post mark isolates after the budget draw of today (:778 saw the old iso): tomorrow's own step must see the new one
+        if (((st >> 19) ^ (st >> 20)) & 1u) ne = min(ne, day + 1);
+    }
+    return Ev{st, texp, ne, oldh, newh};
+}
+
+
 #endif  // CABM_KERNELS_TU
 
 }  // namespace cabm

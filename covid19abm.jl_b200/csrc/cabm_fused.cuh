@@ -28,7 +28,7 @@ constexpr int FUSED_LCAP = 256;        // infectors listed per pass (more are ha
 struct FusedSmem {
     uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
     uint32_t *nb_thr; uint8_t *nb_guide;
-    uint32_t *Y, *W1; uint8_t *Q; uint32_t *touch, *dupm; uint16_t *D;
+    uint32_t *Y, *W1; uint8_t *Q; uint32_t *touch, *dupm, *mpre, *mpost; uint16_t *D;
     uint16_t *list; uint8_t *lcnt, *lE;  // the day's ordered infectious agents, their contact budgets and event counts
     int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
 };
@@ -41,7 +41,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int Np) {
     b += (size_t)(Np / 32) * 4;          // inf
     b += 5 * 256 * 4 + 5 * 256;          // nb tables
     b += FUSED_NT * 4 * 2 + FUSED_NT;    // Y (= cnt), W1, Q
-    b += (size_t)(Np / 32) * 4 * 2;      // touch, dupm bitmasks
+    b += (size_t)(Np / 32) * 4 * 4;      // touch, dupm, mark_pre, mark_post bitmasks
     b += FUSED_NT * 2;                   // D (compacted duplicate events)
     b += FUSED_LCAP * 4;                 // list, lcnt, lE
     return (b + 15) / 16 * 16 + 64;
@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         M.W1 = (uint32_t *)p; p += NT * 4;
         M.touch = (uint32_t *)p; p += (size_t)nwords * 4;
         M.dupm = (uint32_t *)p; p += (size_t)nwords * 4;
+        M.mpre = (uint32_t *)p; p += (size_t)nwords * 4;
+        M.mpost = (uint32_t *)p; p += (size_t)nwords * 4;
         M.D = (uint16_t *)p; p += NT * 2;
         M.list = (uint16_t *)p; p += FUSED_LCAP * 2;
         M.nb_guide = (uint8_t *)p; p += 5 * 256;
@@ -124,9 +126,13 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     __shared__ uint8_t s_ccnt[FUSED_NCAND], s_cag[FUSED_NCAND];
     __shared__ uint8_t s_xh[FUSED_NCAND];
     __shared__ int s_wdup[FUSED_NT / 32];
+    // contact tracing (:647-752): per-candidate chunk of the contact log, the replicate's log fill, index-case queues by day parity
+    __shared__ uint8_t s_ctr[FUSED_NCAND];
+    __shared__ uint32_t s_cbase[FUSED_NCAND], s_logn, s_qcnt[2];
+    __shared__ int s_clen[FUSED_NCAND];
 
     for (int k = tid; k < 5 * 256; k += NT) { M.nb_thr[k] = S.nb_thr[k]; M.nb_guide[k] = S.nb_guide[k]; }
-    for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }
+    for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; M.mpre[k] = 0; M.mpost[k] = 0; }
     if (tid < 4) { s_tlat[tid] = c_tab.lat_thr[tid]; s_tpre[tid] = c_tab.pre_thr[tid]; }
     if (tid < 40) { s_tasy[tid] = c_tab.asy_thr[tid]; s_tinf[tid] = c_tab.inf_thr[tid]; }
     if (tid < 25) s_cm[tid] = c_tab.cm[tid / 5][tid % 5];
@@ -147,6 +153,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid < (int)(sizeof(DevPset) / 4)) reinterpret_cast<uint32_t *>(&s_P)[tid] = reinterpret_cast<const uint32_t *>(&S.psets[S.pset_of[r]])[tid];
         __syncthreads();
         const DevPset &P = s_P;
+        const bool ctr = P.ctstrat != 0;              // this replicate traces contacts
+        if (tid == 0) { s_logn = 0; s_qcnt[0] = 0; s_qcnt[1] = 0; }
         const uint2 key = S.key[r];
         const size_t rb = (size_t)r * Np;
         const unsigned long long *beta = S.beta_thr + (size_t)S.pset_of[r] * T * 4;
@@ -176,6 +184,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             M.expday[i] = (i < N) ? (int16_t)999 : (int16_t)32767;
             M.col[i] = SUS;
             S.dur[a] = d4; S.isovia[a] = via; S.entry[a] = 0; S.sickfrom[a] = UNDEF; S.latday[a] = -999;
+            if (ctr) S.texp[a] = (i < N) ? (int16_t)999 : (int16_t)32767;
             S.tracestart[a] = -1; S.traceend[a] = -1; S.txpday[a] = 0; S.ct_head[a] = CT_NONE;
         }
         for (int k = tid; k < nwords; k += NT) M.inf[k] = 0;
@@ -251,6 +260,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         const Tr t = transition_core(S, P, r, i, 0, st, key, health, true);
                         M.status[i] = (t.st & ~ST_ISOB) | (st & ST_ISOB);    // day-1 budget was drawn with the old iso (:186)
                         M.expday[i] = (int16_t)t.expday;
+                        if (ctr) S.texp[rb + i] = (int16_t)t.expday;
                         M.col[i] = (uint8_t)t.newh;
                         S.sickfrom[rb + i] = INF;                             // :391
                         if (is_infectious(t.newh)) { M.inf[i >> 5] |= 1u << (i & 31); s_ninf += 1; }
@@ -363,6 +373,18 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     s_xh[lane] = (uint8_t)st_health(sx);
                                     s_bthr[lane] = s_beta[beta_class(st_health(sx))];         // :800
                                 }
+                                if (ctr) {                                                     // :817-819 chunk [next, count, <= E targets] per traced infector
+                                    const bool tr = lane < ncand && E > 0 && (M.status[M.list[lpos + lane]] & ST_TRACING);
+                                    int need = tr ? 2 + E : 0, nin = need;
+                                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, nin, o); if (lane >= o) nin += v; }
+                                    const int ntot = __shfl_sync(FULL, nin, 31);
+                                    const uint32_t base0 = s_logn;
+                                    const bool room = base0 + (uint32_t)ntot <= S.ct_cap;
+                                    if (!room && ntot && lane == 0) atomicOr(&S.err[r], ERR_CT_LOG_FULL);
+                                    s_ctr[lane] = (uint8_t)(tr && room); s_cbase[lane] = base0 + (uint32_t)(nin - need); s_clen[lane] = 0;
+                                    __syncwarp();
+                                    if (lane == 0 && room) s_logn = base0 + (uint32_t)ntot;
+                                }
                                 int incl = E;
                                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
                                 s_pref[lane + 1] = incl;
@@ -436,6 +458,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     int xh_inf = -1;
                                     if (rem > 0) {                                                       // :812
                                         rem -= 1;                                                         // :813
+                                        if (ctr && s_ctr[q]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q] + 2u + (uint32_t)atomicAdd(&s_clen[q], 1)] = y;   // :817-819
                                         if (sus && bern(w1, s_bthr[q])) { sus = false; xh_inf = s_xh[q]; }   // :823-827
                                     }
                                     if (isdup) {
@@ -444,6 +467,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                             if (M.Y[e2] != y) continue;
                                             rem -= 1;
                                             const int q2 = M.Q[e2];
+                                            if (ctr && s_ctr[q2]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q2] + 2u + (uint32_t)atomicAdd(&s_clen[q2], 1)] = y;
                                             if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }
                                         }
                                     }
@@ -457,6 +481,12 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 }
                             }
                             __syncthreads();                                                   // B5: status writes visible to the next batch
+                            if (ctr && wid == 0 && lane < cut && s_ctr[lane] && s_clen[lane] > 0) {    // link the day's chunk of each traced infector
+                                const int x = s_cand[lane];
+                                uint32_t *c = S.ct_log + (size_t)r * S.ct_cap + s_cbase[lane];
+                                c[0] = S.ct_head[rb + x]; c[1] = (uint32_t)s_clen[lane];
+                                S.ct_head[rb + x] = s_cbase[lane];
+                            }
                             PHASE(11);
                             if (marked) { M.touch[yw] = 0; M.dupm[yw] = 0; }                   // next marking is after the next B1
                             lpos += cut;
@@ -476,27 +506,52 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 if (day == 1) {                                                // seeds isolated by fpreiso: resync isob (see k_time_update)
                     for (int i = tid; i < N; i += NT) { const uint32_t st = M.status[i]; if (((st >> 19) ^ (st >> 20)) & 1u) M.status[i] = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB); }
                 }
+                if (ctr) {
+                    // pass A of ct_dynamics (:705-716): today's index cases (queued yesterday by agent_event_core) mark their traced
+                    // contacts before anybody is updated. Index cases are few: warp 0 takes them one after another.
+                    const uint32_t nq = s_qcnt[day & 1];
+                    if (nq) {
+                        if (wid == 0) {
+                            const uint32_t *qlist = S.ident_list + ((size_t)r * 2 + (day & 1)) * Np;
+                            for (uint32_t k = 0; k < nq; ++k) ct_identify_warp(S, P, r, (int)qlist[k], day, M.Y, NT, M.mpre, M.mpost);
+                        }
+                        __syncthreads();
+                        if (tid == 0) s_qcnt[day & 1] = 0;
+                    }
+                }
                 const uint32_t dd = (uint32_t)day * 0x10001u;
-                uint32_t mn = 0x7FFF7FFFu;                                     // running min of the expiry days that stay (2 x i16)
+                uint32_t mn = 0x7FFF7FFFu;                                     // running min of the event days that stay (2 x i16)
                 for (int i0 = tid * 8; i0 < N; i0 += NT * 8) {
                     uint4 ex = *reinterpret_cast<const uint4 *>(M.expday + i0);
                     const uint32_t m0 = __vcmples2(ex.x, dd), m1 = __vcmples2(ex.y, dd), m2 = __vcmples2(ex.z, dd), m3 = __vcmples2(ex.w, dd);
-                    if (m0 | m1 | m2 | m3) {                                   // somebody in these 8 expires today (:405)
+                    unsigned pre = 0, post = 0;
+                    if (ctr) {
+                        const unsigned sh = i0 & 31;
+                        pre = (M.mpre[i0 >> 5] >> sh) & 0xFFu; post = (M.mpost[i0 >> 5] >> sh) & 0xFFu;
+                        if (pre) atomicAnd(&M.mpre[i0 >> 5], ~(0xFFu << sh));
+                        if (post) atomicAnd(&M.mpost[i0 >> 5], ~(0xFFu << sh));
+                    }
+                    if (m0 | m1 | m2 | m3 | pre | post) {                      // somebody in these 8 has an event today (:405, marks)
                         unsigned fire = (m0 & 1u) | ((m0 >> 15) & 2u) | ((m1 & 1u) << 2) | ((m1 >> 13) & 8u) | ((m2 & 1u) << 4) | ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u);
+                        fire |= pre | post;
                         while (fire) {
                             const int k = __ffs(fire) - 1; fire &= fire - 1;
                             const int i = i0 + k;
                             if (i >= N) break;
                             const uint32_t st = M.status[i];
-                            const Tr t = transition_core(S, P, r, i, day, st, key, st_swap(st), false);
-                            M.status[i] = t.st;
-                            M.expday[i] = (int16_t)t.expday;
-                            if (t.newh != t.oldh) {
-                                M.col[i] = (uint8_t)t.newh;
-                                atomicAdd(&s_io[day & 1][0][st_ag(st) * 12 + t.newh], 1); atomicAdd(&s_io[day & 1][1][st_ag(st) * 12 + t.oldh], 1);
-                                if (is_infectious(t.newh) != is_infectious(t.oldh)) {
+                            const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];      // without tracing the scan key is the expiry day
+                            const int par = (day + 1) & 1;
+                            const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, (pre >> k) & 1u, (post >> k) & 1u,
+                                                          &s_qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr);
+                            M.status[i] = e.st;
+                            M.expday[i] = (int16_t)e.ne;
+                            if (ctr && e.texp != texp) S.texp[rb + i] = (int16_t)e.texp;
+                            if (e.newh != e.oldh) {
+                                M.col[i] = (uint8_t)e.newh;
+                                atomicAdd(&s_io[day & 1][0][st_ag(st) * 12 + e.newh], 1); atomicAdd(&s_io[day & 1][1][st_ag(st) * 12 + e.oldh], 1);
+                                if (is_infectious(e.newh) != is_infectious(e.oldh)) {
                                     atomicXor(&M.inf[i >> 5], 1u << (i & 31));
-                                    atomicAdd(&s_ninf, is_infectious(t.newh) ? 1 : -1);
+                                    atomicAdd(&s_ninf, is_infectious(e.newh) ? 1 : -1);
                                 }
                             }
                         }
@@ -561,7 +616,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         for (int i = tid; i < Np; i += NT) {
             const uint32_t st = M.status[i];
             S.status[rb + i] = st;
-            S.expday[rb + i] = M.expday[i]; S.texp[rb + i] = M.expday[i];
+            S.expday[rb + i] = M.expday[i];
+            if (!ctr) S.texp[rb + i] = M.expday[i];
             if (i < N && st_health(st) != SUS) {
                 const int f = S.sickfrom[rb + i];
                 if (f == PRE) l[0]++; else if (f == ASYMP) l[1]++; else if (f == MILD || f == MISO) l[2]++;
@@ -569,6 +625,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             }
         }
         for (int k = tid; k < nwords; k += NT) S.infmask[(size_t)r * nwords + k] = M.inf[k];
+        if (ctr && tid == 0) { S.ct_cnt[r] = s_logn; S.ident_cnt[r * 2] = 0; S.ident_cnt[r * 2 + 1] = 0; }
         for (int k = 0; k < 4; ++k) if (l[k]) atomicAdd(&s_infectors[k], l[k]);
         if (bad) atomicOr(&S.err[r], ERR_SICKFROM);
         __syncthreads();

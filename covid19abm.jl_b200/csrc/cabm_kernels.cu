@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
 // One index case, handled by a whole warp: gather its traced contacts (chunks are contiguous, so the reads coalesce),
 // drop repeats (the reference's contact set is a Bool vector, :25) and draw Bernoulli(fcontactst) per distinct contact.
 constexpr int CT_GATHER = 512;          // contacts gathered in shared memory per warp; longer sets take the slow path
-__device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, int x, int day, uint32_t *buf) {
+__device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, int x, int day, uint32_t *buf, int bufcap,
+                                        uint32_t *mpre_row, uint32_t *mpost_row) {
     const int lane = threadIdx.x & 31;
     const size_t a = (size_t)r * S.Np + x;
     const uint2 key = S.key[r];
@@ -401,10 +402,10 @@ __device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, i
         const uint4 w = philox(x, day, S_CTCON, y, key);
         if (!bern(w.x, P.fcontact_thr)) return;               // :711
         atomicAdd(&S.totiso[r], 1ull);                        // :649
-        if (y > (uint32_t)x) atomicOr(&S.mark_pre[(size_t)r * S.nwords + (y >> 5)], 1u << (y & 31));
-        else if (y < (uint32_t)x) atomicOr(&S.mark_post[(size_t)r * S.nwords + (y >> 5)], 1u << (y & 31));
+        if (y > (uint32_t)x) atomicOr(&mpre_row[y >> 5], 1u << (y & 31));
+        else if (y < (uint32_t)x) atomicOr(&mpost_row[y >> 5], 1u << (y & 31));
     };
-    if (n <= CT_GATHER) {
+    if (n <= bufcap) {
         int o = 0;
         for (uint32_t c = head; c != CT_NONE; c = log[c]) {
             const int cnt = (int)log[c + 1];
@@ -457,7 +458,8 @@ __global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
     uint32_t *cnt = &S.ident_cnt[r * 2 + (day & 1)];
     const uint32_t n = *cnt;
     const uint32_t *list = S.ident_list + ((size_t)r * 2 + (day & 1)) * S.Np;
-    for (uint32_t k = wid; k < n; k += 4) ct_identify_warp(S, P, r, (int)list[k], day, buf[wid]);
+    for (uint32_t k = wid; k < n; k += 4)
+        ct_identify_warp(S, P, r, (int)list[k], day, buf[wid], CT_GATHER, S.mark_pre + (size_t)r * S.nwords, S.mark_post + (size_t)r * S.nwords);
     __syncthreads();
     if (threadIdx.x == 0) *cnt = 0;
 }
@@ -477,96 +479,19 @@ __global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
 // tracedxp == txpday - day after today's update.
 __device__ __noinline__ uint32_t agent_event(const Dev &S, int r, int i, int day, bool pre, bool post) {
     const size_t a = (size_t)r * S.Np + i;
-    const DevPset &P = S.psets[S.pset_of[r]];
-    const uint2 key = S.key[r];
-    uint32_t st = S.status[a];
-    const uint32_t st0 = st;
-    int texp = S.texp[a];
-    const bool ct = P.ctstrat != 0;
-    int txp = 0, txp0 = 0;
-    if (ct) {
-        txp = txp0 = S.txpday[a];
-        if (pre) {                                             // apply_ct_strategy :647-656 by an index case with a lower index
-            st |= ST_ISO;
-            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
-            txp = P.qdays > 0 ? day + P.qdays - 1 : 0;         // counted down once more in this same update
-        }
+    const uint32_t st0 = S.status[a];
+    const int texp0 = S.texp[a];
+    const int par = (day + 1) & 1;
+    const Ev e = agent_event_core(S, S.psets[S.pset_of[r]], r, i, day, S.key[r], st0, texp0, pre, post,
+                                  S.ident_cnt ? &S.ident_cnt[r * 2 + par] : nullptr, S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * S.Np : nullptr);
+    if (e.newh != e.oldh) {
+        if (is_infectious(e.newh) != is_infectious(e.oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
+        curve_move(S, r, st_ag(st0), day, e.oldh, e.newh);
     }
-    if (texp <= day || (st_health(st) == SUS && st_swap(st) == LAT)) {      // :405 (an infection today set exp = tis :826)
-        const Tr t = transition_hbm(S, P, r, i, day, st, key, st_swap(st), false, true);
-        st = t.st; texp = t.expday;
-        S.texp[a] = (int16_t)texp;
-    }
-    int ne = texp;
-    if (ct) {
-        const int latday = S.latday[a], doi = day - latday;
-        int ts = S.tracestart[a], te = S.traceend[a];
-        if (st_health(st) == LAT && st_swap(st) != ASYMP && doi == 0) {      // :678
-            const uint4 w = philox(i, day, S_CTWIN, 0, key);
-            if (bern(w.x, P.fctcap_thr)) {
-                const uint32_t d4 = S.dur[a];
-                const int tid = 1 + below(w.y, (int)(d4 >> 24));              // :680
-                const int delta = (int)(d4 & 0xFF) + (int)((d4 >> 16) & 0xFF) + tid;
-                const int q = delta - P.cdaysback;
-                ts = q > 0 ? q : 0; te = delta;
-                S.tracestart[a] = (int16_t)ts; S.traceend[a] = (int16_t)te;
-                st &= ~ST_TRACING;
-                S.ct_head[a] = CT_NONE;                                        // :687
-            }
-        }
-        if (doi >= ts && doi < te) st |= ST_TRACING;                          // :699-701
-        if (doi == te) {                                                      // :705-716 (contacts were handled in pass A)
-            st &= ~ST_TRACING;
-            st |= ST_ISO;
-            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
-            txp = P.qdays > 0 ? day + P.qdays - 1 : 0;
-            atomicAdd(&S.totiso[r], 1ull);
-            S.ct_head[a] = CT_NONE;
-        }
-        if (txp != 0 && txp >= day) {                                         // :718 tracedxp > 0
-            if (!(st & ST_ISO)) atomicOr(&S.err[r], ERR_TRACED_NOT_ISO);
-            if (txp == day) {                                                 // :734 the countdown ends today
-                st &= ~ST_ISO;
-                S.isovia[a] = VIA_NULL;
-                txp = 0;
-                if (P.ctstrat == 3) {
-                    const uint4 w = philox(i, day, S_CT3, 0, key);
-                    const int h = st_health(st);
-                    if ((h == LAT && bern(w.x, c_tab.ct3_lat_thr)) || (h == PRE && bern(w.x, c_tab.ct3_pre_thr)) ||
-                        (h == ASYMP && bern(w.x, c_tab.ct3_asymp_thr)) || h == MILD || h == INF || h == MISO || h == IISO) {
-                        st |= ST_ISO; S.isovia[a] = VIA_CT; txp = day + 14;
-                    }
-                }
-            }
-        }
-    }
-    st = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB);
-    if (ct) {
-        if (post) {                                            // apply_ct_strategy by an index case with a higher index: after this agent's own step
-            st |= ST_ISO;
-            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
-            txp = P.qdays > 0 ? day + P.qdays : 0;
-        }
-        if (txp != txp0) S.txpday[a] = (int16_t)txp;
-        // next event: state expiry, tracing on, the eve of identification (to queue for pass A), identification, end of quarantine
-        const int te = S.traceend[a];
-        if (te >= 0) {
-            const int latday = S.latday[a], ts = S.tracestart[a], idd = latday + te, tron = latday + ts;
-            if (ts < te && tron > day) ne = min(ne, tron);
-            if (idd - 1 > day) ne = min(ne, idd - 1);
-            if (idd > day) ne = min(ne, idd);
-            if (idd == day + 1) {                              // identifies tomorrow (:705): queue for pass A
-                const uint32_t slot = atomicAdd(&S.ident_cnt[r * 2 + ((day + 1) & 1)], 1u);
-                S.ident_list[((size_t)r * 2 + ((day + 1) & 1)) * S.Np + slot] = (uint32_t)i;
-            }
-        }
-        if (txp > day) ne = min(ne, txp);
-        // a post mark isolates after the budget draw of today (:778 saw the old iso): tomorrow's own step must see the new one
-        if (((st >> 19) ^ (st >> 20)) & 1u) ne = min(ne, day + 1);
-    }
-    S.expday[a] = (int16_t)ne;
-    if (st != st0) S.status[a] = st;
-    return (uint32_t)st_health(st);
+    if (e.texp != texp0) S.texp[a] = (int16_t)e.texp;
+    S.expday[a] = (int16_t)e.ne;
+    if (e.st != st0) S.status[a] = e.st;
+    return (uint32_t)e.newh;
 }
 
 __global__ void __launch_bounds__(256) k_time_update(const __grid_constant__ Dev S, int day, int any_ct) {

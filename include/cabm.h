@@ -106,8 +106,8 @@ enum { CABM_K_DYNTRANS = 0, CABM_K_TIME_UPDATE = 1, CABM_K_CT_IDENTIFY = 2, CABM
 int cabm_set_profiling(cabm_handle *h, int on);
 int cabm_get_profile(cabm_handle *h, float *ms /*[CABM_N_KCLASS]*/, int32_t *launches /*[CABM_N_KCLASS]*/);
 /* Execution path of cabm_run. FUSED: one persistent CTA per replicate runs all of main() with the per-agent state in
- * shared memory (needs ctstrat == 0, exact mode, popsize that fits ~21k agents). MULTIKERNEL: one launch per phase per
- * day over HBM-resident state (any popsize, contact tracing). AUTO (default) picks FUSED when eligible. Both give
+ * shared memory (needs the exact schedule and a popsize that fits, ~21k agents). MULTIKERNEL: one launch per phase per
+ * day over HBM-resident state (any popsize, exact or native schedule). AUTO (default) picks FUSED when eligible. Both give
  * bit-identical results. */
 enum { CABM_PATH_AUTO = 0, CABM_PATH_MULTIKERNEL = 1, CABM_PATH_FUSED = 2 };
 int cabm_set_path(cabm_handle *h, int path);

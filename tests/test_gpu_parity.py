@@ -50,8 +50,6 @@ CONFIGS = {
 def _cases():
     for name, kw in CONFIGS.items():
         for path in ("multikernel", "fused"):
-            if path == "fused" and kw.get("ctstrat", 0) != 0:
-                continue          # the fused kernel does not carry contact tracing (cabm.h CABM_PATH_*)
             yield pytest.param(name, path, id=f"{name}-{path}")
 
 
@@ -83,7 +81,8 @@ def test_main_bit_exact(cv, O, name, path, seed):
 def test_ensemble_fused_bit_exact(cv, O):
     """400 replicates (more than the resident CTAs: exercises the work queue) x 2 parameter sets, fused kernel."""
     a = cv.ModelParameters(β=0.0345, prov="ontario", modeltime=120, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3)
-    b = cv.ModelParameters(β=0.09, prov="quebec", modeltime=120, initialinf=4, initialhi=500, quar_grp_frac=0.4, quar_grp=2)
+    b = cv.ModelParameters(β=0.09, prov="quebec", modeltime=120, initialinf=4, initialhi=500, quar_grp_frac=0.4, quar_grp=2,
+                           ctstrat=3, strat3qdays=5, fctcapture=0.7, fcontactst=0.6, cdaysback=4, fmild=0.3, τmild=1)
     nrep = 400
     seeds = [726 * (i + 1) for i in range(nrep)]
     pof = [i % 2 for i in range(nrep)]
@@ -94,6 +93,7 @@ def test_ensemble_fused_bit_exact(cv, O):
     assert (got["hmatrix"] == ref["hmatrix"]).all()
     assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all()
     assert (got["infectors"] == ref["infectors"]).all()
+    assert (got["totalisolated"] == ref["totalisolated"]).all() and ref["totalisolated"].sum() > 0
     assert (got["lat_inc_sum"] == ref["inc"][:, 0, :, 1].sum(axis=1)).all()
 
 
