@@ -326,7 +326,7 @@ extern "C" int cabm_run(cabm_handle *h) {
     if (h->path == CABM_PATH_FUSED && !fused_ok) return fail(h, CABM_E_STATE, "fused path needs the exact schedule and a population that fits shared memory");
     h->last_path = use_fused ? CABM_PATH_FUSED : CABM_PATH_MULTIKERNEL;
     if (use_fused) {
-        timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->stream); });            // :104-142 in one launch
+        timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->any_ct != 0, h->stream); });            // :104-142 in one launch
     } else {
         timed(h, CABM_K_OTHER, [&] { return launch_initialize(S, h->stream); });                                   // :112
         timed(h, CABM_K_OTHER, [&] { return launch_insert_infected(S, 0, 0, 0, 0, 0, 0, h->stream); });            // :117/:119

@@ -85,6 +85,7 @@ __device__ __forceinline__ void bulk_store_wait_read_n() { asm volatile("cp.asyn
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+template <bool CT>      // CT = false: no replicate of the ensemble traces contacts (the tracing code is compiled out)
 __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = FUSED_NT, NW = FUSED_NT / 32;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid < (int)(sizeof(DevPset) / 4)) reinterpret_cast<uint32_t *>(&s_P)[tid] = reinterpret_cast<const uint32_t *>(&S.psets[S.pset_of[r]])[tid];
         __syncthreads();
         const DevPset &P = s_P;
-        const bool ctr = P.ctstrat != 0;              // this replicate traces contacts
+        const bool ctr = CT && P.ctstrat != 0;        // this replicate traces contacts
         if (tid == 0) { s_logn = 0; s_qcnt[0] = 0; s_qcnt[1] = 0; }
         const uint2 key = S.key[r];
         const size_t rb = (size_t)r * Np;
@@ -640,15 +641,21 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 
 size_t fused_smem_bytes_host(int Np) { return fused_smem_bytes(Np); }
 
-int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, cudaStream_t s) {
+int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, bool any_ct, cudaStream_t s) {
     const size_t bytes = fused_smem_bytes(S.Np);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_sim_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes > 200 * 1024 ? 227 * 1024 : 200 * 1024); attr_set = true; }
+    if (!attr_set) {
+        const int lim = (int)bytes > 200 * 1024 ? 227 * 1024 : 200 * 1024;
+        cudaFuncSetAttribute(k_sim_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(k_sim_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        attr_set = true;
+    }
     const int per_sm = bytes <= 113 * 1024 ? 2 : 1;
     int grid = n_sm * per_sm;
     if (grid > S.R) grid = S.R;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned), s);
-    k_sim_fused<<<grid, FUSED_NT, bytes, s>>>(S, work_counter);
+    if (any_ct) k_sim_fused<true><<<grid, FUSED_NT, bytes, s>>>(S, work_counter);
+    else k_sim_fused<false><<<grid, FUSED_NT, bytes, s>>>(S, work_counter);
     return 1;
 }
 

@@ -53,8 +53,10 @@ def run(name, ip, nrep, pof=None, mode=cv.MODE_EXACT, path="auto", store_hm=Fals
 
 B = dict(prov="ontario", initialinf=1, modeltime=500, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3, tpreiso=0)
 if "C" in which:
-    run("C ctstrat=1", cv.ModelParameters(β=0.0345, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000, path="multikernel")
-    run("C ctstrat=3 strat3qdays=14", cv.ModelParameters(β=0.0345, ctstrat=3, strat3qdays=14, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000, path="multikernel")
+    run("C ctstrat=1", cv.ModelParameters(β=0.0345, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000)
+    run("C ctstrat=3 strat3qdays=14", cv.ModelParameters(β=0.0345, ctstrat=3, strat3qdays=14, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000)
+    run("C ctstrat=1 (per-day kernels)", cv.ModelParameters(β=0.0345, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000, path="multikernel")
+    run("C ctstrat=1, beta=0.06 no isolation (larger epidemics)", cv.ModelParameters(β=0.06, prov="ontario", initialinf=1, modeltime=500, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3), 1000)
     run("C ctstrat=1 native", cv.ModelParameters(β=0.0345, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000, path="multikernel", mode=cv.MODE_NATIVE)
 if "D" in which:
     betas = np.linspace(0.0225, 0.085, 20)                     # scripts/local_run.jl:165 range, 20 points
