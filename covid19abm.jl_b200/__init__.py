@@ -34,7 +34,7 @@ FIELDS = {"health": 0, "swap": 1, "sickfrom": 2, "nextday_meetcnt": 3, "ag": 4, 
           "ncontacts": 15}
 ERR_BITS = {1: "swap expired, but no swap set.", 2: "No susceptibles in the population to change status",
             4: "a traced person should always be isolated until the trace is killed", 8: "empty age group sampled",
-            16: "contact log capacity exceeded", 32: "sickfrom not set right"}
+            16: "contact log capacity exceeded", 32: "sickfrom not set right", 64: "kernel implementation limit exceeded"}
 
 
 class CabmError(RuntimeError):

@@ -26,7 +26,7 @@ enum : int { SUS = 0, LAT, PRE, ASYMP, MILD, MISO, INF, IISO, HOS, ICU, REC, DED
 enum : int { VIA_NULL = 0, VIA_QU, VIA_PI, VIA_MI, VIA_CT };
 // draw-contract streams
 enum : uint32_t { S_INIT = 1, S_COUNT = 2, S_SEED = 3, S_TRANS = 4, S_CTWIN = 5, S_CTCON = 6, S_CT3 = 7, S_DT = 8 };
-enum : uint32_t { ERR_NO_SWAP = 1, ERR_NO_SUS = 2, ERR_TRACED_NOT_ISO = 4, ERR_EMPTY_GROUP = 8, ERR_CT_LOG_FULL = 16, ERR_SICKFROM = 32 };
+enum : uint32_t { ERR_NO_SWAP = 1, ERR_NO_SUS = 2, ERR_TRACED_NOT_ISO = 4, ERR_EMPTY_GROUP = 8, ERR_CT_LOG_FULL = 16, ERR_SICKFROM = 32, ERR_INTERNAL = 64 };
 
 constexpr uint32_t ST_ISO = 1u << 19, ST_ISOB = 1u << 20, ST_TRACING = 1u << 21;
 constexpr uint32_t ST_TAGMASK = 0xFFC00000u, ST_REMMASK = 0xFFu;

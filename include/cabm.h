@@ -30,7 +30,8 @@ enum { CABM_ERR_NO_SWAP = 1,        /* :418 "swap expired, but no swap set." */
        CABM_ERR_TRACED_NOT_ISO = 4, /* :719 */
        CABM_ERR_EMPTY_GROUP = 8,    /* rand(grps[i], g) on an empty group (:807 would throw) */
        CABM_ERR_CT_LOG_FULL = 16,   /* contact log capacity exceeded (implementation limit) */
-       CABM_ERR_SICKFROM = 32 };    /* :308 */
+       CABM_ERR_SICKFROM = 32,      /* :308 */
+       CABM_ERR_INTERNAL = 64 };    /* an implementation limit of a kernel was exceeded; results of that replicate are invalid */
 
 /* ModelParameters — src/covid19abm.jl:31-55, field for field.
  * prov_id indexes the rows of get_province_ag (:319-333): 0 alberta, 1 bc, 2 canada, 3 manitoba,
