@@ -237,10 +237,10 @@ __device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int
 struct Ev { uint32_t st; int texp, ne, oldh, newh; };
 
 __device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int i, int day, uint2 key, uint32_t st, int texp,
-                                      bool pre, bool post, uint32_t *queue_cnt /* tomorrow's index cases */, uint32_t *queue) {
+                                      bool ct /* the replicate traces contacts */, bool pre, bool post,
+                                      uint32_t *queue_cnt /* tomorrow's index cases */, uint32_t *queue) {
     const size_t a = (size_t)r * S.Np + i;
     int oldh = st_health(st), newh = oldh;
-    const bool ct = P.ctstrat != 0;
     int txp = 0, txp0 = 0;
     if (ct) {
         txp = txp0 = S.txpday[a];

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         M.lcnt = (uint8_t *)p; p += FUSED_LCAP;
         M.lE = (uint8_t *)p; p += FUSED_LCAP;
     }
-    __shared__ int s_r, s_off[8], s_wcnt[FUSED_NT / 32][5], s_base[5], s_total[5];
+    __shared__ int s_r, s_off[8], s_wcnt[FUSED_NT / 32][5];
     __shared__ int s_sel_tid, s_sel_k, s_Ltot, s_ninf;
     __shared__ int s_io[2][2][60];           // [day parity][entries | exits][(group, state)] — curve deltas of one day
     __shared__ uint32_t s_tlat[4], s_tpre[4], s_tasy[40], s_tinf[40];
@@ -190,58 +190,61 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         }
         for (int k = tid; k < nwords; k += NT) M.inf[k] = 0;
         if (tid < 240) (&s_io[0][0][0])[tid] = 0;
-        if (tid < 5) s_total[tid] = 0;
         if (tid < 4) s_infectors[tid] = 0;
         if (tid == 0) s_ninf = 0;
         __syncthreads();
 
         // ------------------------------------------------------------ get_ag_dist :339-343 (ordered counting sort)
+        // each warp owns a contiguous range of agents: count per group, one prefix over the warps, then every warp scatters
+        // its range in ascending order with warp-local bases — two block barriers in total
         {
+            const int per_warp = ((N + NW - 1) / NW + 31) & ~31, lo = wid * per_warp, hi = min(N, lo + per_warp);
             int c[5] = {0, 0, 0, 0, 0};
-            for (int i = tid; i < N; i += NT) c[st_ag(M.status[i])]++;
+            for (int i0 = lo; i0 < hi; i0 += 32) {
+                const int i = i0 + lane;
+                const int ag = (i < hi) ? st_ag(M.status[i]) : -1;
 #pragma unroll
-            for (int g = 0; g < 5; ++g) {
-                int v = c[g];
-                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                if (lane == 0) atomicAdd(&s_total[g], v);
+                for (int g = 0; g < 5; ++g) c[g] += __popc(__ballot_sync(FULL, ag == g));
             }
+            if (lane == 0) for (int g = 0; g < 5; ++g) s_wcnt[wid][g] = c[g];
             __syncthreads();
             if (tid == 0) {
                 int o = 0;
-                for (int g = 0; g < 5; ++g) { s_off[g] = o; s_base[g] = o; o += s_total[g]; }
+                for (int g = 0; g < 5; ++g) {
+                    s_off[g] = o;
+                    for (int w = 0; w < NW; ++w) { const int v = s_wcnt[w][g]; s_wcnt[w][g] = o; o += v; }      // start of warp w's slice of group g
+                }
                 s_off[5] = o;
             }
             __syncthreads();
-            for (int i0 = 0; i0 < N; i0 += NT) {
-                const int i = i0 + tid;
-                const int ag = (i < N) ? st_ag(M.status[i]) : -1;
-                unsigned m[5];
+            int base[5];
 #pragma unroll
-                for (int g = 0; g < 5; ++g) { m[g] = __ballot_sync(FULL, ag == g); if (lane == 0) s_wcnt[wid][g] = __popc(m[g]); }
-                __syncthreads();
-                if (ag >= 0) {
-                    int pos = s_base[ag];
-                    for (int w = 0; w < wid; ++w) pos += s_wcnt[w][ag];
-                    const unsigned mm = ag == 0 ? m[0] : ag == 1 ? m[1] : ag == 2 ? m[2] : ag == 3 ? m[3] : m[4];
-                    pos += __popc(mm & ((1u << lane) - 1u));
-                    M.grp[pos] = (uint16_t)i;
+            for (int g = 0; g < 5; ++g) base[g] = s_wcnt[wid][g];
+            for (int i0 = lo; i0 < hi; i0 += 32) {
+                const int i = i0 + lane;
+                const int ag = (i < hi) ? st_ag(M.status[i]) : -1;
+#pragma unroll
+                for (int g = 0; g < 5; ++g) {
+                    const unsigned m = __ballot_sync(FULL, ag == g);
+                    if (ag == g) M.grp[base[g] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                    base[g] += __popc(m);
                 }
-                __syncthreads();
-                if (tid < 5) { int s = 0; for (int w = 0; w < NW; ++w) s += s_wcnt[w][tid]; s_base[tid] += s; }
-                __syncthreads();
             }
         }
+        __syncthreads();
 
         // ------------------------------------------------------------ insert_infected :360-395 (PRE seeds, then REC seeds)
         for (int which = 0; which < 2; ++which) {
             if (which == 1 && P.calibration) break;                                          // :116-121
             const int health = which == 0 ? PRE : REC, num = which == 0 ? P.initialinf : P.initialhi;
+            if (which == 1 && num == 0 && N > P.initialinf) continue;                          // sample(l, 0) with l non-empty: nothing to do
             const int seg = (N + NT - 1) / NT, lo = tid * seg, hi = min(N, lo + seg);
             int mine = 0;
             for (int i = lo; i < hi; ++i) mine += (st_health(M.status[i]) == SUS);
             M.cnt[tid] = mine;
+            { int v = mine; for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0) s_wsum[wid] = v; }
             __syncthreads();
-            if (tid == 0) { int L = 0; for (int t = 0; t < NT; ++t) L += M.cnt[t]; s_Ltot = L; }
+            if (tid == 0) { int L = 0; for (int w = 0; w < NW; ++w) L += s_wsum[w]; s_Ltot = L; }
             __syncthreads();
             if (s_Ltot == 0 || num > s_Ltot) { if (tid == 0 && (num > 0 || s_Ltot == 0)) atomicOr(&S.err[r], ERR_NO_SUS); continue; }
             for (int j = 0; j < num; ++j) {
@@ -317,6 +320,24 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         __syncthreads();
         for (int day = 1; day <= T; ++day) {
             const bool active = s_ninf > 0 || day >= nextfire;                 // uniform: s_ninf only changes between S1 and S2
+            if (!active && nextfire > T) {
+                // nobody is infectious and no state expires before the end of the run: the remaining columns and curve rows
+                // repeat the current ones (tis >= exp :405 never fires again) — write them without stepping through the days
+                for (int d = day; d < T; ++d) {
+                    if (tid < 60) {
+                        const size_t b = (((size_t)r * 6 + (tid / 12 + 1)) * (size_t)T + (size_t)d) * 12 + tid % 12;
+                        S.inc[b] = 0; S.prev[b] = run;
+                    } else if (tid >= 64 && tid < 76) {
+                        const size_t b = (((size_t)r * 6 + 0) * (size_t)T + (size_t)d) * 12 + (tid - 64);
+                        S.inc[b] = 0; S.prev[b] = run;
+                    }
+                    if (hm) {
+                        if (tma_ok) { if (tid == 0) { bulk_store_wait_read_n(); bulk_store(hm + (size_t)d * N, M.col, (uint32_t)N); } }
+                        else for (int i = tid; i < N; i += NT) hm[(size_t)d * N + i] = M.col[i];
+                    }
+                }
+                break;
+            }
             if (active) {
                 // ---------------------------------------------------- dyntrans(st) :790-834
                 if (s_ninf > 0) {
@@ -542,7 +563,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const uint32_t st = M.status[i];
                             const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];      // without tracing the scan key is the expiry day
                             const int par = (day + 1) & 1;
-                            const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, (pre >> k) & 1u, (post >> k) & 1u,
+                            const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, ctr, (pre >> k) & 1u, (post >> k) & 1u,
                                                           &s_qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr);
                             M.status[i] = e.st;
                             M.expday[i] = (int16_t)e.ne;

@@ -482,7 +482,8 @@ __device__ __noinline__ uint32_t agent_event(const Dev &S, int r, int i, int day
     const uint32_t st0 = S.status[a];
     const int texp0 = S.texp[a];
     const int par = (day + 1) & 1;
-    const Ev e = agent_event_core(S, S.psets[S.pset_of[r]], r, i, day, S.key[r], st0, texp0, pre, post,
+    const DevPset &P = S.psets[S.pset_of[r]];
+    const Ev e = agent_event_core(S, P, r, i, day, S.key[r], st0, texp0, P.ctstrat != 0, pre, post,
                                   S.ident_cnt ? &S.ident_cnt[r * 2 + par] : nullptr, S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * S.Np : nullptr);
     if (e.newh != e.oldh) {
         if (is_infectious(e.newh) != is_infectious(e.oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
