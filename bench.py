@@ -99,7 +99,7 @@ def run_reference(args, rank, world, emit):
     value = args.steps * nrep * N_AGENTS * T_DAYS / tot
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32/i16 integer state, u32 Philox", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "replicates_per_step": nrep, "note": "CPU restatement of covid19abm.jl in C (oracle/), not Julia: no julia binary in the image"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{nrep} replicates per step, one per thread"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -266,7 +266,7 @@ def main():
         e2e = world * units * args.steps / (e2e_ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u32/i16 integer state, u32 Philox", "data": "synthetic",
+                "dtype": "u32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "replicates_per_gpu": R, "replicates_per_sec": world * R * args.steps / (dev_ms * 1e-3),
                            "mode": "exact (bit-identical to the sequential reference order)", "path": pop.last_path, "hmatrix_in_hbm": not args.no_hmatrix,
                            "l2": "inputs larger than L2: 0.3 GB of agent state + 5 GB state matrix + 0.3 GB curves written per step, rebuilt every step",
