@@ -157,6 +157,7 @@ def lib():
     L.cabm_get_curves.argtypes = [vp, vp, vp]
     L.cabm_get_curves_i16.argtypes = [vp, vp, vp]
     L.cabm_get_mean_curves.argtypes = [vp, vp, vp]
+    L.cabm_set_host_curves_i16.argtypes = [vp, vp, vp]
     L.cabm_get_scalars.argtypes = [vp, vp, vp, vp, vp]
     L.cabm_get_field.argtypes = [vp, i32, i32, vp]
     L.cabm_set_field.argtypes = [vp, i32, i32, i32, C.c_int32]
@@ -338,6 +339,11 @@ class Population:
         else:
             self._chk(self.L.cabm_get_curves(self.h, inc.ctypes.data, prev.ctypes.data))
         return inc, prev
+
+    def stream_curves_to(self, inc, prev):
+        """Register two PinnedArray-backed Int16 arrays [R][6][T][12]: the fused kernel writes each finished replicate's curves
+        into them directly; a later curves(inc, prev) with the same arrays costs only a synchronise. None, None unregisters."""
+        self._chk(self.L.cabm_set_host_curves_i16(self.h, None if inc is None else inc.ctypes.data, None if prev is None else prev.ctypes.data))
 
     def mean_curves(self):
         """compute_yearly_average (scripts/local_run.jl:75-103) on the device: (inc_mean, prev_mean) [6][T][12] float64."""

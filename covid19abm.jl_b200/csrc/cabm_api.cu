@@ -26,6 +26,7 @@ struct cabm_handle {
     unsigned *d_work = nullptr;        // work counter of the fused kernel
     int16_t *d_stage = nullptr; size_t stage_elems = 0;   // Int16 staging for hmatrix read-back
     int n_sm = 148, path = CABM_PATH_AUTO, last_path = 0;
+    int16_t *host_inc = nullptr, *host_prev = nullptr;   // registered by cabm_set_host_curves_i16
     int64_t launches = 0;
     bool ran = false;
     bool poked = false;                // state was edited through cabm_set_field: pass A falls back to the full scan
@@ -277,7 +278,7 @@ static int need_config(cabm_handle *h) {
     return CABM_OK;
 }
 
-static int reset_state(cabm_handle *h) {
+static int reset_state(cabm_handle *h, bool curves_too = true) {
     Dev &S = h->S;
     const size_t W = (size_t)S.R * S.nwords, C = (size_t)S.R * 6 * S.T * 12;
     CU(cudaMemsetAsync(S.mark_pre, 0, W * 4, h->stream)); CU(cudaMemsetAsync(S.mark_post, 0, W * 4, h->stream));
@@ -286,7 +287,7 @@ static int reset_state(cabm_handle *h) {
     h->poked = false;
     CU(cudaMemsetAsync(S.err, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totiso, 0, (size_t)S.R * 8, h->stream));
     CU(cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, h->stream));
-    CU(cudaMemsetAsync(S.inc, 0, C * 4, h->stream)); CU(cudaMemsetAsync(S.prev, 0, C * 4, h->stream));
+    if (curves_too) { CU(cudaMemsetAsync(S.inc, 0, C * 4, h->stream)); CU(cudaMemsetAsync(S.prev, 0, C * 4, h->stream)); }
     CU(cudaMemsetAsync(S.infectors, 0, (size_t)S.R * 32, h->stream)); CU(cudaMemsetAsync(S.latsum, 0, (size_t)S.R * 8, h->stream));
     h->day = 1;
     return CABM_OK;
@@ -317,13 +318,13 @@ extern "C" int cabm_run(cabm_handle *h) {
     int rc = need_config(h); if (rc) return rc;
     const Dev &S = h->S;
     h->pev_used = 0; h->pcls.clear();
-    CU(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = reset_state(h))) return rc;
     // The fused kernel keeps a replicate's hot state in shared memory: usable when it fits two CTAs per SM budget
     // (popsize <= ~21k agents) with the exact schedule; otherwise one kernel per phase per day.
     const bool fused_ok = h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 226 * 1024;
     const bool use_fused = h->path == CABM_PATH_FUSED ? fused_ok : (h->path == CABM_PATH_AUTO && fused_ok);
     if (h->path == CABM_PATH_FUSED && !fused_ok) return fail(h, CABM_E_STATE, "fused path needs the exact schedule and a population that fits shared memory");
+    CU(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = reset_state(h, /*curves_too=*/!use_fused))) return rc;      // the fused kernel writes every curve entry itself
     h->last_path = use_fused ? CABM_PATH_FUSED : CABM_PATH_MULTIKERNEL;
     if (use_fused) {
         timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->any_ct != 0, h->stream); });            // :104-142 in one launch
@@ -475,9 +476,31 @@ extern "C" int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev) {
     CU(cudaStreamSynchronize(h->stream));
     return CABM_OK;
 }
+extern "C" int cabm_set_host_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) {
+    if (!h) return CABM_E_ARG;
+    if ((inc == nullptr) != (prev == nullptr)) return fail(h, CABM_E_ARG, "cabm_set_host_curves_i16: give both buffers or neither");
+    if (inc) {
+        if (h->N > 32767) return fail(h, CABM_E_ARG, "Int16 curves need popsize <= 32767");
+        cudaPointerAttributes pa, pb;
+        CU(cudaPointerGetAttributes(&pa, inc)); CU(cudaPointerGetAttributes(&pb, prev));
+        if (pa.type != cudaMemoryTypeHost || pb.type != cudaMemoryTypeHost)
+            return fail(h, CABM_E_ARG, "cabm_set_host_curves_i16: buffers must be pinned host memory (cabm_host_alloc)");
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaHostGetDevicePointer((void **)&h->S.host_inc, inc, 0)); CU(cudaHostGetDevicePointer((void **)&h->S.host_prev, prev, 0));
+        h->host_inc = inc; h->host_prev = prev;
+    } else {
+        CU(cudaStreamSynchronize(h->stream));
+        h->S.host_inc = h->S.host_prev = nullptr; h->host_inc = h->host_prev = nullptr;
+    }
+    return CABM_OK;
+}
 extern "C" int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) {
     int rc = need_config(h); if (rc) return rc;
     if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");
+    if (inc && inc == h->host_inc && prev == h->host_prev && h->last_path == CABM_PATH_FUSED) {   // streamed there by the kernel already
+        CU(cudaStreamSynchronize(h->stream));
+        return CABM_OK;
+    }
     if (h->N > 32767) return fail(h, CABM_E_ARG, "cabm_get_curves_i16 needs popsize <= 32767");
     if (!inc || !prev) return fail(h, CABM_E_ARG, "cabm_get_curves_i16: bad argument");
     const size_t n = (size_t)h->n_rep * 6 * h->T * 12;

@@ -83,6 +83,8 @@ struct Dev {
     long long *infectors, *latsum;           // [R][4], [R]
     long long *dbg;                          // [R][16] per-phase cycle counts of the fused kernel (diagnostics)
     uint8_t *hm;                             // [R][T][N] health codes (widened to Int16 by cabm_get_hmatrix)
+    int16_t *host_inc, *host_prev;           // optional pinned host buffers [R][6][T][12]: the fused kernel streams each finished
+                                             // replicate's curves there (Int16) so no device->host copy is left at the end
     const DevPset *psets; const unsigned long long *beta_thr;    // [P], [P][T][4]
     const uint32_t *nb_thr; const uint8_t *nb_guide;             // [5][256], [5][256]
     const unsigned long long *gpw;                               // [5][256] five u8 counts packed

@@ -652,6 +652,19 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (bad) atomicOr(&S.err[r], ERR_SICKFROM);
         __syncthreads();
         if (tid < 4) S.infectors[r * 4 + tid] = s_infectors[tid];
+        if (S.host_inc) {                      // this replicate's curves -> pinned host memory, 16-byte posted writes over PCIe
+            __syncthreads();                   // the rows written during the day loop (by threads 0..75) are visible block-wide
+            const size_t per = (size_t)6 * T * 12;                 // multiple of 8
+            const int4 *gi = reinterpret_cast<const int4 *>(S.inc + (size_t)r * per), *gp = reinterpret_cast<const int4 *>(S.prev + (size_t)r * per);
+            uint4 *hi = reinterpret_cast<uint4 *>(S.host_inc + (size_t)r * per), *hp = reinterpret_cast<uint4 *>(S.host_prev + (size_t)r * per);
+            for (int k = tid; k < (int)(per / 8); k += NT) {
+                const int4 a = __ldcg(gi + 2 * k), b = __ldcg(gi + 2 * k + 1), c = __ldcg(gp + 2 * k), e = __ldcg(gp + 2 * k + 1);
+                hi[k] = make_uint4((uint32_t)(a.x & 0xFFFF) | ((uint32_t)a.y << 16), (uint32_t)(a.z & 0xFFFF) | ((uint32_t)a.w << 16),
+                                   (uint32_t)(b.x & 0xFFFF) | ((uint32_t)b.y << 16), (uint32_t)(b.z & 0xFFFF) | ((uint32_t)b.w << 16));
+                hp[k] = make_uint4((uint32_t)(c.x & 0xFFFF) | ((uint32_t)c.y << 16), (uint32_t)(c.z & 0xFFFF) | ((uint32_t)c.w << 16),
+                                   (uint32_t)(e.x & 0xFFFF) | ((uint32_t)e.y << 16), (uint32_t)(e.z & 0xFFFF) | ((uint32_t)e.w << 16));
+            }
+        }
         // diagnostics of the fused path: kilo-cycles spent on this replicate and dyntrans batches issued
         PHASE(6);
         if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; for (int k = 0; k < 16; ++k) S.dbg[(size_t)r * 16 + k] = t_ph[k]; }

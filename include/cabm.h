@@ -143,6 +143,10 @@ int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev);
 /* compute_yearly_average (scripts/local_run.jl:75-103): the mean over all replicates of every curve entry, reduced on the
  * device: inc_mean and prev_mean are double [6][modeltime][12] */
 int cabm_get_mean_curves(cabm_handle *h, double *inc_mean, double *prev_mean);
+/* Optional: register two pinned host buffers (cabm_host_alloc) of [max_replicates][6][modeltime][12] Int16. The fused kernel
+ * then writes every finished replicate's curves straight into them while the other replicates are still running, and a
+ * following cabm_get_curves_i16 with the same pointers only synchronises. Pass NULL, NULL to unregister. */
+int cabm_set_host_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev);
 /* infectors = _count_infectors() :295-313 [n_rep][4]; totalisolated = ct_data.totalisolated :61,649 [n_rep];
  * lat_inc_sum = sum(_get_column_incidence(h, LAT)) (scripts/local_run.jl:143) [n_rep]; err = CABM_ERR_* bits.
  * Any pointer may be NULL. */

@@ -217,3 +217,43 @@ def test_local_run_outputs(cv, O, tmp_path):
     assert m == v.mean() and abs(sd - v.std(ddof=1)) < 1e-12
     a, b, betas, ros = cv.local_run.calibrate_regression(betas=[0.03, 0.05, 0.07], nsims=200, prov="newyork")
     assert 30 < b < 60 and abs(a) < 0.6        # the author's fit: R0 = 46.1761 beta - 0.00285 (scripts/local_run.jl:174)
+
+
+def test_curves_streamed_to_pinned_host_memory(cv):
+    """cabm_set_host_curves_i16: the fused kernel writes finished replicates' curves into registered pinned buffers."""
+    ip = cv.ModelParameters(β=0.15, prov="ontario", modeltime=90, initialinf=4, fmild=0.4, τmild=1)
+    R = 300
+    with cv.Population(R, ip.popsize, ip.modeltime) as pop:
+        a, b = cv.PinnedArray((R, 6, 90, 12), np.int16), cv.PinnedArray((R, 6, 90, 12), np.int16)
+        a.array[:] = -1; b.array[:] = -1
+        pop.stream_curves_to(a.array, b.array)
+        pop.configure(ip, [3 * (i + 1) for i in range(R)])
+        pop.run()
+        assert pop.last_path == "fused"
+        inc, prev = pop.curves()                                  # ordinary int32 read-back
+        assert (a.array == inc).all() and (b.array == prev).all()
+        c, d = pop.curves(a.array, b.array)                        # same pointers: synchronise only
+        assert (c == inc).all() and (d == prev).all()
+        pop.stream_curves_to(None, None)
+        pop.configure(ip, [5 * (i + 1) for i in range(R)])
+        pop.run()
+        inc2, _ = pop.curves()
+        assert (a.array == inc).all() and (inc2 != inc).any()    # unregistered: the old buffers are left alone
+        a.free(); b.free()
+
+
+def test_handle_reuse_leaves_no_residue(cv):
+    """A handle is reconfigured and rerun many times (bench.py, β sweeps): results must not depend on what ran before."""
+    a = cv.ModelParameters(β=0.3, prov="ontario", modeltime=70, initialinf=8, ctstrat=1, fctcapture=0.9, fcontactst=0.9, cdaysback=3)
+    b = cv.ModelParameters(β=0.04, prov="bc", modeltime=70, initialinf=1)
+    seeds = [9 * (i + 1) for i in range(40)]
+    fresh = cv.run_ensemble(b, 40, seeds=seeds)
+    with cv.Population(64, 10000, 70) as pop:
+        for path in ("fused", "multikernel", "fused"):
+            pop.set_path(path)
+            pop.configure(a, [5 * (i + 1) for i in range(64)]); pop.run()
+            pop.configure(b, seeds); pop.run()
+            inc, prev = pop.curves()
+            sc = pop.scalars()
+            assert (inc == fresh["inc"]).all() and (prev == fresh["prev"]).all(), path
+            assert (sc["infectors"] == fresh["infectors"]).all() and (sc["totalisolated"] == 0).all() and (sc["err"] == 0).all()
