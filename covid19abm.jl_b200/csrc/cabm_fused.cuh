@@ -18,6 +18,7 @@
 // before the first infector that an earlier infector of the same batch contacts (its budget :802 would change), and
 // events that share a target are resolved in event order by the lowest event of the group.
 #pragma once
+#include <cstdlib>
 
 namespace cabm {
 
@@ -684,7 +685,8 @@ int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, bool any_ct
         cudaFuncSetAttribute(k_sim_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         attr_set = true;
     }
-    const int per_sm = bytes <= 113 * 1024 ? 2 : 1;
+    int per_sm = bytes <= 113 * 1024 ? 2 : 1;
+    if (const char *e = getenv("CABM_FUSED_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
     int grid = n_sm * per_sm;
     if (grid > S.R) grid = S.R;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned), s);
