@@ -37,9 +37,8 @@ def run(name, ip, nrep, pof=None, mode=cv.MODE_EXACT, path="auto", store_hm=Fals
         out["kernels"] = {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in pr.items() if v[1]}
         if pr["time_update"][1]:
             ct = any(p.ctstrat for p in (ip if isinstance(ip, list) else [ip]))
-            # k_time_update: expday 2 r (+ previous column 1 r + next column 1 w); k_time_update_ct: status 4 + expday 2 + latday/tracestart/
-            # traceend/tracedxp 8 + isovia 1 r (+ column 1 w)
-            bpd = (15 + (1 if store_hm else 0)) if ct else (2 + (2 if store_hm else 0))
+            # k_time_update: next-event day 2 r (+ previous column 1 r + next column 1 w; + 0.25 B of mark bits with tracing)
+            bpd = 2 + (2 if store_hm else 0) + (0.25 if ct else 0)
             tu = pr["time_update"]
             gbs = bpd * nrep * first.popsize / (tu[0] / tu[1] * 1e-3) / 1e9
             out["time_update_roofline"] = {"bytes_per_agent_day": bpd, "achieved_GBps": round(gbs, 1), "frac_of_measured_hbm_peak": round(gbs / peak, 4)}
@@ -56,6 +55,7 @@ if "C" in which:
     run("C ctstrat=1", cv.ModelParameters(β=0.0345, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000)
     run("C ctstrat=3 strat3qdays=14", cv.ModelParameters(β=0.0345, ctstrat=3, strat3qdays=14, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000)
     run("C ctstrat=1 (per-day kernels)", cv.ModelParameters(β=0.0345, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000, path="multikernel")
+    run("B (per-day kernels)", cv.ModelParameters(β=0.0345, **B), 1000, path="multikernel", store_hm=True)
     run("C ctstrat=1, beta=0.06 no isolation (larger epidemics)", cv.ModelParameters(β=0.06, prov="ontario", initialinf=1, modeltime=500, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3), 1000)
     run("C ctstrat=1 native", cv.ModelParameters(β=0.0345, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000, path="multikernel", mode=cv.MODE_NATIVE)
 if "D" in which:
