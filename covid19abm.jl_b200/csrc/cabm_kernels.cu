@@ -582,14 +582,6 @@ __global__ void k_mean_curves(const int *inc, const int *prev, double *minc, dou
     minc[e] = (double)a / (double)R; mprev[e] = (double)b / (double)R;
 }
 
-// clears the pass-A marks after time_update consumed them
-__global__ void k_clear_marks(Dev S) {
-    const size_t n = (size_t)S.R * S.nwords;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        S.mark_pre[i] = 0; S.mark_post[i] = 0;
-    }
-}
-
 // ============================================================================ curves: :259-293 from the transition counters
 // During the run inc[r][g][t][s] counted entries into s first visible in column t and prev[] parked the exits.
 // Every state is entered at most once per agent (SUS->LAT->PRE|ASYMP->...->REC|DED), so first-occurrence incidence
@@ -775,7 +767,6 @@ int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStre
     if (day == 1) { k_resync_isob<<<148 * 8, 256, 0, s>>>(S); ++n; }
     return n;
 }
-int launch_clear_marks(const Dev &S, cudaStream_t s) { k_clear_marks<<<296, 256, 0, s>>>(S); return 1; }
 int launch_curves_finalize(const Dev &S, cudaStream_t s) { k_curves_finalize<<<S.R, 64, 0, s>>>(S); return 1; }
 int launch_count_infectors(const Dev &S, cudaStream_t s) { k_count_infectors<<<S.R, 256, 0, s>>>(S); return 1; }
 int launch_reduce_hmatrix(const int16_t *hm, const int *ags, int M, int N, int T, int *inc, int *prev, cudaStream_t s) {
