@@ -146,11 +146,18 @@ __device__ __forceinline__ void curve_move(const Dev &S, int r, int ag0, int col
 // `day` is st; for seeding it is 0.
 struct Tr { uint32_t st; int expday; int oldh, newh; };
 
+constexpr int DUR_CACHE = 256;          // direct-mapped shared-memory cache of `dur` words for infected agents (fused kernel)
+
 __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
-                                     int target /* swap to apply */, bool seed_simple_inf) {
+                                     int target /* swap to apply */, bool seed_simple_inf, unsigned long long *dcache = nullptr) {
     size_t a = (size_t)r * S.Np + i;
     const int oldh = st_health(st), ag = st_ag(st);
-    const uint32_t d4 = S.dur[a];
+    uint32_t d4;
+    if (dcache) {                        // (agent << 32 | dur) — filled when the agent is infected, so the HBM load is off this path
+        const unsigned long long e = dcache[i & (DUR_CACHE - 1)];
+        if ((uint32_t)(e >> 32) == (uint32_t)i) d4 = (uint32_t)e;
+        else { d4 = S.dur[a]; dcache[i & (DUR_CACHE - 1)] = ((unsigned long long)(uint32_t)i << 32) | d4; }
+    } else d4 = S.dur[a];
     const int d_lat = d4 & 0xFF, d_asy = (d4 >> 8) & 0xFF, d_pre = (d4 >> 16) & 0xFF, d_inf = d4 >> 24;
     bool iso = st & ST_ISO;
     int via = -1;                       // -1: unchanged
@@ -240,7 +247,7 @@ struct Ev { uint32_t st; int texp, ne, oldh, newh; };
 
 __device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int i, int day, uint2 key, uint32_t st, int texp,
                                       bool ct /* the replicate traces contacts */, bool pre, bool post,
-                                      uint32_t *queue_cnt /* tomorrow's index cases */, uint32_t *queue) {
+                                      uint32_t *queue_cnt /* tomorrow's index cases */, uint32_t *queue, unsigned long long *dcache = nullptr) {
     const size_t a = (size_t)r * S.Np + i;
     int oldh = st_health(st), newh = oldh;
     int txp = 0, txp0 = 0;
@@ -253,7 +260,7 @@ __device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int
         }
     }
     if (texp <= day || (st_health(st) == SUS && st_swap(st) == LAT)) {      // :405 (an infection today set exp = tis :826)
-        const Tr t = transition_core(S, P, r, i, day, st, key, st_swap(st), false);
+        const Tr t = transition_core(S, P, r, i, day, st, key, st_swap(st), false, dcache);
         st = t.st; texp = t.expday; oldh = t.oldh; newh = t.newh;
     }
     int ne = texp;

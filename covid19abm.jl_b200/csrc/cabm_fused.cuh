@@ -25,12 +25,14 @@ namespace cabm {
 constexpr int FUSED_NT = 256;          // threads per CTA = max events per batch
 constexpr int FUSED_NCAND = 32;        // infectors per batch
 constexpr int FUSED_LCAP = 256;        // infectors listed per pass (more are handled in further passes)
+static_assert(FUSED_NT == 256 && FUSED_LCAP <= FUSED_NT, "thread-index roles in k_sim_fused are laid out for 256 threads");
 
 struct FusedSmem {
     uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
     uint32_t *nb_thr; uint8_t *nb_guide;
     uint32_t *Y, *W1; uint8_t *Q; uint32_t *touch, *dupm, *mpre, *mpost; uint16_t *D;
     uint16_t *list; uint8_t *lcnt, *lE;  // the day's ordered infectious agents, their contact budgets and event counts
+    unsigned long long *dcache;          // (agent << 32 | dur) of recently infected agents
     int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
 };
 
@@ -45,6 +47,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int Np) {
     b += (size_t)(Np / 32) * 4 * 4;      // touch, dupm, mark_pre, mark_post bitmasks
     b += FUSED_NT * 2;                   // D (compacted duplicate events)
     b += FUSED_LCAP * 4;                 // list, lcnt, lE
+    b += DUR_CACHE * 8;                  // dcache
     return (b + 15) / 16 * 16 + 64;
 }
 
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     FusedSmem M;
     {
         unsigned char *p = smem_raw;
+        M.dcache = (unsigned long long *)p; p += DUR_CACHE * 8;
         M.status = (uint32_t *)p; p += (size_t)Np * 4;
         M.expday = (int16_t *)p; p += (size_t)Np * 2;
         M.grp = (uint16_t *)p; p += (size_t)Np * 2;
@@ -190,7 +194,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             S.tracestart[a] = -1; S.traceend[a] = -1; S.txpday[a] = 0; S.ct_head[a] = CT_NONE;
         }
         for (int k = tid; k < nwords; k += NT) M.inf[k] = 0;
-        if (tid < 240) (&s_io[0][0][0])[tid] = 0;
+        for (int k = tid; k < DUR_CACHE; k += NT) M.dcache[k] = ~0ull;
+        for (int k = tid; k < 240; k += NT) (&s_io[0][0][0])[k] = 0;
         if (tid < 4) s_infectors[tid] = 0;
         if (tid == 0) s_ninf = 0;
         __syncthreads();
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         const uint32_t st = M.status[i];
                         if (st_health(st) != SUS) continue;
                         if (k-- > 0) continue;
-                        const Tr t = transition_core(S, P, r, i, 0, st, key, health, true);
+                        const Tr t = transition_core(S, P, r, i, 0, st, key, health, true, M.dcache);
                         M.status[i] = (t.st & ~ST_ISOB) | (st & ST_ISOB);    // day-1 budget was drawn with the old iso (:186)
                         M.expday[i] = (int16_t)t.expday;
                         if (ctr) S.texp[rb + i] = (int16_t)t.expday;
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             PHASE(8);
                             const int nb = s_nb, Etot = s_pref[nb];
                             // (b) one contact event per thread: target draw (:807), transmission word (:823); mark the target
-                            uint32_t y = 0, w1 = 0, sy = 0; int q = 0, remy = 0; bool ev = tid < Etot;
+                            uint32_t y = 0, w1 = 0, sy = 0, dury = 0; int q = 0, remy = 0; bool ev = tid < Etot;
                             if (ev) {
                                 int lo = 0, hi = nb - 1;                               // last q with pref[q] <= tid
                                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= tid) lo = mid; else hi = mid - 1; }
@@ -439,6 +444,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
                                     y = M.grp[go + below(w.x, len)]; w1 = w.y;
                                     sy = M.status[y];                              // stable until the apply phase of this batch
+                                    dury = __ldg(&S.dur[rb + y]);                  // in flight during the next phases; kept only if y gets infected
                                     remy = budget_of_s(M, key, y, day, sy);        // :811, the target's budget (lazy draw on first touch)
                                     // an infector later in this batch that gets contacted must re-read its budget: cut the batch there
                                     if ((int)y > x && (int)y <= s_cand[nb - 1] && ((M.inf[y >> 5] >> (y & 31)) & 1u)) {
@@ -499,6 +505,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                         ns = st_set_swap(ns, LAT);
                                         S.sickfrom[rb + y] = (uint8_t)xh_inf;
                                         M.expday[y] = (int16_t)day;                // y.exp = y.tis :826 — fires in today's time_update
+                                        M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
                                     }
                                     M.status[y] = ns;
                                 }
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];      // without tracing the scan key is the expiry day
                             const int par = (day + 1) & 1;
                             const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, ctr, (pre >> k) & 1u, (post >> k) & 1u,
-                                                          &s_qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr);
+                                                          &s_qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr, M.dcache);
                             M.status[i] = e.st;
                             M.expday[i] = (int16_t)e.ne;
                             if (ctr && e.texp != texp) S.texp[rb + i] = (int16_t)e.texp;
