@@ -320,7 +320,7 @@ extern "C" int cabm_run(cabm_handle *h) {
     h->pev_used = 0; h->pcls.clear();
     // The fused kernel keeps a replicate's hot state in shared memory: usable when it fits two CTAs per SM budget
     // (popsize <= ~21k agents) with the exact schedule; otherwise one kernel per phase per day.
-    const bool fused_ok = h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 226 * 1024;
+    const bool fused_ok = h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 227 * 1024 - 4096;
     const bool use_fused = h->path == CABM_PATH_FUSED ? fused_ok : (h->path == CABM_PATH_AUTO && fused_ok);
     if (h->path == CABM_PATH_FUSED && !fused_ok) return fail(h, CABM_E_STATE, "fused path needs the exact schedule and a population that fits shared memory");
     CU(cudaEventRecord(h->ev0, h->stream));

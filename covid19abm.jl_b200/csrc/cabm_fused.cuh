@@ -687,7 +687,7 @@ int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, bool any_ct
     const size_t bytes = fused_smem_bytes(S.Np);
     static bool attr_set = false;
     if (!attr_set) {
-        const int lim = (int)bytes > 200 * 1024 ? 227 * 1024 : 200 * 1024;
+        const int lim = 227 * 1024 - 4096;       // the opt-in maximum per CTA minus this kernel's static shared memory
         cudaFuncSetAttribute(k_sim_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         cudaFuncSetAttribute(k_sim_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         attr_set = true;

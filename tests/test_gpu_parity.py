@@ -257,3 +257,22 @@ def test_handle_reuse_leaves_no_residue(cv):
             sc = pop.scalars()
             assert (inc == fresh["inc"]).all() and (prev == fresh["prev"]).all(), path
             assert (sc["infectors"] == fresh["infectors"]).all() and (sc["totalisolated"] == 0).all() and (sc["err"] == 0).all()
+
+
+@pytest.mark.parametrize("n", [12000, 20000])
+def test_fused_one_cta_per_sm_populations(cv, O, n):
+    """Populations between ~10.4k and ~21k agents still fit shared memory, one CTA per SM instead of two."""
+    ip = cv.ModelParameters(β=0.08, prov="ontario", popsize=n, modeltime=60, initialinf=6, fmild=0.4, τmild=1,
+                            ctstrat=1, fctcapture=0.6, fcontactst=0.6, cdaysback=3)
+    got = cv.run_ensemble(ip, 3, seeds=[21, 22, 23], want_hmatrix=True, path="fused")
+    assert got["path"] == "fused"
+    ref = O.run_ensemble([to_oracle(O, ip)], [0, 0, 0], [21, 22, 23], nthreads=3, want_hmatrix=True)
+    assert (got["hmatrix"] == ref["hmatrix"]).all() and (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all()
+    assert (got["totalisolated"] == ref["totalisolated"]).all()
+
+
+def test_fused_refuses_populations_that_do_not_fit(cv):
+    ip = cv.ModelParameters(β=0.08, prov="ontario", popsize=40000, modeltime=20)
+    with pytest.raises(cv.CabmError, match="fused path needs"):
+        cv.run_ensemble(ip, 1, path="fused")
+    assert cv.run_ensemble(ip, 1)["path"] == "multikernel"            # auto falls back to the per-day kernels
