@@ -90,7 +90,7 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <bool CT>      // CT = false: no replicate of the ensemble traces contacts (the tracing code is compiled out)
-__global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work_counter) {
+__global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work /* [0] fresh head, [1] resume head, [2] resume tail, [3] fresh jobs done */, int split_day) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = FUSED_NT, NW = FUSED_NT / 32;
     const int N = S.N, Np = S.Np, T = S.T, nwords = S.nwords;
@@ -146,12 +146,37 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     __syncthreads();
     const bool tma_ok = S.store_hm && (N % 16 == 0);     // cp.async.bulk needs 16-byte size and alignment
 
+    // Two sweeps over an atomic work queue. Sweep 0 starts every replicate; with split_day > 0 a replicate that is still active
+    // after split_day days is parked (state to HBM) and queued, so that the long epidemics — which bound the launch — all resume
+    // early in sweep 1 instead of starting whenever the fresh queue happens to reach them. Everything else finishes in sweep 0.
+    for (int sweep = 0; sweep < 2; ++sweep) {
+    if (sweep == 1 && split_day <= 0) break;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_r = (int)atomicAdd(work_counter, 1u);
+        if (tid == 0) {
+            int got = -1;
+            if (sweep == 0) { const unsigned k = atomicAdd(&work[0], 1u); if (k < (unsigned)S.R) got = (int)k; }
+            else {
+                for (;;) {          // pop a parked replicate; wait while fresh jobs that might still park one are in flight
+                    const unsigned done = *(volatile unsigned *)&work[3];
+                    __threadfence();
+                    const unsigned t = *(volatile unsigned *)&work[2], h = *(volatile unsigned *)&work[1];
+                    if (h < t) {
+                        if (atomicCAS(&work[1], h, h + 1) == h) {
+                            while ((got = *(volatile int *)&S.resume_list[h]) < 0) __nanosleep(100);
+                            break;
+                        }
+                    } else if (done >= (unsigned)S.R) break;
+                    else __nanosleep(500);
+                }
+                __threadfence();
+            }
+            s_r = got;
+        }
         __syncthreads();
         const int r = s_r;
-        if (r >= S.R) break;
+        if (r < 0) break;
+        const bool resumed = sweep == 1;
         const long long t_start = clock64();
         long long t_ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = t_start;   // per-phase cycles seen by thread 0 (diagnostics)
 #define PHASE(k) do { const long long t_now_ = clock64(); t_ph[k] += t_now_ - t_last; t_last = t_now_; } while (0)
@@ -166,6 +191,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         const unsigned long long *beta = S.beta_thr + (size_t)S.pset_of[r] * T * 4;
         uint8_t *hm = S.store_hm ? S.hm + (size_t)r * T * N : nullptr;
 
+        int run = 0;
+        long long latsum = 0;
+        int g0_in = 0;
+        if (!resumed) {
         // ------------------------------------------------------------ initialize :171-188
         for (int i = tid; i < Np; i += NT) {
             const size_t a = rb + i;
@@ -291,7 +320,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             if (h != SUS) { atomicAdd(&s_inc[st_ag(st) * 12 + h], 1); atomicAdd(&s_out[st_ag(st) * 12 + SUS], 1); }
         }
         __syncthreads();
-        int run = 0;                              // running prevalence of (group, state) = (tid/12, tid%12), tid < 60; group 0 in tid 64..75
+        run = 0;                                  // running prevalence of (group, state) = (tid/12, tid%12), tid < 60; group 0 in tid 64..75
         if (tid < 60) {
             const int g = tid / 12, s = tid % 12;
             run = s_inc[tid] + (s == SUS ? (s_off[g + 1] - s_off[g]) - s_out[tid] : 0);
@@ -300,8 +329,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             M.cnt[tid] = run;
         }
         __syncthreads();
-        long long latsum = 0;
-        int g0_in = 0;
         if (tid >= 64 && tid < 76) {
             const int s = tid - 64;
             for (int g = 0; g < 5; ++g) run += M.cnt[g * 12 + s];
@@ -317,14 +344,38 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         }
         __syncthreads();
 
+        } else {
+            // ---------------------------------------------------------- resume a parked replicate: reload the shared-memory state
+            for (int i = tid; i < Np; i += NT) {
+                const uint32_t st = __ldcg(&S.status[rb + i]);           // written by another CTA of this launch: read through L2
+                M.status[i] = st; M.expday[i] = __ldcg(&S.expday[rb + i]); M.col[i] = (uint8_t)st_health(st);
+                M.grp[i] = (uint16_t)__ldcg(&S.grp_idx[rb + i]);
+            }
+            for (int k = tid; k < nwords; k += NT) M.inf[k] = __ldcg(&S.infmask[(size_t)r * nwords + k]);
+            for (int k = tid; k < DUR_CACHE; k += NT) M.dcache[k] = ~0ull;
+            for (int k = tid; k < 240; k += NT) (&s_io[0][0][0])[k] = 0;
+            if (tid < 6) s_off[tid] = __ldcg(&S.grp_off[r * 8 + tid]);
+            if (tid < 4) s_infectors[tid] = 0;
+            if (tid == 0) {
+                s_ninf = __ldcg(&S.resume_aux[r * 2 + 1]);
+                if (ctr) { s_logn = __ldcg(&S.ct_cnt[r]); s_qcnt[0] = __ldcg(&S.ident_cnt[r * 2]); s_qcnt[1] = __ldcg(&S.ident_cnt[r * 2 + 1]); }
+            }
+            if (tid < 60) run = __ldcg(&S.prev[(((size_t)r * 6 + (tid / 12 + 1)) * (size_t)T + (size_t)split_day) * 12 + tid % 12]);
+            else if (tid >= 64 && tid < 76) run = __ldcg(&S.prev[(((size_t)r * 6 + 0) * (size_t)T + (size_t)split_day) * 12 + (tid - 64)]);
+            if (tid == 64 + LAT) latsum = __ldcg(&S.latsum[r]);
+            __syncthreads();
+        }
         PHASE(0);
         // ============================================================ the day loop :131-140
         // s_nextfire = earliest expiry day of any agent. A day with nobody infectious and nothing expiring changes no
         // state: it only repeats the column and the prevalence row, without a single barrier.
         if (tid < 2) s_nf[tid] = 32767;
-        int nextfire = 0, act = 0;                                             // uniform registers
+        int nextfire = resumed ? __ldcg(&S.resume_aux[r * 2]) : 0, act = 0;    // uniform registers
+        const int day_first = resumed ? split_day + 1 : 1;
+        const int day_last = (!resumed && split_day > 0 && split_day < T) ? split_day : T;
+        bool finished = day_last == T;                                         // set early by the fast-forward below
         __syncthreads();
-        for (int day = 1; day <= T; ++day) {
+        for (int day = day_first; day <= day_last; ++day) {
             const bool active = s_ninf > 0 || day >= nextfire;                 // uniform: s_ninf only changes between S1 and S2
             if (!active && nextfire > T) {
                 // nobody is infectious and no state expires before the end of the run: the remaining columns and curve rows
@@ -342,6 +393,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         else for (int i = tid; i < N; i += NT) hm[(size_t)d * N + i] = M.col[i];
                     }
                 }
+                finished = true;
                 break;
             }
             if (active) {
@@ -639,6 +691,30 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         }
         __syncthreads();
 
+        if (!finished) {
+            // ---------------------------------------------------------- park: still active after split_day days -> state to HBM, queue for sweep 1
+            for (int i = tid; i < Np; i += NT) {
+                S.status[rb + i] = M.status[i]; S.expday[rb + i] = M.expday[i]; S.grp_idx[rb + i] = M.grp[i];
+            }
+            for (int k = tid; k < nwords; k += NT) S.infmask[(size_t)r * nwords + k] = M.inf[k];
+            if (tid < 6) S.grp_off[r * 8 + tid] = s_off[tid];
+            if (tid == 64 + LAT) S.latsum[r] = latsum;
+            if (tid == 0) {
+                S.resume_aux[r * 2] = nextfire; S.resume_aux[r * 2 + 1] = s_ninf;
+                if (ctr) { S.ct_cnt[r] = s_logn; S.ident_cnt[r * 2] = s_qcnt[0]; S.ident_cnt[r * 2 + 1] = s_qcnt[1]; }
+                if (hm && tma_ok) bulk_store_wait_all();
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned slot = atomicAdd(&work[2], 1u);
+                __threadfence();
+                *(volatile int *)&S.resume_list[slot] = r;
+                __threadfence();
+                atomicAdd(&work[3], 1u);
+            }
+            continue;
+        }
         // ------------------------------------------------------------ final state back to HBM, _count_infectors :295-313
         if (tid == 64 + LAT) S.latsum[r] = latsum;
         int l[4] = {0, 0, 0, 0};
@@ -678,12 +754,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; for (int k = 0; k < 16; ++k) S.dbg[(size_t)r * 16 + k] = t_ph[k]; }
 #undef PHASE
         if (hm && tma_ok && tid == 0) bulk_store_wait_all();
+        if (!resumed && tid == 0) { __threadfence(); atomicAdd(&work[3], 1u); }
+    }
     }
 }
 
 size_t fused_smem_bytes_host(int Np) { return fused_smem_bytes(Np); }
 
-int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, bool any_ct, cudaStream_t s) {
+int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaStream_t s) {
     const size_t bytes = fused_smem_bytes(S.Np);
     static bool attr_set = false;
     if (!attr_set) {
@@ -696,9 +774,14 @@ int launch_sim_fused(const Dev &S, unsigned *work_counter, int n_sm, bool any_ct
     if (const char *e = getenv("CABM_FUSED_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
     int grid = n_sm * per_sm;
     if (grid > S.R) grid = S.R;
-    cudaMemsetAsync(work_counter, 0, sizeof(unsigned), s);
-    if (any_ct) k_sim_fused<true><<<grid, FUSED_NT, bytes, s>>>(S, work_counter);
-    else k_sim_fused<false><<<grid, FUSED_NT, bytes, s>>>(S, work_counter);
+    // park-and-resume only pays when there are more replicates than resident CTAs and the run is long
+    int split_day = (S.R > grid && S.T >= 150) ? 60 : 0;
+    if (const char *e = getenv("CABM_FUSED_SPLIT_DAY")) split_day = atoi(e);
+    if (split_day >= S.T) split_day = 0;
+    cudaMemsetAsync(work, 0, 4 * sizeof(unsigned), s);
+    if (split_day > 0) cudaMemsetAsync(S.resume_list, 0xFF, (size_t)S.R * sizeof(int), s);
+    if (any_ct) k_sim_fused<true><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day);
+    else k_sim_fused<false><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day);
     return 1;
 }
 
