@@ -15,7 +15,7 @@ from dataclasses import dataclass, fields
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcabm_b200.so")
+LIB_PATH = os.environ.get("CABM_LIB", os.path.join(_HERE, "libcabm_b200.so"))     # CABM_LIB: e.g. the diagnostics build
 
 PROVINCES = ("alberta", "bc", "canada", "manitoba", "newbruns", "newfdland", "nwterrito", "novasco",
              "nunavut", "ontario", "pei", "quebec", "saskat", "yukon", "newyork")     # order of :319-333

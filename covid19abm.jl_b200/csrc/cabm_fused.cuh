@@ -177,10 +177,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         const int r = s_r;
         if (r < 0) break;
         const bool resumed = sweep == 1;
+#ifdef CABM_FUSED_DIAG      // per-phase cycle counts seen by thread 0 (make diag; tools/diag_fused.py)
         const long long t_start = clock64();
-        long long t_ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = t_start;   // per-phase cycles seen by thread 0 (diagnostics)
+        long long t_ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = t_start;
 #define PHASE(k) do { const long long t_now_ = clock64(); t_ph[k] += t_now_ - t_last; t_last = t_now_; } while (0)
         int n_rounds = 0;
+#else
+#define PHASE(k) do { } while (0)
+#endif
         if (tid < (int)(sizeof(DevPset) / 4)) reinterpret_cast<uint32_t *>(&s_P)[tid] = reinterpret_cast<const uint32_t *>(&S.psets[S.pset_of[r]])[tid];
         __syncthreads();
         const DevPset &P = s_P;
@@ -435,7 +439,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         PHASE(2);
                         int lpos = 0;
                         while (lpos < nlist) {
+#ifdef CABM_FUSED_DIAG
                             ++n_rounds;
+#endif
                             // (a) warp 0: the next <= 32 infectors, their budget split over the age groups (:804), event prefix
                             if (wid == 0) {
                                 const int ncand = min(FUSED_NCAND, nlist - lpos);
@@ -751,7 +757,11 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         }
         // diagnostics of the fused path: kilo-cycles spent on this replicate and dyntrans batches issued
         PHASE(6);
+#ifdef CABM_FUSED_DIAG
         if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; for (int k = 0; k < 16; ++k) S.dbg[(size_t)r * 16 + k] = t_ph[k]; }
+#else
+        if (tid == 0) { S.totalmet[r] = 0; S.totalinf[r] = 0; }
+#endif
 #undef PHASE
         if (hm && tma_ok && tid == 0) bulk_store_wait_all();
         if (!resumed && tid == 0) { __threadfence(); atomicAdd(&work[3], 1u); }

@@ -1,4 +1,6 @@
-import sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import os, subprocess, sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+# needs the diagnostics build of the library: make -C covid19abm.jl_b200/csrc diag
+os.environ.setdefault("CABM_LIB", os.path.abspath("covid19abm.jl_b200/libcabm_b200_diag.so"))
 import numpy as np, covid19abm_b200 as cv
 from bench import CFG, seeds_for
 ip = cv.ModelParameters(**CFG)
