@@ -16,6 +16,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def cv():
     import covid19abm_b200 as m
+    if not os.path.exists(m.LIB_PATH):          # clean checkout: the .so files are git-ignored -> build them (nvcc cross-compiles without a GPU)
+        import __graft_entry__
+        __graft_entry__.build()
     return m
 
 
