@@ -408,18 +408,19 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                     for (;;) {
                         // ordered list of (up to FUSED_LCAP) infectious agents at or after `cursor` (:794), built by the whole CTA
                         int lbase = 0, w0 = cursor >> 5;
-                        for (; w0 < nwords && lbase < FUSED_LCAP; w0 += NT) {
-                            const int wi = w0 + tid;
-                            uint32_t m = (wi < nwords) ? M.inf[wi] : 0u;
-                            if (wi == (cursor >> 5)) m &= ~((1u << (cursor & 31)) - 1u);
-                            const int c = __popc(m);
+                        for (; w0 < nwords && lbase < FUSED_LCAP; w0 += 2 * NT) {        // two mask words per thread: 10,000 agents in one pass
+                            const int wi = w0 + 2 * tid;
+                            uint32_t m0 = (wi < nwords) ? M.inf[wi] : 0u, m1 = (wi + 1 < nwords) ? M.inf[wi + 1] : 0u;
+                            if (wi == (cursor >> 5)) m0 &= ~((1u << (cursor & 31)) - 1u);
+                            const int c0 = __popc(m0), c = c0 + __popc(m1);
                             int incl = c;
                             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
                             if (lane == 31) s_wsum[wid] = incl;
                             __syncthreads();
                             int pos = lbase + incl - c, tot = 0;
                             for (int w = 0; w < NW; ++w) { const int v = s_wsum[w]; tot += v; if (w < wid) pos += v; }
-                            while (m && pos < FUSED_LCAP) { const int b = __ffs(m) - 1; m &= m - 1; M.list[pos++] = (uint16_t)((wi << 5) + b); }
+                            while (m0 && pos < FUSED_LCAP) { const int b = __ffs(m0) - 1; m0 &= m0 - 1; M.list[pos++] = (uint16_t)((wi << 5) + b); }
+                            while (m1 && pos < FUSED_LCAP) { const int b = __ffs(m1) - 1; m1 &= m1 - 1; M.list[pos++] = (uint16_t)(((wi + 1) << 5) + b); }
                             lbase += tot;
                             __syncthreads();
                         }
