@@ -124,14 +124,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     __shared__ unsigned long long s_beta[4];
     __shared__ DevPset s_P;                  // this replicate's parameter set (read on every transition)
     __shared__ double s_cm[25];              // contact_matrix :838-848
-    __shared__ int s_nf[2], s_wsum[FUSED_NT / 32], s_g0[2][60];
+    __shared__ int s_nf[2], s_wsum[FUSED_NT / 32];
     __shared__ int s_infectors[4];
     // dyntrans batch
     __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_nb, s_cut;
     __shared__ unsigned long long s_bthr[FUSED_NCAND];
     __shared__ uint8_t s_ccnt[FUSED_NCAND], s_cag[FUSED_NCAND];
     __shared__ uint8_t s_xh[FUSED_NCAND];
-    __shared__ int s_wdup[FUSED_NT / 32];
+    __shared__ int s_wdup[FUSED_NT / 32], s_anydup;
     // contact tracing (:647-752): per-candidate chunk of the contact log, the replicate's log fill, index-case queues by day parity
     __shared__ uint8_t s_ctr[FUSED_NCAND];
     __shared__ uint32_t s_cbase[FUSED_NCAND], s_logn, s_qcnt[2];
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 
     for (int k = tid; k < 5 * 256; k += NT) { M.nb_thr[k] = S.nb_thr[k]; M.nb_guide[k] = S.nb_guide[k]; }
     for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; M.mpre[k] = 0; M.mpost[k] = 0; }
+    if (tid == 0) s_anydup = 0;
     if (tid < 4) { s_tlat[tid] = c_tab.lat_thr[tid]; s_tpre[tid] = c_tab.pre_thr[tid]; }
     if (tid < 40) { s_tasy[tid] = c_tab.asy_thr[tid]; s_tinf[tid] = c_tab.inf_thr[tid]; }
     if (tid < 25) s_cm[tid] = c_tab.cm[tid / 5][tid % 5];
@@ -401,8 +402,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 break;
             }
             if (active) {
+                if (hm && tma_ok && tid == 0) bulk_store_wait_read();          // earlier columns have left shared memory (ordered by the barriers below)
                 // ---------------------------------------------------- dyntrans(st) :790-834
-                if (s_ninf > 0) {
+                const bool had_infectious = s_ninf > 0;                        // uniform
+                if (had_infectious) {
                     if (tid < 4) s_beta[tid] = beta[(size_t)(day - 1) * 4 + tid];              // _get_betavalue :756-769 for today
                     int cursor = 0;                                                            // first agent index not yet listed
                     for (;;) {
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const uint32_t ybit = 1u << (y & 31);
                             const int yw = (int)(y >> 5);
                             // targets hit more than once (by any event of the batch, cut or not) take the ordered path below
-                            if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) atomicOr(&M.dupm[yw], ybit); }
+                            if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) { atomicOr(&M.dupm[yw], ybit); s_anydup = 1; } }
                             __syncthreads();                                                   // B2
                             PHASE(9);
                             const int cut = s_cut;
@@ -528,7 +531,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             // (c) events sharing a target are applied in event order (:809-830) by the first event of the target,
                             //     over the compacted list of such events; every other event is independent
                             int dpos = 0, dtot = 0;
-                            if (__syncthreads_or(isdup)) {                                     // B3
+                            if (s_anydup) {                                                    // uniform (set before B2); rare: B3/B4 only then
                                 const unsigned dm = __ballot_sync(FULL, isdup);
                                 if (lane == 0) s_wdup[wid] = __popc(dm);
                                 __syncthreads();
@@ -578,6 +581,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             }
                             PHASE(11);
                             if (marked) { M.touch[yw] = 0; M.dupm[yw] = 0; }                   // next marking is after the next B1
+                            if (tid == 0) s_anydup = 0;
                             lpos += cut;
                         }
                         PHASE(3);
@@ -588,8 +592,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 }
 
                 // ---------------------------------------------------- time_update() :399-428
-                if (hm && tma_ok && tid == 0) bulk_store_wait_read();          // earlier columns have left shared memory
-                __syncthreads();                                               // S1: dyntrans writes visible; col reusable
+                if (!had_infectious) __syncthreads();                          // S1: col reusable (dyntrans, when it runs, ends with barriers of its own)
                 PHASE(12);
                 if (tid == 0) s_nf[(act + 1) & 1] = 32767;                     // buffer of the next active day (last read after the previous S2)
                 if (day == 1) {                                                // seeds isolated by fpreiso: resync isob (see k_time_update)
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             if (ctr && e.texp != texp) S.texp[rb + i] = (int16_t)e.texp;
                             if (e.newh != e.oldh) {
                                 M.col[i] = (uint8_t)e.newh;
-                                atomicAdd(&s_io[day & 1][0][st_ag(st) * 12 + e.newh], 1); atomicAdd(&s_io[day & 1][1][st_ag(st) * 12 + e.oldh], 1);
+                                atomicAdd(&s_io[act & 1][0][st_ag(st) * 12 + e.newh], 1); atomicAdd(&s_io[act & 1][1][st_ag(st) * 12 + e.oldh], 1);
                                 if (is_infectious(e.newh) != is_infectious(e.oldh)) {
                                     atomicXor(&M.inf[i >> 5], 1u << (i & 31));
                                     atomicAdd(&s_ninf, is_infectious(e.newh) ? 1 : -1);
@@ -662,28 +665,26 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             if (day < T) {
                 // threads 0..59 own one (age group, state) pair each and keep its running prevalence in a register;
                 // threads 64..75 own group 0 ("all" = the sum over the five groups, :91-97). Idle days repeat the values.
-                int in = 0;
-                if (active && tid < 60) {
-                    in = s_io[day & 1][0][tid];
-                    run += in - s_io[day & 1][1][tid];
-                    s_io[day & 1][0][tid] = 0; s_io[day & 1][1][tid] = 0;        // next touched by the atomics after a later S1
-                    s_g0[0][tid] = in; s_g0[1][tid] = run;
-                }
-                if (active && tid < 128) {                                     // warps 0-3, warp-uniform and convergent
-                    __syncwarp();
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
+                // curve deltas of active day k live in s_io[k & 1] (k = act - 1 here); the other buffer, last read two active days ago,
+                // is cleared for the next active day — no barrier needed between the group threads and the group-0 threads
+                const int cur = (act - 1) & 1;
                 if (tid < 60) {
                     const int g = tid / 12, s = tid % 12;
+                    int in = 0;
+                    if (active) {
+                        in = s_io[cur][0][tid];
+                        run += in - s_io[cur][1][tid];
+                        s_io[cur ^ 1][0][tid] = 0; s_io[cur ^ 1][1][tid] = 0;
+                    }
                     const size_t b = (((size_t)r * 6 + (g + 1)) * (size_t)T + (size_t)day) * 12 + s;
                     S.inc[b] = in; S.prev[b] = run;
                 } else if (tid >= 64 && tid < 76) {
                     const int s = tid - 64;
                     g0_in = 0;
                     if (active) {
-                        int pv = 0;
-                        for (int g = 0; g < 5; ++g) { g0_in += s_g0[0][g * 12 + s]; pv += s_g0[1][g * 12 + s]; }
-                        run = pv;
+                        int out = 0;
+                        for (int g = 0; g < 5; ++g) { g0_in += s_io[cur][0][g * 12 + s]; out += s_io[cur][1][g * 12 + s]; }
+                        run += g0_in - out;
                     }
                     const size_t b = (((size_t)r * 6 + 0) * (size_t)T + (size_t)day) * 12 + s;
                     S.inc[b] = g0_in; S.prev[b] = run;
