@@ -32,6 +32,7 @@ struct FusedSmem {
     uint32_t *nb_thr; uint8_t *nb_guide;
     uint32_t *Y, *W1; uint8_t *Q; uint32_t *touch, *dupm, *mpre, *mpost; uint16_t *D;
     uint16_t *list; uint8_t *lcnt, *lE;  // the day's ordered infectious agents, their contact budgets and event counts
+    unsigned long long *lgp;             // ... and the budget split over the five age groups (:804), five packed bytes
     unsigned long long *dcache;          // (agent << 32 | dur) of recently infected agents
     int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
 };
@@ -48,6 +49,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int Np) {
     b += FUSED_NT * 2;                   // D (compacted duplicate events)
     b += FUSED_LCAP * 4;                 // list, lcnt, lE
     b += DUR_CACHE * 8;                  // dcache
+    b += FUSED_LCAP * 8;                 // lgp
     return (b + 15) / 16 * 16 + 64;
 }
 
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     {
         unsigned char *p = smem_raw;
         M.dcache = (unsigned long long *)p; p += DUR_CACHE * 8;
+        M.lgp = (unsigned long long *)p; p += FUSED_LCAP * 8;
         M.status = (uint32_t *)p; p += (size_t)Np * 4;
         M.expday = (int16_t *)p; p += (size_t)Np * 2;
         M.grp = (uint16_t *)p; p += (size_t)Np * 2;
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     // dyntrans batch
     __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_nb, s_cut;
     __shared__ unsigned long long s_bthr[FUSED_NCAND];
-    __shared__ uint8_t s_ccnt[FUSED_NCAND], s_cag[FUSED_NCAND];
+    __shared__ unsigned long long s_gp[FUSED_NCAND];
     __shared__ uint8_t s_xh[FUSED_NCAND];
     __shared__ int s_wdup[FUSED_NT / 32], s_anydup;
     // contact tracing (:647-752): per-candidate chunk of the contact log, the replicate's log fill, index-case queues by day parity
@@ -437,7 +440,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const uint32_t sx = M.status[x];
                             const int cnts = budget_of_s(M, key, x, day, sx);
                             M.lcnt[tid] = (uint8_t)cnts;
-                            M.lE[tid] = (uint8_t)gpw_sum(gpw_pack(s_cm + st_ag(sx) * 5, cnts));
+                            const unsigned long long gp = gpw_pack(s_cm + st_ag(sx) * 5, cnts);
+                            M.lgp[tid] = gp;
+                            M.lE[tid] = (uint8_t)gpw_sum(gp);
                         }
                         __syncthreads();
                         PHASE(2);
@@ -453,13 +458,13 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 if (lane < ncand) {
                                     const int x = M.list[lpos + lane];
                                     const uint32_t sx = M.status[x];
-                                    int cnts = (int)M.lcnt[lpos + lane];
+                                    unsigned long long gp = M.lgp[lpos + lane];
                                     E = (int)M.lE[lpos + lane];
                                     if (st_tag(sx) == day) {                                    // contacted earlier today: budget changed (:813)
-                                        cnts = st_rem(sx);
-                                        E = gpw_sum(gpw_pack(s_cm + st_ag(sx) * 5, cnts));
+                                        gp = gpw_pack(s_cm + st_ag(sx) * 5, st_rem(sx));
+                                        E = gpw_sum(gp);
                                     }
-                                    s_cand[lane] = x; s_ccnt[lane] = (uint8_t)cnts; s_cag[lane] = (uint8_t)st_ag(sx);
+                                    s_cand[lane] = x; s_gp[lane] = gp;
                                     s_xh[lane] = (uint8_t)st_health(sx);
                                     s_bthr[lane] = s_beta[beta_class(st_health(sx))];         // :800
                                 }
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= tid) lo = mid; else hi = mid - 1; }
                                 q = lo;
                                 const int e = tid - s_pref[q];
-                                const unsigned long long gp = gpw_pack(s_cm + s_cag[q] * 5, s_ccnt[q]);   // round.(cm[ag]*cnts) :804
+                                const unsigned long long gp = s_gp[q];                 // round.(cm[ag]*cnts) :804
                                 const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF), p4 = p3 + (int)((gp >> 24) & 0xFF);
                                 const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
                                 const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
