@@ -283,7 +283,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        nrep = max(2 * threads, 32)
+        nrep = max(6 * threads, 96)      # about 30 s of single-core work, ~2 s wall on 16 cores
         v, dt = cpu_sample(nrep, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{nrep} replicates of the same workload, one per thread, {dt:.1f} s wall (C restatement of the reference, not Julia)"}
