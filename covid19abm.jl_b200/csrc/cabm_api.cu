@@ -120,7 +120,7 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8); DA(S.hits, A);
     DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);
     DA(S.totalmet, (size_t)h->R); DA(S.totalinf, (size_t)h->R);
-    DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R); DA(S.dbg, (size_t)h->R * 16); DA(S.resume_list, (size_t)h->R); DA(S.resume_aux, (size_t)h->R * 2);
+    DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R); DA(S.dbg, (size_t)h->R * 32); DA(S.resume_list, (size_t)h->R); DA(S.resume_aux, (size_t)h->R * 2);
     if (S.store_hm) DA(S.hm, (size_t)h->R * h->T * h->N);
     DA(h->d_scratch, (size_t)4 * h->N);
     DA(h->d_work, 8);
@@ -386,7 +386,7 @@ extern "C" int64_t cabm_launch_count(const cabm_handle *h) { return h ? h->launc
 extern "C" int cabm_get_debug(cabm_handle *h, int64_t *out) {
     if (!h || !out) return CABM_E_ARG;
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(out, h->S.dbg, (size_t)h->n_rep * 128, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, h->S.dbg, (size_t)h->n_rep * 256, cudaMemcpyDeviceToHost));
     return CABM_OK;
 }
 extern "C" int cabm_get_day(const cabm_handle *h) { return h ? h->day : -1; }

@@ -81,7 +81,7 @@ struct Dev {
     uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;
     int *inc, *prev;                         // [R][6][T][12]
     long long *infectors, *latsum;           // [R][4], [R]
-    long long *dbg;                          // [R][16] per-phase cycle counts of the fused kernel (diagnostics)
+    long long *dbg;                          // [R][32] per-phase cycle counts of the fused kernel (diagnostics)
     int *resume_list, *resume_aux;           // [R], [R][2]: fused kernel's queue of parked replicates and their (nextfire, ninf)
     uint8_t *hm;                             // [R][T][N] health codes (widened to Int16 by cabm_get_hmatrix)
     int16_t *host_inc, *host_prev;           // optional pinned host buffers [R][6][T][12]: the fused kernel streams each finished

@@ -30,8 +30,8 @@ static_assert(FUSED_NT == 256 && FUSED_LCAP <= FUSED_NT, "thread-index roles in 
 struct FusedSmem {
     uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
     uint32_t *nb_thr; uint8_t *nb_guide;
-    uint32_t *Y, *W1; uint8_t *Q; uint32_t *touch, *dupm, *mpre, *mpost; uint16_t *D;
-    uint16_t *list; uint8_t *lcnt, *lE;  // the day's ordered infectious agents, their contact budgets and event counts
+    uint32_t *Y, *W1; uint32_t *touch, *dupm, *mpre, *mpost; uint16_t *D;   // batch events: (target | budget << 16 | owner << 24), transmission word
+    uint16_t *list; uint8_t *lh, *lE;    // the day's ordered infectious agents, their health (+ tracing flag) and event counts
     unsigned long long *lgp;             // ... and the budget split over the five age groups (:804), five packed bytes
     unsigned long long *dcache;          // (agent << 32 | dur) of recently infected agents
     int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
@@ -44,10 +44,10 @@ __host__ __device__ inline size_t fused_smem_bytes(int Np) {
     b += (size_t)Np;                     // col
     b += (size_t)(Np / 32) * 4;          // inf
     b += 5 * 256 * 4 + 5 * 256;          // nb tables
-    b += FUSED_NT * 4 * 2 + FUSED_NT;    // Y (= cnt), W1, Q
+    b += FUSED_NT * 4 * 2;               // Y (= cnt), W1
     b += (size_t)(Np / 32) * 4 * 4;      // touch, dupm, mark_pre, mark_post bitmasks
     b += FUSED_NT * 2;                   // D (compacted duplicate events)
-    b += FUSED_LCAP * 4;                 // list, lcnt, lE
+    b += FUSED_LCAP * 4;                 // list, lh, lE
     b += DUR_CACHE * 8;                  // dcache
     b += FUSED_LCAP * 8;                 // lgp
     return (b + 15) / 16 * 16 + 64;
@@ -78,6 +78,17 @@ __device__ __forceinline__ unsigned long long gpw_pack(const double *cm_row, int
 }
 __device__ __forceinline__ int gpw_sum(unsigned long long gp) {
     return (int)(gp & 0xFF) + (int)((gp >> 8) & 0xFF) + (int)((gp >> 16) & 0xFF) + (int)((gp >> 24) & 0xFF) + (int)((gp >> 32) & 0xFF);
+}
+
+// An infectious agent y was contacted (:813): its remaining budget is `rem` now, so the events it will generate when its own turn
+// comes (later today) change. Its entry in the day's list is brought up to date (the list is ascending: binary search).
+__device__ __forceinline__ void fused_list_update(const FusedSmem &M, const double *cm, int nlist, uint32_t y, uint32_t sy, int rem) {
+    int a = 0, b = nlist - 1;
+    while (a < b) { const int mid = (a + b) >> 1; if ((uint32_t)M.list[mid] < y) a = mid + 1; else b = mid; }
+    if ((uint32_t)M.list[a] == y) {
+        const unsigned long long gp = gpw_pack(cm + st_ag(sy) * 5, rem);
+        M.lgp[a] = gp; M.lE[a] = (uint8_t)gpw_sum(gp);
+    }
 }
 
 // TMA bulk store of one hmatrix column from shared memory (UBLKCP in SASS)
@@ -116,8 +127,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         M.D = (uint16_t *)p; p += NT * 2;
         M.list = (uint16_t *)p; p += FUSED_LCAP * 2;
         M.nb_guide = (uint8_t *)p; p += 5 * 256;
-        M.Q = (uint8_t *)p; p += NT;
-        M.lcnt = (uint8_t *)p; p += FUSED_LCAP;
+        M.lh = (uint8_t *)p; p += FUSED_LCAP;
         M.lE = (uint8_t *)p; p += FUSED_LCAP;
     }
     __shared__ int s_r, s_off[8], s_wcnt[FUSED_NT / 32][5];
@@ -128,12 +138,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     __shared__ DevPset s_P;                  // this replicate's parameter set (read on every transition)
     __shared__ double s_cm[25];              // contact_matrix :838-848
     __shared__ int s_nf[2], s_wsum[FUSED_NT / 32];
+    __shared__ __align__(16) int s_run[72];  // running prevalence of the six groups, for the idle-tail fill
     __shared__ int s_infectors[4];
     // dyntrans batch
     __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_nb, s_cut;
     __shared__ unsigned long long s_bthr[FUSED_NCAND];
     __shared__ unsigned long long s_gp[FUSED_NCAND];
-    __shared__ uint8_t s_xh[FUSED_NCAND];
+    __shared__ uint8_t s_xh[FUSED_NCAND], s_map[FUSED_NCAND];   // infector's health; position of the batch entry in the list stretch
+    __shared__ int s_adv;
     __shared__ int s_wdup[FUSED_NT / 32], s_anydup;
     // contact tracing (:647-752): per-candidate chunk of the contact log, the replicate's log fill, index-case queues by day parity
     __shared__ uint8_t s_ctr[FUSED_NCAND];
@@ -183,8 +195,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         const bool resumed = sweep == 1;
 #ifdef CABM_FUSED_DIAG      // per-phase cycle counts seen by thread 0 (make diag; tools/diag_fused.py)
         const long long t_start = clock64();
-        long long t_ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = t_start;
-#define PHASE(k) do { const long long t_now_ = clock64(); t_ph[k] += t_now_ - t_last; t_last = t_now_; } while (0)
+        __shared__ long long t_ph[32];
+        long long t_last = t_start;
+        if (tid < 32) t_ph[tid] = 0;
+#define PHASE(k) do { if (tid == 0) { t_ph[k] += clock64() - t_last; t_last = clock64(); } } while (0)
         int n_rounds = 0;
 #else
 #define PHASE(k) do { } while (0)
@@ -236,6 +250,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid < 4) s_infectors[tid] = 0;
         if (tid == 0) s_ninf = 0;
         __syncthreads();
+        PHASE(22);
 
         // ------------------------------------------------------------ get_ag_dist :339-343 (ordered counting sort)
         // each warp owns a contiguous range of agents: count per group, one prefix over the warps, then every warp scatters
@@ -275,6 +290,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             }
         }
         __syncthreads();
+        PHASE(23);
 
         // ------------------------------------------------------------ insert_infected :360-395 (PRE seeds, then REC seeds)
         for (int which = 0; which < 2; ++which) {
@@ -319,6 +335,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             }
         }
         __syncthreads();
+        PHASE(24);
 
         // ------------------------------------------------------------ column 1 (:136 at st = 1) and its curve entries
         // every agent first occurs in its initial state on day 1 (:270-280); nearly all are SUS, so count the others
@@ -388,15 +405,21 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             if (!active && nextfire > T) {
                 // nobody is infectious and no state expires before the end of the run: the remaining columns and curve rows
                 // repeat the current ones (tis >= exp :405 never fires again) — write them without stepping through the days
-                for (int d = day; d < T; ++d) {
-                    if (tid < 60) {
-                        const size_t b = (((size_t)r * 6 + (tid / 12 + 1)) * (size_t)T + (size_t)d) * 12 + tid % 12;
-                        S.inc[b] = 0; S.prev[b] = run;
-                    } else if (tid >= 64 && tid < 76) {
-                        const size_t b = (((size_t)r * 6 + 0) * (size_t)T + (size_t)d) * 12 + (tid - 64);
-                        S.inc[b] = 0; S.prev[b] = run;
+                // curve rows day..T-1 of a group are one contiguous run of 12-int rows (48 B, 16-byte aligned): the whole CTA
+                // fills them with 16-byte stores while thread 0 queues the column copies
+                if (tid < 60) s_run[12 + tid] = run; else if (tid >= 64 && tid < 76) s_run[tid - 64] = run;
+                __syncthreads();
+                {
+                    const int per = (T - day) * 3;                                  // uint4 per group
+                    for (int idx = tid; idx < 6 * per; idx += NT) {
+                        const int G = idx / per, j = idx - G * per;
+                        const size_t b0 = (((size_t)r * 6 + G) * (size_t)T + (size_t)day) * 12;
+                        reinterpret_cast<int4 *>(S.inc + b0)[j] = make_int4(0, 0, 0, 0);
+                        reinterpret_cast<int4 *>(S.prev + b0)[j] = *reinterpret_cast<const int4 *>(&s_run[G * 12 + (j % 3) * 4]);
                     }
-                    if (hm) {
+                }
+                if (hm) {
+                    for (int d = day; d < T; ++d) {
                         if (tma_ok) { if (tid == 0) { bulk_store_wait_read_n(); bulk_store(hm + (size_t)d * N, M.col, (uint32_t)N); } }
                         else for (int i = tid; i < N; i += NT) hm[(size_t)d * N + i] = M.col[i];
                     }
@@ -439,7 +462,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const int x = M.list[tid];
                             const uint32_t sx = M.status[x];
                             const int cnts = budget_of_s(M, key, x, day, sx);
-                            M.lcnt[tid] = (uint8_t)cnts;
+                            // health and the tracing flag of an infector do not change inside dyntrans: keep them with the list
+                            M.lh[tid] = (uint8_t)(st_health(sx) | ((sx & ST_TRACING) ? 0x80u : 0u));
                             const unsigned long long gp = gpw_pack(s_cm + st_ag(sx) * 5, cnts);
                             M.lgp[tid] = gp;
                             M.lE[tid] = (uint8_t)gpw_sum(gp);
@@ -451,54 +475,57 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #ifdef CABM_FUSED_DIAG
                             ++n_rounds;
 #endif
-                            // (a) warp 0: the next <= 32 infectors, their budget split over the age groups (:804), event prefix
+                            // (a) warp 0: the next <= 32 listed infectors. Their event counts come from the list (kept current by the
+                            //     apply phase when an infector is contacted, :813), those without events are dropped, the others are
+                            //     compacted into the batch arrays with their event prefix
                             if (wid == 0) {
-                                const int ncand = min(FUSED_NCAND, nlist - lpos);
-                                int E = 0;
-                                if (lane < ncand) {
-                                    const int x = M.list[lpos + lane];
-                                    const uint32_t sx = M.status[x];
-                                    unsigned long long gp = M.lgp[lpos + lane];
-                                    E = (int)M.lE[lpos + lane];
-                                    if (st_tag(sx) == day) {                                    // contacted earlier today: budget changed (:813)
-                                        gp = gpw_pack(s_cm + st_ag(sx) * 5, st_rem(sx));
-                                        E = gpw_sum(gp);
-                                    }
-                                    s_cand[lane] = x; s_gp[lane] = gp;
-                                    s_xh[lane] = (uint8_t)st_health(sx);
-                                    s_bthr[lane] = s_beta[beta_class(st_health(sx))];         // :800
+                                const int ncand = min(FUSED_NCAND, nlist - lpos), li = lpos + lane;
+                                int E = 0, x = 0, h = 0; unsigned long long gp = 0;
+                                if (lane < ncand) { E = (int)M.lE[li]; x = M.list[li]; gp = M.lgp[li]; h = M.lh[li]; }
+                                int incl = E;
+                                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                                const unsigned fits = __ballot_sync(FULL, lane < ncand && incl <= NT);
+                                const int nfit = fits == FULL ? ncand : min(ncand, __ffs(~fits) - 1);    // E < NT: nfit >= 1
+                                const bool keep = E > 0 && lane < nfit;
+                                const unsigned km = __ballot_sync(FULL, keep);
+                                const int rank = __popc(km & ((1u << lane) - 1u));
+                                if (keep) {
+                                    s_cand[rank] = x; s_gp[rank] = gp; s_xh[rank] = (uint8_t)(h & 0xF); s_map[rank] = (uint8_t)lane;
+                                    s_bthr[rank] = s_beta[beta_class(h & 0xF)];                 // :800
+                                    s_pref[rank + 1] = incl;
                                 }
                                 if (ctr) {                                                     // :817-819 chunk [next, count, <= E targets] per traced infector
-                                    const bool tr = lane < ncand && E > 0 && (M.status[M.list[lpos + lane]] & ST_TRACING);
+                                    const bool tr = keep && (h & 0x80);
                                     int need = tr ? 2 + E : 0, nin = need;
                                     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, nin, o); if (lane >= o) nin += v; }
                                     const int ntot = __shfl_sync(FULL, nin, 31);
                                     const uint32_t base0 = s_logn;
                                     const bool room = base0 + (uint32_t)ntot <= S.ct_cap;
                                     if (!room && ntot && lane == 0) atomicOr(&S.err[r], ERR_CT_LOG_FULL);
-                                    s_ctr[lane] = (uint8_t)(tr && room); s_cbase[lane] = base0 + (uint32_t)(nin - need); s_clen[lane] = 0;
+                                    if (keep) { s_ctr[rank] = (uint8_t)(tr && room); s_cbase[rank] = base0 + (uint32_t)(nin - need); s_clen[rank] = 0; }
                                     __syncwarp();
                                     if (lane == 0 && room) s_logn = base0 + (uint32_t)ntot;
                                 }
-                                int incl = E;
-                                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                                s_pref[lane + 1] = incl;
-                                const unsigned fits = __ballot_sync(FULL, lane < ncand && incl <= NT);
-                                if (lane == 0) {
-                                    s_pref[0] = 0;
-                                    const int nb = fits == FULL ? ncand : min(ncand, __ffs(~fits) - 1);   // candidates whose events fit (E <= 260 < NT: nb >= 1)
-                                    s_nb = nb; s_cut = nb;
-                                }
+                                if (lane == 0) { s_pref[0] = 0; const int nbc = __popc(km); s_nb = nbc; s_cut = nbc; s_adv = nfit; }
                             }
+                            PHASE(15);
                             __syncthreads();                                                   // B1
                             PHASE(8);
-                            const int nb = s_nb, Etot = s_pref[nb];
-                            // (b) one contact event per thread: target draw (:807), transmission word (:823); mark the target
-                            uint32_t y = 0, w1 = 0, sy = 0, dury = 0; int q = 0, remy = 0; bool ev = tid < Etot;
+                            const int nb = s_nb;
+                            if (nb == 0) { lpos += s_adv; __syncthreads(); continue; }          // nobody in this stretch of the list has contacts today
+                            const int Etot = s_pref[nb];
+                            // (b) one contact event per thread: owner, target draw (:807), transmission word (:823); mark the target.
+                            //     Owner of event tid = number of prefix entries <= tid: those at or below the warp's first event are
+                            //     counted by a ballot, the (strictly increasing) ones inside the warp's range are bits of one word
+                            uint32_t y = 0, w1 = 0, sy = 0, dury = 0; int q = 0, remy = 0; bool ev = tid < Etot, yinf = false;
+                            {
+                                const int Pl = lane < nb ? s_pref[lane + 1] : 0x7FFFFFFF, base = tid - lane;
+                                const int below = __popc(__ballot_sync(FULL, Pl <= base));
+                                const unsigned bits = __reduce_or_sync(FULL, (Pl > base && Pl <= base + 31) ? 1u << (Pl - base) : 0u);
+                                q = below + __popc(bits & ((2u << lane) - 1u));
+                            }
+                            PHASE(16);
                             if (ev) {
-                                int lo = 0, hi = nb - 1;                               // last q with pref[q] <= tid
-                                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= tid) lo = mid; else hi = mid - 1; }
-                                q = lo;
                                 const int e = tid - s_pref[q];
                                 const unsigned long long gp = s_gp[q];                 // round.(cm[ag]*cnts) :804
                                 const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF), p4 = p3 + (int)((gp >> 24) & 0xFF);
@@ -511,32 +538,44 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
                                     y = M.grp[go + below(w.x, len)]; w1 = w.y;
                                     sy = M.status[y];                              // stable until the apply phase of this batch
+#ifdef CABM_FUSED_DIAG
+                                    if (sy == 0xFFFFFFFFu) ev = false;             // (never true) makes the load complete before the time stamp
+#endif
+                                    PHASE(17);
                                     dury = __ldg(&S.dur[rb + y]);                  // in flight during the next phases; kept only if y gets infected
                                     remy = budget_of_s(M, key, y, day, sy);        // :811, the target's budget (lazy draw on first touch)
+#ifdef CABM_FUSED_DIAG
+                                    if (remy == 0x7FFFFFFF) ev = false;
+#endif
+                                    PHASE(18);
+                                    yinf = (M.inf[y >> 5] >> (y & 31)) & 1u;
                                     // an infector later in this batch that gets contacted must re-read its budget: cut the batch there
-                                    if ((int)y > x && (int)y <= s_cand[nb - 1] && ((M.inf[y >> 5] >> (y & 31)) & 1u)) {
+                                    if (yinf && (int)y > x && (int)y <= s_cand[nb - 1]) {
                                         int a = q + 1, b = nb - 1;
                                         while (a < b) { const int mid = (a + b) >> 1; if (s_cand[mid] < (int)y) a = mid + 1; else b = mid; }
-                                        atomicMin(&s_cut, a);
+                                        if (s_cand[a] == (int)y) atomicMin(&s_cut, a);     // (a listed infector without events has nothing to redo)
                                     }
                                 }
                             }
-                            M.Y[tid] = ev ? y : 0xFFFFFFFFu; M.W1[tid] = w1; M.Q[tid] = (uint8_t)q;
+                            // event record: target | its budget << 16 | owner << 24
+                            M.Y[tid] = ev ? (y | ((uint32_t)remy << 16) | ((uint32_t)q << 24)) : 0xFFFFFFFFu; M.W1[tid] = w1;
                             const uint32_t ybit = 1u << (y & 31);
                             const int yw = (int)(y >> 5);
                             // targets hit more than once (by any event of the batch, cut or not) take the ordered path below
                             if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) { atomicOr(&M.dupm[yw], ybit); s_anydup = 1; } }
+                            PHASE(19);
                             __syncthreads();                                                   // B2
                             PHASE(9);
                             const int cut = s_cut;
                             const int Ev = s_pref[cut];                                // events of infectors [0, cut) are final
+                            const int adv = cut == nb ? s_adv : (int)s_map[cut];       // list entries this batch consumes
                             const bool marked = ev;
                             ev = ev && tid < Ev;
                             const bool isdup = ev && (M.dupm[yw] & ybit);
-                            // (c) events sharing a target are applied in event order (:809-830) by the first event of the target,
-                            //     over the compacted list of such events; every other event is independent
+                            // (c) events sharing a target are applied in event order (:809-830) by one thread per target, over the
+                            //     compacted list of such events; every other event is independent
                             int dpos = 0, dtot = 0;
-                            if (s_anydup) {                                                    // uniform (set before B2); rare: B3/B4 only then
+                            if (s_anydup) {                                                    // uniform (set before B2); B3/B4 only then
                                 const unsigned dm = __ballot_sync(FULL, isdup);
                                 if (lane == 0) s_wdup[wid] = __popc(dm);
                                 __syncthreads();
@@ -545,38 +584,89 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 __syncthreads();
                             }
                             PHASE(10);
-                            if (ev) {
-                                bool leader = true;
-                                if (isdup) for (int d = 0; d < dpos; ++d) if (M.Y[M.D[d]] == y) { leader = false; break; }
-                                if (leader) {
-                                    int rem = remy;
-                                    bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;             // :822
-                                    int xh_inf = -1;
-                                    if (rem > 0) {                                                       // :812
-                                        rem -= 1;                                                         // :813
-                                        if (ctr && s_ctr[q]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q] + 2u + (uint32_t)atomicAdd(&s_clen[q], 1)] = y;   // :817-819
-                                        if (sus && bern(w1, s_bthr[q])) { sus = false; xh_inf = s_xh[q]; }   // :823-827
+                            // outcome of a target: remaining budget, infected by whom (-1: not infected)
+                            int rem = remy, xh_inf = -1;
+                            bool apply = ev && !isdup;
+                            if (apply && rem > 0) {                                                  // :812
+                                rem -= 1;                                                             // :813
+                                if (ctr && s_ctr[q]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q] + 2u + (uint32_t)atomicAdd(&s_clen[q], 1)] = y;   // :817-819
+                                if (st_health(sy) == SUS && st_swap(sy) == UNDEF && bern(w1, s_bthr[q])) xh_inf = s_xh[q];   // :822-827
+                            }
+                            if (dtot > 0 && dtot <= 32) {
+                                // few shared targets (the usual case): the last warp resolves them, one lane per event, the first
+                                // event of each target leading; the others apply their own events meanwhile
+                                if (wid == NW - 1) {
+                                    if (apply) {        // this warp's own independent events first
+                                        uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
+                                        if (xh_inf >= 0) {
+                                            ns = st_set_swap(ns, LAT);
+                                            S.sickfrom[rb + y] = (uint8_t)xh_inf;
+                                            M.expday[y] = (int16_t)day;
+                                            M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
+                                        }
+                                        M.status[y] = ns;
+                                        if (yinf) fused_list_update(M, s_cm, nlist, y, sy, rem);
+                                        apply = false;
                                     }
-                                    if (isdup) {
-                                        for (int d = dpos + 1; d < dtot && rem > 0; ++d) {
-                                            const int e2 = M.D[d];
-                                            if (M.Y[e2] != y) continue;
-                                            rem -= 1;
-                                            const int q2 = M.Q[e2];
-                                            if (ctr && s_ctr[q2]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q2] + 2u + (uint32_t)atomicAdd(&s_clen[q2], 1)] = y;
-                                            if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }
+                                    const bool have = lane < dtot;
+                                    const uint32_t rec = have ? M.Y[M.D[lane]] : 0u, w1d = have ? M.W1[M.D[lane]] : 0u;
+                                    const uint32_t yd = rec & 0xFFFFu;
+                                    const int qd = (int)(rec >> 24);
+                                    const unsigned peers = __match_any_sync(FULL, have ? yd : 0x10000u + (uint32_t)lane);
+                                    const bool leader = have && lane == __ffs(peers) - 1;
+                                    const int n = __popc(peers), nmax = __reduce_max_sync(FULL, have ? n : 0);
+                                    y = yd; sy = have ? M.status[yd] : 0u; rem = (int)((rec >> 16) & 0xFFu); xh_inf = -1;
+                                    yinf = have && ((M.inf[yd >> 5] >> (yd & 31)) & 1u);
+                                    bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;             // :822
+                                    unsigned m = peers;
+                                    for (int k = 0; k < nmax; ++k) {                                      // k-th event of each target, in event order
+                                        const int src = m ? __ffs(m) - 1 : lane; m &= m - 1u;
+                                        const uint32_t w1s = __shfl_sync(FULL, w1d, src);
+                                        const int qs = __shfl_sync(FULL, qd, src);
+                                        if (leader && k < n && rem > 0) {                                 // :812
+                                            rem -= 1;                                                     // :813
+                                            if (ctr && s_ctr[qs]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[qs] + 2u + (uint32_t)atomicAdd(&s_clen[qs], 1)] = y;
+                                            if (sus && bern(w1s, s_bthr[qs])) { sus = false; xh_inf = s_xh[qs]; }
                                         }
                                     }
-                                    uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
-                                    if (xh_inf >= 0) {
-                                        ns = st_set_swap(ns, LAT);
-                                        S.sickfrom[rb + y] = (uint8_t)xh_inf;
-                                        M.expday[y] = (int16_t)day;                // y.exp = y.tis :826 — fires in today's time_update
-                                        M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
+                                    apply = leader;
+                                    dury = 0xFFFFFFFFu;                                                   // not loaded by this lane: no cache entry
+                                }
+                            } else if (isdup) {
+                                // many shared targets: every first event of a target walks the compacted list
+                                bool leader = true;
+                                for (int d = 0; d < dpos; ++d) if ((M.Y[M.D[d]] & 0xFFFFu) == y) { leader = false; break; }
+                                if (leader) {
+                                    bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;
+                                    if (rem > 0) {
+                                        rem -= 1;
+                                        if (ctr && s_ctr[q]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q] + 2u + (uint32_t)atomicAdd(&s_clen[q], 1)] = y;
+                                        if (sus && bern(w1, s_bthr[q])) { sus = false; xh_inf = s_xh[q]; }
                                     }
-                                    M.status[y] = ns;
+                                    for (int d = dpos + 1; d < dtot && rem > 0; ++d) {
+                                        const int e2 = M.D[d];
+                                        const uint32_t rec = M.Y[e2];
+                                        if ((rec & 0xFFFFu) != y) continue;
+                                        rem -= 1;
+                                        const int q2 = (int)(rec >> 24);
+                                        if (ctr && s_ctr[q2]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q2] + 2u + (uint32_t)atomicAdd(&s_clen[q2], 1)] = y;
+                                        if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }
+                                    }
+                                    apply = true;
                                 }
                             }
+                            if (apply) {
+                                uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
+                                if (xh_inf >= 0) {
+                                    ns = st_set_swap(ns, LAT);
+                                    S.sickfrom[rb + y] = (uint8_t)xh_inf;
+                                    M.expday[y] = (int16_t)day;                // y.exp = y.tis :826 — fires in today's time_update
+                                    if (dury != 0xFFFFFFFFu) M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
+                                }
+                                M.status[y] = ns;
+                                if (yinf) fused_list_update(M, s_cm, nlist, y, sy, rem);    // a contacted infector's budget changed (:813)
+                            }
+                            PHASE(20);
                             __syncthreads();                                                   // B5: status writes visible to the next batch
                             if (ctr && wid == 0 && lane < cut && s_ctr[lane] && s_clen[lane] > 0) {    // link the day's chunk of each traced infector
                                 const int x = s_cand[lane];
@@ -585,9 +675,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 S.ct_head[rb + x] = s_cbase[lane];
                             }
                             PHASE(11);
+                            PHASE(21);
                             if (marked) { M.touch[yw] = 0; M.dupm[yw] = 0; }                   // next marking is after the next B1
                             if (tid == 0) s_anydup = 0;
-                            lpos += cut;
+                            lpos += adv;
                         }
                         PHASE(3);
                         if (w0 >= nwords && lbase <= FUSED_LCAP) break;                        // the list held every infectious agent
@@ -765,7 +856,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         // diagnostics of the fused path: kilo-cycles spent on this replicate and dyntrans batches issued
         PHASE(6);
 #ifdef CABM_FUSED_DIAG
-        if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; for (int k = 0; k < 16; ++k) S.dbg[(size_t)r * 16 + k] = t_ph[k]; }
+        if (tid == 0) { S.totalmet[r] = (int)((clock64() - t_start) >> 10); S.totalinf[r] = n_rounds; for (int k = 0; k < 32; ++k) S.dbg[(size_t)r * 32 + k] = t_ph[k]; }
 #else
         if (tid == 0) { S.totalmet[r] = 0; S.totalinf[r] = 0; }
 #endif

@@ -17,9 +17,14 @@ for r in order[:12]: print(r, "kcyc", met[r], "ms", met[r]*1024/1.965e6, "rounds
 print("takeoff count", (attack>0.1).sum(), "mean attack", attack.mean())
 for r in order[500:503]: print(r, "kcyc", met[r], "rounds", inf[r], "attack", attack[r])
 
-dbg = np.zeros((1000, 16), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
-names = ["setup","list","budgets","(rounds tail)","time_update after S1","curves/idle","writeback","-","round: warp0 cand ->B1","round: events ->B2","round: dup compaction ->B3","round: apply ->B5","dyntrans end -> S1"]
+dbg = np.zeros((1000, 32), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
+names = {22: "setup: initialize", 23: "setup: get_ag_dist", 24: "setup: insert_infected", 0: "setup: column 1 / resume reload", 1: "list", 2: "budgets", 3: "(rounds tail)", 4: "time_update after S1", 5: "curves/idle", 6: "writeback",
+         13: "round: B5 -> cand loads done", 14: "round: -> prefix scan done", 15: "round: -> before B1", 8: "round: B1 wait + nb/Etot loads",
+         16: "round: owner search", 17: "round: target philox + status", 18: "round: target budget", 19: "round: cut check, Y/W1/Q, touch",
+         9: "round: B2 wait", 10: "round: cut/dup compaction", 20: "round: apply", 11: "round: B5 wait", 21: "(timer overhead)", 12: "dyntrans end -> S1"}
 big = attack > 0.1
-print("phase kcycles  take-off mean | extinct mean")
-for k in range(13): print(f"{names[k]:28s} {dbg[big,k].mean()/1e3:10.1f} | {dbg[~big,k].mean()/1e3:10.1f}")
-print("rounds take-off mean", inf[big].mean(), "extinct", inf[~big].mean(), " active days?")
+print("phase kcycles  take-off mean | extinct mean | per round (take-off)")
+nr = max(inf[big].sum(), 1)
+for k in names: print(f"{k:2d} {names[k]:36s} {dbg[big,k].mean()/1e3:10.1f} | {dbg[~big,k].mean()/1e3:10.1f} | {dbg[big,k].sum()/nr:8.0f}")
+print("rounds take-off mean", inf[big].mean(), "extinct", inf[~big].mean())
+print("take-off total kcycles mean", met[big].mean(), "-> ms", met[big].mean() * 1024 / 1.965e6, " max ms", met.max() * 1024 / 1.965e6)
