@@ -129,7 +129,7 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     {
         const Tables &t = tables();
         std::vector<uint32_t> nb(5 * 256, 0xFFFFFFFFu);
-        std::vector<uint8_t> guide(5 * 256, 0);
+        std::vector<uint8_t> guide(5 * 512, 0);     // per group: 256 entries on the top byte of w, 256 on the next byte for the top bucket
         std::vector<unsigned long long> gpw(5 * 256, 0);
         for (int g = 0; g < 5; ++g) {
             const auto &thr = t.nb[g].thr;
@@ -138,7 +138,12 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
             for (int b = 0; b < 256; ++b) {
                 uint32_t wmin = (uint32_t)b << 24; int k = 0;
                 while (k < (int)thr.size() && thr[k] <= wmin) ++k;
-                guide[g * 256 + b] = (uint8_t)k;
+                guide[g * 512 + b] = (uint8_t)k;
+            }
+            for (int b = 0; b < 256; ++b) {     // the top bucket holds the whole tail (~100 thresholds): second level
+                uint32_t wmin = 0xFF000000u | ((uint32_t)b << 16); int k = 0;
+                while (k < (int)thr.size() && thr[k] <= wmin) ++k;
+                guide[g * 512 + 256 + b] = (uint8_t)k;
             }
             for (int cnt = 0; cnt < 256; ++cnt) {
                 int o[5]; gpw_split(g + 1, cnt, o);
@@ -320,7 +325,7 @@ extern "C" int cabm_run(cabm_handle *h) {
     h->pev_used = 0; h->pcls.clear();
     // The fused kernel keeps a replicate's hot state in shared memory: usable when it fits two CTAs per SM budget
     // (popsize <= ~21k agents) with the exact schedule; otherwise one kernel per phase per day.
-    const bool fused_ok = h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 227 * 1024 - 4096;
+    const bool fused_ok = h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 227 * 1024 - 512;
     const bool use_fused = h->path == CABM_PATH_FUSED ? fused_ok : (h->path == CABM_PATH_AUTO && fused_ok);
     if (h->path == CABM_PATH_FUSED && !fused_ok) return fail(h, CABM_E_STATE, "fused path needs the exact schedule and a population that fits shared memory");
     CU(cudaEventRecord(h->ev0, h->stream));

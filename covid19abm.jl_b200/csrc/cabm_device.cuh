@@ -45,7 +45,7 @@ __host__ __device__ inline uint32_t st_make(int health, int swap, int ag0, bool 
 }
 __host__ __device__ inline bool is_infectious(int h) { return h >= PRE && h <= IISO; }  // :794
 // _get_betavalue class :761-767: 0 PRE, 1 ASYMP, 2 MILD/MISO, 3 INF/IISO
-__host__ __device__ inline int beta_class(int h) { return h == PRE ? 0 : h == ASYMP ? 1 : (h == MILD || h == MISO) ? 2 : 3; }
+__host__ __device__ inline int beta_class(int h) { return (int)((0xFFFFFA4Fu >> (2 * h)) & 3u); }    // two bits per health code, no branches
 
 // per-parameter-set constants, thresholds are "w < thr  <=>  rand() < p"
 struct DevPset {
@@ -87,7 +87,7 @@ struct Dev {
     int16_t *host_inc, *host_prev;           // optional pinned host buffers [R][6][T][12]: the fused kernel streams each finished
                                              // replicate's curves there (Int16) so no device->host copy is left at the end
     const DevPset *psets; const unsigned long long *beta_thr;    // [P], [P][T][4]
-    const uint32_t *nb_thr; const uint8_t *nb_guide;             // [5][256], [5][256]
+    const uint32_t *nb_thr; const uint8_t *nb_guide;             // [5][256], [5][512] (top byte of w; next byte inside the top bucket)
     const unsigned long long *gpw;                               // [5][256] five u8 counts packed
 };
 
@@ -124,7 +124,7 @@ __device__ __forceinline__ int fresh_budget(const Dev &S, uint2 key, uint32_t i,
         return (w < 0x80000000u) ? 0 : 1 + (int)(((unsigned long long)(w & 0x7fffffffu) * 3ull) >> 31);
     int ag = st_ag(st);                                                    // :781
     const uint32_t *thr = S.nb_thr + ag * 256;
-    int k = __ldg(&S.nb_guide[ag * 256 + (w >> 24)]), len = c_tab.nb_len[ag];
+    int k = __ldg(&S.nb_guide[ag * 512 + ((w >> 24) == 255u ? 256u + ((w >> 16) & 0xFFu) : (w >> 24))]), len = c_tab.nb_len[ag];
     while (k < len && __ldg(&thr[k]) <= w) ++k;
     return k;
 }

@@ -25,11 +25,36 @@ namespace cabm {
 constexpr int FUSED_NT = 256;          // threads per CTA = max events per batch
 constexpr int FUSED_NCAND = 32;        // infectors per batch
 constexpr int FUSED_LCAP = 256;        // infectors listed per pass (more are handled in further passes)
+constexpr int FUSED_SCAN_U = 5;        // chunks of 8 agents a thread scans at once in time_update (256 x 8 x 5 >= 10,000 agents in one go)
 static_assert(FUSED_NT == 256 && FUSED_LCAP <= FUSED_NT, "thread-index roles in k_sim_fused are laid out for 256 threads");
+
+// Small per-CTA state. It lives at the start of the dynamic shared-memory block (not in static __shared__ arrays) so that every
+// access is "block base + constant offset" from one uniform register.
+struct FusedCtl {
+    DevPset P;                               // this replicate's parameter set (read on every transition)
+    double cm[25];                           // contact_matrix :838-848
+    unsigned long long beta[4];              // _get_betavalue :756-769 thresholds of the day
+    unsigned long long bthr[FUSED_NCAND], gp[FUSED_NCAND];      // batch entries: transmission threshold, budget split (:800, :804)
+    int run[72];                             // running prevalence of the six groups, for the idle-tail fill (16-byte aligned)
+    int io[2][2][60];                        // [day parity][entries | exits][(group, state)] — curve deltas of one day
+    uint32_t tlat[4], tpre[4], tasy[40], tinf[40];
+    int r, off[8], wcnt[FUSED_NT / 32][5];
+    int sel_tid, sel_k, Ltot, ninf;
+    int nf[2], wsum[FUSED_NT / 32];
+    int nb_len[5], pad_[3];
+    int infectors[4];
+    int cand[FUSED_NCAND], pref[FUSED_NCAND + 1], nb, cut, adv;  // batch entries: agent, event prefix; entries, cut, list entries consumed
+    int wdup[FUSED_NT / 32], anydup;
+    // contact tracing (:647-752): per-entry chunk of the contact log, the replicate's log fill, index-case queues by day parity
+    uint32_t cbase[FUSED_NCAND], logn, qcnt[2];
+    int clen[FUSED_NCAND];
+    uint8_t xh[FUSED_NCAND], map[FUSED_NCAND], ctr[FUSED_NCAND];   // infector's health; position of the entry in the list stretch; traced
+};
+static_assert(sizeof(FusedCtl) % 16 == 0, "the arrays behind FusedCtl need 16-byte alignment");
 
 struct FusedSmem {
     uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
-    uint32_t *nb_thr; uint8_t *nb_guide;
+    uint32_t *nb_thr; uint8_t *nb_guide; const int *nb_len;
     uint32_t *Y, *W1; uint32_t *touch, *dupm, *mpre, *mpost; uint16_t *D;   // batch events: (target | budget << 16 | owner << 24), transmission word
     uint16_t *list; uint8_t *lh, *lE;    // the day's ordered infectious agents, their health (+ tracing flag) and event counts
     unsigned long long *lgp;             // ... and the budget split over the five age groups (:804), five packed bytes
@@ -38,12 +63,12 @@ struct FusedSmem {
 };
 
 __host__ __device__ inline size_t fused_smem_bytes(int Np) {
-    size_t b = 0;
+    size_t b = sizeof(FusedCtl);
     b += (size_t)Np * 4;                 // status
     b += (size_t)Np * 2 * 2;             // expday, grp
     b += (size_t)Np;                     // col
     b += (size_t)(Np / 32) * 4;          // inf
-    b += 5 * 256 * 4 + 5 * 256;          // nb tables
+    b += 5 * 256 * 4 + 5 * 512;          // nb tables
     b += FUSED_NT * 4 * 2;               // Y (= cnt), W1
     b += (size_t)(Np / 32) * 4 * 4;      // touch, dupm, mark_pre, mark_post bitmasks
     b += FUSED_NT * 2;                   // D (compacted duplicate events)
@@ -60,8 +85,8 @@ __device__ __forceinline__ int fresh_budget_s(const FusedSmem &M, uint2 key, uin
     if (st & ST_ISOB) return (w < 0x80000000u) ? 0 : 1 + (int)(((unsigned long long)(w & 0x7fffffffu) * 3ull) >> 31);
     const int ag = st_ag(st);
     const uint32_t *thr = M.nb_thr + ag * 256;
-    int k = M.nb_guide[ag * 256 + (w >> 24)];
-    const int len = c_tab.nb_len[ag];
+    int k = M.nb_guide[ag * 512 + ((w >> 24) == 255u ? 256u + ((w >> 16) & 0xFFu) : (w >> 24))];
+    const int len = M.nb_len[ag];
     while (k < len && thr[k] <= w) ++k;
     return k;
 }
@@ -107,9 +132,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = FUSED_NT, NW = FUSED_NT / 32;
     const int N = S.N, Np = S.Np, T = S.T, nwords = S.nwords;
+    FusedCtl &Z = *reinterpret_cast<FusedCtl *>(smem_raw);
     FusedSmem M;
     {
-        unsigned char *p = smem_raw;
+        unsigned char *p = smem_raw + sizeof(FusedCtl);
         M.dcache = (unsigned long long *)p; p += DUR_CACHE * 8;
         M.lgp = (unsigned long long *)p; p += FUSED_LCAP * 8;
         M.status = (uint32_t *)p; p += (size_t)Np * 4;
@@ -126,39 +152,21 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         M.mpost = (uint32_t *)p; p += (size_t)nwords * 4;
         M.D = (uint16_t *)p; p += NT * 2;
         M.list = (uint16_t *)p; p += FUSED_LCAP * 2;
-        M.nb_guide = (uint8_t *)p; p += 5 * 256;
+        M.nb_guide = (uint8_t *)p; p += 5 * 512;
+        M.nb_len = Z.nb_len;
         M.lh = (uint8_t *)p; p += FUSED_LCAP;
         M.lE = (uint8_t *)p; p += FUSED_LCAP;
     }
-    __shared__ int s_r, s_off[8], s_wcnt[FUSED_NT / 32][5];
-    __shared__ int s_sel_tid, s_sel_k, s_Ltot, s_ninf;
-    __shared__ int s_io[2][2][60];           // [day parity][entries | exits][(group, state)] — curve deltas of one day
-    __shared__ uint32_t s_tlat[4], s_tpre[4], s_tasy[40], s_tinf[40];
-    __shared__ unsigned long long s_beta[4];
-    __shared__ DevPset s_P;                  // this replicate's parameter set (read on every transition)
-    __shared__ double s_cm[25];              // contact_matrix :838-848
-    __shared__ int s_nf[2], s_wsum[FUSED_NT / 32];
-    __shared__ __align__(16) int s_run[72];  // running prevalence of the six groups, for the idle-tail fill
-    __shared__ int s_infectors[4];
-    // dyntrans batch
-    __shared__ int s_cand[FUSED_NCAND], s_pref[FUSED_NCAND + 1], s_nb, s_cut;
-    __shared__ unsigned long long s_bthr[FUSED_NCAND];
-    __shared__ unsigned long long s_gp[FUSED_NCAND];
-    __shared__ uint8_t s_xh[FUSED_NCAND], s_map[FUSED_NCAND];   // infector's health; position of the batch entry in the list stretch
-    __shared__ int s_adv;
-    __shared__ int s_wdup[FUSED_NT / 32], s_anydup;
-    // contact tracing (:647-752): per-candidate chunk of the contact log, the replicate's log fill, index-case queues by day parity
-    __shared__ uint8_t s_ctr[FUSED_NCAND];
-    __shared__ uint32_t s_cbase[FUSED_NCAND], s_logn, s_qcnt[2];
-    __shared__ int s_clen[FUSED_NCAND];
 
-    for (int k = tid; k < 5 * 256; k += NT) { M.nb_thr[k] = S.nb_thr[k]; M.nb_guide[k] = S.nb_guide[k]; }
+    for (int k = tid; k < 5 * 256; k += NT) M.nb_thr[k] = S.nb_thr[k];
+    for (int k = tid; k < 5 * 512; k += NT) M.nb_guide[k] = S.nb_guide[k];
+    if (tid < 5) Z.nb_len[tid] = c_tab.nb_len[tid];
     for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; M.mpre[k] = 0; M.mpost[k] = 0; }
-    if (tid == 0) s_anydup = 0;
-    if (tid < 4) { s_tlat[tid] = c_tab.lat_thr[tid]; s_tpre[tid] = c_tab.pre_thr[tid]; }
-    if (tid < 40) { s_tasy[tid] = c_tab.asy_thr[tid]; s_tinf[tid] = c_tab.inf_thr[tid]; }
-    if (tid < 25) s_cm[tid] = c_tab.cm[tid / 5][tid % 5];
-    int *const s_inc = s_io[0][0], *const s_out = s_io[0][1];   // first-column phase uses parity 0
+    if (tid == 0) Z.anydup = 0;
+    if (tid < 4) { Z.tlat[tid] = c_tab.lat_thr[tid]; Z.tpre[tid] = c_tab.pre_thr[tid]; }
+    if (tid < 40) { Z.tasy[tid] = c_tab.asy_thr[tid]; Z.tinf[tid] = c_tab.inf_thr[tid]; }
+    if (tid < 25) Z.cm[tid] = c_tab.cm[tid / 5][tid % 5];
+    int *const s_inc = Z.io[0][0], *const s_out = Z.io[0][1];   // first-column phase uses parity 0
     __syncthreads();
     const bool tma_ok = S.store_hm && (N % 16 == 0);     // cp.async.bulk needs 16-byte size and alignment
 
@@ -187,10 +195,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 }
                 __threadfence();
             }
-            s_r = got;
+            Z.r = got;
         }
         __syncthreads();
-        const int r = s_r;
+        const int r = Z.r;
         if (r < 0) break;
         const bool resumed = sweep == 1;
 #ifdef CABM_FUSED_DIAG      // per-phase cycle counts seen by thread 0 (make diag; tools/diag_fused.py)
@@ -199,15 +207,18 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         long long t_last = t_start;
         if (tid < 32) t_ph[tid] = 0;
 #define PHASE(k) do { if (tid == 0) { t_ph[k] += clock64() - t_last; t_last = clock64(); } } while (0)
+#define PHASEX(k) do { if (tid == FUSED_NT - 32) { t_ph[k] += clock64() - t_lastx; t_lastx = clock64(); } } while (0)
+        long long t_lastx = 0;
         int n_rounds = 0;
 #else
 #define PHASE(k) do { } while (0)
+#define PHASEX(k) do { } while (0)
 #endif
-        if (tid < (int)(sizeof(DevPset) / 4)) reinterpret_cast<uint32_t *>(&s_P)[tid] = reinterpret_cast<const uint32_t *>(&S.psets[S.pset_of[r]])[tid];
+        if (tid < (int)(sizeof(DevPset) / 4)) reinterpret_cast<uint32_t *>(&Z.P)[tid] = reinterpret_cast<const uint32_t *>(&S.psets[S.pset_of[r]])[tid];
         __syncthreads();
-        const DevPset &P = s_P;
+        const DevPset &P = Z.P;
         const bool ctr = CT && P.ctstrat != 0;        // this replicate traces contacts
-        if (tid == 0) { s_logn = 0; s_qcnt[0] = 0; s_qcnt[1] = 0; }
+        if (tid == 0) { Z.logn = 0; Z.qcnt[0] = 0; Z.qcnt[1] = 0; }
         const uint2 key = S.key[r];
         const size_t rb = (size_t)r * Np;
         const unsigned long long *beta = S.beta_thr + (size_t)S.pset_of[r] * T * 4;
@@ -227,10 +238,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 int ag0 = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ag0 += ((unsigned long long)wa.x >= P.age_thr[k]);
-                int latents = table_draw(wa.y, c_tab.lat_base, s_tlat, c_tab.lat_len);
-                const int pres = table_draw(wa.z, c_tab.pre_base, s_tpre, c_tab.pre_len);
-                const int asymps = table_draw(wa.w, c_tab.asy_base, s_tasy, c_tab.asy_len);
-                const int infs = table_draw(wb.x, c_tab.inf_base, s_tinf, c_tab.inf_len);
+                int latents = table_draw(wa.y, c_tab.lat_base, Z.tlat, c_tab.lat_len);
+                const int pres = table_draw(wa.z, c_tab.pre_base, Z.tpre, c_tab.pre_len);
+                const int asymps = table_draw(wa.w, c_tab.asy_base, Z.tasy, c_tab.asy_len);
+                const int infs = table_draw(wb.x, c_tab.inf_base, Z.tinf, c_tab.inf_len);
                 latents -= pres;
                 d4 = (uint32_t)latents | ((uint32_t)asymps << 8) | ((uint32_t)pres << 16) | ((uint32_t)infs << 24);
                 const bool quar = bern(wb.y, P.quar_thr) && ag0 == P.quar_grp0;
@@ -246,9 +257,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         }
         for (int k = tid; k < nwords; k += NT) M.inf[k] = 0;
         for (int k = tid; k < DUR_CACHE; k += NT) M.dcache[k] = ~0ull;
-        for (int k = tid; k < 240; k += NT) (&s_io[0][0][0])[k] = 0;
-        if (tid < 4) s_infectors[tid] = 0;
-        if (tid == 0) s_ninf = 0;
+        for (int k = tid; k < 240; k += NT) (&Z.io[0][0][0])[k] = 0;
+        if (tid < 4) Z.infectors[tid] = 0;
+        if (tid == 0) Z.ninf = 0;
         __syncthreads();
         PHASE(22);
 
@@ -264,20 +275,20 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #pragma unroll
                 for (int g = 0; g < 5; ++g) c[g] += __popc(__ballot_sync(FULL, ag == g));
             }
-            if (lane == 0) for (int g = 0; g < 5; ++g) s_wcnt[wid][g] = c[g];
+            if (lane == 0) for (int g = 0; g < 5; ++g) Z.wcnt[wid][g] = c[g];
             __syncthreads();
             if (tid == 0) {
                 int o = 0;
                 for (int g = 0; g < 5; ++g) {
-                    s_off[g] = o;
-                    for (int w = 0; w < NW; ++w) { const int v = s_wcnt[w][g]; s_wcnt[w][g] = o; o += v; }      // start of warp w's slice of group g
+                    Z.off[g] = o;
+                    for (int w = 0; w < NW; ++w) { const int v = Z.wcnt[w][g]; Z.wcnt[w][g] = o; o += v; }      // start of warp w's slice of group g
                 }
-                s_off[5] = o;
+                Z.off[5] = o;
             }
             __syncthreads();
             int base[5];
 #pragma unroll
-            for (int g = 0; g < 5; ++g) base[g] = s_wcnt[wid][g];
+            for (int g = 0; g < 5; ++g) base[g] = Z.wcnt[wid][g];
             for (int i0 = lo; i0 < hi; i0 += 32) {
                 const int i = i0 + lane;
                 const int ag = (i < hi) ? st_ag(M.status[i]) : -1;
@@ -301,21 +312,21 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             int mine = 0;
             for (int i = lo; i < hi; ++i) mine += (st_health(M.status[i]) == SUS);
             M.cnt[tid] = mine;
-            { int v = mine; for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0) s_wsum[wid] = v; }
+            { int v = mine; for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0) Z.wsum[wid] = v; }
             __syncthreads();
-            if (tid == 0) { int L = 0; for (int w = 0; w < NW; ++w) L += s_wsum[w]; s_Ltot = L; }
+            if (tid == 0) { int L = 0; for (int w = 0; w < NW; ++w) L += Z.wsum[w]; Z.Ltot = L; }
             __syncthreads();
-            if (s_Ltot == 0 || num > s_Ltot) { if (tid == 0 && (num > 0 || s_Ltot == 0)) atomicOr(&S.err[r], ERR_NO_SUS); continue; }
+            if (Z.Ltot == 0 || num > Z.Ltot) { if (tid == 0 && (num > 0 || Z.Ltot == 0)) atomicOr(&S.err[r], ERR_NO_SUS); continue; }
             for (int j = 0; j < num; ++j) {
                 if (tid == 0) {
                     const uint4 w = philox(j, 0, S_SEED, which, key);
-                    int k = below(w.x, s_Ltot - j), t = 0;
+                    int k = below(w.x, Z.Ltot - j), t = 0;
                     while (k >= M.cnt[t]) { k -= M.cnt[t]; ++t; }
-                    s_sel_tid = t; s_sel_k = k;
+                    Z.sel_tid = t; Z.sel_k = k;
                 }
                 __syncthreads();
-                if (tid == s_sel_tid) {
-                    int k = s_sel_k;
+                if (tid == Z.sel_tid) {
+                    int k = Z.sel_k;
                     for (int i = lo; i < hi; ++i) {
                         const uint32_t st = M.status[i];
                         if (st_health(st) != SUS) continue;
@@ -326,7 +337,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         if (ctr) S.texp[rb + i] = (int16_t)t.expday;
                         M.col[i] = (uint8_t)t.newh;
                         S.sickfrom[rb + i] = INF;                             // :391
-                        if (is_infectious(t.newh)) { M.inf[i >> 5] |= 1u << (i & 31); s_ninf += 1; }
+                        if (is_infectious(t.newh)) { M.inf[i >> 5] |= 1u << (i & 31); Z.ninf += 1; }
                         break;
                     }
                     M.cnt[tid] -= 1;
@@ -348,7 +359,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         run = 0;                                  // running prevalence of (group, state) = (tid/12, tid%12), tid < 60; group 0 in tid 64..75
         if (tid < 60) {
             const int g = tid / 12, s = tid % 12;
-            run = s_inc[tid] + (s == SUS ? (s_off[g + 1] - s_off[g]) - s_out[tid] : 0);
+            run = s_inc[tid] + (s == SUS ? (Z.off[g + 1] - Z.off[g]) - s_out[tid] : 0);
             const size_t b = (((size_t)r * 6 + (g + 1)) * (size_t)T + 0) * 12 + s;
             S.inc[b] = run; S.prev[b] = run;
             M.cnt[tid] = run;
@@ -378,12 +389,12 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             }
             for (int k = tid; k < nwords; k += NT) M.inf[k] = __ldcg(&S.infmask[(size_t)r * nwords + k]);
             for (int k = tid; k < DUR_CACHE; k += NT) M.dcache[k] = ~0ull;
-            for (int k = tid; k < 240; k += NT) (&s_io[0][0][0])[k] = 0;
-            if (tid < 6) s_off[tid] = __ldcg(&S.grp_off[r * 8 + tid]);
-            if (tid < 4) s_infectors[tid] = 0;
+            for (int k = tid; k < 240; k += NT) (&Z.io[0][0][0])[k] = 0;
+            if (tid < 6) Z.off[tid] = __ldcg(&S.grp_off[r * 8 + tid]);
+            if (tid < 4) Z.infectors[tid] = 0;
             if (tid == 0) {
-                s_ninf = __ldcg(&S.resume_aux[r * 2 + 1]);
-                if (ctr) { s_logn = __ldcg(&S.ct_cnt[r]); s_qcnt[0] = __ldcg(&S.ident_cnt[r * 2]); s_qcnt[1] = __ldcg(&S.ident_cnt[r * 2 + 1]); }
+                Z.ninf = __ldcg(&S.resume_aux[r * 2 + 1]);
+                if (ctr) { Z.logn = __ldcg(&S.ct_cnt[r]); Z.qcnt[0] = __ldcg(&S.ident_cnt[r * 2]); Z.qcnt[1] = __ldcg(&S.ident_cnt[r * 2 + 1]); }
             }
             if (tid < 60) run = __ldcg(&S.prev[(((size_t)r * 6 + (tid / 12 + 1)) * (size_t)T + (size_t)split_day) * 12 + tid % 12]);
             else if (tid >= 64 && tid < 76) run = __ldcg(&S.prev[(((size_t)r * 6 + 0) * (size_t)T + (size_t)split_day) * 12 + (tid - 64)]);
@@ -394,20 +405,20 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         // ============================================================ the day loop :131-140
         // s_nextfire = earliest expiry day of any agent. A day with nobody infectious and nothing expiring changes no
         // state: it only repeats the column and the prevalence row, without a single barrier.
-        if (tid < 2) s_nf[tid] = 32767;
+        if (tid < 2) Z.nf[tid] = 32767;
         int nextfire = resumed ? __ldcg(&S.resume_aux[r * 2]) : 0, act = 0;    // uniform registers
         const int day_first = resumed ? split_day + 1 : 1;
         const int day_last = (!resumed && split_day > 0 && split_day < T) ? split_day : T;
         bool finished = day_last == T;                                         // set early by the fast-forward below
         __syncthreads();
         for (int day = day_first; day <= day_last; ++day) {
-            const bool active = s_ninf > 0 || day >= nextfire;                 // uniform: s_ninf only changes between S1 and S2
+            const bool active = Z.ninf > 0 || day >= nextfire;                 // uniform: Z.ninf only changes between S1 and S2
             if (!active && nextfire > T) {
                 // nobody is infectious and no state expires before the end of the run: the remaining columns and curve rows
                 // repeat the current ones (tis >= exp :405 never fires again) — write them without stepping through the days
                 // curve rows day..T-1 of a group are one contiguous run of 12-int rows (48 B, 16-byte aligned): the whole CTA
                 // fills them with 16-byte stores while thread 0 queues the column copies
-                if (tid < 60) s_run[12 + tid] = run; else if (tid >= 64 && tid < 76) s_run[tid - 64] = run;
+                if (tid < 60) Z.run[12 + tid] = run; else if (tid >= 64 && tid < 76) Z.run[tid - 64] = run;
                 __syncthreads();
                 {
                     const int per = (T - day) * 3;                                  // uint4 per group
@@ -415,7 +426,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         const int G = idx / per, j = idx - G * per;
                         const size_t b0 = (((size_t)r * 6 + G) * (size_t)T + (size_t)day) * 12;
                         reinterpret_cast<int4 *>(S.inc + b0)[j] = make_int4(0, 0, 0, 0);
-                        reinterpret_cast<int4 *>(S.prev + b0)[j] = *reinterpret_cast<const int4 *>(&s_run[G * 12 + (j % 3) * 4]);
+                        reinterpret_cast<int4 *>(S.prev + b0)[j] = *reinterpret_cast<const int4 *>(&Z.run[G * 12 + (j % 3) * 4]);
                     }
                 }
                 if (hm) {
@@ -430,9 +441,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             if (active) {
                 if (hm && tma_ok && tid == 0) bulk_store_wait_read();          // earlier columns have left shared memory (ordered by the barriers below)
                 // ---------------------------------------------------- dyntrans(st) :790-834
-                const bool had_infectious = s_ninf > 0;                        // uniform
+                const bool had_infectious = Z.ninf > 0;                        // uniform
                 if (had_infectious) {
-                    if (tid < 4) s_beta[tid] = beta[(size_t)(day - 1) * 4 + tid];              // _get_betavalue :756-769 for today
+                    if (tid < 4) Z.beta[tid] = beta[(size_t)(day - 1) * 4 + tid];              // _get_betavalue :756-769 for today
                     int cursor = 0;                                                            // first agent index not yet listed
                     for (;;) {
                         // ordered list of (up to FUSED_LCAP) infectious agents at or after `cursor` (:794), built by the whole CTA
@@ -444,10 +455,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const int c0 = __popc(m0), c = c0 + __popc(m1);
                             int incl = c;
                             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                            if (lane == 31) s_wsum[wid] = incl;
+                            if (lane == 31) Z.wsum[wid] = incl;
                             __syncthreads();
                             int pos = lbase + incl - c, tot = 0;
-                            for (int w = 0; w < NW; ++w) { const int v = s_wsum[w]; tot += v; if (w < wid) pos += v; }
+                            for (int w = 0; w < NW; ++w) { const int v = Z.wsum[w]; tot += v; if (w < wid) pos += v; }
                             while (m0 && pos < FUSED_LCAP) { const int b = __ffs(m0) - 1; m0 &= m0 - 1; M.list[pos++] = (uint16_t)((wi << 5) + b); }
                             while (m1 && pos < FUSED_LCAP) { const int b = __ffs(m1) - 1; m1 &= m1 - 1; M.list[pos++] = (uint16_t)(((wi + 1) << 5) + b); }
                             lbase += tot;
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const int cnts = budget_of_s(M, key, x, day, sx);
                             // health and the tracing flag of an infector do not change inside dyntrans: keep them with the list
                             M.lh[tid] = (uint8_t)(st_health(sx) | ((sx & ST_TRACING) ? 0x80u : 0u));
-                            const unsigned long long gp = gpw_pack(s_cm + st_ag(sx) * 5, cnts);
+                            const unsigned long long gp = gpw_pack(Z.cm + st_ag(sx) * 5, cnts);
                             M.lgp[tid] = gp;
                             M.lE[tid] = (uint8_t)gpw_sum(gp);
                         }
@@ -490,49 +501,49 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 const unsigned km = __ballot_sync(FULL, keep);
                                 const int rank = __popc(km & ((1u << lane) - 1u));
                                 if (keep) {
-                                    s_cand[rank] = x; s_gp[rank] = gp; s_xh[rank] = (uint8_t)(h & 0xF); s_map[rank] = (uint8_t)lane;
-                                    s_bthr[rank] = s_beta[beta_class(h & 0xF)];                 // :800
-                                    s_pref[rank + 1] = incl;
+                                    Z.cand[rank] = x; Z.gp[rank] = gp; Z.xh[rank] = (uint8_t)(h & 0xF); Z.map[rank] = (uint8_t)lane;
+                                    Z.bthr[rank] = Z.beta[beta_class(h & 0xF)];                 // :800
+                                    Z.pref[rank + 1] = incl;
                                 }
                                 if (ctr) {                                                     // :817-819 chunk [next, count, <= E targets] per traced infector
                                     const bool tr = keep && (h & 0x80);
                                     int need = tr ? 2 + E : 0, nin = need;
                                     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, nin, o); if (lane >= o) nin += v; }
                                     const int ntot = __shfl_sync(FULL, nin, 31);
-                                    const uint32_t base0 = s_logn;
+                                    const uint32_t base0 = Z.logn;
                                     const bool room = base0 + (uint32_t)ntot <= S.ct_cap;
                                     if (!room && ntot && lane == 0) atomicOr(&S.err[r], ERR_CT_LOG_FULL);
-                                    if (keep) { s_ctr[rank] = (uint8_t)(tr && room); s_cbase[rank] = base0 + (uint32_t)(nin - need); s_clen[rank] = 0; }
+                                    if (keep) { Z.ctr[rank] = (uint8_t)(tr && room); Z.cbase[rank] = base0 + (uint32_t)(nin - need); Z.clen[rank] = 0; }
                                     __syncwarp();
-                                    if (lane == 0 && room) s_logn = base0 + (uint32_t)ntot;
+                                    if (lane == 0 && room) Z.logn = base0 + (uint32_t)ntot;
                                 }
-                                if (lane == 0) { s_pref[0] = 0; const int nbc = __popc(km); s_nb = nbc; s_cut = nbc; s_adv = nfit; }
+                                if (lane == 0) { Z.pref[0] = 0; const int nbc = __popc(km); Z.nb = nbc; Z.cut = nbc; Z.adv = nfit; }
                             }
                             PHASE(15);
                             __syncthreads();                                                   // B1
                             PHASE(8);
-                            const int nb = s_nb;
-                            if (nb == 0) { lpos += s_adv; __syncthreads(); continue; }          // nobody in this stretch of the list has contacts today
-                            const int Etot = s_pref[nb];
+                            const int nb = Z.nb;
+                            if (nb == 0) { lpos += Z.adv; __syncthreads(); continue; }          // nobody in this stretch of the list has contacts today
+                            const int Etot = Z.pref[nb];
                             // (b) one contact event per thread: owner, target draw (:807), transmission word (:823); mark the target.
                             //     Owner of event tid = number of prefix entries <= tid: those at or below the warp's first event are
                             //     counted by a ballot, the (strictly increasing) ones inside the warp's range are bits of one word
                             uint32_t y = 0, w1 = 0, sy = 0, dury = 0; int q = 0, remy = 0; bool ev = tid < Etot, yinf = false;
                             {
-                                const int Pl = lane < nb ? s_pref[lane + 1] : 0x7FFFFFFF, base = tid - lane;
+                                const int Pl = lane < nb ? Z.pref[lane + 1] : 0x7FFFFFFF, base = tid - lane;
                                 const int below = __popc(__ballot_sync(FULL, Pl <= base));
                                 const unsigned bits = __reduce_or_sync(FULL, (Pl > base && Pl <= base + 31) ? 1u << (Pl - base) : 0u);
                                 q = below + __popc(bits & ((2u << lane) - 1u));
                             }
                             PHASE(16);
                             if (ev) {
-                                const int e = tid - s_pref[q];
-                                const unsigned long long gp = s_gp[q];                 // round.(cm[ag]*cnts) :804
+                                const int e = tid - Z.pref[q];
+                                const unsigned long long gp = Z.gp[q];                 // round.(cm[ag]*cnts) :804
                                 const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF), p4 = p3 + (int)((gp >> 24) & 0xFF);
                                 const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
                                 const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
-                                const int go = s_off[g], len = s_off[g + 1] - go;
-                                const int x = s_cand[q];
+                                const int go = Z.off[g], len = Z.off[g + 1] - go;
+                                const int x = Z.cand[q];
                                 if (len == 0) { atomicOr(&S.err[r], ERR_EMPTY_GROUP); ev = false; }
                                 else {
                                     const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
@@ -550,10 +561,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     PHASE(18);
                                     yinf = (M.inf[y >> 5] >> (y & 31)) & 1u;
                                     // an infector later in this batch that gets contacted must re-read its budget: cut the batch there
-                                    if (yinf && (int)y > x && (int)y <= s_cand[nb - 1]) {
+                                    if (yinf && (int)y > x && (int)y <= Z.cand[nb - 1]) {
                                         int a = q + 1, b = nb - 1;
-                                        while (a < b) { const int mid = (a + b) >> 1; if (s_cand[mid] < (int)y) a = mid + 1; else b = mid; }
-                                        if (s_cand[a] == (int)y) atomicMin(&s_cut, a);     // (a listed infector without events has nothing to redo)
+                                        while (a < b) { const int mid = (a + b) >> 1; if (Z.cand[mid] < (int)y) a = mid + 1; else b = mid; }
+                                        if (Z.cand[a] == (int)y) atomicMin(&Z.cut, a);     // (a listed infector without events has nothing to redo)
                                     }
                                 }
                             }
@@ -562,35 +573,38 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const uint32_t ybit = 1u << (y & 31);
                             const int yw = (int)(y >> 5);
                             // targets hit more than once (by any event of the batch, cut or not) take the ordered path below
-                            if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) { atomicOr(&M.dupm[yw], ybit); s_anydup = 1; } }
+                            if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) { atomicOr(&M.dupm[yw], ybit); Z.anydup = 1; } }
                             PHASE(19);
                             __syncthreads();                                                   // B2
                             PHASE(9);
-                            const int cut = s_cut;
-                            const int Ev = s_pref[cut];                                // events of infectors [0, cut) are final
-                            const int adv = cut == nb ? s_adv : (int)s_map[cut];       // list entries this batch consumes
+                            const int cut = Z.cut;
+                            const int Ev = Z.pref[cut];                                // events of infectors [0, cut) are final
+                            const int adv = cut == nb ? Z.adv : (int)Z.map[cut];       // list entries this batch consumes
                             const bool marked = ev;
                             ev = ev && tid < Ev;
                             const bool isdup = ev && (M.dupm[yw] & ybit);
                             // (c) events sharing a target are applied in event order (:809-830) by one thread per target, over the
                             //     compacted list of such events; every other event is independent
                             int dpos = 0, dtot = 0;
-                            if (s_anydup) {                                                    // uniform (set before B2); B3/B4 only then
+                            if (Z.anydup) {                                                    // uniform (set before B2); B3/B4 only then
                                 const unsigned dm = __ballot_sync(FULL, isdup);
-                                if (lane == 0) s_wdup[wid] = __popc(dm);
+                                if (lane == 0) Z.wdup[wid] = __popc(dm);
                                 __syncthreads();
-                                for (int w = 0; w < NW; ++w) { const int c = s_wdup[w]; dtot += c; if (w < wid) dpos += c; }
+                                for (int w = 0; w < NW; ++w) { const int c = Z.wdup[w]; dtot += c; if (w < wid) dpos += c; }
                                 if (isdup) { dpos += __popc(dm & ((1u << lane) - 1u)); M.D[dpos] = (uint16_t)tid; }
                                 __syncthreads();
                             }
                             PHASE(10);
+#ifdef CABM_FUSED_DIAG
+                            t_lastx = clock64();
+#endif
                             // outcome of a target: remaining budget, infected by whom (-1: not infected)
                             int rem = remy, xh_inf = -1;
                             bool apply = ev && !isdup;
                             if (apply && rem > 0) {                                                  // :812
                                 rem -= 1;                                                             // :813
-                                if (ctr && s_ctr[q]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q] + 2u + (uint32_t)atomicAdd(&s_clen[q], 1)] = y;   // :817-819
-                                if (st_health(sy) == SUS && st_swap(sy) == UNDEF && bern(w1, s_bthr[q])) xh_inf = s_xh[q];   // :822-827
+                                if (ctr && Z.ctr[q]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[q] + 2u + (uint32_t)atomicAdd(&Z.clen[q], 1)] = y;   // :817-819
+                                if (st_health(sy) == SUS && st_swap(sy) == UNDEF && bern(w1, Z.bthr[q])) xh_inf = Z.xh[q];   // :822-827
                             }
                             if (dtot > 0 && dtot <= 32) {
                                 // few shared targets (the usual case): the last warp resolves them, one lane per event, the first
@@ -605,30 +619,37 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                             M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
                                         }
                                         M.status[y] = ns;
-                                        if (yinf) fused_list_update(M, s_cm, nlist, y, sy, rem);
+                                        if (yinf) fused_list_update(M, Z.cm, nlist, y, sy, rem);
                                         apply = false;
                                     }
+                                    PHASEX(27);
                                     const bool have = lane < dtot;
                                     const uint32_t rec = have ? M.Y[M.D[lane]] : 0u, w1d = have ? M.W1[M.D[lane]] : 0u;
                                     const uint32_t yd = rec & 0xFFFFu;
                                     const int qd = (int)(rec >> 24);
-                                    const unsigned peers = __match_any_sync(FULL, have ? yd : 0x10000u + (uint32_t)lane);
+                                    // lanes that share a target form a group led by its first event; the idle lanes form one group of their own
+                                    const unsigned peers = __match_any_sync(FULL, have ? yd : 0x10000u);
                                     const bool leader = have && lane == __ffs(peers) - 1;
                                     const int n = __popc(peers), nmax = __reduce_max_sync(FULL, have ? n : 0);
                                     y = yd; sy = have ? M.status[yd] : 0u; rem = (int)((rec >> 16) & 0xFFu); xh_inf = -1;
                                     yinf = have && ((M.inf[yd >> 5] >> (yd & 31)) & 1u);
                                     bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;             // :822
                                     unsigned m = peers;
+#ifdef CABM_FUSED_DIAG
+                                    if (sus && sy == 0x12345678u) m = 0;
+#endif
+                                    PHASEX(28);
                                     for (int k = 0; k < nmax; ++k) {                                      // k-th event of each target, in event order
                                         const int src = m ? __ffs(m) - 1 : lane; m &= m - 1u;
                                         const uint32_t w1s = __shfl_sync(FULL, w1d, src);
                                         const int qs = __shfl_sync(FULL, qd, src);
                                         if (leader && k < n && rem > 0) {                                 // :812
                                             rem -= 1;                                                     // :813
-                                            if (ctr && s_ctr[qs]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[qs] + 2u + (uint32_t)atomicAdd(&s_clen[qs], 1)] = y;
-                                            if (sus && bern(w1s, s_bthr[qs])) { sus = false; xh_inf = s_xh[qs]; }
+                                            if (ctr && Z.ctr[qs]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[qs] + 2u + (uint32_t)atomicAdd(&Z.clen[qs], 1)] = y;
+                                            if (sus && bern(w1s, Z.bthr[qs])) { sus = false; xh_inf = Z.xh[qs]; }
                                         }
                                     }
+                                    PHASEX(29);
                                     apply = leader;
                                     dury = 0xFFFFFFFFu;                                                   // not loaded by this lane: no cache entry
                                 }
@@ -640,8 +661,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;
                                     if (rem > 0) {
                                         rem -= 1;
-                                        if (ctr && s_ctr[q]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q] + 2u + (uint32_t)atomicAdd(&s_clen[q], 1)] = y;
-                                        if (sus && bern(w1, s_bthr[q])) { sus = false; xh_inf = s_xh[q]; }
+                                        if (ctr && Z.ctr[q]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[q] + 2u + (uint32_t)atomicAdd(&Z.clen[q], 1)] = y;
+                                        if (sus && bern(w1, Z.bthr[q])) { sus = false; xh_inf = Z.xh[q]; }
                                     }
                                     for (int d = dpos + 1; d < dtot && rem > 0; ++d) {
                                         const int e2 = M.D[d];
@@ -649,8 +670,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                         if ((rec & 0xFFFFu) != y) continue;
                                         rem -= 1;
                                         const int q2 = (int)(rec >> 24);
-                                        if (ctr && s_ctr[q2]) S.ct_log[(size_t)r * S.ct_cap + s_cbase[q2] + 2u + (uint32_t)atomicAdd(&s_clen[q2], 1)] = y;
-                                        if (sus && bern(M.W1[e2], s_bthr[q2])) { sus = false; xh_inf = s_xh[q2]; }
+                                        if (ctr && Z.ctr[q2]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[q2] + 2u + (uint32_t)atomicAdd(&Z.clen[q2], 1)] = y;
+                                        if (sus && bern(M.W1[e2], Z.bthr[q2])) { sus = false; xh_inf = Z.xh[q2]; }
                                     }
                                     apply = true;
                                 }
@@ -664,20 +685,21 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     if (dury != 0xFFFFFFFFu) M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
                                 }
                                 M.status[y] = ns;
-                                if (yinf) fused_list_update(M, s_cm, nlist, y, sy, rem);    // a contacted infector's budget changed (:813)
+                                if (yinf) fused_list_update(M, Z.cm, nlist, y, sy, rem);    // a contacted infector's budget changed (:813)
                             }
                             PHASE(20);
+                            PHASEX(30);
                             __syncthreads();                                                   // B5: status writes visible to the next batch
-                            if (ctr && wid == 0 && lane < cut && s_ctr[lane] && s_clen[lane] > 0) {    // link the day's chunk of each traced infector
-                                const int x = s_cand[lane];
-                                uint32_t *c = S.ct_log + (size_t)r * S.ct_cap + s_cbase[lane];
-                                c[0] = S.ct_head[rb + x]; c[1] = (uint32_t)s_clen[lane];
-                                S.ct_head[rb + x] = s_cbase[lane];
+                            if (ctr && wid == 0 && lane < cut && Z.ctr[lane] && Z.clen[lane] > 0) {    // link the day's chunk of each traced infector
+                                const int x = Z.cand[lane];
+                                uint32_t *c = S.ct_log + (size_t)r * S.ct_cap + Z.cbase[lane];
+                                c[0] = S.ct_head[rb + x]; c[1] = (uint32_t)Z.clen[lane];
+                                S.ct_head[rb + x] = Z.cbase[lane];
                             }
                             PHASE(11);
                             PHASE(21);
                             if (marked) { M.touch[yw] = 0; M.dupm[yw] = 0; }                   // next marking is after the next B1
-                            if (tid == 0) s_anydup = 0;
+                            if (tid == 0) Z.anydup = 0;
                             lpos += adv;
                         }
                         PHASE(3);
@@ -690,87 +712,109 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 // ---------------------------------------------------- time_update() :399-428
                 if (!had_infectious) __syncthreads();                          // S1: col reusable (dyntrans, when it runs, ends with barriers of its own)
                 PHASE(12);
-                if (tid == 0) s_nf[(act + 1) & 1] = 32767;                     // buffer of the next active day (last read after the previous S2)
+                if (tid == 0) Z.nf[(act + 1) & 1] = 32767;                     // buffer of the next active day (last read after the previous S2)
                 if (day == 1) {                                                // seeds isolated by fpreiso: resync isob (see k_time_update)
                     for (int i = tid; i < N; i += NT) { const uint32_t st = M.status[i]; if (((st >> 19) ^ (st >> 20)) & 1u) M.status[i] = (st & ST_ISO) ? (st | ST_ISOB) : (st & ~ST_ISOB); }
                 }
                 if (ctr) {
                     // pass A of ct_dynamics (:705-716): today's index cases (queued yesterday by agent_event_core) mark their traced
                     // contacts before anybody is updated. Index cases are few: warp 0 takes them one after another.
-                    const uint32_t nq = s_qcnt[day & 1];
+                    const uint32_t nq = Z.qcnt[day & 1];
                     if (nq) {
                         if (wid == 0) {
                             const uint32_t *qlist = S.ident_list + ((size_t)r * 2 + (day & 1)) * Np;
                             for (uint32_t k = 0; k < nq; ++k) ct_identify_warp(S, P, r, (int)qlist[k], day, M.Y, NT, M.mpre, M.mpost);
                         }
                         __syncthreads();
-                        if (tid == 0) s_qcnt[day & 1] = 0;
+                        if (tid == 0) Z.qcnt[day & 1] = 0;
                     }
                 }
+                // every thread looks at FUSED_SCAN_U chunks of 8 expiry days at once (independent loads and compares), then handles
+                // the few agents that have an event today (:405, marks) one after another
                 const uint32_t dd = (uint32_t)day * 0x10001u;
                 uint32_t mn = 0x7FFF7FFFu;                                     // running min of the event days that stay (2 x i16)
-                for (int i0 = tid * 8; i0 < N; i0 += NT * 8) {
-                    uint4 ex = *reinterpret_cast<const uint4 *>(M.expday + i0);
-                    const uint32_t m0 = __vcmples2(ex.x, dd), m1 = __vcmples2(ex.y, dd), m2 = __vcmples2(ex.z, dd), m3 = __vcmples2(ex.w, dd);
-                    unsigned pre = 0, post = 0;
-                    if (ctr) {
-                        const unsigned sh = i0 & 31;
-                        pre = (M.mpre[i0 >> 5] >> sh) & 0xFFu; post = (M.mpost[i0 >> 5] >> sh) & 0xFFu;
-                        if (pre) atomicAnd(&M.mpre[i0 >> 5], ~(0xFFu << sh));
-                        if (post) atomicAnd(&M.mpost[i0 >> 5], ~(0xFFu << sh));
+                for (int b0 = tid * 8; b0 < N; b0 += NT * 8 * FUSED_SCAN_U) {
+                    uint4 ex[FUSED_SCAN_U];
+                    unsigned long long fire = 0, pre = 0, post = 0;            // 8 bits per chunk
+#pragma unroll
+                    for (int u = 0; u < FUSED_SCAN_U; ++u) {
+                        const int i0 = b0 + u * NT * 8;
+                        ex[u] = i0 < N ? *reinterpret_cast<const uint4 *>(M.expday + i0) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
+                        if (ctr && i0 < N) {
+                            const unsigned sh = i0 & 31;
+                            pre |= (unsigned long long)((M.mpre[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
+                            post |= (unsigned long long)((M.mpost[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
+                        }
                     }
-                    if (m0 | m1 | m2 | m3 | pre | post) {                      // somebody in these 8 has an event today (:405, marks)
-                        unsigned fire = (m0 & 1u) | ((m0 >> 15) & 2u) | ((m1 & 1u) << 2) | ((m1 >> 13) & 8u) | ((m2 & 1u) << 4) | ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u);
-                        fire |= pre | post;
+#pragma unroll
+                    for (int u = 0; u < FUSED_SCAN_U; ++u) {
+                        const uint32_t m0 = __vcmples2(ex[u].x, dd), m1 = __vcmples2(ex[u].y, dd), m2 = __vcmples2(ex[u].z, dd), m3 = __vcmples2(ex[u].w, dd);
+                        const unsigned f = (m0 & 1u) | ((m0 >> 15) & 2u) | ((m1 & 1u) << 2) | ((m1 >> 13) & 8u) | ((m2 & 1u) << 4) | ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u);
+                        fire |= (unsigned long long)f << (8 * u);
+                    }
+                    fire |= pre | post;
+                    if (fire) {                                                // somebody in these chunks has an event today
                         while (fire) {
-                            const int k = __ffs(fire) - 1; fire &= fire - 1;
-                            const int i = i0 + k;
-                            if (i >= N) break;
+                            const int bit = __ffsll((long long)fire) - 1; fire &= fire - 1;
+                            const int i = b0 + (bit >> 3) * NT * 8 + (bit & 7);
+                            if (i >= N) continue;
+                            const unsigned pb = (unsigned)(pre >> bit) & 1u, qb = (unsigned)(post >> bit) & 1u;
+                            if (ctr) {
+                                if (pb) atomicAnd(&M.mpre[i >> 5], ~(1u << (i & 31)));
+                                if (qb) atomicAnd(&M.mpost[i >> 5], ~(1u << (i & 31)));
+                            }
                             const uint32_t st = M.status[i];
                             const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];      // without tracing the scan key is the expiry day
                             const int par = (day + 1) & 1;
-                            const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, ctr, (pre >> k) & 1u, (post >> k) & 1u,
-                                                          &s_qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr, M.dcache);
+                            const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, ctr, pb, qb,
+                                                          &Z.qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr, M.dcache);
                             M.status[i] = e.st;
                             M.expday[i] = (int16_t)e.ne;
                             if (ctr && e.texp != texp) S.texp[rb + i] = (int16_t)e.texp;
                             if (e.newh != e.oldh) {
                                 M.col[i] = (uint8_t)e.newh;
-                                atomicAdd(&s_io[act & 1][0][st_ag(st) * 12 + e.newh], 1); atomicAdd(&s_io[act & 1][1][st_ag(st) * 12 + e.oldh], 1);
+                                atomicAdd(&Z.io[act & 1][0][st_ag(st) * 12 + e.newh], 1); atomicAdd(&Z.io[act & 1][1][st_ag(st) * 12 + e.oldh], 1);
                                 if (is_infectious(e.newh) != is_infectious(e.oldh)) {
                                     atomicXor(&M.inf[i >> 5], 1u << (i & 31));
-                                    atomicAdd(&s_ninf, is_infectious(e.newh) ? 1 : -1);
+                                    atomicAdd(&Z.ninf, is_infectious(e.newh) ? 1 : -1);
                                 }
                             }
                         }
-                        ex = *reinterpret_cast<const uint4 *>(M.expday + i0);  // with the new expiry days
+#pragma unroll
+                        for (int u = 0; u < FUSED_SCAN_U; ++u) {               // with the new expiry days
+                            const int i0 = b0 + u * NT * 8;
+                            if (i0 < N) ex[u] = *reinterpret_cast<const uint4 *>(M.expday + i0);
+                        }
                     }
-                    mn = __vmins2(mn, __vmins2(__vmins2(ex.x, ex.y), __vmins2(ex.z, ex.w)));
+#pragma unroll
+                    for (int u = 0; u < FUSED_SCAN_U; ++u) mn = __vmins2(mn, __vmins2(__vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w)));
                 }
+                PHASE(25);
                 {
                     int v = min((int)(short)(mn & 0xFFFF), (int)(short)(mn >> 16));
                     for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
-                    if (lane == 0) atomicMin(&s_nf[act & 1], v);
+                    if (lane == 0) atomicMin(&Z.nf[act & 1], v);
                 }
                 if (hm && tma_ok) bulk_store_g2s_fence();
+                PHASE(26);
                 __syncthreads();                                               // S2
-                nextfire = s_nf[act & 1]; ++act;
+                nextfire = Z.nf[act & 1]; ++act;
                 PHASE(4);
             }
             // -------------------------------------------------------- column st+1 (:136 of the next day) and its curves
             if (day < T) {
                 // threads 0..59 own one (age group, state) pair each and keep its running prevalence in a register;
                 // threads 64..75 own group 0 ("all" = the sum over the five groups, :91-97). Idle days repeat the values.
-                // curve deltas of active day k live in s_io[k & 1] (k = act - 1 here); the other buffer, last read two active days ago,
+                // curve deltas of active day k live in Z.io[k & 1] (k = act - 1 here); the other buffer, last read two active days ago,
                 // is cleared for the next active day — no barrier needed between the group threads and the group-0 threads
                 const int cur = (act - 1) & 1;
                 if (tid < 60) {
                     const int g = tid / 12, s = tid % 12;
                     int in = 0;
                     if (active) {
-                        in = s_io[cur][0][tid];
-                        run += in - s_io[cur][1][tid];
-                        s_io[cur ^ 1][0][tid] = 0; s_io[cur ^ 1][1][tid] = 0;
+                        in = Z.io[cur][0][tid];
+                        run += in - Z.io[cur][1][tid];
+                        Z.io[cur ^ 1][0][tid] = 0; Z.io[cur ^ 1][1][tid] = 0;
                     }
                     const size_t b = (((size_t)r * 6 + (g + 1)) * (size_t)T + (size_t)day) * 12 + s;
                     S.inc[b] = in; S.prev[b] = run;
@@ -779,7 +823,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                     g0_in = 0;
                     if (active) {
                         int out = 0;
-                        for (int g = 0; g < 5; ++g) { g0_in += s_io[cur][0][g * 12 + s]; out += s_io[cur][1][g * 12 + s]; }
+                        for (int g = 0; g < 5; ++g) { g0_in += Z.io[cur][0][g * 12 + s]; out += Z.io[cur][1][g * 12 + s]; }
                         run += g0_in - out;
                     }
                     const size_t b = (((size_t)r * 6 + 0) * (size_t)T + (size_t)day) * 12 + s;
@@ -801,11 +845,11 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 S.status[rb + i] = M.status[i]; S.expday[rb + i] = M.expday[i]; S.grp_idx[rb + i] = M.grp[i];
             }
             for (int k = tid; k < nwords; k += NT) S.infmask[(size_t)r * nwords + k] = M.inf[k];
-            if (tid < 6) S.grp_off[r * 8 + tid] = s_off[tid];
+            if (tid < 6) S.grp_off[r * 8 + tid] = Z.off[tid];
             if (tid == 64 + LAT) S.latsum[r] = latsum;
             if (tid == 0) {
-                S.resume_aux[r * 2] = nextfire; S.resume_aux[r * 2 + 1] = s_ninf;
-                if (ctr) { S.ct_cnt[r] = s_logn; S.ident_cnt[r * 2] = s_qcnt[0]; S.ident_cnt[r * 2 + 1] = s_qcnt[1]; }
+                S.resume_aux[r * 2] = nextfire; S.resume_aux[r * 2 + 1] = Z.ninf;
+                if (ctr) { S.ct_cnt[r] = Z.logn; S.ident_cnt[r * 2] = Z.qcnt[0]; S.ident_cnt[r * 2 + 1] = Z.qcnt[1]; }
                 if (hm && tma_ok) bulk_store_wait_all();
             }
             __threadfence();
@@ -835,11 +879,11 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             }
         }
         for (int k = tid; k < nwords; k += NT) S.infmask[(size_t)r * nwords + k] = M.inf[k];
-        if (ctr && tid == 0) { S.ct_cnt[r] = s_logn; S.ident_cnt[r * 2] = 0; S.ident_cnt[r * 2 + 1] = 0; }
-        for (int k = 0; k < 4; ++k) if (l[k]) atomicAdd(&s_infectors[k], l[k]);
+        if (ctr && tid == 0) { S.ct_cnt[r] = Z.logn; S.ident_cnt[r * 2] = 0; S.ident_cnt[r * 2 + 1] = 0; }
+        for (int k = 0; k < 4; ++k) if (l[k]) atomicAdd(&Z.infectors[k], l[k]);
         if (bad) atomicOr(&S.err[r], ERR_SICKFROM);
         __syncthreads();
-        if (tid < 4) S.infectors[r * 4 + tid] = s_infectors[tid];
+        if (tid < 4) S.infectors[r * 4 + tid] = Z.infectors[tid];
         if (S.host_inc) {                      // this replicate's curves -> pinned host memory, 16-byte posted writes over PCIe
             __syncthreads();                   // the rows written during the day loop (by threads 0..75) are visible block-wide
             const size_t per = (size_t)6 * T * 12;                 // multiple of 8
@@ -861,6 +905,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid == 0) { S.totalmet[r] = 0; S.totalinf[r] = 0; }
 #endif
 #undef PHASE
+#undef PHASEX
         if (hm && tma_ok && tid == 0) bulk_store_wait_all();
         if (!resumed && tid == 0) { __threadfence(); atomicAdd(&work[3], 1u); }
     }
@@ -873,7 +918,7 @@ int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaSt
     const size_t bytes = fused_smem_bytes(S.Np);
     static bool attr_set = false;
     if (!attr_set) {
-        const int lim = 227 * 1024 - 4096;       // the opt-in maximum per CTA minus this kernel's static shared memory
+        const int lim = 227 * 1024 - 512;        // the opt-in maximum per CTA minus this kernel's (diagnostic) static shared memory
         cudaFuncSetAttribute(k_sim_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         cudaFuncSetAttribute(k_sim_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         attr_set = true;
