@@ -116,6 +116,14 @@ __device__ __forceinline__ int table_draw(uint32_t w, int base, const uint32_t *
     return base + v;
 }
 
+// the same count by a branch-free binary search (tables of up to 63 thresholds: no divergence between lanes)
+__device__ __forceinline__ int table_draw_bs(uint32_t w, int base, const uint32_t *thr, int len) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 32; step; step >>= 1) { const int m = lo + step; if (m <= len && thr[m - 1] <= w) lo = m; }
+    return base + lo;
+}
+
 // get_nextday_counts :772-788, evaluated on demand for day `day` from the agent's status word
 __device__ __forceinline__ int fresh_budget(const Dev &S, uint2 key, uint32_t i, uint32_t day, uint32_t st) {
     if (st_health(st) == DED) return 0;                                    // :783-785

@@ -25,6 +25,7 @@ namespace cabm {
 constexpr int FUSED_NT = 256;          // threads per CTA = max events per batch
 constexpr int FUSED_NCAND = 32;        // infectors per batch
 constexpr int FUSED_LCAP = 256;        // infectors listed per pass (more are handled in further passes)
+constexpr unsigned FUSED_TAIL_CTAS = 8;  // CTAs that copy finished curves to the host at any one time (PCIe saturates with ~8)
 constexpr int FUSED_SCAN_U = 5;        // chunks of 8 agents a thread scans at once in time_update (256 x 8 x 5 >= 10,000 agents in one go)
 static_assert(FUSED_NT == 256 && FUSED_LCAP <= FUSED_NT, "thread-index roles in k_sim_fused are laid out for 256 threads");
 
@@ -41,7 +42,7 @@ struct FusedCtl {
     int r, off[8], wcnt[FUSED_NT / 32][5];
     int sel_tid, sel_k, Ltot, ninf;
     int nf[2], wsum[FUSED_NT / 32];
-    int nb_len[5], pad_[3];
+    int nb_len[5], kind, pad_[2];
     int infectors[4];
     int cand[FUSED_NCAND], pref[FUSED_NCAND + 1], nb, cut, adv;  // batch entries: agent, event prefix; entries, cut, list entries consumed
     int wdup[FUSED_NT / 32], anydup;
@@ -128,7 +129,7 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <bool CT>      // CT = false: no replicate of the ensemble traces contacts (the tracing code is compiled out)
-__global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work /* [0] fresh head, [1] resume head, [2] resume tail, [3] fresh jobs done */, int split_day) {
+__global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work /* queue heads and tails, see below */, int split_day, unsigned tail_cta_limit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = FUSED_NT, NW = FUSED_NT / 32;
     const int N = S.N, Np = S.Np, T = S.T, nwords = S.nwords;
@@ -173,15 +174,56 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     // Two sweeps over an atomic work queue. Sweep 0 starts every replicate; with split_day > 0 a replicate that is still active
     // after split_day days is parked (state to HBM) and queued, so that the long epidemics — which bound the launch — all resume
     // early in sweep 1 instead of starting whenever the fresh queue happens to reach them. Everything else finishes in sweep 0.
+    // Curve rows d0..T-1 of replicate r once nothing changes any more: incidence 0, prevalence = Z.run. The rows of a group are one
+    // contiguous run of 12-int rows (48 B, 16-byte aligned), filled by the whole CTA with 16-byte stores.
+    auto fill_idle_rows = [&](int r, int d0) {
+        const int per = (T - d0) * 3;                                          // uint4 per group
+        for (int idx = tid; idx < 6 * per; idx += NT) {
+            const int G = idx / per, j = idx - G * per;
+            const size_t b0 = (((size_t)r * 6 + G) * (size_t)T + (size_t)d0) * 12;
+            reinterpret_cast<int4 *>(S.inc + b0)[j] = make_int4(0, 0, 0, 0);
+            reinterpret_cast<int4 *>(S.prev + b0)[j] = *reinterpret_cast<const int4 *>(&Z.run[G * 12 + (j % 3) * 4]);
+        }
+    };
+    // hmatrix columns d0..T-1 of replicate r = the column in M.col (TMA bulk copies queued by thread 0)
+    auto fill_idle_columns = [&](uint8_t *hm, int d0) {
+        for (int d = d0; d < T; ++d) {
+            if (tma_ok) { if (tid == 0) { bulk_store_wait_read_n(); bulk_store(hm + (size_t)d * N, M.col, (uint32_t)N); } }
+            else for (int i = tid; i < N; i += NT) hm[(size_t)d * N + i] = M.col[i];
+        }
+    };
+    // replicate r's curves -> pinned host memory (Int16), 16-byte posted writes over PCIe
+    auto stream_curves_to_host = [&](int r) {
+        const size_t per = (size_t)6 * T * 12;                 // multiple of 8
+        const int4 *gi = reinterpret_cast<const int4 *>(S.inc + (size_t)r * per), *gp = reinterpret_cast<const int4 *>(S.prev + (size_t)r * per);
+        uint4 *hi = reinterpret_cast<uint4 *>(S.host_inc + (size_t)r * per), *hp = reinterpret_cast<uint4 *>(S.host_prev + (size_t)r * per);
+        for (int k = tid; k < (int)(per / 8); k += NT) {
+            const int4 a = __ldcg(gi + 2 * k), b = __ldcg(gi + 2 * k + 1), c = __ldcg(gp + 2 * k), e = __ldcg(gp + 2 * k + 1);
+            hi[k] = make_uint4((uint32_t)(a.x & 0xFFFF) | ((uint32_t)a.y << 16), (uint32_t)(a.z & 0xFFFF) | ((uint32_t)a.w << 16),
+                               (uint32_t)(b.x & 0xFFFF) | ((uint32_t)b.y << 16), (uint32_t)(b.z & 0xFFFF) | ((uint32_t)b.w << 16));
+            hp[k] = make_uint4((uint32_t)(c.x & 0xFFFF) | ((uint32_t)c.y << 16), (uint32_t)(c.z & 0xFFFF) | ((uint32_t)c.w << 16),
+                               (uint32_t)(e.x & 0xFFFF) | ((uint32_t)e.y << 16), (uint32_t)(e.z & 0xFFFF) | ((uint32_t)e.w << 16));
+        }
+    };
+
+    // Two sweeps over atomic work queues. Sweep 0 starts every replicate and runs it for split_day days (split_day = 0: to the end).
+    // By then most epidemics have died out: their state is final, and what is left of them — the idle tail of the curves and the
+    // state matrix, the copy of the curves to the host — is pure output, queued as a "tail job". A replicate that is still active
+    // is parked (state to HBM) and queued for sweep 1. Sweep 1 resumes the parked replicates first — they are the long ones that
+    // bound the launch — and CTAs without one work the tail jobs off meanwhile, so the output traffic (HBM, PCIe) overlaps the
+    // latency-bound epidemics instead of delaying their start.
+    //   work[0] fresh head | [1],[2] parked head, tail | [3] fresh jobs finished | [4],[5] tail-job head, tail | [6] CTAs on tail jobs
+    // resume_list holds the parked replicates from the bottom and the tail jobs from the top (each replicate is one or the other).
+    const unsigned tail_ctas = tail_cta_limit;
     for (int sweep = 0; sweep < 2; ++sweep) {
     if (sweep == 1 && split_day <= 0) break;
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            int got = -1;
+            int got = -1, kind = 0;
             if (sweep == 0) { const unsigned k = atomicAdd(&work[0], 1u); if (k < (unsigned)S.R) got = (int)k; }
             else {
-                for (;;) {          // pop a parked replicate; wait while fresh jobs that might still park one are in flight
+                for (;;) {          // wait while fresh jobs that might still queue something are in flight
                     const unsigned done = *(volatile unsigned *)&work[3];
                     __threadfence();
                     const unsigned t = *(volatile unsigned *)&work[2], h = *(volatile unsigned *)&work[1];
@@ -190,16 +232,55 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             while ((got = *(volatile int *)&S.resume_list[h]) < 0) __nanosleep(100);
                             break;
                         }
-                    } else if (done >= (unsigned)S.R) break;
-                    else __nanosleep(500);
+                        continue;
+                    }
+                    const unsigned ft = *(volatile unsigned *)&work[5], fh = *(volatile unsigned *)&work[4];
+                    if (fh < ft) {
+                        if (atomicCAS(&work[4], fh, fh + 1) == fh) {
+                            while ((got = *(volatile int *)&S.resume_list[S.R - 1 - (int)fh]) < 0) __nanosleep(100);
+                            kind = 1;
+                            break;
+                        }
+                        continue;
+                    }
+                    if (done >= (unsigned)S.R) break;
+                    __nanosleep(500);
                 }
                 __threadfence();
             }
-            Z.r = got;
+            Z.r = got; Z.kind = kind;
         }
         __syncthreads();
         const int r = Z.r;
         if (r < 0) break;
+        if (Z.kind == 1) {
+            // -------------------------------------------------------- tail job: the output that is left of a replicate that died out
+            const int d0 = __ldcg(&S.resume_aux[r * 2]);                       // first row that is not written yet (>= 1)
+            uint8_t *hm = S.store_hm ? S.hm + (size_t)r * T * N : nullptr;
+            if (tid < 72) Z.run[tid] = __ldcg(&S.prev[(((size_t)r * 6 + tid / 12) * (size_t)T + (size_t)(d0 - 1)) * 12 + tid % 12]);
+            if (hm) {                                                          // the column of day d0 - 1 repeats to the end
+                const uint8_t *src = hm + (size_t)(d0 - 1) * N;
+                if (tma_ok) for (int k = tid; k < N / 16; k += NT) reinterpret_cast<uint4 *>(M.col)[k] = __ldcg(reinterpret_cast<const uint4 *>(src) + k);
+                else for (int i = tid; i < N; i += NT) M.col[i] = __ldcg(src + i);
+                if (tma_ok) bulk_store_g2s_fence();
+            }
+            __syncthreads();
+            fill_idle_rows(r, d0);
+            if (hm) fill_idle_columns(hm, d0);
+            if (S.host_inc) {
+                // a few CTAs saturate the PCIe link; more of them only get in the way of the running epidemics: take a ticket
+                if (tid == 0) for (;;) {
+                    if (*(volatile unsigned *)&work[6] < tail_ctas) { if (atomicAdd(&work[6], 1u) < tail_ctas) break; atomicSub(&work[6], 1u); }
+                    __nanosleep(1000);
+                }
+                __syncthreads();
+                stream_curves_to_host(r);
+                __syncthreads();
+                if (tid == 0) { __threadfence(); atomicSub(&work[6], 1u); }
+            }
+            if (hm && tma_ok && tid == 0) bulk_store_wait_all();
+            continue;
+        }
         const bool resumed = sweep == 1;
 #ifdef CABM_FUSED_DIAG      // per-phase cycle counts seen by thread 0 (make diag; tools/diag_fused.py)
         const long long t_start = clock64();
@@ -240,8 +321,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 for (int k = 0; k < 4; ++k) ag0 += ((unsigned long long)wa.x >= P.age_thr[k]);
                 int latents = table_draw(wa.y, c_tab.lat_base, Z.tlat, c_tab.lat_len);
                 const int pres = table_draw(wa.z, c_tab.pre_base, Z.tpre, c_tab.pre_len);
-                const int asymps = table_draw(wa.w, c_tab.asy_base, Z.tasy, c_tab.asy_len);
-                const int infs = table_draw(wb.x, c_tab.inf_base, Z.tinf, c_tab.inf_len);
+                const int asymps = table_draw_bs(wa.w, c_tab.asy_base, Z.tasy, c_tab.asy_len);
+                const int infs = table_draw_bs(wb.x, c_tab.inf_base, Z.tinf, c_tab.inf_len);
                 latents -= pres;
                 d4 = (uint32_t)latents | ((uint32_t)asymps << 8) | ((uint32_t)pres << 16) | ((uint32_t)infs << 24);
                 const bool quar = bern(wb.y, P.quar_thr) && ag0 == P.quar_grp0;
@@ -410,6 +491,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         const int day_first = resumed ? split_day + 1 : 1;
         const int day_last = (!resumed && split_day > 0 && split_day < T) ? split_day : T;
         bool finished = day_last == T;                                         // set early by the fast-forward below
+        int tail_day = 0;                                                      // > 0: rows tail_day..T-1 are left to a tail job
         __syncthreads();
         for (int day = day_first; day <= day_last; ++day) {
             const bool active = Z.ninf > 0 || day >= nextfire;                 // uniform: Z.ninf only changes between S1 and S2
@@ -418,24 +500,12 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 // repeat the current ones (tis >= exp :405 never fires again) — write them without stepping through the days
                 // curve rows day..T-1 of a group are one contiguous run of 12-int rows (48 B, 16-byte aligned): the whole CTA
                 // fills them with 16-byte stores while thread 0 queues the column copies
+                finished = true;
+                if (!resumed && split_day > 0) { tail_day = day; break; }       // sweep 0: the tail is somebody else's job (see above)
                 if (tid < 60) Z.run[12 + tid] = run; else if (tid >= 64 && tid < 76) Z.run[tid - 64] = run;
                 __syncthreads();
-                {
-                    const int per = (T - day) * 3;                                  // uint4 per group
-                    for (int idx = tid; idx < 6 * per; idx += NT) {
-                        const int G = idx / per, j = idx - G * per;
-                        const size_t b0 = (((size_t)r * 6 + G) * (size_t)T + (size_t)day) * 12;
-                        reinterpret_cast<int4 *>(S.inc + b0)[j] = make_int4(0, 0, 0, 0);
-                        reinterpret_cast<int4 *>(S.prev + b0)[j] = *reinterpret_cast<const int4 *>(&Z.run[G * 12 + (j % 3) * 4]);
-                    }
-                }
-                if (hm) {
-                    for (int d = day; d < T; ++d) {
-                        if (tma_ok) { if (tid == 0) { bulk_store_wait_read_n(); bulk_store(hm + (size_t)d * N, M.col, (uint32_t)N); } }
-                        else for (int i = tid; i < N; i += NT) hm[(size_t)d * N + i] = M.col[i];
-                    }
-                }
-                finished = true;
+                fill_idle_rows(r, day);
+                if (hm) fill_idle_columns(hm, day);
                 break;
             }
             if (active) {
@@ -635,18 +705,20 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     yinf = have && ((M.inf[yd >> 5] >> (yd & 31)) & 1u);
                                     bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;             // :822
                                     unsigned m = peers;
+                                    // would this lane's event transmit (:823)? decided here, once, so that the ordered loop is shuffles only
+                                    const int hit = (have && bern(w1d, Z.bthr[qd])) ? (int)Z.xh[qd] : -1;
 #ifdef CABM_FUSED_DIAG
                                     if (sus && sy == 0x12345678u) m = 0;
 #endif
                                     PHASEX(28);
                                     for (int k = 0; k < nmax; ++k) {                                      // k-th event of each target, in event order
                                         const int src = m ? __ffs(m) - 1 : lane; m &= m - 1u;
-                                        const uint32_t w1s = __shfl_sync(FULL, w1d, src);
+                                        const int hs = __shfl_sync(FULL, hit, src);
                                         const int qs = __shfl_sync(FULL, qd, src);
                                         if (leader && k < n && rem > 0) {                                 // :812
                                             rem -= 1;                                                     // :813
                                             if (ctr && Z.ctr[qs]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[qs] + 2u + (uint32_t)atomicAdd(&Z.clen[qs], 1)] = y;
-                                            if (sus && bern(w1s, Z.bthr[qs])) { sus = false; xh_inf = Z.xh[qs]; }
+                                            if (sus && hs >= 0) { sus = false; xh_inf = hs; }
                                         }
                                     }
                                     PHASEX(29);
@@ -746,14 +818,17 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             post |= (unsigned long long)((M.mpost[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
                         }
                     }
+                    uint32_t anyf = 0;
 #pragma unroll
-                    for (int u = 0; u < FUSED_SCAN_U; ++u) {
-                        const uint32_t m0 = __vcmples2(ex[u].x, dd), m1 = __vcmples2(ex[u].y, dd), m2 = __vcmples2(ex[u].z, dd), m3 = __vcmples2(ex[u].w, dd);
-                        const unsigned f = (m0 & 1u) | ((m0 >> 15) & 2u) | ((m1 & 1u) << 2) | ((m1 >> 13) & 8u) | ((m2 & 1u) << 4) | ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u);
-                        fire |= (unsigned long long)f << (8 * u);
-                    }
-                    fire |= pre | post;
-                    if (fire) {                                                // somebody in these chunks has an event today
+                    for (int u = 0; u < FUSED_SCAN_U; ++u) anyf |= __vcmples2(ex[u].x, dd) | __vcmples2(ex[u].y, dd) | __vcmples2(ex[u].z, dd) | __vcmples2(ex[u].w, dd);
+                    if (anyf | (uint32_t)((pre | post) != 0)) {                // somebody in these chunks has an event today
+#pragma unroll
+                        for (int u = 0; u < FUSED_SCAN_U; ++u) {
+                            const uint32_t m0 = __vcmples2(ex[u].x, dd), m1 = __vcmples2(ex[u].y, dd), m2 = __vcmples2(ex[u].z, dd), m3 = __vcmples2(ex[u].w, dd);
+                            const unsigned f = (m0 & 1u) | ((m0 >> 15) & 2u) | ((m1 & 1u) << 2) | ((m1 >> 13) & 8u) | ((m2 & 1u) << 4) | ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u);
+                            fire |= (unsigned long long)f << (8 * u);
+                        }
+                        fire |= pre | post;
                         while (fire) {
                             const int bit = __ffsll((long long)fire) - 1; fire &= fire - 1;
                             const int i = b0 + (bit >> 3) * NT * 8 + (bit & 7);
@@ -884,18 +959,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (bad) atomicOr(&S.err[r], ERR_SICKFROM);
         __syncthreads();
         if (tid < 4) S.infectors[r * 4 + tid] = Z.infectors[tid];
-        if (S.host_inc) {                      // this replicate's curves -> pinned host memory, 16-byte posted writes over PCIe
+        if (S.host_inc && tail_day == 0) {
             __syncthreads();                   // the rows written during the day loop (by threads 0..75) are visible block-wide
-            const size_t per = (size_t)6 * T * 12;                 // multiple of 8
-            const int4 *gi = reinterpret_cast<const int4 *>(S.inc + (size_t)r * per), *gp = reinterpret_cast<const int4 *>(S.prev + (size_t)r * per);
-            uint4 *hi = reinterpret_cast<uint4 *>(S.host_inc + (size_t)r * per), *hp = reinterpret_cast<uint4 *>(S.host_prev + (size_t)r * per);
-            for (int k = tid; k < (int)(per / 8); k += NT) {
-                const int4 a = __ldcg(gi + 2 * k), b = __ldcg(gi + 2 * k + 1), c = __ldcg(gp + 2 * k), e = __ldcg(gp + 2 * k + 1);
-                hi[k] = make_uint4((uint32_t)(a.x & 0xFFFF) | ((uint32_t)a.y << 16), (uint32_t)(a.z & 0xFFFF) | ((uint32_t)a.w << 16),
-                                   (uint32_t)(b.x & 0xFFFF) | ((uint32_t)b.y << 16), (uint32_t)(b.z & 0xFFFF) | ((uint32_t)b.w << 16));
-                hp[k] = make_uint4((uint32_t)(c.x & 0xFFFF) | ((uint32_t)c.y << 16), (uint32_t)(c.z & 0xFFFF) | ((uint32_t)c.w << 16),
-                                   (uint32_t)(e.x & 0xFFFF) | ((uint32_t)e.y << 16), (uint32_t)(e.z & 0xFFFF) | ((uint32_t)e.w << 16));
-            }
+            stream_curves_to_host(r);
         }
         // diagnostics of the fused path: kilo-cycles spent on this replicate and dyntrans batches issued
         PHASE(6);
@@ -907,6 +973,16 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #undef PHASE
 #undef PHASEX
         if (hm && tma_ok && tid == 0) bulk_store_wait_all();
+        if (tail_day > 0) {                    // queue the tail job: rows < tail_day of the curves and the state matrix are in HBM
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                S.resume_aux[r * 2] = tail_day;
+                const unsigned slot = atomicAdd(&work[5], 1u);
+                __threadfence();
+                *(volatile int *)&S.resume_list[S.R - 1 - (int)slot] = r;
+            }
+        }
         if (!resumed && tid == 0) { __threadfence(); atomicAdd(&work[3], 1u); }
     }
     }
@@ -931,10 +1007,12 @@ int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaSt
     int split_day = (S.R > grid && S.T >= 150) ? 60 : 0;
     if (const char *e = getenv("CABM_FUSED_SPLIT_DAY")) split_day = atoi(e);
     if (split_day >= S.T) split_day = 0;
-    cudaMemsetAsync(work, 0, 4 * sizeof(unsigned), s);
+    cudaMemsetAsync(work, 0, 8 * sizeof(unsigned), s);
     if (split_day > 0) cudaMemsetAsync(S.resume_list, 0xFF, (size_t)S.R * sizeof(int), s);
-    if (any_ct) k_sim_fused<true><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day);
-    else k_sim_fused<false><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day);
+    unsigned tail_ctas = FUSED_TAIL_CTAS;
+    if (const char *e = getenv("CABM_FUSED_TAIL_CTAS")) tail_ctas = (unsigned)atoi(e);                                       // experiments
+    if (any_ct) k_sim_fused<true><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
+    else k_sim_fused<false><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
     return 1;
 }
 
