@@ -523,11 +523,16 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             uint32_t m0 = (wi < nwords) ? M.inf[wi] : 0u, m1 = (wi + 1 < nwords) ? M.inf[wi + 1] : 0u;
                             if (wi == (cursor >> 5)) m0 &= ~((1u << (cursor & 31)) - 1u);
                             const int c0 = __popc(m0), c = c0 + __popc(m1);
-                            int incl = c;
-                            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                            if (lane == 31) Z.wsum[wid] = incl;
+                            // exclusive prefix of c over the lanes, bit-sliced: one ballot per bit that occurs (c is 0..2 nearly always)
+                            const int cmax = __reduce_max_sync(FULL, c);
+                            int excl = 0, wtot = 0;
+                            for (int b = 0; (cmax >> b) != 0; ++b) {
+                                const unsigned bm = __ballot_sync(FULL, (c >> b) & 1);
+                                excl += __popc(bm & ((1u << lane) - 1u)) << b; wtot += __popc(bm) << b;
+                            }
+                            if (lane == 0) Z.wsum[wid] = wtot;
                             __syncthreads();
-                            int pos = lbase + incl - c, tot = 0;
+                            int pos = lbase + excl, tot = 0;
                             for (int w = 0; w < NW; ++w) { const int v = Z.wsum[w]; tot += v; if (w < wid) pos += v; }
                             while (m0 && pos < FUSED_LCAP) { const int b = __ffs(m0) - 1; m0 &= m0 - 1; M.list[pos++] = (uint16_t)((wi << 5) + b); }
                             while (m1 && pos < FUSED_LCAP) { const int b = __ffs(m1) - 1; m1 &= m1 - 1; M.list[pos++] = (uint16_t)(((wi + 1) << 5) + b); }
@@ -867,7 +872,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 PHASE(25);
                 {
                     int v = min((int)(short)(mn & 0xFFFF), (int)(short)(mn >> 16));
-                    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+                    v = __reduce_min_sync(FULL, v);
                     if (lane == 0) atomicMin(&Z.nf[act & 1], v);
                 }
                 if (hm && tma_ok) bulk_store_g2s_fence();
