@@ -161,6 +161,7 @@ __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int 
                                      int target /* swap to apply */, bool seed_simple_inf, unsigned long long *dcache = nullptr) {
     size_t a = (size_t)r * S.Np + i;
     const int oldh = st_health(st), ag = st_ag(st);
+    const uint8_t via0 = S.isovia[a];   // needed by a few targets only, but loaded here so that its latency hides behind the draws
     uint32_t d4;
     if (dcache) {                        // (agent << 32 | dur) — filled when the agent is infected, so the HBM load is off this path
         const unsigned long long e = dcache[i & (DUR_CACHE - 1)];
@@ -225,7 +226,7 @@ __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int 
         atomicOr(&S.err[r], ERR_NO_SWAP);
         return Tr{st, 32767, oldh, oldh};
     }
-    if (via >= 0 && S.isovia[a] == VIA_NULL) S.isovia[a] = (uint8_t)via;   // _set_isolation :432-444 only fills a :null isovia
+    if (via >= 0 && via0 == VIA_NULL) S.isovia[a] = (uint8_t)via;   // _set_isolation :432-444 only fills a :null isovia
     S.entry[a] = (int16_t)day;
     st = st_set_swap(st_set_health(st, newh), newsw);
     st = iso ? (st | ST_ISO | ST_ISOB) : (st & ~(ST_ISO | ST_ISOB));

@@ -106,17 +106,6 @@ __device__ __forceinline__ int gpw_sum(unsigned long long gp) {
     return (int)(gp & 0xFF) + (int)((gp >> 8) & 0xFF) + (int)((gp >> 16) & 0xFF) + (int)((gp >> 24) & 0xFF) + (int)((gp >> 32) & 0xFF);
 }
 
-// An infectious agent y was contacted (:813): its remaining budget is `rem` now, so the events it will generate when its own turn
-// comes (later today) change. Its entry in the day's list is brought up to date (the list is ascending: binary search).
-__device__ __forceinline__ void fused_list_update(const FusedSmem &M, const double *cm, int nlist, uint32_t y, uint32_t sy, int rem) {
-    int a = 0, b = nlist - 1;
-    while (a < b) { const int mid = (a + b) >> 1; if ((uint32_t)M.list[mid] < y) a = mid + 1; else b = mid; }
-    if ((uint32_t)M.list[a] == y) {
-        const unsigned long long gp = gpw_pack(cm + st_ag(sy) * 5, rem);
-        M.lgp[a] = gp; M.lE[a] = (uint8_t)gpw_sum(gp);
-    }
-}
-
 // TMA bulk store of one hmatrix column from shared memory (UBLKCP in SASS)
 __device__ __forceinline__ void bulk_store_g2s_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
@@ -561,13 +550,20 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #ifdef CABM_FUSED_DIAG
                             ++n_rounds;
 #endif
-                            // (a) warp 0: the next <= 32 listed infectors. Their event counts come from the list (kept current by the
-                            //     apply phase when an infector is contacted, :813), those without events are dropped, the others are
+                            // (a) warp 0: the next <= 32 listed infectors. Their event counts come from the list unless the infector was
+                            //     contacted today (tag in its status word, :813); those without events are dropped, the others are
                             //     compacted into the batch arrays with their event prefix
                             if (wid == 0) {
                                 const int ncand = min(FUSED_NCAND, nlist - lpos), li = lpos + lane;
                                 int E = 0, x = 0, h = 0; unsigned long long gp = 0;
-                                if (lane < ncand) { E = (int)M.lE[li]; x = M.list[li]; gp = M.lgp[li]; h = M.lh[li]; }
+                                if (lane < ncand) {
+                                    E = (int)M.lE[li]; x = M.list[li]; gp = M.lgp[li]; h = M.lh[li];
+                                    const uint32_t sx = M.status[x];
+                                    if (st_tag(sx) == day) {                                    // contacted earlier today: budget changed (:813)
+                                        gp = gpw_pack(Z.cm + st_ag(sx) * 5, st_rem(sx));
+                                        E = gpw_sum(gp);
+                                    }
+                                }
                                 int incl = E;
                                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
                                 const unsigned fits = __ballot_sync(FULL, lane < ncand && incl <= NT);
@@ -694,7 +690,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                             M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
                                         }
                                         M.status[y] = ns;
-                                        if (yinf) fused_list_update(M, Z.cm, nlist, y, sy, rem);
                                         apply = false;
                                     }
                                     PHASEX(27);
@@ -707,7 +702,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     const bool leader = have && lane == __ffs(peers) - 1;
                                     const int n = __popc(peers), nmax = __reduce_max_sync(FULL, have ? n : 0);
                                     y = yd; sy = have ? M.status[yd] : 0u; rem = (int)((rec >> 16) & 0xFFu); xh_inf = -1;
-                                    yinf = have && ((M.inf[yd >> 5] >> (yd & 31)) & 1u);
                                     bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;             // :822
                                     unsigned m = peers;
                                     // would this lane's event transmit (:823)? decided here, once, so that the ordered loop is shuffles only
@@ -762,7 +756,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     if (dury != 0xFFFFFFFFu) M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
                                 }
                                 M.status[y] = ns;
-                                if (yinf) fused_list_update(M, Z.cm, nlist, y, sy, rem);    // a contacted infector's budget changed (:813)
                             }
                             PHASE(20);
                             PHASEX(30);
