@@ -36,7 +36,7 @@ struct FusedCtl {
     double cm[25];                           // contact_matrix :838-848
     unsigned long long beta[4];              // _get_betavalue :756-769 thresholds of the day
     unsigned long long bthr[FUSED_NCAND], gp[FUSED_NCAND];      // batch entries: transmission threshold, budget split (:800, :804)
-    int run[72];                             // running prevalence of the six groups, for the idle-tail fill (16-byte aligned)
+    alignas(16) int run[72];                 // running prevalence of the six groups, for the idle-tail fill (16-byte aligned)
     int io[2][2][60];                        // [day parity][entries | exits][(group, state)] — curve deltas of one day
     uint32_t tlat[4], tpre[4], tasy[40], tinf[40];
     int r, off[8], wcnt[FUSED_NT / 32][5];
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         const bool resumed = sweep == 1;
 #ifdef CABM_FUSED_DIAG      // per-phase cycle counts seen by thread 0 (make diag; tools/diag_fused.py)
         const long long t_start = clock64();
-        __shared__ long long t_ph[32];
+        __shared__ long long t_ph[32], t_wdt[8];
         long long t_last = t_start;
         if (tid < 32) t_ph[tid] = 0;
 #define PHASE(k) do { if (tid == 0) { t_ph[k] += clock64() - t_last; t_last = clock64(); } } while (0)
@@ -648,6 +648,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             PHASE(19);
                             __syncthreads();                                                   // B2
                             PHASE(9);
+#ifdef CABM_FUSED_DIAG
+                            const long long t_b2 = clock64();
+#endif
                             const int cut = Z.cut;
                             const int Ev = Z.pref[cut];                                // events of infectors [0, cut) are final
                             const int adv = cut == nb ? Z.adv : (int)Z.map[cut];       // list entries this batch consumes
@@ -692,7 +695,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                         M.status[y] = ns;
                                         apply = false;
                                     }
-                                    PHASEX(27);
                                     const bool have = lane < dtot;
                                     const uint32_t rec = have ? M.Y[M.D[lane]] : 0u, w1d = have ? M.W1[M.D[lane]] : 0u;
                                     const uint32_t yd = rec & 0xFFFFu;
@@ -709,7 +711,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #ifdef CABM_FUSED_DIAG
                                     if (sus && sy == 0x12345678u) m = 0;
 #endif
-                                    PHASEX(28);
                                     for (int k = 0; k < nmax; ++k) {                                      // k-th event of each target, in event order
                                         const int src = m ? __ffs(m) - 1 : lane; m &= m - 1u;
                                         const int hs = __shfl_sync(FULL, hit, src);
@@ -720,7 +721,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                             if (sus && hs >= 0) { sus = false; xh_inf = hs; }
                                         }
                                     }
-                                    PHASEX(29);
                                     apply = leader;
                                     dury = 0xFFFFFFFFu;                                                   // not loaded by this lane: no cache entry
                                 }
@@ -758,8 +758,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 M.status[y] = ns;
                             }
                             PHASE(20);
-                            PHASEX(30);
+#ifdef CABM_FUSED_DIAG
+                            if (lane == 0) t_wdt[wid] = clock64() - t_b2;
+#endif
                             __syncthreads();                                                   // B5: status writes visible to the next batch
+#ifdef CABM_FUSED_DIAG
+                            if (tid == 0) { const int slot[8] = {7, 13, 14, 27, 28, 29, 30, 31}; long long mx = 0; for (int w = 0; w < 8; ++w) mx = max(mx, t_wdt[w]);
+                                            for (int w = 0; w < 8; ++w) if (t_wdt[w] == mx) { t_ph[slot[w]] += 1; break; } t_ph[3] += mx; }
+#endif
                             if (ctr && wid == 0 && lane < cut && Z.ctr[lane] && Z.clen[lane] > 0) {    // link the day's chunk of each traced infector
                                 const int x = Z.cand[lane];
                                 uint32_t *c = S.ct_log + (size_t)r * S.ct_cap + Z.cbase[lane];
@@ -772,7 +778,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             if (tid == 0) Z.anydup = 0;
                             lpos += adv;
                         }
-                        PHASE(3);
+                        PHASE(12);
                         if (w0 >= nwords && lbase <= FUSED_LCAP) break;                        // the list held every infectious agent
                         cursor = (int)M.list[FUSED_LCAP - 1] + 1;
                         __syncthreads();

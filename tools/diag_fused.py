@@ -18,10 +18,10 @@ print("takeoff count", (attack>0.1).sum(), "mean attack", attack.mean())
 for r in order[500:503]: print(r, "kcyc", met[r], "rounds", inf[r], "attack", attack[r])
 
 dbg = np.zeros((1000, 32), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
-names = {22: "setup: initialize", 23: "setup: get_ag_dist", 24: "setup: insert_infected", 0: "setup: column 1 / resume reload", 1: "list", 2: "budgets", 3: "(rounds tail)", 25: "time_update: S1 -> own scan done", 26: "time_update: min-reduce", 4: "time_update: S2 wait", 5: "curves/idle", 6: "writeback",
-         13: "round: B5 -> cand loads done", 14: "round: -> prefix scan done", 15: "round: -> before B1", 8: "round: B1 wait + nb/Etot loads",
+names = {22: "setup: initialize", 23: "setup: get_ag_dist", 24: "setup: insert_infected", 0: "setup: column 1 / resume reload", 1: "list", 2: "budgets", 25: "time_update: S1 -> own scan done", 26: "time_update: min-reduce", 4: "time_update: S2 wait", 5: "curves/idle", 6: "writeback",
+         15: "round: -> before B1", 8: "round: B1 wait + nb/Etot loads",
          16: "round: owner search", 17: "round: target philox + status", 18: "round: target budget", 19: "round: cut check, Y/W1/Q, touch",
-         9: "round: B2 wait", 10: "round: cut/dup compaction", 20: "round: apply", 11: "round: B5 wait", 21: "(timer overhead)", 27: "last warp: own apply", 28: "last warp: dup loads+match", 29: "last warp: dup loop", 30: "last warp: final apply (or idle)", 12: "dyntrans end -> S1"}
+         9: "round: B2 wait", 10: "round: cut/dup compaction", 20: "round: apply", 11: "round: B5 wait", 21: "(timer overhead)", 3: "B2 -> B5, slowest warp (cycles)", 7: "slowest = warp 0 (count)", 13: "slowest = warp 1", 14: "slowest = warp 2", 27: "slowest = warp 3", 28: "slowest = warp 4", 29: "slowest = warp 5", 30: "slowest = warp 6", 31: "slowest = warp 7", 12: "dyntrans end -> S1"}
 big = attack > 0.1
 print("phase kcycles  take-off mean | extinct mean | per round (take-off)")
 nr = max(inf[big].sum(), 1)
