@@ -276,3 +276,42 @@ def test_fused_refuses_populations_that_do_not_fit(cv):
     with pytest.raises(cv.CabmError, match="fused path needs"):
         cv.run_ensemble(ip, 1, path="fused")
     assert cv.run_ensemble(ip, 1)["path"] == "multikernel"            # auto falls back to the per-day kernels
+
+
+@pytest.mark.parametrize("popsize,split", [(10000, None), (10007, None), (10000, "25")])
+def test_fused_parked_replicates_and_tail_jobs_bit_exact(cv, O, popsize, split, monkeypatch):
+    """More replicates than resident CTAs and a long run: the fused kernel runs every replicate for `split_day` days, parks the
+    ones that are still active and queues the idle tail of the others (curve rows, state-matrix columns, host copy) as tail
+    jobs. Everything must equal the oracle's sequential runs, with the curves also streamed to pinned host memory. popsize
+    10007 takes the path without TMA bulk stores (columns are not 16-byte multiples); split 25 parks nearly everything that
+    was seeded with several cases."""
+    if split is not None:
+        monkeypatch.setenv("CABM_FUSED_SPLIT_DAY", split)
+    T = 160
+    a = cv.ModelParameters(β=0.0345, prov="ontario", popsize=popsize, modeltime=T, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3)
+    b = cv.ModelParameters(β=0.08, prov="alberta", popsize=popsize, modeltime=T, initialinf=3, ctstrat=1, fctcapture=0.6, fcontactst=0.6,
+                           cdaysback=3, fmild=0.4, τmild=1)
+    nrep = 330
+    seeds = [41 * (i + 1) for i in range(nrep)]
+    pof = [1 if i % 3 == 0 else 0 for i in range(nrep)]
+    ref = O.run_ensemble([to_oracle(O, a), to_oracle(O, b)], pof, seeds, nthreads=16, want_hmatrix=True)
+    with cv.Population(nrep, popsize, T, store_hmatrix=True) as pop:
+        pi, pp = cv.PinnedArray((nrep, 6, T, 12), np.int16), cv.PinnedArray((nrep, 6, T, 12), np.int16)
+        pi.array[:] = -1; pp.array[:] = -1
+        pop.set_path("fused")
+        pop.stream_curves_to(pi.array, pp.array)
+        pop.configure([a, b], seeds, pof)
+        pop.run()
+        assert pop.last_path == "fused"
+        inc, prev = pop.curves()
+        sc = pop.scalars()
+        hm = pop.hmatrix_all()
+        assert (sc["err"] == 0).all()
+        assert (inc == ref["inc"]).all() and (prev == ref["prev"]).all()
+        assert (pi.array == ref["inc"]).all() and (pp.array == ref["prev"]).all()
+        assert (hm == ref["hmatrix"]).all()
+        assert (sc["infectors"] == ref["infectors"]).all() and (sc["totalisolated"] == ref["totalisolated"]).all()
+        extinct = ref["prev"][:, 0, -1, 2:8].sum(axis=1) == 0                   # nobody infectious at the end ...
+        assert extinct.any() and (~extinct).any()                               # ... for some replicates but not for all: both kinds of job ran
+        pop.stream_curves_to(None, None)
+        pi.free(); pp.free()
