@@ -161,6 +161,7 @@ def main():
     import torch
     import covid19abm_b200 as cv
 
+    numa_bound = cv.bind_host_thread_to_gpu(local) if world > 1 else False     # before the pinned buffers are allocated
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -299,7 +300,8 @@ def main():
                            "l2": "inputs larger than L2: 0.3 GB of agent state + 5 GB state matrix + 0.3 GB curves written per step, rebuilt every step",
                            "wall_ms_per_step": wall_ms / args.steps, "attack_rate_mean": attack},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] Int16 x2 (narrowed on device) and per-replicate scalars (runsim :77-101), pinned host buffers"},
+                        "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] Int16 x2 (narrowed on device) and per-replicate scalars (runsim :77-101), pinned host buffers",
+                        "host_numa_bound": numa_bound},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
                 "cpu_baseline": cpu}
         emit(line)

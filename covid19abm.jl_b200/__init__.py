@@ -483,6 +483,19 @@ def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_
     return out
 
 
+def bind_host_thread_to_gpu(device):
+    """One process per GPU: keep this process (and the pinned result buffers it allocates afterwards) on the CPU socket the GPU
+    hangs off, so that eight ranks streaming curves to the host do not all cross the same inter-socket link. Best effort:
+    returns False when NVML is not available or the affinity cannot be set."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(device))
+        return True
+    except Exception:
+        return False
+
+
 # ------------------------------------------------------------------ multi-GPU: replicate sharding (SURVEY §8e)
 def shard_indices(nsims, rank, world):
     """Replicate r runs on rank r mod world (interleaved, so a β sweep spreads evenly): no hot-path traffic."""
