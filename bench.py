@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU per step")
     ap.add_argument("--no-hmatrix", action="store_true", help="do not keep the state matrices in HBM (curves only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pipeline", type=int, default=2, help="handles (CUDA streams) the steps alternate over; 1 = one step after the other")
     ap.add_argument("--path", default="auto", choices=["auto", "multikernel", "fused"], help="execution path (include/cabm.h CABM_PATH_*)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -182,47 +183,63 @@ def main():
 
     R = args.replicates
     ip = cv.ModelParameters(**CFG)
-    pop = cv.Population(R, N_AGENTS, T_DAYS, store_hmatrix=not args.no_hmatrix, device=local)
-    pop.set_path(args.path)
+    # Steps alternate over `--pipeline` handles (each with its own stream, state and pinned result buffers): the replicates of
+    # step k+1 that die out fill the SMs which the few long epidemics of step k leave idle (cv.EnsemblePipeline — the public API
+    # for ensembles larger than one batch). Every step is still one full pass over its own 1000 replicates.
+    P = max(1, args.pipeline)
+    pipe = cv.EnsemblePipeline(R, N_AGENTS, T_DAYS, handles=P, store_hmatrix=not args.no_hmatrix, device=local, path=args.path, copy=False)
+    pops, pop = pipe.pops, pipe.pops[0]
+    pin_inc, pin_prev = pipe.bufs[0]
+    for q in pops:
+        q.stream_curves_to(None, None)                 # the device-resident leg leaves the results in HBM
     shape = (R, 6, T_DAYS, 12)
-    pin_inc, pin_prev = cv.PinnedArray(shape, np.int16), cv.PinnedArray(shape, np.int16)   # counts <= popsize = 10000 fit Int16
     units = R * N_AGENTS * T_DAYS                      # agent-days per step per GPU
 
-    for w in range(args.warmup):
-        pop.configure(ip, seeds_for(1000 + w, rank, R))
-        pop.run()
-    pop.check_errors()
+    for w in range(max(args.warmup, P)):
+        q = pops[w % P]
+        q.configure(ip, seeds_for(1000 + w, rank, R))
+        q.run()
+    for q in pops:
+        q.check_errors()
+    one_ms = pop.last_run_ms                           # one step alone on the GPU (nothing else in flight)
 
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- value: device-resident, CUDA-event time of exactly K steps
+    # ---- value: device-resident, CUDA-event time of exactly K steps (mark on the first handle's stream -> end of every handle's last run)
     barrier()
-    l0 = pop.launch_count
-    dev_ms, t0 = 0.0, time.perf_counter()
+    l0 = sum(q.launch_count for q in pops)
+    t0 = time.perf_counter()
+    pop.mark()
     for k in range(args.steps):
-        pop.configure(ip, seeds_for(k, rank, R))       # seeds + thresholds: ~10 KB, resident before the timed run
-        pop.run(sync=False)
-        dev_ms += pop.last_run_ms                      # events recorded on the library's stream around the run
+        q = pops[k % P]
+        q.configure(ip, seeds_for(k, rank, R))         # seeds + thresholds: ~10 KB, resident before the run that uses them
+        q.run(sync=False)
+    dev_ms = max(q.ms_since_mark(pop) for q in pops[:min(P, args.steps)])
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
-    launches = pop.launch_count - l0
+    launches = sum(q.launch_count for q in pops) - l0
     dev_ms = max_over_ranks(dev_ms)
     wall_ms = max_over_ranks(wall_ms)
     # ---- e2e: host params -> host curves/scalars through the public API, copies inside the timed region
-    # the result buffers are pinned host memory registered with the handle: the fused kernel writes each finished replicate's
-    # curves into them over PCIe while the rest of the batch is still running (cabm_set_host_curves_i16), so curves() below only
-    # waits for the run; on the per-day-kernel path it is an ordinary device->host copy
-    pop.stream_curves_to(pin_inc.array, pin_prev.array)
+    # the result buffers are pinned host memory registered with the handles: the fused kernel writes each finished replicate's
+    # curves into them over PCIe while the rest of the batch is still running (cabm_set_host_curves_i16), so collecting a batch
+    # only waits for its run and reads the scalars; on the per-day-kernel path it is an ordinary device->host copy
+    for q, bufs in zip(pops, pipe.bufs):
+        q.stream_curves_to(bufs[0].array, bufs[1].array)
     barrier()
     t0 = time.perf_counter()
+    got = 0
     for k in range(args.steps):
-        pop.configure(ip, seeds_for(100 + k, rank, R))
-        pop.run(sync=False)
-        pop.curves(pin_inc.array, pin_prev.array)
-        sc = pop.scalars()
+        r = pipe.submit(ip, seeds_for(100 + k, rank, R))
+        got += r is not None
+    rest = pipe.drain()
+    got += len(rest)
+    sc = rest[-1]
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
-    pop.stream_curves_to(None, None)
+    assert got == args.steps
+    for q in pops:
+        q.stream_curves_to(None, None)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     h2d = R * 8 + R * 4 + 280 + 4 * T_DAYS * 8
@@ -269,6 +286,11 @@ def main():
                     "note": "algorithmic bytes = u8 state matrix + per-agent HBM fields + curves; agent state itself never leaves shared memory. "
                             "At the reference-width figure of SURVEY 8(d) (14 B/agent-day) the same launch would read "
                             f"{round(14 * R * N_AGENTS * T_DAYS / (ms / n * 1e-3) / 1e9, 1)} GB/s"}
+        # `achieved` is this kernel timed alone (one launch on an otherwise idle GPU, as ncu sees it). In the timed region launches
+        # of consecutive steps overlap; the bytes of the region over its duration are given beside it
+        roofline["launch_ms_alone"] = round(ms / n, 3)
+        roofline["achieved_in_timed_region"] = round(alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9, 1)
+        roofline["frac_in_timed_region"] = round(alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9 / peak, 4)
     else:
         # algorithmic bytes per agent-day of k_time_update in the HBM layout: expday 2 r + previous column 1 r + next column 1 w
         tu_bytes = (2 + (0 if args.no_hmatrix else 2)) * R * N_AGENTS
@@ -298,14 +320,16 @@ def main():
                 "config": {"workload": WORKLOAD, "replicates_per_gpu": R, "replicates_per_sec": world * R * args.steps / (dev_ms * 1e-3),
                            "mode": "exact (bit-identical to the sequential reference order)", "path": pop.last_path, "hmatrix_in_hbm": not args.no_hmatrix,
                            "l2": "inputs larger than L2: 0.3 GB of agent state + 5 GB state matrix + 0.3 GB curves written per step, rebuilt every step",
-                           "wall_ms_per_step": wall_ms / args.steps, "attack_rate_mean": attack},
+                           "wall_ms_per_step": wall_ms / args.steps, "attack_rate_mean": attack,
+                           "pipeline": f"steps alternate over {P} handles/streams on the GPU: the short replicates of step k+1 run beside the long epidemics of step k",
+                           "ms_one_step_alone": one_ms},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] Int16 x2 (narrowed on device) and per-replicate scalars (runsim :77-101), pinned host buffers",
                         "host_numa_bound": numa_bound},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
                 "cpu_baseline": cpu}
         emit(line)
-    pop.close()
+    pipe.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -142,6 +142,7 @@ def lib():
     L.cabm_configure.argtypes = [vp, vp, i32, vp, i32, vp, i32]
     L.cabm_run.argtypes = [vp]; L.cabm_sync.argtypes = [vp]
     L.cabm_last_run_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.cabm_mark.argtypes = [vp]; L.cabm_ms_since_mark.argtypes = [vp, vp, C.POINTER(C.c_float)]
     L.cabm_launch_count.argtypes = [vp]; L.cabm_launch_count.restype = i64
     L.cabm_set_profiling.argtypes = [vp, i32]
     L.cabm_set_path.argtypes = [vp, i32]
@@ -262,6 +263,16 @@ class Population:
     def last_run_ms(self):
         ms = C.c_float(0)
         self._chk(self.L.cabm_last_run_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def mark(self):
+        """Record a device time stamp on this handle's stream (cabm_mark)."""
+        self._chk(self.L.cabm_mark(self.h))
+
+    def ms_since_mark(self, marked=None):
+        """Device milliseconds from `marked`'s mark (default: this handle's) to the end of this handle's last run."""
+        ms = C.c_float(0)
+        self._chk(self.L.cabm_ms_since_mark((marked or self).h, self.h, C.byref(ms)))
         return ms.value
 
     @property
@@ -481,6 +492,101 @@ def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_
         if own:
             pop.close()
     return out
+
+
+class EnsemblePipeline:
+    """pmap(x -> runsim(x, ip), 1:nsims) for ensembles larger than one batch: `handles` Population handles of `batch` replicates
+    on one GPU, used round-robin. Each handle has its own stream, so consecutive batches overlap: the replicates of batch k+1
+    that die out fill the SMs which the few long epidemics of batch k leave idle (the reference's pmap balances replicates over
+    workers dynamically in the same way, scripts/local_run.jl:28-30). Results are identical to running the batches one by one.
+
+        with cv.EnsemblePipeline(1000, ip.popsize, ip.modeltime) as pipe:
+            for k in range(20):
+                pipe.submit(ip, seeds_of_batch[k])          # waits for (and returns) the batch that last used this slot
+            rest = pipe.drain()
+    """
+
+    def __init__(self, batch, popsize, modeltime, handles=2, store_hmatrix=False, device=0, path="auto", pinned=True, copy=True):
+        self.batch, self.T, self.copy = batch, modeltime, copy   # copy=False: results are views of the slot's pinned buffers, valid until it is reused
+        self.pops = [Population(batch, popsize, modeltime, store_hmatrix=store_hmatrix, device=device) for _ in range(handles)]
+        self.bufs = []
+        shape = (batch, 6, modeltime, 12)
+        for p in self.pops:
+            p.set_path(path)
+            if pinned and popsize <= 32767:          # Int16 curves streamed into pinned memory by the fused kernel
+                a, b = PinnedArray(shape, np.int16), PinnedArray(shape, np.int16)
+                p.stream_curves_to(a.array, b.array)
+                self.bufs.append((a, b))
+            else:
+                self.bufs.append(None)
+        self.pending = [None] * handles           # user tag of the batch in flight on each handle
+        self.k = 0
+
+    def _collect(self, j):
+        p, tag = self.pops[j], self.pending[j]
+        if tag is None:
+            return None
+        self.pending[j] = None
+        if self.bufs[j] is not None:
+            inc, prev = p.curves(self.bufs[j][0].array, self.bufs[j][1].array)      # same pointers: waits for the run only
+            if self.copy:
+                inc, prev = inc.copy(), prev.copy()
+        else:
+            inc, prev = p.curves()
+        return dict(tag=tag, inc=inc, prev=prev, **p.scalars())
+
+    def submit(self, psets, seeds, pset_of_rep=None, tag=None, mode=MODE_EXACT, collect=True):
+        """Start one batch; returns the results of the batch that used this handle before (None the first time round, or
+        with collect=False, where the previous results are dropped — timing loops)."""
+        j = self.k % len(self.pops)
+        prev = self._collect(j) if collect else None
+        p = self.pops[j]
+        p.configure(psets, seeds, pset_of_rep, mode)
+        p.run(sync=False)
+        self.pending[j] = self.k if tag is None else tag
+        self.k += 1
+        return prev
+
+    def drain(self):
+        """Results of the batches still in flight, oldest first."""
+        n = len(self.pops)
+        order = [(self.k + i) % n for i in range(n)]
+        return [r for r in (self._collect(j) for j in order) if r is not None]
+
+    def sync(self):
+        for p in self.pops:
+            p.sync()
+
+    def close(self):
+        for p, b in zip(self.pops, self.bufs):
+            p.close()
+            if b is not None:
+                b[0].free(); b[1].free()
+        self.pops, self.bufs = [], []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def run_ensemble_pipelined(ip, nsims, batch=1000, handles=2, seeds=None, device=0, path="auto"):
+    """run_ensemble for nsims > batch: the batches are pipelined over `handles` handles (EnsemblePipeline)."""
+    first = ip[0] if isinstance(ip, (list, tuple)) else ip
+    if seeds is None:
+        seeds = [726 * (i + 1) for i in range(nsims)]
+    if nsims % batch:
+        raise ValueError("nsims must be a multiple of batch")
+    parts = []
+    with EnsemblePipeline(batch, first.popsize, first.modeltime, handles=handles, device=device, path=path) as pipe:
+        for k in range(nsims // batch):
+            r = pipe.submit(ip, seeds[k * batch:(k + 1) * batch])
+            if r is not None:
+                parts.append(r)
+        parts += pipe.drain()
+    parts.sort(key=lambda r: r["tag"])
+    return {k: np.concatenate([r[k] for r in parts]) for k in parts[0] if k != "tag"}
 
 
 def bind_host_thread_to_gpu(device):

@@ -18,7 +18,7 @@ struct cabm_handle {
     int device = 0, R = 0, N = 0, Np = 0, T = 0, flags = 0;
     int n_rep = 0, n_psets = 0, mode = 0, day = 1, any_ct = 0, all_ct = 0, configured = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mark = nullptr;
     Dev S{};
     std::vector<void *> allocs;
     DevPset *d_psets = nullptr; unsigned long long *d_beta = nullptr; int psets_cap = 0;
@@ -108,7 +108,7 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
-    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "event");
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess || (e = cudaEventCreate(&h->ev_mark)) != cudaSuccess) return bail(e, "event");
     Dev &S = h->S;
     S.R = h->R; S.N = h->N; S.Np = h->Np; S.T = h->T; S.store_hm = (flags & CABM_STORE_HMATRIX) ? 1 : 0; S.nwords = h->Np / 32;
     S.ct_cap = 0;
@@ -181,6 +181,7 @@ extern "C" void cabm_destroy(cabm_handle *h) {
     for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_mark) cudaEventDestroy(h->ev_mark);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -377,6 +378,21 @@ extern "C" int cabm_sync(cabm_handle *h) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    return CABM_OK;
+}
+
+extern "C" int cabm_mark(cabm_handle *h) {
+    if (!h) return CABM_E_ARG;
+    cudaSetDevice(h->device);
+    CU(cudaEventRecord(h->ev_mark, h->stream));
+    return CABM_OK;
+}
+
+extern "C" int cabm_ms_since_mark(cabm_handle *marked, cabm_handle *h, float *ms) {
+    if (!marked || !h || !ms) return CABM_E_ARG;
+    cudaSetDevice(h->device);
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(ms, marked->ev_mark, h->ev1));
     return CABM_OK;
 }
 

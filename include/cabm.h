@@ -99,6 +99,13 @@ int cabm_run(cabm_handle *h);
 int cabm_sync(cabm_handle *h);
 /* device time of the last cabm_run in milliseconds (CUDA events on the handle's stream) */
 int cabm_last_run_ms(cabm_handle *h, float *ms);
+/* Several handles on one GPU run concurrently (each has its own stream): consecutive batches of an ensemble overlap, the
+ * short replicates of one batch filling the SMs that the long epidemics of the previous batch leave idle (the reference
+ * gets the same effect from pmap's dynamic scheduling, scripts/local_run.jl:28-30). To time such a pipeline on the
+ * device: cabm_mark records an event on the handle's stream now; cabm_ms_since_mark waits for the end of h's last
+ * cabm_run and returns the milliseconds since the mark of `marked` (which may be another handle of the same GPU). */
+int cabm_mark(cabm_handle *h);
+int cabm_ms_since_mark(cabm_handle *marked, cabm_handle *h, float *ms);
 /* Per-kernel-class device time of a run: with profiling on, cabm_run brackets every launch with CUDA events on
  * the handle's stream (and synchronises at the end); cabm_get_profile returns the summed milliseconds and the launch
  * count per class. Classes: dyntrans :790-834, time_update :399-428 (+snapshot), ct_dynamics pass A :705-716,

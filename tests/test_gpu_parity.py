@@ -315,3 +315,21 @@ def test_fused_parked_replicates_and_tail_jobs_bit_exact(cv, O, popsize, split, 
         assert extinct.any() and (~extinct).any()                               # ... for some replicates but not for all: both kinds of job ran
         pop.stream_curves_to(None, None)
         pi.free(); pp.free()
+
+
+@pytest.mark.parametrize("handles", [2, 3])
+def test_pipelined_batches_equal_one_big_ensemble(cv, handles):
+    """cv.EnsemblePipeline: consecutive batches run concurrently on several handles of one GPU (own stream, state and pinned result
+    buffers each). Replicates are independent, so the concatenated batches must equal the same replicates run as one ensemble —
+    whatever else shares the SMs while a batch runs."""
+    ip = cv.ModelParameters(β=0.05, prov="ontario", modeltime=160, initialinf=2, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3)
+    nsims, batch = 960, 320
+    seeds = [17 * (i + 1) for i in range(nsims)]
+    whole = cv.run_ensemble(ip, nsims, seeds=seeds)
+    parts = cv.run_ensemble_pipelined(ip, nsims, batch=batch, handles=handles, seeds=seeds)
+    assert whole["path"] == "fused" and (whole["err"] == 0).all() and (parts["err"] == 0).all()
+    assert parts["inc"].dtype == np.int16                      # streamed into pinned host memory by the kernel
+    for k in ("inc", "prev", "infectors", "totalisolated", "lat_inc_sum"):
+        assert (parts[k] == whole[k]).all(), k
+    attack = 1 - whole["prev"][:, 0, -1, 0] / ip.popsize
+    assert (attack > 0.05).any() and (attack < 0.01).any()      # long and short replicates share the GPU
