@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU per step")
     ap.add_argument("--no-hmatrix", action="store_true", help="do not keep the state matrices in HBM (curves only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--pipeline", type=int, default=2, help="handles (CUDA streams) the steps alternate over; 1 = one step after the other")
+    ap.add_argument("--pipeline", type=int, default=3, help="handles (CUDA streams) the steps alternate over; 1 = one step after the other")
     ap.add_argument("--path", default="auto", choices=["auto", "multikernel", "fused"], help="execution path (include/cabm.h CABM_PATH_*)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -506,7 +506,7 @@ class EnsemblePipeline:
             rest = pipe.drain()
     """
 
-    def __init__(self, batch, popsize, modeltime, handles=2, store_hmatrix=False, device=0, path="auto", pinned=True, copy=True):
+    def __init__(self, batch, popsize, modeltime, handles=3, store_hmatrix=False, device=0, path="auto", pinned=True, copy=True):
         self.batch, self.T, self.copy = batch, modeltime, copy   # copy=False: results are views of the slot's pinned buffers, valid until it is reused
         self.pops = [Population(batch, popsize, modeltime, store_hmatrix=store_hmatrix, device=device) for _ in range(handles)]
         self.bufs = []
@@ -571,7 +571,7 @@ class EnsemblePipeline:
         self.close()
 
 
-def run_ensemble_pipelined(ip, nsims, batch=1000, handles=2, seeds=None, device=0, path="auto"):
+def run_ensemble_pipelined(ip, nsims, batch=1000, handles=3, seeds=None, device=0, path="auto"):
     """run_ensemble for nsims > batch: the batches are pipelined over `handles` handles (EnsemblePipeline)."""
     first = ip[0] if isinstance(ip, (list, tuple)) else ip
     if seeds is None:

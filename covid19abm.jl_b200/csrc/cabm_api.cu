@@ -120,10 +120,10 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8); DA(S.hits, A);
     DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);
     DA(S.totalmet, (size_t)h->R); DA(S.totalinf, (size_t)h->R);
-    DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R); DA(S.dbg, (size_t)h->R * 32); DA(S.resume_list, (size_t)h->R); DA(S.resume_aux, (size_t)h->R * 2);
+    DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R); DA(S.dbg, (size_t)h->R * 32); DA(S.resume_list, (size_t)h->R); DA(S.resume_aux, (size_t)h->R * 2); DA(S.copy_list, (size_t)h->R);
     if (S.store_hm) DA(S.hm, (size_t)h->R * h->T * h->N);
     DA(h->d_scratch, (size_t)4 * h->N);
-    DA(h->d_work, 8);
+    DA(h->d_work, 16);
     { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) h->n_sm = pr.multiProcessorCount; }
     // shared tables
     {

@@ -196,14 +196,18 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     };
 
     // Two sweeps over atomic work queues. Sweep 0 starts every replicate and runs it for split_day days (split_day = 0: to the end).
-    // By then most epidemics have died out: their state is final, and what is left of them — the idle tail of the curves and the
-    // state matrix, the copy of the curves to the host — is pure output, queued as a "tail job". A replicate that is still active
-    // is parked (state to HBM) and queued for sweep 1. Sweep 1 resumes the parked replicates first — they are the long ones that
-    // bound the launch — and CTAs without one work the tail jobs off meanwhile, so the output traffic (HBM, PCIe) overlaps the
-    // latency-bound epidemics instead of delaying their start.
-    //   work[0] fresh head | [1],[2] parked head, tail | [3] fresh jobs finished | [4],[5] tail-job head, tail | [6] CTAs on tail jobs
-    // resume_list holds the parked replicates from the bottom and the tail jobs from the top (each replicate is one or the other).
-    const unsigned tail_ctas = tail_cta_limit;
+    // By then most epidemics have died out: their state is final, and what is left of them is pure output — the idle tail of the
+    // curves and of the state matrix (a "fill job") and the copy of the curves to the host (a "copy job"). A replicate that is
+    // still active is parked (state to HBM) and queued for sweep 1. Sweep 1 resumes the parked replicates first — they are the
+    // long ones that bound the launch — and CTAs without one work the output jobs off meanwhile, so the output traffic (HBM,
+    // PCIe) overlaps the latency-bound epidemics instead of delaying their start. A few CTAs saturate the PCIe link and more of
+    // them only get in the way of the running epidemics, so at most `tail_cta_limit` CTAs become copiers (and stay so until
+    // the copy queue has run dry); every other CTA leaves as soon as there is nothing else to do and frees its SM for the
+    // next batch of the ensemble (cabm.h: several handles on one GPU).
+    //   work[0] fresh head | [1],[2] parked head, tail | [3] fresh jobs finished | [4],[5] fill-job head, tail | [6] copiers
+    //   [7] fill jobs finished | [8],[9] copy-job head, tail
+    // resume_list holds the parked replicates from the bottom and the fill jobs from the top (each replicate is one or the other).
+    bool copier = false;                                                        // (thread 0)
     for (int sweep = 0; sweep < 2; ++sweep) {
     if (sweep == 1 && split_day <= 0) break;
     for (;;) {
@@ -212,18 +216,38 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             int got = -1, kind = 0;
             if (sweep == 0) { const unsigned k = atomicAdd(&work[0], 1u); if (k < (unsigned)S.R) got = (int)k; }
             else {
-                for (;;) {          // wait while fresh jobs that might still queue something are in flight
+                for (;;) {          // wait while jobs that might still queue something are in flight
                     const unsigned done = *(volatile unsigned *)&work[3];
                     __threadfence();
                     const unsigned t = *(volatile unsigned *)&work[2], h = *(volatile unsigned *)&work[1];
-                    if (h < t) {
+                    if (h < t && !copier) {                                  // (a copier would sit on its ticket for a whole epidemic)
                         if (atomicCAS(&work[1], h, h + 1) == h) {
                             while ((got = *(volatile int *)&S.resume_list[h]) < 0) __nanosleep(100);
                             break;
                         }
                         continue;
                     }
+                    const unsigned filled = *(volatile unsigned *)&work[7];
+                    __threadfence();
                     const unsigned ft = *(volatile unsigned *)&work[5], fh = *(volatile unsigned *)&work[4];
+                    if (S.host_inc) {
+                        const unsigned ct = *(volatile unsigned *)&work[9], ch = *(volatile unsigned *)&work[8];
+                        if (ch < ct) {
+                            if (!copier && *(volatile unsigned *)&work[6] < tail_cta_limit) {
+                                if (atomicAdd(&work[6], 1u) < tail_cta_limit) copier = true; else atomicSub(&work[6], 1u);
+                            }
+                            if (copier) {
+                                if (atomicCAS(&work[8], ch, ch + 1) == ch) {
+                                    while ((got = *(volatile int *)&S.copy_list[ch]) < 0) __nanosleep(100);
+                                    kind = 2;
+                                    break;
+                                }
+                                continue;
+                            }
+                        } else if (copier && done >= (unsigned)S.R && filled >= ft) {      // nothing can queue a copy job any more
+                            atomicSub(&work[6], 1u); copier = false;
+                        }
+                    }
                     if (fh < ft) {
                         if (atomicCAS(&work[4], fh, fh + 1) == fh) {
                             while ((got = *(volatile int *)&S.resume_list[S.R - 1 - (int)fh]) < 0) __nanosleep(100);
@@ -232,18 +256,24 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         }
                         continue;
                     }
-                    if (done >= (unsigned)S.R) break;
+                    if (done >= (unsigned)S.R && !copier) break;
                     __nanosleep(500);
                 }
                 __threadfence();
             }
             Z.r = got; Z.kind = kind;
+            if (S.store_hm) bulk_store_wait_read();                              // column copies of the previous job have left shared memory
         }
         __syncthreads();
         const int r = Z.r;
         if (r < 0) break;
+        if (Z.kind == 2) {
+            // -------------------------------------------------------- copy job: a finished replicate's curves -> pinned host memory
+            stream_curves_to_host(r);
+            continue;
+        }
         if (Z.kind == 1) {
-            // -------------------------------------------------------- tail job: the output that is left of a replicate that died out
+            // -------------------------------------------------------- fill job: the idle tail of a replicate that died out
             const int d0 = __ldcg(&S.resume_aux[r * 2]);                       // first row that is not written yet (>= 1)
             uint8_t *hm = S.store_hm ? S.hm + (size_t)r * T * N : nullptr;
             if (tid < 72) Z.run[tid] = __ldcg(&S.prev[(((size_t)r * 6 + tid / 12) * (size_t)T + (size_t)(d0 - 1)) * 12 + tid % 12]);
@@ -256,18 +286,17 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             __syncthreads();
             fill_idle_rows(r, d0);
             if (hm) fill_idle_columns(hm, d0);
-            if (S.host_inc) {
-                // a few CTAs saturate the PCIe link; more of them only get in the way of the running epidemics: take a ticket
-                if (tid == 0) for (;;) {
-                    if (*(volatile unsigned *)&work[6] < tail_ctas) { if (atomicAdd(&work[6], 1u) < tail_ctas) break; atomicSub(&work[6], 1u); }
-                    __nanosleep(1000);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                if (S.host_inc) {
+                    const unsigned slot = atomicAdd(&work[9], 1u);
+                    __threadfence();
+                    *(volatile int *)&S.copy_list[slot] = r;
+                    __threadfence();
                 }
-                __syncthreads();
-                stream_curves_to_host(r);
-                __syncthreads();
-                if (tid == 0) { __threadfence(); atomicSub(&work[6], 1u); }
+                atomicAdd(&work[7], 1u);
             }
-            if (hm && tma_ok && tid == 0) bulk_store_wait_all();
             continue;
         }
         const bool resumed = sweep == 1;
@@ -990,6 +1019,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (!resumed && tid == 0) { __threadfence(); atomicAdd(&work[3], 1u); }
     }
     }
+    if (tid == 0 && S.store_hm) bulk_store_wait_all();     // column copies of the last fill job
 }
 
 size_t fused_smem_bytes_host(int Np) { return fused_smem_bytes(Np); }
@@ -1011,9 +1041,10 @@ int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaSt
     int split_day = (S.R > grid && S.T >= 150) ? 60 : 0;
     if (const char *e = getenv("CABM_FUSED_SPLIT_DAY")) split_day = atoi(e);
     if (split_day >= S.T) split_day = 0;
-    cudaMemsetAsync(work, 0, 8 * sizeof(unsigned), s);
-    if (split_day > 0) cudaMemsetAsync(S.resume_list, 0xFF, (size_t)S.R * sizeof(int), s);
+    cudaMemsetAsync(work, 0, 16 * sizeof(unsigned), s);
+    if (split_day > 0) { cudaMemsetAsync(S.resume_list, 0xFF, (size_t)S.R * sizeof(int), s); cudaMemsetAsync(S.copy_list, 0xFF, (size_t)S.R * sizeof(int), s); }
     unsigned tail_ctas = FUSED_TAIL_CTAS;
+    if (tail_ctas > (unsigned)grid / 4) tail_ctas = grid / 4 > 0 ? grid / 4 : 1;      // copiers do not resume parked replicates
     if (const char *e = getenv("CABM_FUSED_TAIL_CTAS")) tail_ctas = (unsigned)atoi(e);                                       // experiments
     if (any_ct) k_sim_fused<true><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
     else k_sim_fused<false><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
