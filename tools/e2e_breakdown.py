@@ -26,3 +26,9 @@ for mode in ("no streaming", "streaming"):
     print("  configure+run(sync) ms", round(t(step2), 3))
     pop.run(sync=True)
     print("  curves() alone ms", round(t(lambda: pop.curves(pin_inc.array, pin_prev.array)), 3), " scalars() alone ms", round(t(lambda: pop.scalars()), 3))
+# main(ip) returns the full state matrix (:141): what its read-back costs for the whole batch (Int16, widened on the device)
+hm = cv.PinnedArray((R, T_DAYS, N_AGENTS), np.int16)
+pop.run(sync=True)
+print("hmatrix_all() ms (1000 x 500 x 10000 Int16 = 10 GB over PCIe)", round(t(lambda: pop.hmatrix_all(hm.array), 2), 1))
+one = np.zeros((N_AGENTS, T_DAYS), np.int16, order="F")
+print("hmatrix(0) ms (one replicate, 10 MB)", round(t(lambda: pop.hmatrix(0), 5), 3))
