@@ -154,7 +154,7 @@ def lib():
     L.cabm_step_dyntrans.argtypes = [vp]; L.cabm_step_time_update.argtypes = [vp]
     L.cabm_get_day.argtypes = [vp]
     L.cabm_get_dyntrans_counters.argtypes = [vp, vp, vp]
-    L.cabm_get_hmatrix.argtypes = [vp, i32, vp]; L.cabm_get_hmatrix_all.argtypes = [vp, vp]
+    L.cabm_get_hmatrix.argtypes = [vp, i32, vp]; L.cabm_get_hmatrix_all.argtypes = [vp, vp]; L.cabm_get_hmatrix_all_u8.argtypes = [vp, vp]
     L.cabm_get_curves.argtypes = [vp, vp, vp]
     L.cabm_get_curves_i16.argtypes = [vp, vp, vp]
     L.cabm_get_mean_curves.argtypes = [vp, vp, vp]
@@ -334,10 +334,14 @@ class Population:
         self._chk(self.L.cabm_get_hmatrix(self.h, replicate, buf.ctypes.data))
         return buf.T
 
-    def hmatrix_all(self, out=None):
+    def hmatrix_all(self, out=None, dtype=np.int16):
+        """[n_rep][T][N] state matrices; dtype int16 as main returns them (:111), or uint8 as the device keeps them (half the bytes)."""
         if out is None:
-            out = np.zeros((self.n_rep, self.T, self.N), dtype=np.int16)
-        self._chk(self.L.cabm_get_hmatrix_all(self.h, out.ctypes.data))
+            out = np.zeros((self.n_rep, self.T, self.N), dtype=dtype)
+        if out.dtype == np.uint8:
+            self._chk(self.L.cabm_get_hmatrix_all_u8(self.h, out.ctypes.data))
+        else:
+            self._chk(self.L.cabm_get_hmatrix_all(self.h, out.ctypes.data))
         return out
 
     def curves(self, inc=None, prev=None, dtype=np.int32):

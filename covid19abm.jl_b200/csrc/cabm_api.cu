@@ -488,6 +488,14 @@ extern "C" int cabm_get_hmatrix_all(cabm_handle *h, int16_t *out) {
     if (!out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix_all: bad argument");
     return copy_hmatrix(h, 0, (size_t)h->n_rep * h->T * h->N, out);
 }
+extern "C" int cabm_get_hmatrix_all_u8(cabm_handle *h, uint8_t *out) {
+    int rc = need_config(h); if (rc) return rc;
+    if (!h->S.store_hm) return fail(h, CABM_E_STATE, "handle was created without CABM_STORE_HMATRIX");
+    if (!out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix_all_u8: bad argument");
+    CU(cudaMemcpyAsync(out, h->S.hm, (size_t)h->n_rep * h->T * h->N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CABM_OK;
+}
 extern "C" int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev) {
     int rc = need_config(h); if (rc) return rc;
     if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");

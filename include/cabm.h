@@ -142,6 +142,9 @@ int cabm_get_dyntrans_counters(cabm_handle *h, int32_t *totalmet, int32_t *total
 int cabm_get_hmatrix(cabm_handle *h, int replicate, int16_t *out);
 /* every replicate's matrix, [n_rep][modeltime][popsize] */
 int cabm_get_hmatrix_all(cabm_handle *h, int16_t *out);
+/* the same matrices as the device keeps them: one byte per agent-day (health codes are 0..11), half the PCIe traffic of the
+ * Int16 form; out is [n_replicates][modeltime][popsize] */
+int cabm_get_hmatrix_all_u8(cabm_handle *h, uint8_t *out);
 /* _get_incidence_and_prev :259-268 for "all" (group 0) and the five _splitstate groups (:247-256), as
  * runsim collects them (:91-97): inc and prev are int32 [n_rep][6][modeltime][12]. */
 int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev);

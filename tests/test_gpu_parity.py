@@ -306,6 +306,7 @@ def test_fused_parked_replicates_and_tail_jobs_bit_exact(cv, O, popsize, split, 
         inc, prev = pop.curves()
         sc = pop.scalars()
         hm = pop.hmatrix_all()
+        assert (pop.hmatrix_all(dtype=np.uint8) == hm).all()                    # one byte per agent-day, as the device keeps it
         assert (sc["err"] == 0).all()
         assert (inc == ref["inc"]).all() and (prev == ref["prev"]).all()
         assert (pi.array == ref["inc"]).all() and (pp.array == ref["prev"]).all()

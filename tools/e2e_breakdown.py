@@ -30,5 +30,6 @@ for mode in ("no streaming", "streaming"):
 hm = cv.PinnedArray((R, T_DAYS, N_AGENTS), np.int16)
 pop.run(sync=True)
 print("hmatrix_all() ms (1000 x 500 x 10000 Int16 = 10 GB over PCIe)", round(t(lambda: pop.hmatrix_all(hm.array), 2), 1))
-one = np.zeros((N_AGENTS, T_DAYS), np.int16, order="F")
+hm.free(); hm8 = cv.PinnedArray((R, T_DAYS, N_AGENTS), np.uint8)
+print("hmatrix_all(uint8) ms (5 GB)", round(t(lambda: pop.hmatrix_all(hm8.array), 2), 1))
 print("hmatrix(0) ms (one replicate, 10 MB)", round(t(lambda: pop.hmatrix(0), 5), 3))
