@@ -10,7 +10,12 @@ scenario with isolation on (fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3, tprei
 NCCL gather of the summary curves). A step = one full pass of the hot path (main(ip) :104-142 for every
 replicate of the batch: initialize, seed, 500 x (dyntrans, time_update + snapshot), reductions).
 
-`value` is device time (CUDA events on the library's stream) with parameters and seeds already resident;
+Steps alternate over `--pipeline` handles of the GPU (default 3; cv.EnsemblePipeline): each handle has its own stream, state
+and pinned result buffers, so the replicates of step k+1 that die out run beside the few long epidemics of step k, which
+would otherwise leave most SMs idle while they finish. Every step is one full pass over its own 1000 replicates; all K
+steps lie inside the timed region. `--pipeline 1` runs one step after the other (config.ms_one_step_alone).
+
+`value` is device time (CUDA events: a mark on the first handle's stream to the end of every handle's last run) with parameters and seeds already resident;
 `e2e` goes through the public API from host parameter structs to host result buffers (curves + scalars as
 runsim returns them, :77-101), copies included. The Julia reference cannot run in this image (no julia):
 the CPU arm is the C restatement in oracle/ ("port"), one replicate per core on all host cores.
