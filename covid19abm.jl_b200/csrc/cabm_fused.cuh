@@ -1026,12 +1026,14 @@ size_t fused_smem_bytes_host(int Np) { return fused_smem_bytes(Np); }
 
 int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaStream_t s) {
     const size_t bytes = fused_smem_bytes(S.Np);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};      // per device: function attributes belong to the device's copy of the kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         const int lim = 227 * 1024 - 512;        // the opt-in maximum per CTA minus this kernel's (diagnostic) static shared memory
         cudaFuncSetAttribute(k_sim_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         cudaFuncSetAttribute(k_sim_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     int per_sm = bytes <= 113 * 1024 ? 2 : 1;
     if (const char *e = getenv("CABM_FUSED_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments

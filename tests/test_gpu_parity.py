@@ -334,3 +334,22 @@ def test_pipelined_batches_equal_one_big_ensemble(cv, handles):
         assert (parts[k] == whole[k]).all(), k
     attack = 1 - whole["prev"][:, 0, -1, 0] / ip.popsize
     assert (attack > 0.05).any() and (attack < 0.01).any()      # long and short replicates share the GPU
+
+
+def test_second_device_in_the_same_process(cv):
+    """Handles on two GPUs of one process (kernel attributes and constant tables are per device): same replicates, same bytes."""
+    import ctypes
+    try:
+        n = ctypes.c_int(0)
+        rt = ctypes.CDLL("libcudart.so")
+        rt.cudaGetDeviceCount(ctypes.byref(n))
+    except OSError:
+        pytest.skip("no libcudart to count devices with")
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    ip = cv.ModelParameters(β=0.06, prov="ontario", modeltime=80, initialinf=3)
+    a = cv.run_ensemble(ip, 64, device=0)
+    b = cv.run_ensemble(ip, 64, device=1)
+    assert a["path"] == b["path"] == "fused"
+    for k in ("inc", "prev", "infectors", "lat_inc_sum"):
+        assert (a[k] == b[k]).all(), k
