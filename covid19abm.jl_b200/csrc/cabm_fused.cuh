@@ -17,6 +17,14 @@
 // order in batches of up to 32 whose contact events (<= NT, one per thread) are drawn in parallel; a batch is cut
 // before the first infector that an earlier infector of the same batch contacts (its budget :802 would change), and
 // events that share a target are resolved in event order by the lowest event of the group.
+//
+// Map of the kernel body (k_sim_fused):
+//   work queues   sweep 0: fresh replicates for split_day days -> finished (fill job) or parked; sweep 1: parked replicates,
+//                 copy jobs (curves -> pinned host memory, a few "copier" CTAs), fill jobs (idle tails of curves and state matrix)
+//   per replicate initialize :171-188 -> get_ag_dist :339-343 -> insert_infected :360-395 -> column 1 -> day loop -> write-back
+//   per active day infector list -> budgets -> batches { preparation (warp 0) | B1 | events | B2 | shared targets | apply | B5 }
+//                 -> time_update scan + events | S2 -> curves row + TMA store of the column
+//   idle days     (nobody infectious, nothing due) repeat column and prevalence row; an idle tail is filled in one go
 #pragma once
 #include <cstdlib>
 
