@@ -524,6 +524,8 @@ class EnsemblePipeline:
             else:
                 self.bufs.append(None)
         self.pending = [None] * handles           # user tag of the batch in flight on each handle
+        self.outs = [None] * handles              # caller-supplied pinned result arrays of that batch (submit(out=...))
+        self.own = [b is not None for b in self.bufs]   # the handle currently streams into its own buffers
         self.k = 0
 
     def _collect(self, j):
@@ -531,7 +533,10 @@ class EnsemblePipeline:
         if tag is None:
             return None
         self.pending[j] = None
-        if self.bufs[j] is not None:
+        if self.outs[j] is not None:               # the kernel wrote straight into the caller's pinned arrays
+            inc, prev = p.curves(self.outs[j][0], self.outs[j][1])
+            self.outs[j] = None
+        elif self.bufs[j] is not None:
             inc, prev = p.curves(self.bufs[j][0].array, self.bufs[j][1].array)      # same pointers: waits for the run only
             if self.copy:
                 inc, prev = inc.copy(), prev.copy()
@@ -539,12 +544,20 @@ class EnsemblePipeline:
             inc, prev = p.curves()
         return dict(tag=tag, inc=inc, prev=prev, **p.scalars())
 
-    def submit(self, psets, seeds, pset_of_rep=None, tag=None, mode=MODE_EXACT, collect=True):
+    def submit(self, psets, seeds, pset_of_rep=None, tag=None, mode=MODE_EXACT, collect=True, out=None):
         """Start one batch; returns the results of the batch that used this handle before (None the first time round, or
-        with collect=False, where the previous results are dropped — timing loops)."""
+        with collect=False, where the previous results are dropped — timing loops). out=(inc, prev): Int16 arrays
+        [batch][6][T][12] in pinned host memory (e.g. slices of one PinnedArray for the whole ensemble) that this batch's
+        curves are written into by the kernel — no copy on the host at all."""
         j = self.k % len(self.pops)
         prev = self._collect(j) if collect else None
         p = self.pops[j]
+        if out is not None:
+            p.stream_curves_to(out[0], out[1])
+            self.outs[j], self.own[j] = out, False
+        elif self.bufs[j] is not None and not self.own[j]:       # back to the slot's own buffers
+            p.stream_curves_to(self.bufs[j][0].array, self.bufs[j][1].array)
+            self.own[j] = True
         p.configure(psets, seeds, pset_of_rep, mode)
         p.run(sync=False)
         self.pending[j] = self.k if tag is None else tag
@@ -575,22 +588,44 @@ class EnsemblePipeline:
         self.close()
 
 
-def run_ensemble_pipelined(ip, nsims, batch=1000, handles=3, seeds=None, device=0, path="auto"):
-    """run_ensemble for nsims > batch: the batches are pipelined over `handles` handles (EnsemblePipeline)."""
+def run_ensemble_pipelined(ip, nsims, batch=1000, handles=3, seeds=None, device=0, path="auto", pipe=None, pinned=None):
+    """run_ensemble for nsims > batch: the batches are pipelined over `handles` handles (EnsemblePipeline). With popsize <= 32767
+    the curves come back as Int16 views of two pinned arrays for the whole ensemble (kept alive by the returned dict), written
+    by the kernels themselves: the host never copies them. Creating the handles (several GB of device memory) and the pinned
+    arrays takes a few hundred milliseconds — far longer than the simulation of a few thousand replicates — so repeated
+    calls (β sweeps, calibration) should pass their own `pipe` (an EnsemblePipeline(batch, popsize, modeltime, pinned=False))
+    and `pinned` (two PinnedArray((nsims, 6, modeltime, 12), int16)) and keep them."""
     first = ip[0] if isinstance(ip, (list, tuple)) else ip
     if seeds is None:
         seeds = [726 * (i + 1) for i in range(nsims)]
     if nsims % batch:
         raise ValueError("nsims must be a multiple of batch")
+    T = first.modeltime
+    direct = first.popsize <= 32767
+    if direct and pinned is None:
+        pinned = (PinnedArray((nsims, 6, T, 12), np.int16), PinnedArray((nsims, 6, T, 12), np.int16))
+    own_pipe = pipe is None
+    if own_pipe:
+        pipe = EnsemblePipeline(batch, first.popsize, T, handles=handles, device=device, path=path, pinned=False)
     parts = []
-    with EnsemblePipeline(batch, first.popsize, first.modeltime, handles=handles, device=device, path=path) as pipe:
+    try:
+        base = pipe.k
         for k in range(nsims // batch):
-            r = pipe.submit(ip, seeds[k * batch:(k + 1) * batch])
+            sl = slice(k * batch, (k + 1) * batch)
+            r = pipe.submit(ip, seeds[sl], tag=base + k, out=(pinned[0].array[sl], pinned[1].array[sl]) if direct else None)
             if r is not None:
                 parts.append(r)
         parts += pipe.drain()
+    finally:
+        if own_pipe:
+            pipe.close()
     parts.sort(key=lambda r: r["tag"])
-    return {k: np.concatenate([r[k] for r in parts]) for k in parts[0] if k != "tag"}
+    res = {k: np.concatenate([r[k] for r in parts]) for k in parts[0] if k not in ("tag", "inc", "prev")}
+    if direct:
+        res["inc"], res["prev"], res["_pinned"] = pinned[0].array, pinned[1].array, pinned
+    else:
+        res["inc"], res["prev"] = np.concatenate([r["inc"] for r in parts]), np.concatenate([r["prev"] for r in parts])
+    return res
 
 
 def bind_host_thread_to_gpu(device):
