@@ -1,14 +1,15 @@
 """Runs the BASELINE.json configurations other than the bench workload and prints one JSON line each:
+ A  main(ip) for one replicate (configs[0]): latency on a kept handle, state matrix read back
  C  contact tracing ctstrat 1 and 3 (multikernel path), 1000 replicates
  D  calibration beta sweep: 20 beta points x 500 replicates, T = 50 (fused path)
  E  1,000,000 agents x 500 days x R replicates with a quarantined age group (multikernel path, native schedule)
-Usage: python tools/run_configs.py [C] [D] [E] [--e-reps 100] [--profile]"""
+Usage: python tools/run_configs.py [A] [C] [D] [E] [--e-reps 100] [--profile]"""
 import json, sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
 import covid19abm_b200 as cv
 
-which = [a for a in sys.argv[1:] if a in ("C", "D", "E")] or ["C", "D", "E"]
+which = [a for a in sys.argv[1:] if a in ("A", "C", "D", "E")] or ["A", "C", "D", "E"]
 e_reps = int(sys.argv[sys.argv.index("--e-reps") + 1]) if "--e-reps" in sys.argv else 100
 profile = "--profile" in sys.argv
 peak = 6546.2
@@ -51,6 +52,21 @@ def run(name, ip, nrep, pof=None, mode=cv.MODE_EXACT, path="auto", store_hm=Fals
 
 
 B = dict(prov="ontario", initialinf=1, modeltime=500, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3, tpreiso=0)
+if "A" in which:
+    ipa = cv.ModelParameters(β=0.0345, prov="ontario", initialinf=1, modeltime=500)
+    with cv.Population(1, ipa.popsize, ipa.modeltime, store_hmatrix=True) as pop:
+        dev, e2e, att = [], [], []
+        for k in range(41):
+            t0 = time.perf_counter()
+            pop.configure(ipa, [726 * (k + 1)]); pop.run(sync=False); hm = pop.hmatrix(0)      # runsim's seed :78, main's return value :141
+            e2e.append(1e3 * (time.perf_counter() - t0)); dev.append(pop.last_run_ms); att.append(float((hm[:, -1] != 0).mean()))
+        dev, e2e, att = np.array(dev[1:]), np.array(e2e[1:]), np.array(att[1:])
+        big = att > 0.1
+        print(json.dumps({"config": "A main(ip), one replicate, 10000 agents x 500 days, no isolation", "path": pop.last_path, "seeds": 40,
+                          "device_ms_median": round(float(np.median(dev)), 3), "device_ms_max": round(float(dev.max()), 3),
+                          "host_to_host_ms_median (configure + run + Matrix{Int16} read back)": round(float(np.median(e2e)), 3), "host_to_host_ms_max": round(float(e2e.max()), 3),
+                          "epidemics_that_take_off": int(big.sum()), "device_ms_when_taking_off_median": round(float(np.median(dev[big])), 3) if big.any() else None,
+                          "device_ms_when_dying_out_median": round(float(np.median(dev[~big])), 3) if (~big).any() else None}), flush=True)
 if "C" in which:
     run("C ctstrat=1", cv.ModelParameters(β=0.0345, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000)
     run("C ctstrat=3 strat3qdays=14", cv.ModelParameters(β=0.0345, ctstrat=3, strat3qdays=14, fctcapture=0.5, fcontactst=0.5, cdaysback=3, **B), 1000)
