@@ -104,5 +104,56 @@ function run_ensemble(ip::ModelParameters, nsims::Integer; device = 0)
     end
 end
 
-export ModelParameters, HEALTH, main, run_ensemble
+"""
+Ensembles larger than one batch: `handles` handles of `batch` replicates on one GPU, used round-robin. Each handle has its own
+stream, so consecutive batches overlap on the device (the short replicates of batch k+1 fill the SMs that the long epidemics of
+batch k leave idle), and the kernels write every finished replicate's Int16 curves straight into one pinned host array for the
+whole ensemble (cabm_set_host_curves_i16): the host copies nothing. Curves come back as [12, T, 6, nsims].
+"""
+function run_ensemble_pipelined(ip::ModelParameters, nsims::Integer; batch = 1000, handles = 3, device = 0)
+    nsims % batch == 0 || error("nsims must be a multiple of batch")
+    per = 12 * ip.modeltime * 6                                                    # Int16 elements per replicate
+    bytes = UInt64(2 * per * nsims)
+    pinc = ccall((:cabm_host_alloc, LIB), Ptr{Int16}, (UInt64,), bytes); pprev = ccall((:cabm_host_alloc, LIB), Ptr{Int16}, (UInt64,), bytes)
+    (pinc == C_NULL || pprev == C_NULL) && error("cabm_host_alloc failed")
+    hs = Ptr{Cvoid}[]
+    infectors = Matrix{Int64}(undef, 4, nsims); tiso = Vector{Int64}(undef, nsims)
+    try
+        for _ in 1:handles
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            rc = ccall((:cabm_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint), h, device, batch, ip.popsize, ip.modeltime, 0)
+            rc == 0 || error(unsafe_string(ccall((:cabm_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+            push!(hs, h[])
+        end
+        p = Ref(to_c(ip))
+        inflight = fill(0, handles)                                                 # batch number running on each handle
+        collect!(j) = begin                                                          # wait for the batch on handle j, read its scalars
+            k = inflight[j]; k == 0 && return
+            r0 = (k - 1) * batch
+            check(hs[j], ccall((:cabm_sync, LIB), Cint, (Ptr{Cvoid},), hs[j]))
+            check(hs[j], ccall((:cabm_get_scalars, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{UInt32}),
+                               hs[j], pointer(infectors, 4 * r0 + 1), pointer(tiso, r0 + 1), C_NULL, C_NULL))
+            inflight[j] = 0
+        end
+        for k in 1:(nsims ÷ batch)
+            j = (k - 1) % handles + 1
+            collect!(j)
+            r0 = (k - 1) * batch
+            seeds = UInt64[726 * x for x in (r0 + 1):(r0 + batch)]                  # :78
+            check(hs[j], ccall((:cabm_set_host_curves_i16, LIB), Cint, (Ptr{Cvoid}, Ptr{Int16}, Ptr{Int16}), hs[j], pinc + 2 * per * r0, pprev + 2 * per * r0))
+            check(hs[j], ccall((:cabm_configure, LIB), Cint, (Ptr{Cvoid}, Ref{CabmParams}, Cint, Ptr{Int32}, Cint, Ptr{UInt64}, Cint),
+                               hs[j], p, 1, C_NULL, batch, seeds, 0))
+            check(hs[j], ccall((:cabm_run, LIB), Cint, (Ptr{Cvoid},), hs[j]))         # asynchronous on the handle's stream
+            inflight[j] = k
+        end
+        foreach(collect!, 1:handles)
+        inc = copy(unsafe_wrap(Array, pinc, (12, ip.modeltime, 6, nsims))); prev = copy(unsafe_wrap(Array, pprev, (12, ip.modeltime, 6, nsims)))
+        return (inc = inc, prev = prev, infectors = infectors, totalisolated = tiso)
+    finally
+        foreach(h -> ccall((:cabm_destroy, LIB), Cvoid, (Ptr{Cvoid},), h), hs)
+        ccall((:cabm_host_free, LIB), Cvoid, (Ptr{Cvoid},), pinc); ccall((:cabm_host_free, LIB), Cvoid, (Ptr{Cvoid},), pprev)
+    end
+end
+
+export ModelParameters, HEALTH, main, run_ensemble, run_ensemble_pipelined
 end
