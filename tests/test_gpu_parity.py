@@ -353,3 +353,39 @@ def test_second_device_in_the_same_process(cv):
     assert a["path"] == b["path"] == "fused"
     for k in ("inc", "prev", "infectors", "lat_inc_sum"):
         assert (a[k] == b[k]).all(), k
+
+
+@pytest.mark.parametrize("mode", ["exact", "native"])
+def test_per_day_kernels_replayed_from_a_cuda_graph(cv, mode):
+    """The per-day kernel path captures its launch sequence into a CUDA graph on the third run of a handle with the same arguments
+    and replays it afterwards: runs 1, 2 (direct launches), 3 (capture) and 4, 5 (replay) must give what a fresh handle gives for
+    the same seeds, also after the arguments change (tracing on: direct launches again, then a new graph)."""
+    a = cv.ModelParameters(β=0.08, prov="ontario", modeltime=60, initialinf=3, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3)
+    b = cv.ModelParameters(β=0.08, prov="ontario", modeltime=60, initialinf=3, ctstrat=1, fctcapture=0.7, fcontactst=0.7, cdaysback=3)
+    m = cv.MODE_NATIVE if mode == "native" else cv.MODE_EXACT
+    R = 48
+    with cv.Population(R, a.popsize, 60) as pop:
+        pop.set_path("multikernel")
+        for k, ip in enumerate([a, a, a, a, a, b, b, b, b, a]):
+            seeds = [31 * (i + 1) + k for i in range(R)]
+            pop.configure(ip, seeds, mode=m); pop.run()
+            assert pop.last_path == "multikernel"
+            inc, prev = pop.curves(); sc = pop.scalars()
+            if mode == "exact":
+                fresh = cv.run_ensemble(ip, R, seeds=seeds, path="fused")          # the other path, a fresh handle: same bytes
+                assert (inc == fresh["inc"]).all() and (prev == fresh["prev"]).all(), k
+                assert (sc["infectors"] == fresh["infectors"]).all() and (sc["totalisolated"] == fresh["totalisolated"]).all(), k
+            else:
+                fresh = cv.run_ensemble(ip, R, seeds=seeds, path="multikernel", mode=m)
+                assert (prev[:, 0].sum(axis=2) == a.popsize).all() and (sc["err"] == 0).all(), k
+                # the native schedule is not bit-reproducible between runs (atomics decide), its size is
+                assert abs(int(prev[:, 0, -1, 0].sum()) - int(fresh["prev"][:, 0, -1, 0].sum())) < 0.2 * R * a.popsize
+    # launch accounting still counts kernels, replayed or not
+    with cv.Population(8, a.popsize, 60) as pop:
+        pop.set_path("multikernel")
+        counts = []
+        for k in range(5):
+            l0 = pop.launch_count
+            pop.configure(a, [5 * (i + 1) for i in range(8)], mode=m); pop.run()
+            counts.append(pop.launch_count - l0)
+        assert len(set(counts)) == 1 and counts[0] >= 2 * 60
