@@ -243,6 +243,22 @@ def main():
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     assert got == args.steps
+    # ---- the same loop with the rows-only form of the streamed curves (cabm_set_host_curve_rows): a replicate whose epidemic has
+    # died out repeats its last row, so only the rows before that cross PCIe; reported beside `e2e`, which stays the dense form
+    rows_bufs = [cv.PinnedArray((R,), np.int32) for _ in pops]
+    for q, bufs, rb_ in zip(pops, pipe.bufs, rows_bufs):
+        q.stream_curves_to(bufs[0].array, bufs[1].array, rb_.array)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        pipe.submit(ip, seeds_for(100 + k, rank, R))
+    pipe.drain()
+    barrier()
+    e2e_rows_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    # rows sent per step: the row counts of the last batch on every handle (they stay in the rows arrays after the drain)
+    nb_ = min(P, args.steps)
+    sent_rows = sum(int(rb_.array.sum()) for rb_ in rows_bufs[:nb_]) / nb_
+    rows_d2h = sent_rows * 6 * 12 * 2 * 2 + R * (32 + 8 + 8 + 4 + 4)
     for q in pops:
         q.stream_curves_to(None, None)
     sampler.stop_flag = True
@@ -330,7 +346,10 @@ def main():
                            "ms_one_step_alone": one_ms},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] Int16 x2 (narrowed on device) and per-replicate scalars (runsim :77-101), pinned host buffers",
-                        "host_numa_bound": numa_bound},
+                        "host_numa_bound": numa_bound,
+                        "rows_only": {"value": world * units * args.steps / (e2e_rows_ms * 1e-3), "ms_per_step": e2e_rows_ms / args.steps, "d2h_bytes_per_step": int(rows_d2h),
+                                      "note": "optional form of the result (cabm_set_host_curve_rows): only the rows of each replicate's curves before its epidemic died out are sent, "
+                                              "plus their number; the rest repeat. Lossless; cv.expand_curves rebuilds the dense arrays on the host"}},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
                 "cpu_baseline": cpu}
         emit(line)

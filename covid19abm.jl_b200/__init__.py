@@ -142,6 +142,7 @@ def lib():
     L.cabm_configure.argtypes = [vp, vp, i32, vp, i32, vp, i32]
     L.cabm_run.argtypes = [vp]; L.cabm_sync.argtypes = [vp]
     L.cabm_last_run_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.cabm_set_host_curve_rows.argtypes = [vp, vp]
     L.cabm_mark.argtypes = [vp]; L.cabm_ms_since_mark.argtypes = [vp, vp, C.POINTER(C.c_float)]
     L.cabm_launch_count.argtypes = [vp]; L.cabm_launch_count.restype = i64
     L.cabm_set_profiling.argtypes = [vp, i32]
@@ -355,9 +356,13 @@ class Population:
             self._chk(self.L.cabm_get_curves(self.h, inc.ctypes.data, prev.ctypes.data))
         return inc, prev
 
-    def stream_curves_to(self, inc, prev):
+    def stream_curves_to(self, inc, prev, rows=None):
         """Register two PinnedArray-backed Int16 arrays [R][6][T][12]: the fused kernel writes each finished replicate's curves
-        into them directly; a later curves(inc, prev) with the same arrays costs only a synchronise. None, None unregisters."""
+        into them directly; a later curves(inc, prev) with the same arrays costs only a synchronise. None, None unregisters.
+        rows: optional PinnedArray-backed int32 array [R]. With it the kernel sends only the leading rows (days) of a replicate
+        that differ — after an epidemic has died out incidence is 0 and prevalence repeats — and stores their number in
+        rows[r]; expand_curves(inc, prev, rows) fills the rest in on the host when dense arrays are wanted."""
+        self._chk(self.L.cabm_set_host_curve_rows(self.h, None if rows is None else rows.ctypes.data))
         self._chk(self.L.cabm_set_host_curves_i16(self.h, None if inc is None else inc.ctypes.data, None if prev is None else prev.ctypes.data))
 
     def mean_curves(self):
@@ -496,6 +501,17 @@ def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_
         if own:
             pop.close()
     return out
+
+
+def expand_curves(inc, prev, rows):
+    """Dense curves from the rows-only form of stream_curves_to(..., rows): for every replicate the rows from rows[r] on are
+    incidence 0 and the prevalence of row rows[r] - 1. In place; returns (inc, prev)."""
+    T = inc.shape[2]
+    for r in np.nonzero(np.asarray(rows) < T)[0]:
+        d = int(rows[r])
+        inc[r, :, d:, :] = 0
+        prev[r, :, d:, :] = prev[r, :, d - 1:d, :]
+    return inc, prev
 
 
 class EnsemblePipeline:

@@ -558,6 +558,17 @@ extern "C" int cabm_set_host_curves_i16(cabm_handle *h, int16_t *inc, int16_t *p
     }
     return CABM_OK;
 }
+extern "C" int cabm_set_host_curve_rows(cabm_handle *h, int32_t *rows) {
+    if (!h) return CABM_E_ARG;
+    CU(cudaStreamSynchronize(h->stream));
+    if (rows) {
+        cudaPointerAttributes pa;
+        CU(cudaPointerGetAttributes(&pa, rows));
+        if (pa.type != cudaMemoryTypeHost) return fail(h, CABM_E_ARG, "cabm_set_host_curve_rows: the array must be pinned host memory (cabm_host_alloc)");
+        CU(cudaHostGetDevicePointer((void **)&h->S.host_rows, rows, 0));
+    } else h->S.host_rows = nullptr;
+    return CABM_OK;
+}
 extern "C" int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) {
     int rc = need_config(h); if (rc) return rc;
     if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");

@@ -85,6 +85,7 @@ struct Dev {
     int *resume_list, *resume_aux;           // [R], [R][2]: fused kernel's queue of parked replicates and their (nextfire, ninf)
     int *copy_list;                          // [R]: fused kernel's queue of finished replicates whose curves go to the host
     uint8_t *hm;                             // [R][T][N] health codes (widened to Int16 by cabm_get_hmatrix)
+    int *host_rows;                          // optional pinned host array [R]: rows of a replicate's curves that were sent (the rest repeat)
     int16_t *host_inc, *host_prev;           // optional pinned host buffers [R][6][T][12]: the fused kernel streams each finished
                                              // replicate's curves there (Int16) so no device->host copy is left at the end
     const DevPset *psets; const unsigned long long *beta_thr;    // [P], [P][T][4]

@@ -189,18 +189,25 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             else for (int i = tid; i < N; i += NT) hm[(size_t)d * N + i] = M.col[i];
         }
     };
-    // replicate r's curves -> pinned host memory (Int16), 16-byte posted writes over PCIe
-    auto stream_curves_to_host = [&](int r) {
+    // replicate r's curves -> pinned host memory (Int16), 16-byte posted writes over PCIe. Rows d0..T-1 repeat (incidence 0,
+    // prevalence of row d0-1): with a rows array registered (cabm_set_host_curve_rows) only the rows before them cross the link
+    // and the host learns how many they are.
+    auto stream_curves_to_host = [&](int r, int d0) {
         const size_t per = (size_t)6 * T * 12;                 // multiple of 8
+        const int rows = (S.host_rows && (T & 1) == 0) ? min(T, (d0 + 1) & ~1) : T;      // even: every group's rows start and end on 16 bytes
         const int4 *gi = reinterpret_cast<const int4 *>(S.inc + (size_t)r * per), *gp = reinterpret_cast<const int4 *>(S.prev + (size_t)r * per);
         uint4 *hi = reinterpret_cast<uint4 *>(S.host_inc + (size_t)r * per), *hp = reinterpret_cast<uint4 *>(S.host_prev + (size_t)r * per);
-        for (int k = tid; k < (int)(per / 8); k += NT) {
+        const int pg = rows * 12 / 8, full = T * 12 / 8;       // uint4 of Int16 per group: sent, and in the array (exact when rows < T: both even)
+        const int nq = rows == T ? (int)(per / 8) : 6 * pg;
+        for (int q = tid; q < nq; q += NT) {
+            const int k = rows == T ? q : (q / pg) * full + q % pg;
             const int4 a = __ldcg(gi + 2 * k), b = __ldcg(gi + 2 * k + 1), c = __ldcg(gp + 2 * k), e = __ldcg(gp + 2 * k + 1);
             hi[k] = make_uint4((uint32_t)(a.x & 0xFFFF) | ((uint32_t)a.y << 16), (uint32_t)(a.z & 0xFFFF) | ((uint32_t)a.w << 16),
                                (uint32_t)(b.x & 0xFFFF) | ((uint32_t)b.y << 16), (uint32_t)(b.z & 0xFFFF) | ((uint32_t)b.w << 16));
             hp[k] = make_uint4((uint32_t)(c.x & 0xFFFF) | ((uint32_t)c.y << 16), (uint32_t)(c.z & 0xFFFF) | ((uint32_t)c.w << 16),
                                (uint32_t)(e.x & 0xFFFF) | ((uint32_t)e.y << 16), (uint32_t)(e.z & 0xFFFF) | ((uint32_t)e.w << 16));
         }
+        if (S.host_rows && tid == 0) S.host_rows[r] = rows;
     };
 
     // Two sweeps over atomic work queues. Sweep 0 starts every replicate and runs it for split_day days (split_day = 0: to the end).
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (r < 0) break;
         if (Z.kind == 2) {
             // -------------------------------------------------------- copy job: a finished replicate's curves -> pinned host memory
-            stream_curves_to_host(r);
+            stream_curves_to_host(r, __ldcg(&S.resume_aux[r * 2]));
             continue;
         }
         if (Z.kind == 1) {
@@ -518,6 +525,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         const int day_last = (!resumed && split_day > 0 && split_day < T) ? split_day : T;
         bool finished = day_last == T;                                         // set early by the fast-forward below
         int tail_day = 0;                                                      // > 0: rows tail_day..T-1 are left to a tail job
+        int idle_from = 0;                                                     // > 0: rows idle_from..T-1 were filled here as an idle tail
         __syncthreads();
         for (int day = day_first; day <= day_last; ++day) {
             const bool active = Z.ninf > 0 || day >= nextfire;                 // uniform: Z.ninf only changes between S1 and S2
@@ -528,6 +536,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 // fills them with 16-byte stores while thread 0 queues the column copies
                 finished = true;
                 if (!resumed && split_day > 0) { tail_day = day; break; }       // sweep 0: the tail is somebody else's job (see above)
+                idle_from = day;
                 if (tid < 60) Z.run[12 + tid] = run; else if (tid >= 64 && tid < 76) Z.run[tid - 64] = run;
                 __syncthreads();
                 fill_idle_rows(r, day);
@@ -1002,7 +1011,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid < 4) S.infectors[r * 4 + tid] = Z.infectors[tid];
         if (S.host_inc && tail_day == 0) {
             __syncthreads();                   // the rows written during the day loop (by threads 0..75) are visible block-wide
-            stream_curves_to_host(r);
+            stream_curves_to_host(r, idle_from > 0 ? idle_from : T);
         }
         // diagnostics of the fused path: kilo-cycles spent on this replicate and dyntrans batches issued
         PHASE(6);

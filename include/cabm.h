@@ -157,6 +157,12 @@ int cabm_get_mean_curves(cabm_handle *h, double *inc_mean, double *prev_mean);
  * then writes every finished replicate's curves straight into them while the other replicates are still running, and a
  * following cabm_get_curves_i16 with the same pointers only synchronises. Pass NULL, NULL to unregister. */
 int cabm_set_host_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev);
+/* Optional, with the buffers above: rows[replicate] (pinned, int32 [max_replicates]) receives the number of leading rows (days) of
+ * that replicate's curves the kernel sent. The rows after them were not written: they repeat — incidence 0, prevalence equal to
+ * the last row sent — because nobody was infectious and nothing was due any more (most replicates of a sub-critical scenario die
+ * out within weeks: about a quarter of the bytes cross PCIe). NULL switches it off (every row is sent). modeltime must be even,
+ * otherwise every row is sent and rows[r] = modeltime. */
+int cabm_set_host_curve_rows(cabm_handle *h, int32_t *rows);
 /* infectors = _count_infectors() :295-313 [n_rep][4]; totalisolated = ct_data.totalisolated :61,649 [n_rep];
  * lat_inc_sum = sum(_get_column_incidence(h, LAT)) (scripts/local_run.jl:143) [n_rep]; err = CABM_ERR_* bits.
  * Any pointer may be NULL. */

@@ -389,3 +389,33 @@ def test_per_day_kernels_replayed_from_a_cuda_graph(cv, mode):
             pop.configure(a, [5 * (i + 1) for i in range(8)], mode=m); pop.run()
             counts.append(pop.launch_count - l0)
         assert len(set(counts)) == 1 and counts[0] >= 2 * 60
+
+
+@pytest.mark.parametrize("T", [160, 151])
+def test_streamed_curves_rows_only(cv, T):
+    """cabm_set_host_curve_rows: the kernel sends only the rows of a replicate's curves that differ (an epidemic that died out
+    repeats its last row) and reports how many; expanded on the host they equal the dense curves. An odd modeltime sends
+    everything (rows do not end on 16 bytes)."""
+    ip = cv.ModelParameters(β=0.0345, prov="ontario", modeltime=T, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3)
+    R = 340
+    with cv.Population(R, ip.popsize, T) as pop:
+        a, b, rows = cv.PinnedArray((R, 6, T, 12), np.int16), cv.PinnedArray((R, 6, T, 12), np.int16), cv.PinnedArray((R,), np.int32)
+        a.array[:] = -7; b.array[:] = -7; rows.array[:] = -1
+        pop.stream_curves_to(a.array, b.array, rows.array)
+        pop.configure(ip, [13 * (i + 1) for i in range(R)])
+        pop.run()
+        pop.sync()
+        inc, prev = pop.curves()                                   # dense int32 read-back of the same run
+        n = rows.array.copy()
+        assert (n >= 1).all() and (n <= T).all()
+        if T % 2:
+            assert (n == T).all()
+        else:
+            assert (n < T // 2).mean() > 0.5                       # most of these epidemics die out early ...
+            sent = a.array != -7
+            for r in (0, int(np.argmin(n)), int(np.argmax(n))):
+                assert sent[r, :, :n[r]].all() and not sent[r, :, n[r]:].any()     # ... and only their first rows crossed the link
+        ei, ep = cv.expand_curves(a.array.copy(), b.array.copy(), n)
+        assert (ei == inc).all() and (ep == prev).all()
+        pop.stream_curves_to(None, None)
+        a.free(); b.free(); rows.free()
