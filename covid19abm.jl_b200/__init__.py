@@ -551,7 +551,12 @@ class EnsemblePipeline:
         self.pending[j] = None
         if self.outs[j] is not None:               # the kernel wrote straight into the caller's pinned arrays
             inc, prev = p.curves(self.outs[j][0], self.outs[j][1])
+            rows = self.outs[j][2] if len(self.outs[j]) > 2 else None
             self.outs[j] = None
+            res = dict(tag=tag, inc=inc, prev=prev, **p.scalars())
+            if rows is not None:
+                res["rows"] = rows
+            return res
         elif self.bufs[j] is not None:
             inc, prev = p.curves(self.bufs[j][0].array, self.bufs[j][1].array)      # same pointers: waits for the run only
             if self.copy:
@@ -568,11 +573,11 @@ class EnsemblePipeline:
         j = self.k % len(self.pops)
         prev = self._collect(j) if collect else None
         p = self.pops[j]
-        if out is not None:
-            p.stream_curves_to(out[0], out[1])
+        if out is not None:                                      # (inc, prev) or (inc, prev, rows): see Population.stream_curves_to
+            p.stream_curves_to(*out)
             self.outs[j], self.own[j] = out, False
         elif self.bufs[j] is not None and not self.own[j]:       # back to the slot's own buffers
-            p.stream_curves_to(self.bufs[j][0].array, self.bufs[j][1].array)
+            p.stream_curves_to(self.bufs[j][0].array, self.bufs[j][1].array, None)
             self.own[j] = True
         p.configure(psets, seeds, pset_of_rep, mode)
         p.run(sync=False)
@@ -604,13 +609,15 @@ class EnsemblePipeline:
         self.close()
 
 
-def run_ensemble_pipelined(ip, nsims, batch=1000, handles=3, seeds=None, device=0, path="auto", pipe=None, pinned=None):
+def run_ensemble_pipelined(ip, nsims, batch=1000, handles=3, seeds=None, device=0, path="auto", pipe=None, pinned=None, rows_only=False):
     """run_ensemble for nsims > batch: the batches are pipelined over `handles` handles (EnsemblePipeline). With popsize <= 32767
     the curves come back as Int16 views of two pinned arrays for the whole ensemble (kept alive by the returned dict), written
     by the kernels themselves: the host never copies them. Creating the handles (several GB of device memory) and the pinned
     arrays takes a few hundred milliseconds — far longer than the simulation of a few thousand replicates — so repeated
     calls (β sweeps, calibration) should pass their own `pipe` (an EnsemblePipeline(batch, popsize, modeltime, pinned=False))
-    and `pinned` (two PinnedArray((nsims, 6, modeltime, 12), int16)) and keep them."""
+    and `pinned` (two PinnedArray((nsims, 6, modeltime, 12), int16)) and keep them. rows_only=True (even modeltime): the kernels
+    send only the rows of each replicate's curves before its epidemic died out; the result then has "rows" [nsims] and the arrays
+    hold valid data in rows < rows[r] only (expand_curves fills the rest in)."""
     first = ip[0] if isinstance(ip, (list, tuple)) else ip
     if seeds is None:
         seeds = [726 * (i + 1) for i in range(nsims)]
@@ -620,6 +627,7 @@ def run_ensemble_pipelined(ip, nsims, batch=1000, handles=3, seeds=None, device=
     direct = first.popsize <= 32767
     if direct and pinned is None:
         pinned = (PinnedArray((nsims, 6, T, 12), np.int16), PinnedArray((nsims, 6, T, 12), np.int16))
+    rows = PinnedArray((nsims,), np.int32) if (direct and rows_only) else None
     own_pipe = pipe is None
     if own_pipe:
         pipe = EnsemblePipeline(batch, first.popsize, T, handles=handles, device=device, path=path, pinned=False)
@@ -628,7 +636,10 @@ def run_ensemble_pipelined(ip, nsims, batch=1000, handles=3, seeds=None, device=
         base = pipe.k
         for k in range(nsims // batch):
             sl = slice(k * batch, (k + 1) * batch)
-            r = pipe.submit(ip, seeds[sl], tag=base + k, out=(pinned[0].array[sl], pinned[1].array[sl]) if direct else None)
+            out = None
+            if direct:
+                out = (pinned[0].array[sl], pinned[1].array[sl]) + ((rows.array[sl],) if rows is not None else ())
+            r = pipe.submit(ip, seeds[sl], tag=base + k, out=out)
             if r is not None:
                 parts.append(r)
         parts += pipe.drain()
@@ -636,9 +647,11 @@ def run_ensemble_pipelined(ip, nsims, batch=1000, handles=3, seeds=None, device=
         if own_pipe:
             pipe.close()
     parts.sort(key=lambda r: r["tag"])
-    res = {k: np.concatenate([r[k] for r in parts]) for k in parts[0] if k not in ("tag", "inc", "prev")}
+    res = {k: np.concatenate([r[k] for r in parts]) for k in parts[0] if k not in ("tag", "inc", "prev", "rows")}
     if direct:
         res["inc"], res["prev"], res["_pinned"] = pinned[0].array, pinned[1].array, pinned
+        if rows is not None:
+            res["rows"], res["_pinned_rows"] = rows.array, rows
     else:
         res["inc"], res["prev"] = np.concatenate([r["inc"] for r in parts]), np.concatenate([r["prev"] for r in parts])
     return res

@@ -13,7 +13,7 @@ class FakePopulation:
         FakePopulation.made.append(self)
 
     def set_path(self, path): self.log.append(("path", path))
-    def stream_curves_to(self, inc, prev): self.host = (inc, prev)
+    def stream_curves_to(self, inc, prev, rows=None): self.host = (inc, prev)
     def configure(self, psets, seeds, pset_of_rep=None, mode=0): self.seeds = np.asarray(seeds); self.log.append(("configure", int(self.seeds[0])))
     def run(self, sync=True): self.log.append(("run", sync))
     def sync(self): self.log.append(("sync",))

@@ -35,4 +35,7 @@ for rep in range(2):
     t0 = time.perf_counter(); big2 = cv.run_ensemble_pipelined(ip, 6000, pipe=pipe, pinned=pinned); dt = time.perf_counter() - t0
     assert (big2["inc"] == big["inc"]).all() if rep == 0 else True
     print("with a kept pipeline and pinned arrays: %.2f ms per 1000 replicates" % (1e3 * dt / 6))
+big3 = cv.run_ensemble_pipelined(ip, 6000, pipe=pipe, rows_only=True)
+ei, ep = cv.expand_curves(big3['inc'].copy(), big3['prev'].copy(), big3['rows'])
+assert (ei == big['inc']).all() and (ep == big['prev']).all(); print('rows-only ensemble expands to the dense one; mean rows sent', big3['rows'].mean())
 pipe.close()
