@@ -259,6 +259,7 @@ def main():
     nb_ = min(P, args.steps)
     sent_rows = sum(int(rb_.array.sum()) for rb_ in rows_bufs[:nb_]) / nb_
     rows_d2h = sent_rows * 6 * 12 * 2 * 2 + R * (32 + 8 + 8 + 4 + 4)
+    rows_only_ok = pop.last_path == "fused"            # the per-day kernels copy the curves after the run, all rows
     for q in pops:
         q.stream_curves_to(None, None)
     sampler.stop_flag = True
@@ -347,7 +348,7 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps, "returns": "incidence+prevalence curves [R][6][T][12] Int16 x2 (narrowed on device) and per-replicate scalars (runsim :77-101), pinned host buffers",
                         "host_numa_bound": numa_bound,
-                        "rows_only": {"value": world * units * args.steps / (e2e_rows_ms * 1e-3), "ms_per_step": e2e_rows_ms / args.steps, "d2h_bytes_per_step": int(rows_d2h),
+                        "rows_only": None if not rows_only_ok else {"value": world * units * args.steps / (e2e_rows_ms * 1e-3), "ms_per_step": e2e_rows_ms / args.steps, "d2h_bytes_per_step": int(rows_d2h),
                                       "note": "optional form of the result (cabm_set_host_curve_rows): only the rows of each replicate's curves before its epidemic died out are sent, "
                                               "plus their number; the rest repeat. Lossless; cv.expand_curves rebuilds the dense arrays on the host"}},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
