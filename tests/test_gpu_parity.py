@@ -419,3 +419,37 @@ def test_streamed_curves_rows_only(cv, T):
         assert (ei == inc).all() and (ep == prev).all()
         pop.stream_curves_to(None, None)
         a.free(); b.free(); rows.free()
+
+
+def _random_scenario(rng):
+    provs = ["alberta", "bc", "manitoba", "newbruns", "newfdland", "nwterrito", "novasco", "nunavut", "ontario", "pei", "quebec", "saskat", "yukon", "newyork"]
+    ct = int(rng.choice([0, 0, 1, 3]))
+    kw = dict(β=float(rng.choice([0.0, 0.02, 0.05, 0.1, 0.3, 0.8])), prov=str(rng.choice(provs)),
+              popsize=int(rng.choice([1999, 2048, 3000, 4097, 6000, 10000, 12345])), modeltime=int(rng.integers(2, 140)),
+              initialinf=int(rng.integers(0, 25)), initialhi=int(rng.choice([0, 0, 50, 900])), seasonal=bool(rng.integers(0, 2)),
+              frelasymp=float(rng.choice([0.0, 0.11, 0.5, 1.0])), calibration=bool(rng.random() < 0.15),
+              τmild=int(rng.integers(0, 6)), fmild=float(rng.choice([0.0, 0.3, 1.0])), fsevere=float(rng.choice([0.0, 0.6, 1.0])),
+              tpreiso=int(rng.integers(0, 30)), fpreiso=float(rng.choice([0.0, 0.3, 1.0])),
+              quar_grp=int(rng.integers(1, 6)), quar_grp_frac=float(rng.choice([0.0, 0.0, 0.4, 1.0])),
+              ctstrat=ct, fctcapture=float(rng.choice([0.2, 0.7, 1.0])) if ct else 0.0, fcontactst=float(rng.choice([0.2, 0.7, 1.0])) if ct else 0.0,
+              cdaysback=int(rng.integers(0, 8)) if ct else 0, strat3qdays=int(rng.integers(0, 15)) if ct == 3 else 0)
+    if kw["initialinf"] + kw["initialhi"] > kw["popsize"] - 10:
+        kw["initialhi"] = 0
+    return kw
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_random_scenarios_bit_exact(cv, O, block):
+    """Seeded random draws over the whole parameter space (every switch of ModelParameters, odd population sizes, short and long
+    runs), six replicates each, fused kernel and per-day kernels against the oracle: state matrix, curves, scalars."""
+    rng = np.random.default_rng(20260 + block)
+    for k in range(8):
+        kw = _random_scenario(rng)
+        ip = cv.ModelParameters(**kw)
+        seeds = [int(s) for s in rng.integers(1, 2 ** 62, size=6)]
+        ref = O.run_ensemble([to_oracle(O, ip)], [0] * 6, seeds, nthreads=6, want_hmatrix=True)
+        for path in (("fused", "multikernel") if k % 2 == 0 else ("fused",)):
+            got = cv.run_ensemble(ip, 6, seeds=seeds, want_hmatrix=True, path=path)
+            assert (got["hmatrix"] == ref["hmatrix"]).all(), (path, kw)
+            assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all(), (path, kw)
+            assert (got["infectors"] == ref["infectors"]).all() and (got["totalisolated"] == ref["totalisolated"]).all(), (path, kw)
