@@ -141,6 +141,7 @@ def lib():
     L.cabm_destroy.argtypes = [vp]; L.cabm_destroy.restype = None
     L.cabm_configure.argtypes = [vp, vp, i32, vp, i32, vp, i32]
     L.cabm_run.argtypes = [vp]; L.cabm_sync.argtypes = [vp]
+    L.cabm_set_strict.argtypes = [vp, i32]
     L.cabm_last_run_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.cabm_set_host_curve_rows.argtypes = [vp, vp]
     L.cabm_mark.argtypes = [vp]; L.cabm_ms_since_mark.argtypes = [vp, vp, C.POINTER(C.c_float)]
@@ -259,6 +260,12 @@ class Population:
 
     def sync(self):
         self._chk(self.L.cabm_sync(self.h))
+
+    def set_strict(self, on=True):
+        """strict (default): after a run, sync() and the result getters raise CabmError with the reference's error("...") text
+        when any replicate hit one of the in-model errors (:308,:371-372,:418,:719) or an implementation limit; off: the caller
+        inspects errors() itself."""
+        self._chk(self.L.cabm_set_strict(self.h, int(on)))
 
     @property
     def last_run_ms(self):
@@ -478,9 +485,10 @@ def runsim(simnum, ip, device=0):
     return res
 
 
-def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_hmatrix=False, device=0, pop=None, path="auto"):
+def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_hmatrix=False, device=0, pop=None, path="auto", strict=True):
     """pmap(x -> runsim(x, ip), 1:nsims) (scripts/local_run.jl:28-30) as one device launch sequence.
-    ip may be a list of ModelParameters with pset_of_rep choosing one per replicate (β sweeps)."""
+    ip may be a list of ModelParameters with pset_of_rep choosing one per replicate (β sweeps).
+    A replicate that hits one of the reference's error("...") conditions raises CabmError (strict=False: returned in "err")."""
     first = ip[0] if isinstance(ip, (list, tuple)) else ip
     if seeds is None:
         seeds = [726 * (i + 1) for i in range(nsims)]
@@ -490,6 +498,7 @@ def run_ensemble(ip, nsims, seeds=None, pset_of_rep=None, mode=MODE_EXACT, want_
     try:
         pop.configure(ip, seeds, pset_of_rep=pset_of_rep, mode=mode)
         pop.set_path(path)
+        pop.set_strict(strict)
         pop.run()
         inc, prev = pop.curves()
         out = dict(inc=inc, prev=prev, **pop.scalars())
@@ -676,15 +685,19 @@ def shard_indices(nsims, rank, world):
     return list(range(rank, nsims, world))
 
 
-def gather_ensemble(local, nsims, rank, world, dist=None, device="cpu", keys=("inc", "prev", "infectors", "totalisolated", "lat_inc_sum", "err")):
+def gather_ensemble(local, nsims, rank, world, dist=None, device="cpu", keys=("inc", "prev", "infectors", "totalisolated", "lat_inc_sum", "err"),
+                    keep_on_device=False, events=None):
     """The path's single collective: end-of-run gather of the per-replicate summaries (pmap's implicit gather,
-    scripts/local_run.jl:28-30,40-45) over torch.distributed (NCCL on GPUs, gloo in the CPU tests). `local[k]` holds this
-    rank's replicates in shard order; every rank returns the full arrays in replicate order."""
+    scripts/local_run.jl:28-30,40-45) over torch.distributed (NCCL all_gather over NVLink on GPUs, gloo in the CPU tests).
+    `local[k]` holds this rank's replicates in shard order (replicate r lives on rank r mod world); every rank returns the full
+    arrays in replicate order — numpy arrays, or torch tensors left on `device` with keep_on_device=True (a further reduction
+    on the GPU, e.g. compute_yearly_average, then needs no second copy). events=(start, end): CUDA events recorded around the
+    collectives themselves (the host->device staging of the local arrays stays outside)."""
     if world == 1 or dist is None:
         return {k: np.asarray(local[k]) for k in keys if k in local}
     import torch
     nmax = (nsims + world - 1) // world
-    out = {}
+    staged = {}
     for k in keys:
         if k not in local:
             continue
@@ -693,15 +706,22 @@ def gather_ensemble(local, nsims, rank, world, dist=None, device="cpu", keys=("i
             a = a.astype(np.int64)
         pad = np.zeros((nmax,) + a.shape[1:], dtype=a.dtype)
         pad[:a.shape[0]] = a
-        t = torch.from_numpy(pad).to(device)
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t)
-        full = np.zeros((nsims,) + a.shape[1:], dtype=a.dtype)
-        for rk in range(world):
-            idx = shard_indices(nsims, rk, world)
-            full[idx] = parts[rk].cpu().numpy()[:len(idx)]
-        out[k] = full
-    return out
+        staged[k] = torch.from_numpy(pad).to(device)
+    if events is not None:
+        events[0].record()
+    gathered = {}
+    for k, t in staged.items():
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out.view((world * t.shape[0],) + tuple(t.shape[1:])), t)
+        gathered[k] = out
+    if events is not None:
+        events[1].record()
+    res = {}
+    for k, out in gathered.items():
+        # out[rk, j] is replicate rk + j * world: replicate order is the transpose of (rank, slot)
+        full = out.transpose(0, 1).reshape((nmax * world,) + tuple(out.shape[2:]))[:nsims]
+        res[k] = full.contiguous() if keep_on_device else full.cpu().numpy()
+    return res
 
 
 def run_ensemble_sharded(ip, nsims, rank, world, dist=None, device_index=0, seeds=None, pset_of_rep=None, **kw):

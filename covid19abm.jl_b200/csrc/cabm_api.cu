@@ -29,6 +29,10 @@ struct cabm_handle {
     int16_t *host_inc = nullptr, *host_prev = nullptr;   // registered by cabm_set_host_curves_i16
     int64_t launches = 0;
     bool ran = false;
+    // in-model error()s of the reference (:308,:371-372,:418,:719) surface as CABM_E_MODEL from cabm_sync / cabm_get_* after a run
+    int strict = 1; bool err_checked = false; int err_rc = 0;
+    size_t ct_words_per_agent = 0;     // contact-log capacity the current allocation was sized for
+    double *d_mean = nullptr; size_t mean_elems = 0;   // scratch of cabm_get_mean_curves
     bool poked = false;                // state was edited through cabm_set_field: pass A falls back to the full scan
     // optional per-kernel-class timing (cabm_set_profiling): events around every launch of the next cabm_run
     int profiling = 0;
@@ -40,7 +44,7 @@ struct cabm_handle {
     std::string err;
 };
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;     // per calling thread: distinct handles (and their creation) are independent
 
 #define CU(call)                                                                                       \
     do {                                                                                               \
@@ -157,9 +161,9 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
         }
         uint32_t *d_nb; uint8_t *d_guide; unsigned long long *d_gpw;
         DA(d_nb, nb.size()); DA(d_guide, guide.size()); DA(d_gpw, gpw.size());
-        cudaMemcpy(d_nb, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(d_guide, guide.data(), guide.size(), cudaMemcpyHostToDevice);
-        cudaMemcpy(d_gpw, gpw.data(), gpw.size() * 8, cudaMemcpyHostToDevice);
+        if ((e = cudaMemcpy(d_nb, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "nb table upload");
+        if ((e = cudaMemcpy(d_guide, guide.data(), guide.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "nb guide upload");
+        if ((e = cudaMemcpy(d_gpw, gpw.data(), gpw.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "gpw table upload");
         S.nb_thr = d_nb; S.nb_guide = d_guide; S.gpw = d_gpw;
         ConstTables c = make_const_tables();
         upload_const_tables(c, h->stream);
@@ -181,6 +185,7 @@ extern "C" void cabm_destroy(cabm_handle *h) {
     if (h->S.ident_list) cudaFree(h->S.ident_list);
     if (h->S.ident_cnt) cudaFree(h->S.ident_cnt);
     if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_mean) cudaFree(h->d_mean);
     for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -264,15 +269,32 @@ extern "C" int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_ps
     for (int r = 0; r < n_rep; ++r) keys[r] = make_uint2((uint32_t)seeds[r], (uint32_t)(seeds[r] >> 32));
     CU(cudaMemcpy(h->S.key, keys.data(), sizeof(uint2) * n_rep, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->S.pset_of, pof.data(), sizeof(int) * n_rep, cudaMemcpyHostToDevice));
-    if (any_ct && !h->S.ct_log) {
-        // contact log: one chunk [next, count, targets...] per (traced agent, day). 128 words per agent cover a full epidemic
-        // with cdaysback of a few days (mean ~13 contacts/day for the ~half of infections that are captured).
-        size_t cap = (size_t)128 * h->N;                    // 32-bit words per replicate
-        if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
-        CU(cudaMalloc((void **)&h->S.ct_log, sizeof(uint32_t) * cap * h->R));
-        h->S.ct_cap = (uint32_t)cap;
-        CU(cudaMalloc((void **)&h->S.ident_list, sizeof(uint32_t) * 2 * (size_t)h->R * h->Np));
-        CU(cudaMalloc((void **)&h->S.ident_cnt, sizeof(uint32_t) * 2 * (size_t)h->R));
+    if (any_ct) {
+        // contact log: one chunk [next, count, targets...] per (traced agent, day); a traced agent logs on at most cdaysback days
+        // (:683-685, :699) and a day's chunk holds its admitted contacts (negative-binomial budgets, mean 8-17, :855). Sized from the
+        // largest cdaysback of the parameter sets: 2 + 30 words per traced day (twice the mean budget), at least 128 words per
+        // agent, bounded by a third of the free device memory. A log that still overflows raises CABM_ERR_CT_LOG_FULL, which
+        // cabm_sync / cabm_get_* report as CABM_E_MODEL — never a silently truncated contact set.
+        int maxback = 0;
+        for (int q = 0; q < n_psets; ++q) if (psets[q].ctstrat != 0 && psets[q].cdaysback > maxback) maxback = psets[q].cdaysback;
+        size_t per_agent = (size_t)32 * (size_t)(maxback > 0 ? maxback : 1);
+        if (per_agent < 128) per_agent = 128;
+        if (!h->S.ct_log || per_agent > h->ct_words_per_agent) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            if (h->S.ct_log) { free_b += sizeof(uint32_t) * (size_t)h->S.ct_cap * h->R; CU(cudaFree(h->S.ct_log)); h->S.ct_log = nullptr; h->S.ct_cap = 0; }
+            size_t cap = per_agent * (size_t)h->N;          // 32-bit words per replicate
+            const size_t budget = free_b / 3 / sizeof(uint32_t) / (size_t)h->R;
+            if (cap > budget) cap = budget;
+            if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+            if (cap < (size_t)128 * h->N && cap < budget) cap = (size_t)128 * h->N;
+            CU(cudaMalloc((void **)&h->S.ct_log, sizeof(uint32_t) * cap * h->R));
+            h->S.ct_cap = (uint32_t)cap; h->ct_words_per_agent = per_agent;
+        }
+        if (!h->S.ident_list) {
+            CU(cudaMalloc((void **)&h->S.ident_list, sizeof(uint32_t) * 2 * (size_t)h->R * h->Np));
+            CU(cudaMalloc((void **)&h->S.ident_cnt, sizeof(uint32_t) * 2 * (size_t)h->R));
+        }
     }
     h->S.psets = h->d_psets; h->S.beta_thr = h->d_beta; h->S.P = n_psets;
     h->n_rep = n_rep; h->n_psets = n_psets; h->mode = mode; h->any_ct = any_ct; h->all_ct = all_ct; h->configured = 1; h->day = 1; h->ran = false;
@@ -285,6 +307,32 @@ static int need_config(cabm_handle *h) {
     if (!h->configured) return fail(h, CABM_E_STATE, "cabm_configure has not been called");
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) return fail(h, CABM_E_CUDA, cudaGetErrorString(e));
+    return CABM_OK;
+}
+
+// After a run has completed (stream synchronised): any replicate whose device error word is set fails the call with the
+// reference's error("...") text, like the Julia exception would have ended that replicate (:308, :371-372, :418, :719).
+static int model_check(cabm_handle *h) {
+    if (!h->strict || !h->ran) return CABM_OK;
+    if (h->err_checked) return h->err_rc ? fail(h, h->err_rc, h->err) : CABM_OK;
+    std::vector<uint32_t> err((size_t)h->n_rep);
+    CU(cudaMemcpy(err.data(), h->S.err, 4 * (size_t)h->n_rep, cudaMemcpyDeviceToHost));
+    h->err_checked = true; h->err_rc = CABM_OK;
+    for (int r = 0; r < h->n_rep; ++r) {
+        const uint32_t e = err[r];
+        if (!e) continue;
+        const char *msg = (e & ERR_NO_SWAP) ? "swap expired, but no swap set." :
+                          (e & ERR_NO_SUS) ? "No susceptibles in the population to change status" :
+                          (e & ERR_TRACED_NOT_ISO) ? "a traced person should always be isolated until the trace is killed" :
+                          (e & ERR_SICKFROM) ? "sickfrom not set right" :
+                          (e & ERR_EMPTY_GROUP) ? "an empty age group was sampled (rand(grps[i], g) on an empty collection)" :
+                          (e & ERR_CT_LOG_FULL) ? "contact log capacity exceeded: the traced contact set would be truncated" :
+                          "an implementation limit of a kernel was exceeded";
+        int nbad = 0;
+        for (int q = r; q < h->n_rep; ++q) nbad += err[q] != 0;
+        h->err_rc = CABM_E_MODEL;
+        return fail(h, CABM_E_MODEL, std::string(msg) + " (replicate " + std::to_string(r) + ", error word " + std::to_string(e) + "; " + std::to_string(nbad) + " replicate(s) flagged)");
+    }
     return CABM_OK;
 }
 
@@ -384,7 +432,7 @@ extern "C" int cabm_run(cabm_handle *h) {
     }
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaGetLastError());
-    h->day = h->T + 1; h->ran = true;
+    h->day = h->T + 1; h->ran = true; h->err_checked = false; h->err_rc = CABM_OK;
     if (h->profiling) {
         CU(cudaStreamSynchronize(h->stream));
         for (int c = 0; c < CABM_N_KCLASS; ++c) { h->prof_ms[c] = 0; h->prof_n[c] = 0; }
@@ -413,8 +461,9 @@ extern "C" int cabm_sync(cabm_handle *h) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
-    return CABM_OK;
+    return model_check(h);
 }
+extern "C" int cabm_set_strict(cabm_handle *h, int on) { if (!h) return CABM_E_ARG; h->strict = on ? 1 : 0; h->err_checked = false; return CABM_OK; }
 
 extern "C" int cabm_mark(cabm_handle *h) {
     if (!h) return CABM_E_ARG;
@@ -515,13 +564,15 @@ extern "C" int cabm_get_hmatrix(cabm_handle *h, int replicate, int16_t *out) {
     if (!h->S.store_hm) return fail(h, CABM_E_STATE, "handle was created without CABM_STORE_HMATRIX");
     if (replicate < 0 || replicate >= h->n_rep || !out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix: bad argument");
     const size_t n = (size_t)h->T * h->N;
-    return copy_hmatrix(h, (size_t)replicate * n, n, out);
+    if ((rc = copy_hmatrix(h, (size_t)replicate * n, n, out))) return rc;
+    return model_check(h);
 }
 extern "C" int cabm_get_hmatrix_all(cabm_handle *h, int16_t *out) {
     int rc = need_config(h); if (rc) return rc;
     if (!h->S.store_hm) return fail(h, CABM_E_STATE, "handle was created without CABM_STORE_HMATRIX");
     if (!out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix_all: bad argument");
-    return copy_hmatrix(h, 0, (size_t)h->n_rep * h->T * h->N, out);
+    if ((rc = copy_hmatrix(h, 0, (size_t)h->n_rep * h->T * h->N, out))) return rc;
+    return model_check(h);
 }
 extern "C" int cabm_get_hmatrix_all_u8(cabm_handle *h, uint8_t *out) {
     int rc = need_config(h); if (rc) return rc;
@@ -529,7 +580,7 @@ extern "C" int cabm_get_hmatrix_all_u8(cabm_handle *h, uint8_t *out) {
     if (!out) return fail(h, CABM_E_ARG, "cabm_get_hmatrix_all_u8: bad argument");
     CU(cudaMemcpyAsync(out, h->S.hm, (size_t)h->n_rep * h->T * h->N, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return CABM_OK;
+    return model_check(h);
 }
 extern "C" int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev) {
     int rc = need_config(h); if (rc) return rc;
@@ -538,7 +589,7 @@ extern "C" int cabm_get_curves(cabm_handle *h, int32_t *inc, int32_t *prev) {
     if (inc) CU(cudaMemcpyAsync(inc, h->S.inc, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (prev) CU(cudaMemcpyAsync(prev, h->S.prev, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return CABM_OK;
+    return model_check(h);
 }
 extern "C" int cabm_set_host_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) {
     if (!h) return CABM_E_ARG;
@@ -574,7 +625,7 @@ extern "C" int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) 
     if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");
     if (inc && inc == h->host_inc && prev == h->host_prev && h->last_path == CABM_PATH_FUSED) {   // streamed there by the kernel already
         CU(cudaStreamSynchronize(h->stream));
-        return CABM_OK;
+        return model_check(h);
     }
     if (h->N > 32767) return fail(h, CABM_E_ARG, "cabm_get_curves_i16 needs popsize <= 32767");
     if (!inc || !prev) return fail(h, CABM_E_ARG, "cabm_get_curves_i16: bad argument");
@@ -589,22 +640,25 @@ extern "C" int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) 
     CU(cudaMemcpyAsync(inc, h->d_stage, n * 2, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(prev, h->d_stage + n, n * 2, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return CABM_OK;
+    return model_check(h);
 }
 extern "C" int cabm_get_mean_curves(cabm_handle *h, double *inc_mean, double *prev_mean) {
     int rc = need_config(h); if (rc) return rc;
     if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");
     if (!inc_mean || !prev_mean) return fail(h, CABM_E_ARG, "cabm_get_mean_curves: bad argument");
     const size_t per_rep = (size_t)6 * h->T * 12;
-    double *d = nullptr;
-    CU(cudaMalloc((void **)&d, per_rep * 2 * sizeof(double)));
+    if (h->mean_elems < 2 * per_rep) {                       // scratch kept with the handle
+        if (h->d_mean) cudaFree(h->d_mean);
+        h->d_mean = nullptr; h->mean_elems = 0;
+        CU(cudaMalloc((void **)&h->d_mean, per_rep * 2 * sizeof(double)));
+        h->mean_elems = 2 * per_rep;
+    }
+    double *d = h->d_mean;
     h->launches += launch_mean_curves(h->S.inc, h->S.prev, d, d + per_rep, h->n_rep, per_rep, h->stream);
-    cudaError_t e = cudaMemcpyAsync(inc_mean, d, per_rep * 8, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(prev_mean, d + per_rep, per_rep * 8, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d);
-    if (e != cudaSuccess) return fail(h, CABM_E_CUDA, cudaGetErrorString(e));
-    return CABM_OK;
+    CU(cudaMemcpyAsync(inc_mean, d, per_rep * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(prev_mean, d + per_rep, per_rep * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return model_check(h);
 }
 extern "C" int cabm_get_scalars(cabm_handle *h, int64_t *infectors, int64_t *totalisolated, int64_t *lat_inc_sum, uint32_t *err) {
     int rc = need_config(h); if (rc) return rc;
@@ -615,7 +669,7 @@ extern "C" int cabm_get_scalars(cabm_handle *h, int64_t *infectors, int64_t *tot
     if (lat_inc_sum) CU(cudaMemcpyAsync(lat_inc_sum, h->S.latsum, R * 8, cudaMemcpyDeviceToHost, h->stream));
     if (err) CU(cudaMemcpyAsync(err, h->S.err, R * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return CABM_OK;
+    return err ? CABM_OK : model_check(h);       // a caller that collects the error words itself decides what they mean
 }
 extern "C" int cabm_get_field(cabm_handle *h, int field, int replicate, int32_t *out) {
     int rc = need_config(h); if (rc) return rc;

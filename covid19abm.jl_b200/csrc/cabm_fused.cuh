@@ -27,6 +27,7 @@
 //   idle days     (nobody infectious, nothing due) repeat column and prevalence row; an idle tail is filled in one go
 #pragma once
 #include <cstdlib>
+#include <mutex>
 
 namespace cabm {
 
@@ -1043,28 +1044,44 @@ size_t fused_smem_bytes_host(int Np) { return fused_smem_bytes(Np); }
 
 int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaStream_t s) {
     const size_t bytes = fused_smem_bytes(S.Np);
-    static bool attr_set[64] = {false};      // per device: function attributes belong to the device's copy of the kernel
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        const int lim = 227 * 1024 - 512;        // the opt-in maximum per CTA minus this kernel's (diagnostic) static shared memory
-        cudaFuncSetAttribute(k_sim_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(k_sim_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    {   // per device: function attributes belong to the device's copy of the kernel. Handles of several host threads may get here
+        // at once, so the flags sit behind a lock.
+        static std::mutex mu;
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            const int lim = 227 * 1024 - 512;        // the opt-in maximum per CTA minus this kernel's (diagnostic) static shared memory
+            cudaFuncSetAttribute(k_sim_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(k_sim_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
+    // Experiment overrides (environment) are validated: a value that would break the forward-progress argument of the work queues
+    // is ignored. That argument: every counter a CTA spins on (work[3], work[7], the *_list slots) is advanced by a CTA that is already
+    // resident and running (the grid never exceeds the resident CTA slots), and while copy jobs can still be queued at least one CTA
+    // stays eligible to become a copier (tail_ctas >= 1 whenever curves are streamed to the host).
+    auto env_int = [](const char *name, int lo, int hi, int dflt) {
+        const char *e = getenv(name);
+        if (!e || !*e) return dflt;
+        char *end = nullptr;
+        const long v = strtol(e, &end, 10);
+        return (end && *end == 0 && v >= lo && v <= hi) ? (int)v : dflt;
+    };
     int per_sm = bytes <= 113 * 1024 ? 2 : 1;
-    if (const char *e = getenv("CABM_FUSED_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
+    per_sm = env_int("CABM_FUSED_CTAS_PER_SM", 1, per_sm, per_sm);
     int grid = n_sm * per_sm;
     if (grid > S.R) grid = S.R;
     // park-and-resume only pays when there are more replicates than resident CTAs and the run is long
     int split_day = (S.R > grid && S.T >= 150) ? 60 : 0;
-    if (const char *e = getenv("CABM_FUSED_SPLIT_DAY")) split_day = atoi(e);
+    split_day = env_int("CABM_FUSED_SPLIT_DAY", 0, S.T - 1, split_day);
     if (split_day >= S.T) split_day = 0;
     cudaMemsetAsync(work, 0, 16 * sizeof(unsigned), s);
     if (split_day > 0) { cudaMemsetAsync(S.resume_list, 0xFF, (size_t)S.R * sizeof(int), s); cudaMemsetAsync(S.copy_list, 0xFF, (size_t)S.R * sizeof(int), s); }
     unsigned tail_ctas = FUSED_TAIL_CTAS;
     if (tail_ctas > (unsigned)grid / 4) tail_ctas = grid / 4 > 0 ? grid / 4 : 1;      // copiers do not resume parked replicates
-    if (const char *e = getenv("CABM_FUSED_TAIL_CTAS")) tail_ctas = (unsigned)atoi(e);                                       // experiments
+    tail_ctas = (unsigned)env_int("CABM_FUSED_TAIL_CTAS", 1, grid, (int)tail_ctas);
     if (any_ct) k_sim_fused<true><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
     else k_sim_fused<false><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
     return 1;

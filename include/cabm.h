@@ -4,7 +4,8 @@
  * Each entry point below names the Julia interface it replaces (file:line under /root/reference).
  * Plain C types only; no exceptions cross the ABI: every call returns 0 or a CABM_E_* code and
  * cabm_last_error() gives the message (the reference's error("...") strings where one exists).
- * One handle = one GPU = one stream; a handle is not thread-safe, distinct handles are independent.
+ * One handle = one GPU = one stream; a handle is not thread-safe, distinct handles are independent (no unsynchronised
+ * process-wide state: the creation error string is per calling thread, kernel attributes are set under a lock).
  * There is no CPU fallback: without a CUDA device cabm_create fails with CABM_E_CUDA.
  */
 #ifndef CABM_H
@@ -29,7 +30,7 @@ enum { CABM_ERR_NO_SWAP = 1,        /* :418 "swap expired, but no swap set." */
        CABM_ERR_NO_SUSCEPTIBLE = 2, /* :371-372 */
        CABM_ERR_TRACED_NOT_ISO = 4, /* :719 */
        CABM_ERR_EMPTY_GROUP = 8,    /* rand(grps[i], g) on an empty group (:807 would throw) */
-       CABM_ERR_CT_LOG_FULL = 16,   /* contact log capacity exceeded (implementation limit) */
+       CABM_ERR_CT_LOG_FULL = 16,   /* contact log capacity exceeded (sized from cdaysback at cabm_configure; implementation limit) */
        CABM_ERR_SICKFROM = 32,      /* :308 */
        CABM_ERR_INTERNAL = 64 };    /* an implementation limit of a kernel was exceeded; results of that replicate are invalid */
 
@@ -70,8 +71,9 @@ typedef struct cabm_handle cabm_handle;
 /* cabm_create flags */
 enum { CABM_STORE_HMATRIX = 1 };   /* keep the popsize x modeltime state matrix of every replicate in HBM */
 /* dyntrans schedule */
-enum { CABM_MODE_EXACT = 0,        /* serial-equivalent: bit-identical to the sequential reference order */
-       CABM_MODE_NATIVE = 1 };     /* per-infector parallel with atomics: ensemble-equivalent */
+enum { CABM_MODE_EXACT = 0,        /* serial-equivalent: bit-identical to the sequential-order C oracle (oracle/, keyed Philox draws);
+                                      distribution-equivalent to the Julia reference, whose RNG streams are unpinned */
+       CABM_MODE_NATIVE = 1 };     /* per-infector parallel with atomics: ensemble-equivalent to the exact schedule */
 
 /* field ids for cabm_get_field / cabm_set_field — the members of `Human` (src/covid19abm.jl:8-27) */
 enum { CABM_F_HEALTH = 0, CABM_F_SWAP, CABM_F_SICKFROM, CABM_F_NEXTDAY_MEETCNT, CABM_F_AG, CABM_F_TIS,
@@ -96,7 +98,13 @@ int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_psets, const 
  * incidence/prevalence reductions (:259-293) and _count_infectors (:295-313), all on device.
  * Asynchronous on the handle's stream; cabm_sync or any cabm_get_* waits. */
 int cabm_run(cabm_handle *h);
+/* Waits for the run. In-model error()s of the reference (:308 "sickfrom not set right", :371-372 "No susceptibles in the
+ * population to change status", :418 "swap expired, but no swap set.", :719) and implementation limits (an empty age group
+ * sampled, contact log full) are recorded per replicate on the device; after a run cabm_sync and every cabm_get_* result call
+ * return CABM_E_MODEL with that message if any replicate is flagged (cabm_get_scalars only when its err argument is NULL: a
+ * caller that reads the error words decides itself). cabm_set_strict(h, 0) switches the check off. */
 int cabm_sync(cabm_handle *h);
+int cabm_set_strict(cabm_handle *h, int on);
 /* device time of the last cabm_run in milliseconds (CUDA events on the handle's stream) */
 int cabm_last_run_ms(cabm_handle *h, float *ms);
 /* Several handles on one GPU run concurrently (each has its own stream): consecutive batches of an ensemble overlap, the

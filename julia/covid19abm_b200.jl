@@ -36,7 +36,7 @@ const LIB = get(ENV, "CABM_LIB", joinpath(@__DIR__, "..", "covid19abm.jl_b200", 
     strat3qdays::Int8 = 0
 end
 
-# struct cabm_params (include/cabm.h) — isbits, same layout as the C struct (192 bytes)
+# struct cabm_params (include/cabm.h) — isbits, same layout as the C struct (192 bytes; asserted below)
 struct CabmParams
     beta::Cdouble; frelasymp::Cdouble
     seasonal::Int32; popsize::Int32; prov_id::Int32; calibration::Int32; modeltime::Int32
@@ -46,6 +46,8 @@ struct CabmParams
     tpreiso::Int32; quar_grp::Int32; ctstrat::Int32; cdaysback::Int32; strat3qdays::Int32
     fctcapture::Cfloat; fcontactst::Cfloat; _pad::Int32
 end
+
+@assert sizeof(CabmParams) == 192 "CabmParams does not match struct cabm_params of include/cabm.h"
 
 const PROVINCES = (:alberta, :bc, :canada, :manitoba, :newbruns, :newfdland, :nwterrito, :novasco,
                    :nunavut, :ontario, :pei, :quebec, :saskat, :yukon, :newyork)               # :319-333
@@ -63,10 +65,15 @@ function check(h, rc)
     error(unsafe_string(ccall((:cabm_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))   # the reference's error("...") text
 end
 
+# Random.seed!(simnum*726) (:78) seeds Julia's global RNG; here the replicate's draws are keyed Philox (DESIGN.md §3), so the
+# "seed" is the Philox key. seed!(s) sets the key the next main(ip) uses, exactly where the reference calls Random.seed!.
 const CURRENT_SEED = Ref{UInt64}(0)
-seed!(s) = (CURRENT_SEED[] = UInt64(s))            # stands in for Random.seed!(simnum*726) :78
+seed!(s) = (CURRENT_SEED[] = UInt64(s))
 
-"main(ip) :104-142 — returns Matrix{Int16}(popsize, modeltime)"
+# what the reference leaves in its globals after main (`humans`, `ct_data` :69-73) and runsim reads back (:84-90)
+const LAST = Ref{Any}(nothing)
+
+"main(ip) :104-142 — returns Matrix{Int16}(popsize, modeltime). In-model error()s come back as Julia errors (cabm_sync: CABM_E_MODEL)."
 function main(ip::ModelParameters; device = 0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:cabm_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint), h, device, 1, ip.popsize, ip.modeltime, 1)
@@ -76,12 +83,44 @@ function main(ip::ModelParameters; device = 0)
         check(h[], ccall((:cabm_configure, LIB), Cint, (Ptr{Cvoid}, Ref{CabmParams}, Cint, Ptr{Int32}, Cint, Ptr{UInt64}, Cint),
                          h[], p, 1, C_NULL, 1, seeds, 0))
         check(h[], ccall((:cabm_run, LIB), Cint, (Ptr{Cvoid},), h[]))
+        check(h[], ccall((:cabm_sync, LIB), Cint, (Ptr{Cvoid},), h[]))      # raises the reference's error("...") text if the replicate hit one
         hmatrix = Matrix{Int16}(undef, ip.popsize, ip.modeltime)          # column-major: one day per column (:111,:221)
         check(h[], ccall((:cabm_get_hmatrix, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int16}), h[], 0, hmatrix))
+        inc = Array{Int32}(undef, 12, ip.modeltime, 6); prev = similar(inc)                       # C order [6][T][12]
+        check(h[], ccall((:cabm_get_curves, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), h[], inc, prev))
+        infectors = Vector{Int64}(undef, 4); tiso = Vector{Int64}(undef, 1)
+        check(h[], ccall((:cabm_get_scalars, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{UInt32}), h[], infectors, tiso, C_NULL, C_NULL))
+        ags = Vector{Int32}(undef, ip.popsize)
+        check(h[], ccall((:cabm_get_field, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}), h[], 4, 0, ags))   # CABM_F_AG
+        LAST[] = (inc = inc, prev = prev, infectors = infectors, totalisolated = tiso[1], ags = ags)
         return hmatrix
     finally
         ccall((:cabm_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
     end
+end
+
+const STATES = ("SUS", "LAT", "PRE", "ASYMP", "MILD", "MISO", "INF", "IISO", "HOS", "ICU", "REC", "DED")
+
+"_collectdf :226-245 for one group, from the device-reduced curves: NamedTuple of columns (time, secondarys, <S>_INC..., <S>_PREV...)"
+function _collectdf(inc::AbstractMatrix, prev::AbstractMatrix)          # [12, T]
+    T = size(inc, 2)
+    sec = [Float64(inc[2, t]) / Float64(sum(prev[3:8, t])) for t in 1:T]   # LAT_INC ./ sum(PRE..IISO prevalence) :237-239
+    sec[isnan.(sec)] .= 0; sec[isinf.(sec)] .= 0                            # :240-241
+    cols = Pair{Symbol, Any}[:time => collect(1:T), :secondarys => sec]
+    for (s, n) in enumerate(STATES); push!(cols, Symbol(n, "_INC") => Int64.(inc[s, :])); end
+    for (s, n) in enumerate(STATES); push!(cols, Symbol(n, "_PREV") => Int64.(prev[s, :])); end
+    return (; cols...)
+end
+
+"runsim(simnum, ip) :77-101: seed simnum*726 (:78), main, and the result tuple (a, g1..g5, infectors, ct_numbers)"
+function runsim(simnum, ip::ModelParameters; device = 0)
+    seed!(simnum * 726)
+    main(ip; device = device)
+    L = LAST[]
+    grp(k) = merge(_collectdf(view(L.inc, :, :, k), view(L.prev, :, :, k)), (sim = fill(simnum, ip.modeltime),))
+    ct_numbers = (0, 0, Int(L.totalisolated), 0, 0, 0, 0)                   # :86-87 — only totalisolated is ever written (:649)
+    return (a = grp(1), g1 = grp(2), g2 = grp(3), g3 = grp(4), g4 = grp(5), g5 = grp(6),
+            infectors = Tuple(Int.(L.infectors)), ct_numbers = ct_numbers)
 end
 
 "pmap(x -> runsim(x, ip), 1:nsims) (scripts/local_run.jl:28-30) as one device run: curves [12, T, 6, nsims]"
@@ -155,5 +194,5 @@ function run_ensemble_pipelined(ip::ModelParameters, nsims::Integer; batch = 100
     end
 end
 
-export ModelParameters, HEALTH, main, run_ensemble, run_ensemble_pipelined
+export ModelParameters, HEALTH, main, runsim, seed!, run_ensemble, run_ensemble_pipelined
 end

@@ -10,8 +10,11 @@
  * the reference's sequential order and array-of-structs agents, and replaces "position in Julia's
  * global RNG stream" by the keyed Philox4x32-10 draw contract written down in DESIGN.md §3.
  * It is pinned by: Random123's published Philox known-answer vectors, the analytic moments of every
- * variate table (tests/test_tables.py), and the invariants of test/runtests.jl re-expressed in
- * tests/test_oracle_invariants.py.
+ * variate table (tests/test_tables.py), the invariants of test/runtests.jl re-expressed in
+ * tests/test_invariants.py, and the one trajectory-level number the reference holds: the author's calibration
+ * fit R0 = 46.1761*beta - 0.00285 (scripts/local_run.jl:164-175), reproduced by this oracle on the same design
+ * (tests/test_calibration_pin.py; tools/calibration_pin.py). Parity with an actual Julia run remains unpinned
+ * (no julia binary in the image, no seeds or goldens in the reference).
  */
 #pragma once
 #include <stdint.h>

@@ -1,7 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs — bit-exact.
 
 The reference's own tests hold no golden vectors (test/runtests.jl is invariants only), so the
-oracle (oracle/abm_oracle.c, pinned in tests/test_oracle_*.py) is the comparison; tolerance is zero:
+oracle (oracle/abm_oracle.c, pinned in tests/test_tables.py, test_invariants.py, test_golden.py and
+test_calibration_pin.py) is the comparison; tolerance is zero:
 every element of the Int16 state matrix, every curve entry and every scalar must be equal.
 """
 import numpy as np

@@ -7,7 +7,9 @@ rate, peak day and peak ICU, ensemble means within 3 standard errors of the diff
 comparison of two independent samples, not a replay. A 2-SE criterion on independent samples raises a false alarm for
 ~5 % of seed sets per statistic (and early-growth luck is shared by all scenarios run on one seed set), so the bound here
 is 3 SE; the north star's 2-SE requirement is checked in the much sharper paired form at the bottom of this file, where
-both schedules run the same seeds and the mean difference must stay below half a standard error of the ensemble."""
+both schedules run the same seeds and the mean difference must stay below half a standard error of the ensemble; and, to
+the north star's letter, on BASELINE configs B and C at full size (1000 replicates x 500 days): two-sample KS p > 0.01 on
+attack rate, peak day and peak ICU and ensemble means within 2 standard errors (test_native_full_size_configs)."""
 import numpy as np
 import pytest
 from scipy import stats
@@ -16,7 +18,7 @@ from test_gpu_parity import to_oracle
 
 pytestmark = pytest.mark.gpu
 
-NREP, T, N = 600, 300, 10000
+NREP, T, N = 1000, 300, 10000
 
 
 def summary(prev):
@@ -76,3 +78,49 @@ def test_native_vs_exact_common_random_numbers(cv, kw):
     se_ens = xa.std(ddof=1) / np.sqrt(R)
     assert abs(d.mean()) < 0.5 * se_ens, (d.mean(), se_ens)
     assert (b["prev"][:, 0].sum(axis=2) == N).all()
+
+
+C_TRACE = dict(ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3)
+B_FULL = dict(β=0.0345, prov="ontario", initialinf=1, modeltime=500, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3, tpreiso=0)
+
+
+@pytest.mark.parametrize("kw", [B_FULL, dict(B_FULL, **C_TRACE), dict(B_FULL, ctstrat=3, strat3qdays=14, fctcapture=0.5, fcontactst=0.5, cdaysback=3)],
+                         ids=["configB", "configC-ctstrat1", "configC-ctstrat3"])
+def test_native_full_size_configs(cv, kw):
+    """BASELINE configs[1] and [2] as stated (1000 replicates x 10,000 agents x 500 days), native schedule against the exact one
+    (which is bit-identical to the oracle, tests/test_full_size_parity.py) on the same seeds: KS p > 0.01 on attack rate, peak
+    day and peak ICU; means within 2 standard errors of the ensemble mean; same replicates die out."""
+    ip = cv.ModelParameters(**kw)
+    R = 1000
+    seeds = [726 * (i + 1) for i in range(R)]
+    a = cv.run_ensemble(ip, R, seeds=seeds, mode=cv.MODE_EXACT)
+    b = cv.run_ensemble(ip, R, seeds=seeds, mode=cv.MODE_NATIVE)
+    assert a["path"] == "fused" and b["path"] == "multikernel" and (b["err"] == 0).all()
+    sa, sb = summary(a["prev"]), summary(b["prev"])
+    assert ((sa[0] < 0.02) == (sb[0] < 0.02)).mean() > 0.97
+    for name, x, y in zip(("attack", "peak_day", "peak_icu"), sa, sb):
+        p = stats.ks_2samp(x, y).pvalue
+        assert p > 0.01, (name, p)
+        se = np.sqrt(x.var(ddof=1) / R + y.var(ddof=1) / R)
+        assert abs(x.mean() - y.mean()) < 2 * se, (name, x.mean(), y.mean(), se)
+    assert (b["prev"][:, 0].sum(axis=2) == N).all()
+    if ip.ctstrat:
+        ta, tb = a["totalisolated"].astype(np.float64), b["totalisolated"].astype(np.float64)
+        assert abs(ta.mean() - tb.mean()) < 2 * np.sqrt(ta.var(ddof=1) / R + tb.var(ddof=1) / R)
+
+
+def test_native_vs_exact_at_100k_agents(cv):
+    """BASELINE configs[4] ingredients at 100,000 agents (the exact schedule on the per-day kernels is the comparison there):
+    paired common-random-number runs and KS tests, sheltered age group, 64 replicates x 150 days."""
+    ip = cv.ModelParameters(β=0.0345, prov="ontario", popsize=100000, modeltime=150, initialinf=10, quar_grp_frac=0.5, quar_grp=5)
+    R, Nl = 64, 100000
+    seeds = [726 * (i + 1) for i in range(R)]
+    a = cv.run_ensemble(ip, R, seeds=seeds, mode=cv.MODE_EXACT)
+    b = cv.run_ensemble(ip, R, seeds=seeds, mode=cv.MODE_NATIVE)
+    assert a["path"] == "multikernel" and b["path"] == "multikernel" and (b["err"] == 0).all() and (a["err"] == 0).all()
+    xa, xb = 1.0 - a["prev"][:, 0, -1, 0] / Nl, 1.0 - b["prev"][:, 0, -1, 0] / Nl
+    assert stats.ks_2samp(xa, xb).pvalue > 0.01
+    assert abs(xa.mean() - xb.mean()) < 2 * np.sqrt(xa.var(ddof=1) / R + xb.var(ddof=1) / R)
+    ia, ib = a["prev"][:, 0, :, 9].max(axis=1).astype(np.float64), b["prev"][:, 0, :, 9].max(axis=1).astype(np.float64)
+    assert stats.ks_2samp(ia, ib).pvalue > 0.01
+    assert (b["prev"][:, 0].sum(axis=2) == Nl).all()

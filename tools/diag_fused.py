@@ -1,23 +1,31 @@
-import os, subprocess, sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
-# needs the diagnostics build of the library: make -C covid19abm.jl_b200/csrc diag
+"""Per-phase cycle counts of k_sim_fused (diagnostics build: make -C covid19abm.jl_b200/csrc diag).
+Usage: python tools/diag_fused.py [B|REF|HOT|C1] [nrep]
+  B    bench workload (BASELINE configs[1])          REF  the reference's timed scenario (test/runtests.jl:408-428)
+  HOT  beta=0.06 ontario, no isolation, no tracing   C1   beta=0.06 with contact tracing ctstrat=1"""
+import os, sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 os.environ.setdefault("CABM_LIB", os.path.abspath("covid19abm.jl_b200/libcabm_b200_diag.so"))
 import numpy as np, covid19abm_b200 as cv
 from bench import CFG, seeds_for
-ip = cv.ModelParameters(**CFG)
-pop = cv.Population(1000, 10000, 500, store_hmatrix=False)
-pop.configure(ip, seeds_for(0,0,1000)); pop.run(); pop.run()
-print("ms", pop.last_run_ms)
-met = np.zeros(1000, np.int32); inf = np.zeros(1000, np.int32)
+which = sys.argv[1] if len(sys.argv) > 1 else "B"
+R = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+cfgs = {"B": CFG,
+        "REF": dict(β=0.0525, prov="newyork", modeltime=300),
+        "HOT": dict(β=0.06, prov="ontario", initialinf=1, modeltime=500),
+        "C1": dict(β=0.06, prov="ontario", initialinf=1, modeltime=500, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3)}
+ip = cv.ModelParameters(**cfgs[which])
+T = ip.modeltime
+pop = cv.Population(R, 10000, T, store_hmatrix=False)
+pop.configure(ip, seeds_for(0, 0, R)); pop.run(); pop.run()
+print("config", which, "ms", pop.last_run_ms)
+met = np.zeros(R, np.int32); inf = np.zeros(R, np.int32)
 pop._chk(pop.L.cabm_get_dyntrans_counters(pop.h, met.ctypes.data, inf.ctypes.data))
 inc, prev = pop.curves()
-attack = 1 - prev[:,0,-1,0]/10000
+attack = 1 - prev[:, 0, -1, 0] / 10000
 order = np.argsort(-met)
 print("kcycles sum", met.sum(), "max", met.max(), "mean", met.mean())
-for r in order[:12]: print(r, "kcyc", met[r], "ms", met[r]*1024/1.965e6, "rounds", inf[r], "attack", attack[r], "peak inf", prev[r,0,:,2:8].sum(axis=1).max(), "cyc/round", met[r]*1024/max(inf[r],1))
-print("takeoff count", (attack>0.1).sum(), "mean attack", attack.mean())
-for r in order[500:503]: print(r, "kcyc", met[r], "rounds", inf[r], "attack", attack[r])
-
-dbg = np.zeros((1000, 32), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
+for r in order[:6]: print(r, "kcyc", met[r], "ms", met[r] * 1024 / 1.965e6, "rounds", inf[r], "attack", attack[r], "peak inf", prev[r, 0, :, 2:8].sum(axis=1).max(), "cyc/round", met[r] * 1024 / max(inf[r], 1))
+print("takeoff count", (attack > 0.1).sum(), "mean attack", attack.mean())
+dbg = np.zeros((R, 32), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
 names = {22: "setup: initialize", 23: "setup: get_ag_dist", 24: "setup: insert_infected", 0: "setup: column 1 / resume reload", 1: "list", 2: "budgets", 25: "time_update: S1 -> own scan done", 26: "time_update: min-reduce", 4: "time_update: S2 wait", 5: "curves/idle", 6: "writeback",
          15: "round: -> before B1", 8: "round: B1 wait + nb/Etot loads",
          16: "round: owner search", 17: "round: target philox + status", 18: "round: target budget", 19: "round: cut check, Y/W1/Q, touch",
