@@ -125,6 +125,7 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.latday, A); DA(S.tracestart, A); DA(S.traceend, A); DA(S.txpday, A); DA(S.ct_head, A);
     DA(S.mark_pre, W); DA(S.mark_post, W); DA(S.infmask, W); DA(S.ct_cnt, (size_t)h->R);
     DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8); DA(S.hits, A);
+    if (h->N <= 65535) DA(S.grp16, A);
     DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);
     DA(S.totalmet, (size_t)h->R); DA(S.totalinf, (size_t)h->R);
     DA(S.inc, C); DA(S.prev, C); DA(S.infectors, (size_t)h->R * 4); DA(S.latsum, (size_t)h->R); DA(S.dbg, (size_t)h->R * 32); DA(S.resume_list, (size_t)h->R); DA(S.resume_aux, (size_t)h->R * 2); DA(S.copy_list, (size_t)h->R);

@@ -76,6 +76,7 @@ struct Dev {
     uint32_t *ct_log; uint32_t *ct_cnt;      // [R][ct_cap] words: chunks [next chunk, count, targets...] per (traced agent, day); [R] words used
     uint32_t *ident_list, *ident_cnt;        // [R][2][Np], [R][2]: agents whose identification day is today / tomorrow
     uint32_t *grp_idx; int *grp_off;         // [R][Np], [R][8]
+    uint16_t *grp16;                         // [R][Np] the same index tables as 16-bit words: the fused kernel's copy (popsize <= 65535)
     uint32_t *infmask;                       // [R][nwords]
     uint32_t *hits;                          // 2 x [R][Np/2] of 2 x u16: native mode, contacts received from lower-indexed infectors
     uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;

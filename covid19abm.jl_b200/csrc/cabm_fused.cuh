@@ -7,23 +7,34 @@
 //     s_status u32[Np]  (the word dyntrans gathers/scatters; cabm_device.cuh)
 //     s_expday i16[Np]  (time_update's only per-agent-day read)
 //     s_col    u8[Np]   (the current hmatrix column; transitions patch it, one TMA bulk store per day writes it)
-//     s_grp    u16[Np]  (get_ag_dist index tables :339-343, "staged in shared memory")
 // HBM traffic per agent-day is therefore just the 1-byte hmatrix element (:221, widened to Int16 on the way out); the rarely-touched fields
-// (dur, entry, sickfrom, isovia, latday) stay in HBM and are read on state transitions only.
+// (dur, entry, sickfrom, isovia, latday) stay in HBM and are read on state transitions only. The age-group index tables of
+// get_ag_dist (:339-343, u16, 2 B per agent) are written once per replicate and read through L2/L1: a target draw is one load of
+// many that are in flight per thread, so its latency is hidden, and the 20 KB of shared memory pay for the chunk buffers.
 // CTAs pull replicate indices from an atomic work counter (grid = resident CTAs), so long epidemics and early
 // extinctions balance across SMs.
 //
-// dyntrans keeps the reference's sequential semantics (:797-832): infectious agents are taken in ascending index
-// order in batches of up to 32 whose contact events (<= NT, one per thread) are drawn in parallel; a batch is cut
-// before the first infector that an earlier infector of the same batch contacts (its budget :802 would change), and
-// events that share a target are resolved in event order by the lowest event of the group.
+// dyntrans keeps the reference's sequential semantics (:797-832) without walking the infectors one after another. A day's
+// infectious agents are listed in ascending index order and taken in CHUNKS of up to 256 infectors / FUSED_EVCAP contact events;
+// inside a chunk everything is parallel:
+//   * every potential event (infector x, age group g, slot k) of the chunk is drawn at once (:807) — targets, transmission
+//     draws, and the targets' lazy contact budgets (written into their status words: tag = today);
+//   * the only order dependence BETWEEN infectors is x's own budget (:802), which earlier infectors reduce when they contact x
+//     (:813). Such events (target infectious, later in the same chunk) are rare; they are collected as the edges of a DAG and
+//     resolved by relaxation: hits on x -> smaller budget -> fewer events of x (the reduced budget's events are a subset of the
+//     drawn ones, because round.(cm*cnts) :804 is monotone in cnts) -> fewer hits on later infectors ..., converging in
+//     (longest dependency chain) sweeps;
+//   * the order dependence ON A TARGET (its budget admits the first rem events :811-813, the first admitted event that transmits
+//     infects :822-827) only matters for targets hit more than once in the chunk: those events are compacted in event order and
+//     resolved per target by warps (each warp owns the targets of one residue class), everything else applies independently.
+// Chunks are sequential (a later chunk sees the budgets the earlier ones left behind).
 //
 // Map of the kernel body (k_sim_fused):
 //   work queues   sweep 0: fresh replicates for split_day days -> finished (fill job) or parked; sweep 1: parked replicates,
 //                 copy jobs (curves -> pinned host memory, a few "copier" CTAs), fill jobs (idle tails of curves and state matrix)
 //   per replicate initialize :171-188 -> get_ag_dist :339-343 -> insert_infected :360-395 -> column 1 -> day loop -> write-back
-//   per active day infector list -> budgets -> batches { preparation (warp 0) | B1 | events | B2 | shared targets | apply | B5 }
-//                 -> time_update scan + events | S2 -> curves row + TMA store of the column
+//   per active day infector list -> chunks { budgets + prefix | C1 | events | C2 | [DAG sweeps] | apply singles, count shared | C3 |
+//                 compact shared | C4 | resolve shared | C5 } -> time_update scan + events | S2 -> curves row + TMA store of the column
 //   idle days     (nobody infectious, nothing due) repeat column and prevalence row; an idle tail is filled in one go
 #pragma once
 #include <cstdlib>
@@ -31,12 +42,15 @@
 
 namespace cabm {
 
-constexpr int FUSED_NT = 256;          // threads per CTA = max events per batch
-constexpr int FUSED_NCAND = 32;        // infectors per batch
-constexpr int FUSED_LCAP = 256;        // infectors listed per pass (more are handled in further passes)
+constexpr int FUSED_NT = 256;          // threads per CTA
+constexpr int FUSED_LCAP = 256;        // infectors listed per pass = infectors per chunk at most
+constexpr int FUSED_EVCAP = 2048;      // contact events per chunk
+constexpr int FUSED_NEDGE = 512;       // events of a chunk that hit a later infector of the same chunk (more: the chunk is halved)
 constexpr unsigned FUSED_TAIL_CTAS = 8;  // CTAs that copy finished curves to the host at any one time (PCIe saturates with ~8)
 constexpr int FUSED_SCAN_U = 5;        // chunks of 8 agents a thread scans at once in time_update (256 x 8 x 5 >= 10,000 agents in one go)
-static_assert(FUSED_NT == 256 && FUSED_LCAP <= FUSED_NT, "thread-index roles in k_sim_fused are laid out for 256 threads");
+static_assert(FUSED_NT == 256 && FUSED_LCAP <= FUSED_NT && FUSED_EVCAP % 32 == 0 && FUSED_EVCAP <= 2048, "thread-index roles and record fields in k_sim_fused");
+// event record: target [0:16) | transmits [16] | owner (chunk entry) [17:25) | dropped by a reduced budget [25]
+constexpr uint32_t EV_SUCC = 1u << 16, EV_DROPPED = 1u << 25, EV_NONE = 0xFFFFFFFFu;
 
 // Small per-CTA state. It lives at the start of the dynamic shared-memory block (not in static __shared__ arrays) so that every
 // access is "block base + constant offset" from one uniform register.
@@ -44,47 +58,49 @@ struct FusedCtl {
     DevPset P;                               // this replicate's parameter set (read on every transition)
     double cm[25];                           // contact_matrix :838-848
     unsigned long long beta[4];              // _get_betavalue :756-769 thresholds of the day
-    unsigned long long bthr[FUSED_NCAND], gp[FUSED_NCAND];      // batch entries: transmission threshold, budget split (:800, :804)
     alignas(16) int run[72];                 // running prevalence of the six groups, for the idle-tail fill (16-byte aligned)
     int io[2][2][60];                        // [day parity][entries | exits][(group, state)] — curve deltas of one day
     uint32_t tlat[4], tpre[4], tasy[40], tinf[40];
     int r, off[8], wcnt[FUSED_NT / 32][5];
     int sel_tid, sel_k, Ltot, ninf;
-    int nf[2], wsum[FUSED_NT / 32];
-    int nb_len[5], kind, pad_[2];
+    int nf[2], wsum[FUSED_NT / 32], wsum2[FUSED_NT / 32];
+    int nb_len[5], kind;
     int infectors[4];
-    int cand[FUSED_NCAND], pref[FUSED_NCAND + 1], nb, cut, adv;  // batch entries: agent, event prefix; entries, cut, list entries consumed
-    int wdup[FUSED_NT / 32], anydup;
-    // contact tracing (:647-752): per-entry chunk of the contact log, the replicate's log fill, index-case queues by day parity
-    uint32_t cbase[FUSED_NCAND], logn, qcnt[2];
-    int clen[FUSED_NCAND];
-    uint8_t xh[FUSED_NCAND], map[FUSED_NCAND], ctr[FUSED_NCAND];   // infector's health; position of the entry in the list stretch; traced
+    int nb, mlist, needtot, nedge;           // chunk: entries with events, list entries consumed, contact-log words reserved, DAG edges
+    int wdup[FUSED_NT / 32];
+    uint32_t logn, qcnt[2];                  // contact tracing (:647-752): the replicate's log fill, index-case queues by day parity
+    int pad_[3];
 };
 static_assert(sizeof(FusedCtl) % 16 == 0, "the arrays behind FusedCtl need 16-byte alignment");
 
 struct FusedSmem {
-    uint32_t *status; int16_t *expday; uint8_t *col; uint16_t *grp; uint32_t *inf;
+    uint32_t *status; int16_t *expday; uint8_t *col; uint32_t *inf;
     uint32_t *nb_thr; uint8_t *nb_guide; const int *nb_len;
-    uint32_t *Y, *W1; uint32_t *touch, *dupm, *mpre, *mpost; uint16_t *D;   // batch events: (target | budget << 16 | owner << 24), transmission word
-    uint16_t *list; uint8_t *lh, *lE;    // the day's ordered infectious agents, their health (+ tracing flag) and event counts
-    unsigned long long *lgp;             // ... and the budget split over the five age groups (:804), five packed bytes
+    uint32_t *touch, *dupm, *mpre, *mpost;
+    uint32_t *ev;                        // [EVCAP] event records of the chunk, in event order
+    uint16_t *D;                         // [EVCAP] events on shared targets, in event order
+    uint32_t *edges;                     // [NEDGE] event [0:11) | entry of the target [11:19) | g [19:22) | k [22:30)
+    uint16_t *list;                      // [LCAP] the day's infectious agents from the cursor on, ascending
+    uint16_t *cx;                        // chunk entries (infectors with events): agent,
+    uint8_t *ch, *cb, *cc, *cflag;       //   health | ag << 4 | tracing << 7; budget at chunk start; budget after hits; 1 = log contacts
+    int *pref, *hits;                    //   event prefix [LCAP + 1]; hits by earlier entries of the chunk
+    unsigned long long *gp0;             //   budget split over the five age groups (:804) at the chunk-start budget, five packed bytes
+    uint32_t *cbase; int *clen;          //   contact-log chunk of a traced entry, contacts logged so far
     unsigned long long *dcache;          // (agent << 32 | dur) of recently infected agents
-    int *cnt;                            // NT ints scratch (seeding, first column); aliases Y
+    int *cnt;                            // NT ints scratch (seeding, first column); aliases ev
 };
 
 __host__ __device__ inline size_t fused_smem_bytes(int Np) {
     size_t b = sizeof(FusedCtl);
     b += (size_t)Np * 4;                 // status
-    b += (size_t)Np * 2 * 2;             // expday, grp
+    b += (size_t)Np * 2;                 // expday
     b += (size_t)Np;                     // col
     b += (size_t)(Np / 32) * 4;          // inf
     b += 5 * 256 * 4 + 5 * 512;          // nb tables
-    b += FUSED_NT * 4 * 2;               // Y (= cnt), W1
     b += (size_t)(Np / 32) * 4 * 4;      // touch, dupm, mark_pre, mark_post bitmasks
-    b += FUSED_NT * 2;                   // D (compacted duplicate events)
-    b += FUSED_LCAP * 4;                 // list, lh, lE
+    b += FUSED_EVCAP * 4 + FUSED_EVCAP * 2 + FUSED_NEDGE * 4;        // ev, D, edges
+    b += FUSED_LCAP * (2 + 2 + 4 * 1 + 4 + 8 + 4 + 4) + (FUSED_LCAP + 1) * 4 + 12;   // list, cx, ch/cb/cc/cflag, hits, gp0, cbase, clen, pref
     b += DUR_CACHE * 8;                  // dcache
-    b += FUSED_LCAP * 8;                 // lgp
     return (b + 15) / 16 * 16 + 64;
 }
 
@@ -136,32 +152,38 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     {
         unsigned char *p = smem_raw + sizeof(FusedCtl);
         M.dcache = (unsigned long long *)p; p += DUR_CACHE * 8;
-        M.lgp = (unsigned long long *)p; p += FUSED_LCAP * 8;
+        M.gp0 = (unsigned long long *)p; p += FUSED_LCAP * 8;
         M.status = (uint32_t *)p; p += (size_t)Np * 4;
-        M.expday = (int16_t *)p; p += (size_t)Np * 2;
-        M.grp = (uint16_t *)p; p += (size_t)Np * 2;
+        M.expday = (int16_t *)p; p += (size_t)Np * 2;          // Np is a multiple of 32: every array below stays 16-byte aligned
         M.col = (uint8_t *)p; p += (size_t)Np;
         M.inf = (uint32_t *)p; p += (size_t)nwords * 4;
         M.nb_thr = (uint32_t *)p; p += 5 * 256 * 4;
-        M.Y = (uint32_t *)p; M.cnt = (int *)p; p += NT * 4;
-        M.W1 = (uint32_t *)p; p += NT * 4;
+        M.ev = (uint32_t *)p; M.cnt = (int *)p; p += FUSED_EVCAP * 4;
+        M.edges = (uint32_t *)p; p += FUSED_NEDGE * 4;
         M.touch = (uint32_t *)p; p += (size_t)nwords * 4;
         M.dupm = (uint32_t *)p; p += (size_t)nwords * 4;
         M.mpre = (uint32_t *)p; p += (size_t)nwords * 4;
         M.mpost = (uint32_t *)p; p += (size_t)nwords * 4;
-        M.D = (uint16_t *)p; p += NT * 2;
+        M.pref = (int *)p; p += (FUSED_LCAP + 1) * 4;
+        M.hits = (int *)p; p += FUSED_LCAP * 4;
+        M.cbase = (uint32_t *)p; p += FUSED_LCAP * 4;
+        M.clen = (int *)p; p += FUSED_LCAP * 4;
+        M.D = (uint16_t *)p; p += FUSED_EVCAP * 2;
         M.list = (uint16_t *)p; p += FUSED_LCAP * 2;
+        M.cx = (uint16_t *)p; p += FUSED_LCAP * 2;
         M.nb_guide = (uint8_t *)p; p += 5 * 512;
         M.nb_len = Z.nb_len;
-        M.lh = (uint8_t *)p; p += FUSED_LCAP;
-        M.lE = (uint8_t *)p; p += FUSED_LCAP;
+        M.ch = (uint8_t *)p; p += FUSED_LCAP;
+        M.cb = (uint8_t *)p; p += FUSED_LCAP;
+        M.cc = (uint8_t *)p; p += FUSED_LCAP;
+        M.cflag = (uint8_t *)p; p += FUSED_LCAP;
     }
 
     for (int k = tid; k < 5 * 256; k += NT) M.nb_thr[k] = S.nb_thr[k];
     for (int k = tid; k < 5 * 512; k += NT) M.nb_guide[k] = S.nb_guide[k];
     if (tid < 5) Z.nb_len[tid] = c_tab.nb_len[tid];
     for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; M.mpre[k] = 0; M.mpost[k] = 0; }
-    if (tid == 0) Z.anydup = 0;
+    if (tid == 0) { Z.nb = 0; Z.mlist = 0; Z.needtot = 0; Z.nedge = 0; }
     if (tid < 4) { Z.tlat[tid] = c_tab.lat_thr[tid]; Z.tpre[tid] = c_tab.pre_thr[tid]; }
     if (tid < 40) { Z.tasy[tid] = c_tab.asy_thr[tid]; Z.tinf[tid] = c_tab.inf_thr[tid]; }
     if (tid < 25) Z.cm[tid] = c_tab.cm[tid / 5][tid % 5];
@@ -336,6 +358,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid == 0) { Z.logn = 0; Z.qcnt[0] = 0; Z.qcnt[1] = 0; }
         const uint2 key = S.key[r];
         const size_t rb = (size_t)r * Np;
+        uint16_t *const grp = S.grp16 + rb;             // get_ag_dist :339-343 index tables of this replicate (global memory, read through L2/L1)
         const unsigned long long *beta = S.beta_thr + (size_t)S.pset_of[r] * T * 4;
         uint8_t *hm = S.store_hm ? S.hm + (size_t)r * T * N : nullptr;
 
@@ -410,7 +433,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #pragma unroll
                 for (int g = 0; g < 5; ++g) {
                     const unsigned m = __ballot_sync(FULL, ag == g);
-                    if (ag == g) M.grp[base[g] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                    if (ag == g) grp[base[g] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
                     base[g] += __popc(m);
                 }
             }
@@ -500,7 +523,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
             for (int i = tid; i < Np; i += NT) {
                 const uint32_t st = __ldcg(&S.status[rb + i]);           // written by another CTA of this launch: read through L2
                 M.status[i] = st; M.expday[i] = __ldcg(&S.expday[rb + i]); M.col[i] = (uint8_t)st_health(st);
-                M.grp[i] = (uint16_t)__ldcg(&S.grp_idx[rb + i]);
             }
             for (int k = tid; k < nwords; k += NT) M.inf[k] = __ldcg(&S.infmask[(size_t)r * nwords + k]);
             for (int k = tid; k < DUR_CACHE; k += NT) M.dcache[k] = ~0ull;
@@ -578,252 +600,275 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                         const int nlist = min(lbase, FUSED_LCAP);
                         PHASE(1);
                         if (nlist == 0) break;
-                        // the day's contact budget of every listed infector (:802), drawn once; a later hit by an earlier
-                        // infector shows up as tag == day in its status word and overrides this value
-                        if (tid < nlist) {
-                            const int x = M.list[tid];
-                            const uint32_t sx = M.status[x];
-                            const int cnts = budget_of_s(M, key, x, day, sx);
-                            // health and the tracing flag of an infector do not change inside dyntrans: keep them with the list
-                            M.lh[tid] = (uint8_t)(st_health(sx) | ((sx & ST_TRACING) ? 0x80u : 0u));
-                            const unsigned long long gp = gpw_pack(Z.cm + st_ag(sx) * 5, cnts);
-                            M.lgp[tid] = gp;
-                            M.lE[tid] = (uint8_t)gpw_sum(gp);
-                        }
-                        __syncthreads();
-                        PHASE(2);
-                        int lpos = 0;
+                        int lpos = 0, lim = FUSED_LCAP;       // lim: list entries the next chunk may take (halved when its DAG has too many edges)
                         while (lpos < nlist) {
 #ifdef CABM_FUSED_DIAG
                             ++n_rounds;
 #endif
-                            // (a) warp 0: the next <= 32 listed infectors. Their event counts come from the list unless the infector was
-                            //     contacted today (tag in its status word, :813); those without events are dropped, the others are
-                            //     compacted into the batch arrays with their event prefix
-                            if (wid == 0) {
-                                const int ncand = min(FUSED_NCAND, nlist - lpos), li = lpos + lane;
-                                int E = 0, x = 0, h = 0; unsigned long long gp = 0;
-                                if (lane < ncand) {
-                                    E = (int)M.lE[li]; x = M.list[li]; gp = M.lgp[li]; h = M.lh[li];
-                                    const uint32_t sx = M.status[x];
-                                    if (st_tag(sx) == day) {                                    // contacted earlier today: budget changed (:813)
-                                        gp = gpw_pack(Z.cm + st_ag(sx) * 5, st_rem(sx));
-                                        E = gpw_sum(gp);
-                                    }
-                                }
-                                int incl = E;
-                                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                                const unsigned fits = __ballot_sync(FULL, lane < ncand && incl <= NT);
-                                const int nfit = fits == FULL ? ncand : min(ncand, __ffs(~fits) - 1);    // E < NT: nfit >= 1
-                                const bool keep = E > 0 && lane < nfit;
-                                const unsigned km = __ballot_sync(FULL, keep);
-                                const int rank = __popc(km & ((1u << lane) - 1u));
-                                if (keep) {
-                                    Z.cand[rank] = x; Z.gp[rank] = gp; Z.xh[rank] = (uint8_t)(h & 0xF); Z.map[rank] = (uint8_t)lane;
-                                    Z.bthr[rank] = Z.beta[beta_class(h & 0xF)];                 // :800
-                                    Z.pref[rank + 1] = incl;
-                                }
-                                if (ctr) {                                                     // :817-819 chunk [next, count, <= E targets] per traced infector
-                                    const bool tr = keep && (h & 0x80);
-                                    int need = tr ? 2 + E : 0, nin = need;
-                                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, nin, o); if (lane >= o) nin += v; }
-                                    const int ntot = __shfl_sync(FULL, nin, 31);
-                                    const uint32_t base0 = Z.logn;
-                                    const bool room = base0 + (uint32_t)ntot <= S.ct_cap;
-                                    if (!room && ntot && lane == 0) atomicOr(&S.err[r], ERR_CT_LOG_FULL);
-                                    if (keep) { Z.ctr[rank] = (uint8_t)(tr && room); Z.cbase[rank] = base0 + (uint32_t)(nin - need); Z.clen[rank] = 0; }
-                                    __syncwarp();
-                                    if (lane == 0 && room) Z.logn = base0 + (uint32_t)ntot;
-                                }
-                                if (lane == 0) { Z.pref[0] = 0; const int nbc = __popc(km); Z.nb = nbc; Z.cut = nbc; Z.adv = nfit; }
+                            // ---- (a) chunk = the longest stretch of the list from lpos whose events fit FUSED_EVCAP. One entry per thread:
+                            //      today's budget (:802; hits by earlier chunks show up as tag == day), its split over the age groups (:804)
+                            const int li = lpos + tid;
+                            const bool have = li < nlist && tid < lim;
+                            int E = 0, cnts = 0, x = 0, hx = 0; unsigned long long gp = 0; bool tr = false;
+                            if (have) {
+                                x = M.list[li];
+                                const uint32_t sx = M.status[x];
+                                cnts = budget_of_s(M, key, x, day, sx);
+                                gp = gpw_pack(Z.cm + st_ag(sx) * 5, cnts);
+                                E = gpw_sum(gp);
+                                hx = st_health(sx) | (st_ag(sx) << 4) | ((sx & ST_TRACING) ? 0x80 : 0);
+                                tr = ctr && (sx & ST_TRACING) && E > 0;                        // :817-819 logs its contacts: chunk [next, count, <= E targets]
                             }
-                            PHASE(15);
-                            __syncthreads();                                                   // B1
-                            PHASE(8);
-                            const int nb = Z.nb;
-                            if (nb == 0) { lpos += Z.adv; __syncthreads(); continue; }          // nobody in this stretch of the list has contacts today
-                            const int Etot = Z.pref[nb];
-                            // (b) one contact event per thread: owner, target draw (:807), transmission word (:823); mark the target.
-                            //     Owner of event tid = number of prefix entries <= tid: those at or below the warp's first event are
-                            //     counted by a ballot, the (strictly increasing) ones inside the warp's range are bits of one word
-                            uint32_t y = 0, w1 = 0, sy = 0, dury = 0; int q = 0, remy = 0; bool ev = tid < Etot, yinf = false;
+                            // inclusive scan over the threads of (events [0:16) | entries with events [16:32)) and of the contact-log words
+                            int v = E | ((E > 0) << 16), v2 = tr ? 2 + E : 0;
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int a = __shfl_up_sync(FULL, v, o), b = __shfl_up_sync(FULL, v2, o);
+                                if (lane >= o) { v += a; v2 += b; }
+                            }
+                            if (lane == 31) { Z.wsum[wid] = v; Z.wsum2[wid] = v2; }
+                            __syncthreads();                                                   // C0
+                            for (int w = 0; w < wid; ++w) { v += Z.wsum[w]; v2 += Z.wsum2[w]; }
+                            const int inclE = v & 0xFFFF, nkept = v >> 16;
+                            const bool fits = have && inclE <= FUSED_EVCAP;                    // a prefix of the threads (the first entry always fits)
+                            if (fits && E > 0) {
+                                const int q = nkept - 1;
+                                M.cx[q] = (uint16_t)x; M.ch[q] = (uint8_t)hx; M.cb[q] = (uint8_t)cnts; M.cc[q] = (uint8_t)cnts; M.gp0[q] = gp;
+                                M.pref[q + 1] = inclE;
+                                if (ctr) { M.cflag[q] = tr ? 1 : 0; M.cbase[q] = (uint32_t)(v2 - (tr ? 2 + E : 0)); M.clen[q] = 0; }
+                            }
                             {
-                                const int Pl = lane < nb ? Z.pref[lane + 1] : 0x7FFFFFFF, base = tid - lane;
-                                const int below = __popc(__ballot_sync(FULL, Pl <= base));
-                                const unsigned bits = __reduce_or_sync(FULL, (Pl > base && Pl <= base + 31) ? 1u << (Pl - base) : 0u);
-                                q = below + __popc(bits & ((2u << lane) - 1u));
-                            }
-                            PHASE(16);
-                            if (ev) {
-                                const int e = tid - Z.pref[q];
-                                const unsigned long long gp = Z.gp[q];                 // round.(cm[ag]*cnts) :804
-                                const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF), p4 = p3 + (int)((gp >> 24) & 0xFF);
-                                const int g = (e >= p1) + (e >= p2) + (e >= p3) + (e >= p4);
-                                const int k = e - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
-                                const int go = Z.off[g], len = Z.off[g + 1] - go;
-                                const int x = Z.cand[q];
-                                if (len == 0) { atomicOr(&S.err[r], ERR_EMPTY_GROUP); ev = false; }
-                                else {
-                                    const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
-                                    y = M.grp[go + below(w.x, len)]; w1 = w.y;
-                                    sy = M.status[y];                              // stable until the apply phase of this batch
-#ifdef CABM_FUSED_DIAG
-                                    if (sy == 0xFFFFFFFFu) ev = false;             // (never true) makes the load complete before the time stamp
-#endif
-                                    PHASE(17);
-                                    dury = __ldg(&S.dur[rb + y]);                  // in flight during the next phases; kept only if y gets infected
-                                    remy = budget_of_s(M, key, y, day, sy);        // :811, the target's budget (lazy draw on first touch)
-#ifdef CABM_FUSED_DIAG
-                                    if (remy == 0x7FFFFFFF) ev = false;
-#endif
-                                    PHASE(18);
-                                    yinf = (M.inf[y >> 5] >> (y & 31)) & 1u;
-                                    // an infector later in this batch that gets contacted must re-read its budget: cut the batch there
-                                    if (yinf && (int)y > x && (int)y <= Z.cand[nb - 1]) {
-                                        int a = q + 1, b = nb - 1;
-                                        while (a < b) { const int mid = (a + b) >> 1; if (Z.cand[mid] < (int)y) a = mid + 1; else b = mid; }
-                                        if (Z.cand[a] == (int)y) atomicMin(&Z.cut, a);     // (a listed infector without events has nothing to redo)
-                                    }
+                                const unsigned fm = __ballot_sync(FULL, fits);
+                                if (fm && lane == 31 - __clz(fm)) {                            // the warp's last fitting entry carries its totals
+                                    atomicMax(&Z.mlist, tid + 1); atomicMax(&Z.nb, nkept);
+                                    if (ctr) atomicMax(&Z.needtot, v2);
                                 }
                             }
-                            // event record: target | its budget << 16 | owner << 24
-                            M.Y[tid] = ev ? (y | ((uint32_t)remy << 16) | ((uint32_t)q << 24)) : 0xFFFFFFFFu; M.W1[tid] = w1;
-                            const uint32_t ybit = 1u << (y & 31);
-                            const int yw = (int)(y >> 5);
-                            // targets hit more than once (by any event of the batch, cut or not) take the ordered path below
-                            if (ev) { const uint32_t old = atomicOr(&M.touch[yw], ybit); if (old & ybit) { atomicOr(&M.dupm[yw], ybit); Z.anydup = 1; } }
-                            PHASE(19);
-                            __syncthreads();                                                   // B2
-                            PHASE(9);
-#ifdef CABM_FUSED_DIAG
-                            const long long t_b2 = clock64();
-#endif
-                            const int cut = Z.cut;
-                            const int Ev = Z.pref[cut];                                // events of infectors [0, cut) are final
-                            const int adv = cut == nb ? Z.adv : (int)Z.map[cut];       // list entries this batch consumes
-                            const bool marked = ev;
-                            ev = ev && tid < Ev;
-                            const bool isdup = ev && (M.dupm[yw] & ybit);
-                            // (c) events sharing a target are applied in event order (:809-830) by one thread per target, over the
-                            //     compacted list of such events; every other event is independent
-                            int dpos = 0, dtot = 0;
-                            if (Z.anydup) {                                                    // uniform (set before B2); B3/B4 only then
-                                const unsigned dm = __ballot_sync(FULL, isdup);
-                                if (lane == 0) Z.wdup[wid] = __popc(dm);
+                            if (tid == 0) M.pref[0] = 0;
+                            __syncthreads();                                                   // C1
+                            const int nb = Z.nb, mlist = Z.mlist, Etot = nb ? M.pref[nb] : 0;
+                            const uint32_t base0 = Z.logn;
+                            const int needtot = ctr ? Z.needtot : 0;
+                            const bool room = ctr && base0 + (uint32_t)needtot <= S.ct_cap;
+                            if (ctr && !room && needtot && tid == 0) atomicOr(&S.err[r], ERR_CT_LOG_FULL);
+                            PHASE(8);
+                            if (nb == 0) {                                                     // nobody in this stretch of the list has contacts today
                                 __syncthreads();
-                                for (int w = 0; w < NW; ++w) { const int c = Z.wdup[w]; dtot += c; if (w < wid) dpos += c; }
-                                if (isdup) { dpos += __popc(dm & ((1u << lane) - 1u)); M.D[dpos] = (uint16_t)tid; }
+                                if (tid == 0) { Z.nb = 0; Z.mlist = 0; Z.needtot = 0; }
+                                lpos += mlist; lim = FUSED_LCAP;
+                                continue;
+                            }
+                            // ---- (b) all events of the chunk, in event order: warp w draws windows [win0, win1) of 32 consecutive events.
+                            //      Owner of an event = the entry whose prefix range holds it: the (strictly increasing) prefix entries that
+                            //      fall into the window are bits of one word; q0 walks along with the windows.
+                            const int nwin = (Etot + 31) >> 5, wpw = (nwin + NW - 1) / NW;
+                            const int win0 = wid * wpw, win1 = min(nwin, win0 + wpw);
+                            const int xlast = M.cx[nb - 1];
+                            int q0 = 0;
+                            if (win0 < win1 && win0 > 0) {                                     // owner of the event before the first window
+                                const int tgt = win0 * 32 - 1;
+                                int lo = 0, hi = nb - 1;
+                                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.pref[mid] <= tgt) lo = mid; else hi = mid - 1; }
+                                q0 = lo;
+                            }
+                            for (int win = win0; win < win1; ++win) {
+                                const int base = win << 5, e = base + lane;
+                                const int Pl = (q0 + 1 + lane <= nb) ? M.pref[q0 + 1 + lane] : 0x7FFFFFFF;      // >= base: q0 owns event base - 1
+                                const unsigned bits = __reduce_or_sync(FULL, (Pl <= base + 31) ? 1u << (Pl - base) : 0u);
+                                const int q = q0 + __popc(bits & ((2u << lane) - 1u));
+                                q0 = __shfl_sync(FULL, q, 31);
+                                uint32_t rec = EV_NONE;
+                                if (e < Etot) {
+                                    const int el = e - M.pref[q];
+                                    const unsigned long long gq = M.gp0[q];                     // round.(cm[ag]*cnts) :804
+                                    const int p1 = (int)(gq & 0xFF), p2 = p1 + (int)((gq >> 8) & 0xFF), p3 = p2 + (int)((gq >> 16) & 0xFF), p4 = p3 + (int)((gq >> 24) & 0xFF);
+                                    const int g = (el >= p1) + (el >= p2) + (el >= p3) + (el >= p4);
+                                    const int k = el - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
+                                    const int go = Z.off[g], len = Z.off[g + 1] - go;
+                                    const int xq = M.cx[q];
+                                    if (len == 0) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
+                                    else {
+                                        const uint4 w = philox(xq, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                                        const uint32_t y = grp[go + below(w.x, len)];                                   // :807
+                                        rec = y | (bern(w.y, Z.beta[beta_class(M.ch[q] & 0xF)]) ? EV_SUCC : 0u) | ((uint32_t)q << 17);   // :800, :823
+                                        // the target's budget for today (:811), drawn on first touch and kept in its status word (tag = today)
+                                        const uint32_t sy = M.status[y];
+                                        if (st_tag(sy) != day)
+                                            M.status[y] = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)fresh_budget_s(M, key, y, (uint32_t)day, sy) | ((uint32_t)day << 22);
+                                        // targets hit more than once (by any event of the chunk, dropped later or not) take the ordered path
+                                        const uint32_t ybit = 1u << (y & 31);
+                                        const uint32_t old = atomicOr(&M.touch[y >> 5], ybit);
+                                        if (old & ybit) atomicOr(&M.dupm[y >> 5], ybit);
+                                        // a later infector of this chunk that gets contacted starts its turn with a smaller budget (:802, :813): DAG edge
+                                        if (((M.inf[y >> 5] >> (y & 31)) & 1u) && (int)y > xq && (int)y <= xlast) {
+                                            int a = q + 1, b = nb - 1;
+                                            while (a < b) { const int mid = (a + b) >> 1; if ((int)M.cx[mid] < (int)y) a = mid + 1; else b = mid; }
+                                            if ((int)M.cx[a] == (int)y) {                        // (a listed infector without events has nothing to lose)
+                                                const int slot = atomicAdd(&Z.nedge, 1);
+                                                if (slot < FUSED_NEDGE) M.edges[slot] = (uint32_t)e | ((uint32_t)a << 11) | ((uint32_t)g << 19) | ((uint32_t)k << 22);
+                                            }
+                                        }
+                                    }
+                                }
+                                M.ev[e] = rec;
+                            }
+                            PHASE(9);
+                            __syncthreads();                                                   // C2
+                            const int ne = Z.nedge;
+                            if (ne > FUSED_NEDGE) {
+                                // too many order dependences for the edge list (tiny populations with most agents infectious): take half the entries
+                                __syncthreads();
+                                for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }
+                                if (tid == 0) { Z.nb = 0; Z.mlist = 0; Z.needtot = 0; Z.nedge = 0; }
+                                lim = max(1, mlist >> 1);
+                                __syncthreads();
+                                continue;
+                            }
+                            // ---- (c) budgets of entries that earlier entries of the chunk contact: relax until nothing changes
+                            if (ne > 0) {
+#ifdef CABM_FUSED_DIAG
+                                if (tid == 0) t_ph[18] += ne;
+#endif
+                                for (;;) {
+#ifdef CABM_FUSED_DIAG
+                                    if (tid == 0) t_ph[19] += 1;
+#endif
+                                    if (tid < nb) M.hits[tid] = 0;
+                                    __syncthreads();
+                                    for (int j = tid; j < ne; j += NT) {
+                                        const uint32_t ed = M.edges[j];
+                                        const int q = (int)((M.ev[ed & 2047u] >> 17) & 255u), g = (int)((ed >> 19) & 7u), k = (int)(ed >> 22);
+                                        const int cq = M.cc[q];
+                                        bool valid = cq == (int)M.cb[q];
+                                        if (!valid) valid = k < (int)((gpw_pack(Z.cm + ((M.ch[q] >> 4) & 7) * 5, cq) >> (8 * g)) & 0xFF);
+                                        if (valid) atomicAdd(&M.hits[(ed >> 11) & 255u], 1);
+                                    }
+                                    __syncthreads();
+                                    bool chg = false;
+                                    if (tid < nb) {
+                                        const int nc = max(0, (int)M.cb[tid] - M.hits[tid]);      // admitted hits = min(budget, hits) :811-813
+                                        if (nc != (int)M.cc[tid]) { M.cc[tid] = (uint8_t)nc; chg = true; }
+                                    }
+                                    if (!__syncthreads_or(chg)) break;
+                                }
+                                // events a reduced budget no longer has: (g, k) with k >= round(cm[ag][g] * cnts')
+                                for (int e = tid; e < Etot; e += NT) {
+                                    const uint32_t rec = M.ev[e];
+                                    if (rec == EV_NONE) continue;
+                                    const int q = (int)((rec >> 17) & 255u), cq = M.cc[q];
+                                    if (cq == (int)M.cb[q]) continue;
+                                    const int el = e - M.pref[q];
+                                    const unsigned long long gq = M.gp0[q];
+                                    const int p1 = (int)(gq & 0xFF), p2 = p1 + (int)((gq >> 8) & 0xFF), p3 = p2 + (int)((gq >> 16) & 0xFF), p4 = p3 + (int)((gq >> 24) & 0xFF);
+                                    const int g = (el >= p1) + (el >= p2) + (el >= p3) + (el >= p4);
+                                    const int k = el - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
+                                    if (k >= (int)((gpw_pack(Z.cm + ((M.ch[q] >> 4) & 7) * 5, cq) >> (8 * g)) & 0xFF)) M.ev[e] = rec | EV_DROPPED;
+                                }
                                 __syncthreads();
                             }
                             PHASE(10);
-#ifdef CABM_FUSED_DIAG
-                            t_lastx = clock64();
-#endif
-                            // outcome of a target: remaining budget, infected by whom (-1: not infected)
-                            int rem = remy, xh_inf = -1;
-                            bool apply = ev && !isdup;
-                            if (apply && rem > 0) {                                                  // :812
-                                rem -= 1;                                                             // :813
-                                if (ctr && Z.ctr[q]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[q] + 2u + (uint32_t)atomicAdd(&Z.clen[q], 1)] = y;   // :817-819
-                                if (st_health(sy) == SUS && st_swap(sy) == UNDEF && bern(w1, Z.bthr[q])) xh_inf = Z.xh[q];   // :822-827
+                            // ---- (d) apply. One event on a target: independent of everything else in the chunk (:809-830)
+                            auto log_contact = [&](int q, uint32_t y) {                          // :817-819
+                                S.ct_log[(size_t)r * S.ct_cap + base0 + M.cbase[q] + 2u + (uint32_t)atomicAdd(&M.clen[q], 1)] = y;
+                            };
+                            int ndl = 0;
+                            for (int win = win0; win < win1; ++win) {
+                                const int e = (win << 5) + lane;
+                                const uint32_t rec = e < Etot ? M.ev[e] : EV_NONE;
+                                const bool live = rec != EV_NONE && !(rec & EV_DROPPED);
+                                const uint32_t y = rec & 0xFFFFu;
+                                const bool shared = live && ((M.dupm[y >> 5] >> (y & 31)) & 1u);
+                                if (live && !shared) {
+                                    const uint32_t sy = M.status[y];                               // tag == today since (b)
+                                    const int rem = st_rem(sy);
+                                    if (rem > 0) {                                                  // :812
+                                        const int q = (int)((rec >> 17) & 255u);
+                                        uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)(rem - 1);     // :813
+                                        if (ctr && room && M.cflag[q]) log_contact(q, y);
+                                        if (st_health(sy) == SUS && st_swap(sy) == UNDEF && (rec & EV_SUCC)) {   // :822-827
+                                            ns = st_set_swap(ns, LAT);
+                                            S.sickfrom[rb + y] = (uint8_t)(M.ch[q] & 0xF);
+                                            M.expday[y] = (int16_t)day;                             // y.exp = y.tis :826 — fires in today's time_update
+                                        }
+                                        M.status[y] = ns;
+                                    }
+                                }
+                                ndl += __popc(__ballot_sync(FULL, shared));
                             }
-                            if (dtot > 0 && dtot <= 32) {
-                                // few shared targets (the usual case): the last warp resolves them, one lane per event, the first
-                                // event of each target leading; the others apply their own events meanwhile
-                                if (wid == NW - 1) {
-                                    if (apply) {        // this warp's own independent events first
-                                        uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
+                            if (lane == 0) Z.wdup[wid] = ndl;
+                            PHASE(11);
+                            __syncthreads();                                                   // C3
+                            int dpos = 0, ndup = 0;
+                            for (int w = 0; w < NW; ++w) { const int c = Z.wdup[w]; ndup += c; if (w < wid) dpos += c; }
+                            if (ndup > 0) {
+                                // events that share a target, compacted in event order
+                                for (int win = win0; win < win1; ++win) {
+                                    const int e = (win << 5) + lane;
+                                    const uint32_t rec = e < Etot ? M.ev[e] : EV_NONE;
+                                    const uint32_t y = rec & 0xFFFFu;
+                                    const bool shared = rec != EV_NONE && !(rec & EV_DROPPED) && ((M.dupm[y >> 5] >> (y & 31)) & 1u);
+                                    const unsigned dm = __ballot_sync(FULL, shared);
+                                    if (shared) M.D[dpos + __popc(dm & ((1u << lane) - 1u))] = (uint16_t)e;
+                                    dpos += __popc(dm);
+                                }
+                                PHASE(13);
+                                __syncthreads();                                               // C4
+#ifdef CABM_FUSED_DIAG
+                                if (tid == 0) t_ph[17] += ndup;
+#endif
+                                // warp w owns the targets y with y mod 8 == w: it walks the list 32 entries at a time and applies its
+                                // targets' events in list (= event) order; lanes that share a target form a group led by its first event
+                                for (int base = 0; base < ndup; base += 32) {
+                                    const int idx = base + lane;
+                                    const uint32_t rec = idx < ndup ? M.ev[M.D[idx]] : EV_NONE;
+                                    const uint32_t y = rec & 0xFFFFu;
+                                    const bool mine = rec != EV_NONE && (int)(y & (NW - 1)) == wid;
+                                    if (!__any_sync(FULL, mine)) continue;
+                                    const int qd = (int)((rec >> 17) & 255u);
+                                    const unsigned peers = __match_any_sync(FULL, mine ? y : 0x10000u);
+                                    const bool leader = mine && lane == __ffs(peers) - 1;
+                                    const int n = __popc(peers), nmax = __reduce_max_sync(FULL, mine ? n : 0);
+                                    const uint32_t sy = mine ? M.status[y] : 0u;
+                                    int rem = st_rem(sy), xh_inf = -1;
+                                    bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;                 // :822
+                                    const int hit = (mine && (rec & EV_SUCC)) ? (int)(M.ch[qd] & 0xF) : -1;     // would this event transmit (:823)?
+                                    unsigned m = peers;
+                                    for (int k = 0; k < nmax; ++k) {                                          // k-th event of each target, in event order
+                                        const int src = m ? __ffs(m) - 1 : lane; m &= m - 1u;
+                                        const int hs = __shfl_sync(FULL, hit, src);
+                                        const int qs = __shfl_sync(FULL, qd, src);
+                                        if (leader && k < n && rem > 0) {                                     // :812
+                                            rem -= 1;                                                         // :813
+                                            if (ctr && room && M.cflag[qs]) log_contact(qs, y);
+                                            if (sus && hs >= 0) { sus = false; xh_inf = hs; }
+                                        }
+                                    }
+                                    if (leader) {
+                                        uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)rem;
                                         if (xh_inf >= 0) {
                                             ns = st_set_swap(ns, LAT);
                                             S.sickfrom[rb + y] = (uint8_t)xh_inf;
                                             M.expday[y] = (int16_t)day;
-                                            M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
                                         }
                                         M.status[y] = ns;
-                                        apply = false;
                                     }
-                                    const bool have = lane < dtot;
-                                    const uint32_t rec = have ? M.Y[M.D[lane]] : 0u, w1d = have ? M.W1[M.D[lane]] : 0u;
-                                    const uint32_t yd = rec & 0xFFFFu;
-                                    const int qd = (int)(rec >> 24);
-                                    // lanes that share a target form a group led by its first event; the idle lanes form one group of their own
-                                    const unsigned peers = __match_any_sync(FULL, have ? yd : 0x10000u);
-                                    const bool leader = have && lane == __ffs(peers) - 1;
-                                    const int n = __popc(peers), nmax = __reduce_max_sync(FULL, have ? n : 0);
-                                    y = yd; sy = have ? M.status[yd] : 0u; rem = (int)((rec >> 16) & 0xFFu); xh_inf = -1;
-                                    bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;             // :822
-                                    unsigned m = peers;
-                                    // would this lane's event transmit (:823)? decided here, once, so that the ordered loop is shuffles only
-                                    const int hit = (have && bern(w1d, Z.bthr[qd])) ? (int)Z.xh[qd] : -1;
-#ifdef CABM_FUSED_DIAG
-                                    if (sus && sy == 0x12345678u) m = 0;
-#endif
-                                    for (int k = 0; k < nmax; ++k) {                                      // k-th event of each target, in event order
-                                        const int src = m ? __ffs(m) - 1 : lane; m &= m - 1u;
-                                        const int hs = __shfl_sync(FULL, hit, src);
-                                        const int qs = __shfl_sync(FULL, qd, src);
-                                        if (leader && k < n && rem > 0) {                                 // :812
-                                            rem -= 1;                                                     // :813
-                                            if (ctr && Z.ctr[qs]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[qs] + 2u + (uint32_t)atomicAdd(&Z.clen[qs], 1)] = y;
-                                            if (sus && hs >= 0) { sus = false; xh_inf = hs; }
-                                        }
-                                    }
-                                    apply = leader;
-                                    dury = 0xFFFFFFFFu;                                                   // not loaded by this lane: no cache entry
-                                }
-                            } else if (isdup) {
-                                // many shared targets: every first event of a target walks the compacted list
-                                bool leader = true;
-                                for (int d = 0; d < dpos; ++d) if ((M.Y[M.D[d]] & 0xFFFFu) == y) { leader = false; break; }
-                                if (leader) {
-                                    bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;
-                                    if (rem > 0) {
-                                        rem -= 1;
-                                        if (ctr && Z.ctr[q]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[q] + 2u + (uint32_t)atomicAdd(&Z.clen[q], 1)] = y;
-                                        if (sus && bern(w1, Z.bthr[q])) { sus = false; xh_inf = Z.xh[q]; }
-                                    }
-                                    for (int d = dpos + 1; d < dtot && rem > 0; ++d) {
-                                        const int e2 = M.D[d];
-                                        const uint32_t rec = M.Y[e2];
-                                        if ((rec & 0xFFFFu) != y) continue;
-                                        rem -= 1;
-                                        const int q2 = (int)(rec >> 24);
-                                        if (ctr && Z.ctr[q2]) S.ct_log[(size_t)r * S.ct_cap + Z.cbase[q2] + 2u + (uint32_t)atomicAdd(&Z.clen[q2], 1)] = y;
-                                        if (sus && bern(M.W1[e2], Z.bthr[q2])) { sus = false; xh_inf = Z.xh[q2]; }
-                                    }
-                                    apply = true;
+                                    __syncwarp();
                                 }
                             }
-                            if (apply) {
-                                uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)rem | ((uint32_t)day << 22);
-                                if (xh_inf >= 0) {
-                                    ns = st_set_swap(ns, LAT);
-                                    S.sickfrom[rb + y] = (uint8_t)xh_inf;
-                                    M.expday[y] = (int16_t)day;                // y.exp = y.tis :826 — fires in today's time_update
-                                    if (dury != 0xFFFFFFFFu) M.dcache[y & (DUR_CACHE - 1)] = ((unsigned long long)y << 32) | dury;
-                                }
-                                M.status[y] = ns;
+                            PHASE(14);
+                            __syncthreads();                                                   // C5: status writes visible to the next chunk / time_update
+                            if (ctr && room && tid < nb && M.cflag[tid] && M.clen[tid] > 0) {     // link the day's chunk of each traced infector
+                                const int xq = M.cx[tid];
+                                uint32_t *c = S.ct_log + (size_t)r * S.ct_cap + base0 + M.cbase[tid];
+                                c[0] = S.ct_head[rb + xq]; c[1] = (uint32_t)M.clen[tid];
+                                S.ct_head[rb + xq] = base0 + M.cbase[tid];
                             }
-                            PHASE(20);
+                            for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }   // next marking is after the next C1
+                            if (tid == 0) { Z.nb = 0; Z.mlist = 0; Z.needtot = 0; Z.nedge = 0; if (room) Z.logn = base0 + (uint32_t)needtot; }
 #ifdef CABM_FUSED_DIAG
-                            if (lane == 0) t_wdt[wid] = clock64() - t_b2;
+                            if (tid == 0) t_ph[16] += Etot;
 #endif
-                            __syncthreads();                                                   // B5: status writes visible to the next batch
-#ifdef CABM_FUSED_DIAG
-                            if (tid == 0) { const int slot[8] = {7, 13, 14, 27, 28, 29, 30, 31}; long long mx = 0; for (int w = 0; w < 8; ++w) mx = max(mx, t_wdt[w]);
-                                            for (int w = 0; w < 8; ++w) if (t_wdt[w] == mx) { t_ph[slot[w]] += 1; break; } t_ph[3] += mx; }
-#endif
-                            if (ctr && wid == 0 && lane < cut && Z.ctr[lane] && Z.clen[lane] > 0) {    // link the day's chunk of each traced infector
-                                const int x = Z.cand[lane];
-                                uint32_t *c = S.ct_log + (size_t)r * S.ct_cap + Z.cbase[lane];
-                                c[0] = S.ct_head[rb + x]; c[1] = (uint32_t)Z.clen[lane];
-                                S.ct_head[rb + x] = Z.cbase[lane];
-                            }
-                            PHASE(11);
-                            PHASE(21);
-                            if (marked) { M.touch[yw] = 0; M.dupm[yw] = 0; }                   // next marking is after the next B1
-                            if (tid == 0) Z.anydup = 0;
-                            lpos += adv;
+                            PHASE(15);
+                            lpos += mlist; lim = FUSED_LCAP;
                         }
                         PHASE(12);
                         if (w0 >= nwords && lbase <= FUSED_LCAP) break;                        // the list held every infectious agent
@@ -841,12 +886,18 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 }
                 if (ctr) {
                     // pass A of ct_dynamics (:705-716): today's index cases (queued yesterday by agent_event_core) mark their traced
-                    // contacts before anybody is updated. Index cases are few: warp 0 takes them one after another.
+                    // contacts before anybody is updated (marks are bitmask ORs and keyed draws: the index cases are independent of each other).
                     const uint32_t nq = Z.qcnt[day & 1];
                     if (nq) {
-                        if (wid == 0) {
+                        __syncthreads();        // the contact chunks linked after today's last dyntrans chunk (by many warps) are visible to every warp
+                        {   // one index case per warp at a time, each warp gathering contacts in its own slice of the event buffer
                             const uint32_t *qlist = S.ident_list + ((size_t)r * 2 + (day & 1)) * Np;
-                            for (uint32_t k = 0; k < nq; ++k) ct_identify_warp(S, P, r, (int)qlist[k], day, M.Y, NT, M.mpre, M.mpost);
+#ifdef CABM_PASSA_SERIAL
+                            if (wid == 0) for (uint32_t k = 0; k < nq; ++k)
+#else
+                            for (uint32_t k = wid; k < nq; k += NW)
+#endif
+                                ct_identify_warp(S, P, r, (int)qlist[k], day, M.ev + wid * (FUSED_EVCAP / NW), FUSED_EVCAP / NW, M.mpre, M.mpost);
                         }
                         __syncthreads();
                         if (tid == 0) Z.qcnt[day & 1] = 0;
@@ -968,7 +1019,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (!finished) {
             // ---------------------------------------------------------- park: still active after split_day days -> state to HBM, queue for sweep 1
             for (int i = tid; i < Np; i += NT) {
-                S.status[rb + i] = M.status[i]; S.expday[rb + i] = M.expday[i]; S.grp_idx[rb + i] = M.grp[i];
+                S.status[rb + i] = M.status[i]; S.expday[rb + i] = M.expday[i];
             }
             for (int k = tid; k < nwords; k += NT) S.infmask[(size_t)r * nwords + k] = M.inf[k];
             if (tid < 6) S.grp_off[r * 8 + tid] = Z.off[tid];

@@ -23,16 +23,17 @@ inc, prev = pop.curves()
 attack = 1 - prev[:, 0, -1, 0] / 10000
 order = np.argsort(-met)
 print("kcycles sum", met.sum(), "max", met.max(), "mean", met.mean())
-for r in order[:6]: print(r, "kcyc", met[r], "ms", met[r] * 1024 / 1.965e6, "rounds", inf[r], "attack", attack[r], "peak inf", prev[r, 0, :, 2:8].sum(axis=1).max(), "cyc/round", met[r] * 1024 / max(inf[r], 1))
+for r in order[:6]: print(r, "kcyc", met[r], "ms", met[r] * 1024 / 1.965e6, "chunks", inf[r], "attack", attack[r], "peak inf", prev[r, 0, :, 2:8].sum(axis=1).max(), "cyc/chunk", met[r] * 1024 / max(inf[r], 1))
 print("takeoff count", (attack > 0.1).sum(), "mean attack", attack.mean())
 dbg = np.zeros((R, 32), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
-names = {22: "setup: initialize", 23: "setup: get_ag_dist", 24: "setup: insert_infected", 0: "setup: column 1 / resume reload", 1: "list", 2: "budgets", 25: "time_update: S1 -> own scan done", 26: "time_update: min-reduce", 4: "time_update: S2 wait", 5: "curves/idle", 6: "writeback",
-         15: "round: -> before B1", 8: "round: B1 wait + nb/Etot loads",
-         16: "round: owner search", 17: "round: target philox + status", 18: "round: target budget", 19: "round: cut check, Y/W1/Q, touch",
-         9: "round: B2 wait", 10: "round: cut/dup compaction", 20: "round: apply", 11: "round: B5 wait", 21: "(timer overhead)", 3: "B2 -> B5, slowest warp (cycles)", 7: "slowest = warp 0 (count)", 13: "slowest = warp 1", 14: "slowest = warp 2", 27: "slowest = warp 3", 28: "slowest = warp 4", 29: "slowest = warp 5", 30: "slowest = warp 6", 31: "slowest = warp 7", 12: "dyntrans end -> S1"}
+names = {22: "setup: initialize", 23: "setup: get_ag_dist", 24: "setup: insert_infected", 0: "setup: column 1 / resume reload", 1: "list",
+         8: "chunk: budgets + prefix -> C1", 9: "chunk: event generation", 10: "chunk: C2 wait + DAG", 11: "chunk: apply singles + count shared",
+         13: "chunk: C3 + compaction", 14: "chunk: C4 + resolve shared", 15: "chunk: C5 + link/clear", 12: "dyntrans end -> S1",
+         25: "time_update: S1 -> own scan done", 26: "time_update: min-reduce", 4: "time_update: S2 wait", 5: "curves/idle", 6: "writeback",
+         16: "(count) events", 17: "(count) shared-target events", 18: "(count) DAG edges", 19: "(count) DAG sweeps"}
 big = attack > 0.1
-print("phase kcycles  take-off mean | extinct mean | per round (take-off)")
+print("phase kcycles  take-off mean | extinct mean | per chunk (take-off)")
 nr = max(inf[big].sum(), 1)
 for k in names: print(f"{k:2d} {names[k]:36s} {dbg[big,k].mean()/1e3:10.1f} | {dbg[~big,k].mean()/1e3:10.1f} | {dbg[big,k].sum()/nr:8.0f}")
-print("rounds take-off mean", inf[big].mean(), "extinct", inf[~big].mean())
+print("chunks take-off mean", inf[big].mean(), "extinct", inf[~big].mean())
 print("take-off total kcycles mean", met[big].mean(), "-> ms", met[big].mean() * 1024 / 1.965e6, " max ms", met.max() * 1024 / 1.965e6)
