@@ -37,6 +37,10 @@ ERR_BITS = {1: "swap expired, but no swap set.", 2: "No susceptibles in the popu
             16: "contact log capacity exceeded", 32: "sickfrom not set right", 64: "kernel implementation limit exceeded"}
 
 
+TAPE_DTYPE = np.dtype([("seed", "<u8"), ("ctr", "<u4", (4,)), ("w", "<u4", (4,))])       # struct cabm_tape_entry (40 bytes)
+STREAMS = {"INIT": 1, "COUNT": 2, "SEED": 3, "TRANS": 4, "CTWIN": 5, "CTCON": 6, "CT3": 7, "DT": 8}   # draw-contract streams
+
+
 class CabmError(RuntimeError):
     """Stands in for Julia's ErrorException: raised with the reference's error("...") message where one exists."""
 
@@ -142,6 +146,7 @@ def lib():
     L.cabm_configure.argtypes = [vp, vp, i32, vp, i32, vp, i32]
     L.cabm_run.argtypes = [vp]; L.cabm_sync.argtypes = [vp]
     L.cabm_set_strict.argtypes = [vp, i32]
+    L.cabm_set_tape.argtypes = [vp, vp, C.c_uint64]
     L.cabm_last_run_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.cabm_set_host_curve_rows.argtypes = [vp, vp]
     L.cabm_mark.argtypes = [vp]; L.cabm_ms_since_mark.argtypes = [vp, vp, C.POINTER(C.c_float)]
@@ -267,6 +272,16 @@ class Population:
         inspects errors() itself."""
         self._chk(self.L.cabm_set_strict(self.h, int(on)))
 
+    def set_tape(self, entries=None):
+        """Replay tape (include/cabm.h cabm_set_tape): `entries` is a numpy array of TAPE_DTYPE — (seed, ctr[4] = (index, day,
+        stream, sub), w[4]) — listing draws that take the given words instead of their Philox value; None removes the tape.
+        With a tape the per-day kernels run (path "multikernel")."""
+        if entries is None or len(entries) == 0:
+            self._chk(self.L.cabm_set_tape(self.h, None, 0))
+            return
+        a = np.ascontiguousarray(entries, dtype=TAPE_DTYPE)
+        self._chk(self.L.cabm_set_tape(self.h, a.ctypes.data, len(a)))
+
     @property
     def last_run_ms(self):
         ms = C.c_float(0)
@@ -298,12 +313,12 @@ class Population:
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(["dyntrans", "time_update", "ct_identify", "other", "fused"])}
 
     def set_path(self, path):
-        """'auto' | 'multikernel' | 'fused' (include/cabm.h CABM_PATH_*)."""
-        self._chk(self.L.cabm_set_path(self.h, {"auto": 0, "multikernel": 1, "fused": 2}[path]))
+        """'auto' | 'multikernel' | 'fused' | 'fused-global' (include/cabm.h CABM_PATH_*)."""
+        self._chk(self.L.cabm_set_path(self.h, {"auto": 0, "multikernel": 1, "fused": 2, "fused-global": 3}[path]))
 
     @property
     def last_path(self):
-        return {0: None, 1: "multikernel", 2: "fused"}[self.L.cabm_get_last_path(self.h)]
+        return {0: None, 1: "multikernel", 2: "fused", 3: "fused-global"}[self.L.cabm_get_last_path(self.h)]
 
     @property
     def day(self):

@@ -4,6 +4,7 @@
 #include "cabm_kernels.h"
 #include "cabm_tables.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -33,6 +34,7 @@ struct cabm_handle {
     int strict = 1; bool err_checked = false; int err_rc = 0;
     size_t ct_words_per_agent = 0;     // contact-log capacity the current allocation was sized for
     double *d_mean = nullptr; size_t mean_elems = 0;   // scratch of cabm_get_mean_curves
+    uint32_t *d_tape_keys = nullptr; uint4 *d_tape_w = nullptr;   // replay tape (cabm_set_tape)
     bool poked = false;                // state was edited through cabm_set_field: pass A falls back to the full scan
     // optional per-kernel-class timing (cabm_set_profiling): events around every launch of the next cabm_run
     int profiling = 0;
@@ -124,6 +126,8 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.status, A); DA(S.expday, A); DA(S.texp, A); DA(S.entry, A); DA(S.dur, A); DA(S.sickfrom, A); DA(S.isovia, A);
     DA(S.latday, A); DA(S.tracestart, A); DA(S.traceend, A); DA(S.txpday, A); DA(S.ct_head, A);
     DA(S.mark_pre, W); DA(S.mark_post, W); DA(S.infmask, W); DA(S.ct_cnt, (size_t)h->R);
+    DA(S.touch_g, W); DA(S.dupm_g, W); DA(S.col_g, A);
+    if ((e = cudaMemset(S.touch_g, 0, W * 4)) != cudaSuccess || (e = cudaMemset(S.dupm_g, 0, W * 4)) != cudaSuccess) return bail(e, "memset");
     DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8); DA(S.hits, A);
     if (h->N <= 65535) DA(S.grp16, A);
     DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);
@@ -187,6 +191,8 @@ extern "C" void cabm_destroy(cabm_handle *h) {
     if (h->S.ident_cnt) cudaFree(h->S.ident_cnt);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->d_mean) cudaFree(h->d_mean);
+    if (h->d_tape_keys) cudaFree(h->d_tape_keys);
+    if (h->d_tape_w) cudaFree(h->d_tape_w);
     for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -346,6 +352,7 @@ static int reset_state(cabm_handle *h, bool curves_too = true) {
     h->poked = false;
     CU(cudaMemsetAsync(S.err, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totiso, 0, (size_t)S.R * 8, h->stream));
     CU(cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, h->stream));
+    CU(cudaMemsetAsync(S.touch_g, 0, W * 4, h->stream)); CU(cudaMemsetAsync(S.dupm_g, 0, W * 4, h->stream));
     if (curves_too) { CU(cudaMemsetAsync(S.inc, 0, C * 4, h->stream)); CU(cudaMemsetAsync(S.prev, 0, C * 4, h->stream)); }
     CU(cudaMemsetAsync(S.infectors, 0, (size_t)S.R * 32, h->stream)); CU(cudaMemsetAsync(S.latsum, 0, (size_t)S.R * 8, h->stream));
     h->day = 1;
@@ -379,14 +386,20 @@ extern "C" int cabm_run(cabm_handle *h) {
     h->pev_used = 0; h->pcls.clear();
     // The fused kernel keeps a replicate's hot state in shared memory: usable when it fits two CTAs per SM budget
     // (popsize <= ~21k agents) with the exact schedule; otherwise one kernel per phase per day.
-    const bool fused_ok = h->mode == CABM_MODE_EXACT && h->N <= 65535 && fused_smem_bytes_host(h->Np) <= 227 * 1024 - 512;
-    const bool use_fused = h->path == CABM_PATH_FUSED ? fused_ok : (h->path == CABM_PATH_AUTO && fused_ok);
+    // (shared-memory variant: popsize <= ~21k agents; otherwise the same kernel with the per-agent arrays in global memory, any popsize)
+    const bool exact = h->mode == CABM_MODE_EXACT;
+    if (S.tape_n && h->path != CABM_PATH_AUTO && h->path != CABM_PATH_MULTIKERNEL) return fail(h, CABM_E_STATE, "a replay tape is consulted by the per-day kernels only (CABM_PATH_AUTO or CABM_PATH_MULTIKERNEL)");
+    const bool fused_ok = !S.tape_n && exact && h->N <= 65535 && fused_smem_bytes_host(h->Np, false) <= 227 * 1024 - 512;
     if (h->path == CABM_PATH_FUSED && !fused_ok) return fail(h, CABM_E_STATE, "fused path needs the exact schedule and a population that fits shared memory");
+    if (h->path == CABM_PATH_FUSED_GLOBAL && !exact) return fail(h, CABM_E_STATE, "fused path needs the exact schedule");
+    const bool use_smem = h->path == CABM_PATH_FUSED || (h->path == CABM_PATH_AUTO && fused_ok);
+    const bool use_global = h->path == CABM_PATH_FUSED_GLOBAL || (h->path == CABM_PATH_AUTO && exact && !fused_ok && !S.tape_n);
+    const bool use_fused = use_smem || use_global;
     CU(cudaEventRecord(h->ev0, h->stream));
     if ((rc = reset_state(h, /*curves_too=*/!use_fused))) return rc;      // the fused kernel writes every curve entry itself
-    h->last_path = use_fused ? CABM_PATH_FUSED : CABM_PATH_MULTIKERNEL;
+    h->last_path = use_smem ? CABM_PATH_FUSED : use_global ? CABM_PATH_FUSED_GLOBAL : CABM_PATH_MULTIKERNEL;
     if (use_fused) {
-        timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->any_ct != 0, h->stream); });            // :104-142 in one launch
+        timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->any_ct != 0, use_global, h->stream); });  // :104-142 in one launch
     } else {
         auto enqueue = [&] {
             timed(h, CABM_K_OTHER, [&] { return launch_initialize(S, h->stream); });                                   // :112
@@ -446,7 +459,7 @@ extern "C" int cabm_run(cabm_handle *h) {
 }
 
 extern "C" int cabm_set_path(cabm_handle *h, int path) {
-    if (!h || path < CABM_PATH_AUTO || path > CABM_PATH_FUSED) return CABM_E_ARG;
+    if (!h || path < CABM_PATH_AUTO || path > CABM_PATH_FUSED_GLOBAL) return CABM_E_ARG;
     h->path = path; return CABM_OK;
 }
 extern "C" int cabm_get_last_path(const cabm_handle *h) { return h ? h->last_path : -1; }
@@ -465,6 +478,43 @@ extern "C" int cabm_sync(cabm_handle *h) {
     return model_check(h);
 }
 extern "C" int cabm_set_strict(cabm_handle *h, int on) { if (!h) return CABM_E_ARG; h->strict = on ? 1 : 0; h->err_checked = false; return CABM_OK; }
+
+// Replay tape: draws whose (seed, counter) key is listed take the listed words instead of the Philox output.
+extern "C" int cabm_set_tape(cabm_handle *h, const cabm_tape_entry *entries, uint64_t n) {
+    if (!h) return CABM_E_ARG;
+    if (n && !entries) return fail(h, CABM_E_ARG, "cabm_set_tape: bad argument");
+    if (n > 0xFFFFFFF0ull) return fail(h, CABM_E_ARG, "cabm_set_tape: too many entries");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->d_tape_keys) { cudaFree(h->d_tape_keys); h->d_tape_keys = nullptr; }
+    if (h->d_tape_w) { cudaFree(h->d_tape_w); h->d_tape_w = nullptr; }
+    h->S.tape_keys = nullptr; h->S.tape_w = nullptr; h->S.tape_n = 0;
+    if (n == 0) return CABM_OK;
+    std::vector<uint64_t> order(n);
+    for (uint64_t i = 0; i < n; ++i) order[i] = i;
+    auto less = [&](uint64_t a, uint64_t b) {
+        const cabm_tape_entry &x = entries[a], &y = entries[b];
+        if (x.seed != y.seed) return x.seed < y.seed;
+        for (int k = 0; k < 4; ++k) if (x.ctr[k] != y.ctr[k]) return x.ctr[k] < y.ctr[k];
+        return false;
+    };
+    std::sort(order.begin(), order.end(), less);
+    std::vector<uint32_t> keys(n * 6); std::vector<uint4> words(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const cabm_tape_entry &e = entries[order[i]];
+        if (i && !less(order[i - 1], order[i])) return fail(h, CABM_E_ARG, "cabm_set_tape: duplicate key");
+        keys[i * 6 + 0] = (uint32_t)e.seed; keys[i * 6 + 1] = (uint32_t)(e.seed >> 32);
+        for (int k = 0; k < 4; ++k) keys[i * 6 + 2 + k] = e.ctr[k];
+        words[i] = make_uint4(e.w[0], e.w[1], e.w[2], e.w[3]);
+    }
+    CU(cudaMalloc((void **)&h->d_tape_keys, keys.size() * 4));
+    CU(cudaMalloc((void **)&h->d_tape_w, words.size() * sizeof(uint4)));
+    CU(cudaMemcpy(h->d_tape_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_tape_w, words.data(), words.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    h->S.tape_keys = h->d_tape_keys; h->S.tape_w = h->d_tape_w; h->S.tape_n = (unsigned)n;
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; h->graph_key = 0; }
+    return CABM_OK;
+}
 
 extern "C" int cabm_mark(cabm_handle *h) {
     if (!h) return CABM_E_ARG;
@@ -624,7 +674,7 @@ extern "C" int cabm_set_host_curve_rows(cabm_handle *h, int32_t *rows) {
 extern "C" int cabm_get_curves_i16(cabm_handle *h, int16_t *inc, int16_t *prev) {
     int rc = need_config(h); if (rc) return rc;
     if (!h->ran) return fail(h, CABM_E_STATE, "curves exist after cabm_run");
-    if (inc && inc == h->host_inc && prev == h->host_prev && h->last_path == CABM_PATH_FUSED) {   // streamed there by the kernel already
+    if (inc && inc == h->host_inc && prev == h->host_prev && (h->last_path == CABM_PATH_FUSED || h->last_path == CABM_PATH_FUSED_GLOBAL)) {   // streamed there by the kernel already
         CU(cudaStreamSynchronize(h->stream));
         return model_check(h);
     }
@@ -650,6 +700,8 @@ extern "C" int cabm_get_mean_curves(cabm_handle *h, double *inc_mean, double *pr
     const size_t per_rep = (size_t)6 * h->T * 12;
     if (h->mean_elems < 2 * per_rep) {                       // scratch kept with the handle
         if (h->d_mean) cudaFree(h->d_mean);
+    if (h->d_tape_keys) cudaFree(h->d_tape_keys);
+    if (h->d_tape_w) cudaFree(h->d_tape_w);
         h->d_mean = nullptr; h->mean_elems = 0;
         CU(cudaMalloc((void **)&h->d_mean, per_rep * 2 * sizeof(double)));
         h->mean_elems = 2 * per_rep;

@@ -78,6 +78,8 @@ struct Dev {
     uint32_t *grp_idx; int *grp_off;         // [R][Np], [R][8]
     uint16_t *grp16;                         // [R][Np] the same index tables as 16-bit words: the fused kernel's copy (popsize <= 65535)
     uint32_t *infmask;                       // [R][nwords]
+    uint32_t *touch_g, *dupm_g;              // [R][nwords] target marks of the fused kernel when its state lives in global memory
+    uint8_t *col_g;                          // [R][Np] its current hmatrix column
     uint32_t *hits;                          // 2 x [R][Np/2] of 2 x u16: native mode, contacts received from lower-indexed infectors
     uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;
     int *inc, *prev;                         // [R][6][T][12]
@@ -91,6 +93,7 @@ struct Dev {
                                              // replicate's curves there (Int16) so no device->host copy is left at the end
     const DevPset *psets; const unsigned long long *beta_thr;    // [P], [P][T][4]
     const uint32_t *nb_thr; const uint8_t *nb_guide;             // [5][256], [5][512] (top byte of w; next byte inside the top bucket)
+    const uint32_t *tape_keys; const uint4 *tape_w; unsigned tape_n;   // replay tape (cabm_set_tape): sorted keys (seed lo, seed hi, counter x4), words
     const unsigned long long *gpw;                               // [5][256] five u8 counts packed
 };
 
@@ -108,6 +111,27 @@ __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, u
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+// Replay tape (cabm_set_tape): a draw whose (seed, counter) is on the tape takes the tape's words instead of the Philox
+// output. Only the per-day kernels consult it (TP = true; the fused kernel never runs with a tape), through one uniform test.
+__device__ __noinline__ bool tape_lookup(const uint32_t *keys, const uint4 *words, unsigned n, uint2 key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint4 *out) {
+    const uint32_t want[6] = {key.x, key.y, c0, c1, c2, c3};
+    unsigned lo = 0, hi = n;
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        const uint32_t *k = keys + (size_t)mid * 6;
+        int cmp = 0;
+        // order: seed (hi word first, as a 64-bit number), then the counter words
+        const uint32_t a[6] = {k[1], k[0], k[2], k[3], k[4], k[5]}, b[6] = {want[1], want[0], want[2], want[3], want[4], want[5]};
+        for (int j = 0; j < 6 && cmp == 0; ++j) cmp = a[j] < b[j] ? -1 : a[j] > b[j] ? 1 : 0;
+        if (cmp == 0) { *out = words[mid]; return true; }
+        if (cmp < 0) lo = mid + 1; else hi = mid;
+    }
+    return false;
+}
+template <bool TP> __device__ __forceinline__ uint4 draw4(const Dev &S, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint2 key) {
+    if (TP && S.tape_n) { uint4 o; if (tape_lookup(S.tape_keys, S.tape_w, S.tape_n, key, c0, c1, c2, c3, &o)) return o; }
+    return philox(c0, c1, c2, c3, key);
 }
 __device__ __forceinline__ uint32_t pick(uint4 w, uint32_t k) { return k == 0 ? w.x : k == 1 ? w.y : k == 2 ? w.z : w.w; }
 __device__ __forceinline__ int below(uint32_t w, int n) { return (int)__umulhi(w, (uint32_t)n); }
@@ -128,9 +152,9 @@ __device__ __forceinline__ int table_draw_bs(uint32_t w, int base, const uint32_
 }
 
 // get_nextday_counts :772-788, evaluated on demand for day `day` from the agent's status word
-__device__ __forceinline__ int fresh_budget(const Dev &S, uint2 key, uint32_t i, uint32_t day, uint32_t st) {
+template <bool TP = false> __device__ __forceinline__ int fresh_budget(const Dev &S, uint2 key, uint32_t i, uint32_t day, uint32_t st) {
     if (st_health(st) == DED) return 0;                                    // :783-785
-    uint32_t w = pick(philox(i >> 2, day, S_COUNT, 0, key), i & 3u);
+    uint32_t w = pick(draw4<TP>(S, i >> 2, day, S_COUNT, 0, key), i & 3u);
     if (st & ST_ISOB)                                                      // :778-779
         return (w < 0x80000000u) ? 0 : 1 + (int)(((unsigned long long)(w & 0x7fffffffu) * 3ull) >> 31);
     int ag = st_ag(st);                                                    // :781
@@ -139,8 +163,8 @@ __device__ __forceinline__ int fresh_budget(const Dev &S, uint2 key, uint32_t i,
     while (k < len && __ldg(&thr[k]) <= w) ++k;
     return k;
 }
-__device__ __forceinline__ int budget_of(const Dev &S, uint2 key, uint32_t i, int day, uint32_t st) {
-    return st_tag(st) == day ? st_rem(st) : fresh_budget(S, key, i, (uint32_t)day, st);
+template <bool TP = false> __device__ __forceinline__ int budget_of(const Dev &S, uint2 key, uint32_t i, int day, uint32_t st) {
+    return st_tag(st) == day ? st_rem(st) : fresh_budget<TP>(S, key, i, (uint32_t)day, st);
 }
 
 __device__ __forceinline__ void curve_move(const Dev &S, int r, int ag0, int col, int oldh, int newh) {
@@ -160,7 +184,7 @@ struct Tr { uint32_t st; int expday; int oldh, newh; };
 
 constexpr int DUR_CACHE = 256;          // direct-mapped shared-memory cache of `dur` words for infected agents (fused kernel)
 
-__device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
+template <bool TP = false> __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
                                      int target /* swap to apply */, bool seed_simple_inf, unsigned long long *dcache = nullptr) {
     size_t a = (size_t)r * S.Np + i;
     const int oldh = st_health(st), ag = st_ag(st);
@@ -177,14 +201,14 @@ __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int 
     int newh = target, newsw = UNDEF, exp = 999;
     switch (target) {
     case LAT: {                          // move_to_latent :446-461
-        uint4 w = philox(i, day, S_TRANS, 0, key);
+        uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key);
         exp = d_lat; newsw = bern(w.x, P.asymp_thr[ag]) ? ASYMP : PRE;
         if (P.calibration) { newsw = LAT; exp = 999; }
         S.latday[a] = (int16_t)day;
         break; }
     case ASYMP: exp = d_asy; newsw = REC; break;                       // :464-472
     case PRE: {                          // move_to_pre :475-488
-        uint4 w = philox(i, day, S_TRANS, 0, key);
+        uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key);
         exp = d_pre; newsw = bern(w.x, P.mild_thr[ag]) ? MILD : INF;
         bool active = (day == 0) || (P.tpreiso >= 1 && day >= P.tpreiso);   // main :124-125,:133-135
         if (active && bern(w.y, P.fpreiso_thr)) { iso = true; via = VIA_PI; }
@@ -192,7 +216,7 @@ __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int 
     case MILD: {                         // move_to_mild :491-507
         exp = d_inf; newsw = REC;
         bool go = iso;
-        if (!go) { uint4 w = philox(i, day, S_TRANS, 0, key); go = bern(w.x, P.fmild_thr); }
+        if (!go) { uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key); go = bern(w.x, P.fmild_thr); }
         if (go) { newsw = MISO; exp = P.tau_mild; }
         break; }
     case MISO: exp = d_inf - P.tau_mild; newsw = REC; iso = true; via = VIA_MI; break;   // :510-517
@@ -201,7 +225,7 @@ __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int 
             exp = d_inf; newsw = REC; iso = false; break;    // _set_isolation(x, false, :null) leaves isovia as is
         }
         // move_to_inf :530-569
-        uint4 wa = philox(i, day, S_TRANS, 0, key), wb = philox(i, day, S_TRANS, 1, key);
+        uint4 wa = draw4<TP>(S, i, day, S_TRANS, 0, key), wb = draw4<TP>(S, i, day, S_TRANS, 1, key);
         double h = __dadd_rn(c_tab.hlo[ag], __dmul_rn(c_tab.hspan[ag], u01(wa.x)));
         double c = __dadd_rn(c_tab.clo[ag], __dmul_rn(c_tab.cspan[ag], u01(wa.y)));
         unsigned long long mthr = c_tab.mh_inf_thr[ag];
@@ -216,7 +240,7 @@ __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int 
         break; }
     case IISO: exp = d_inf - 1; newsw = REC; iso = true; via = VIA_MI; break;            // :571-578
     case HOS: case ICU: {                // move_to_hospicu :580-622
-        uint4 w = philox(i, day, S_TRANS, 0, key);
+        uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key);
         int psi = table_draw(w.x, c_tab.psi_base, c_tab.psi_thr, c_tab.psi_len);
         int mu = table_draw(w.y, c_tab.mu_base, c_tab.mu_thr, c_tab.mu_len);
         iso = true;                                                                        // :599
@@ -238,16 +262,16 @@ __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int 
 
 // HBM-resident variants used by the per-day kernels: flip the infectious bitmask, count the curves (transition_hbm) and
 // store the expiry day both as texp and as the scan key (transition).
-__device__ inline Tr transition_hbm(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
+template <bool TP = false> __device__ inline Tr transition_hbm(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
                                     int target, bool seed_simple_inf, bool count_curves) {
-    const Tr t = transition_core(S, P, r, i, day, st, key, target, seed_simple_inf);
+    const Tr t = transition_core<TP>(S, P, r, i, day, st, key, target, seed_simple_inf);
     if (is_infectious(t.newh) != is_infectious(t.oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
     if (count_curves) curve_move(S, r, st_ag(st), day, t.oldh, t.newh);
     return t;
 }
-__device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
+template <bool TP = false> __device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
                                       int target, bool seed_simple_inf, bool count_curves) {
-    const Tr t = transition_hbm(S, P, r, i, day, st, key, target, seed_simple_inf, count_curves);
+    const Tr t = transition_hbm<TP>(S, P, r, i, day, st, key, target, seed_simple_inf, count_curves);
     S.texp[(size_t)r * S.Np + i] = (int16_t)t.expday;
     S.expday[(size_t)r * S.Np + i] = (int16_t)t.expday;
     return t.st;
@@ -258,7 +282,7 @@ __device__ inline uint32_t transition(const Dev &S, const DevPset &P, int r, int
 // stores status / texp / next event day and does the infectious-set and curve accounting from (oldh, newh).
 struct Ev { uint32_t st; int texp, ne, oldh, newh; };
 
-__device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int i, int day, uint2 key, uint32_t st, int texp,
+template <bool TP = false> __device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int i, int day, uint2 key, uint32_t st, int texp,
                                       bool ct /* the replicate traces contacts */, bool pre, bool post,
                                       uint32_t *queue_cnt /* tomorrow's index cases */, uint32_t *queue, unsigned long long *dcache = nullptr) {
     const size_t a = (size_t)r * S.Np + i;
@@ -273,7 +297,7 @@ __device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int
         }
     }
     if (texp <= day || (st_health(st) == SUS && st_swap(st) == LAT)) {      // :405 (an infection today set exp = tis :826)
-        const Tr t = transition_core(S, P, r, i, day, st, key, st_swap(st), false, dcache);
+        const Tr t = transition_core<TP>(S, P, r, i, day, st, key, st_swap(st), false, dcache);
         st = t.st; texp = t.expday; oldh = t.oldh; newh = t.newh;
     }
     int ne = texp;
@@ -281,7 +305,7 @@ __device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int
         const int latday = S.latday[a], doi = day - latday;
         int ts = S.tracestart[a], te = S.traceend[a];
         if (st_health(st) == LAT && st_swap(st) != ASYMP && doi == 0) {      // :678
-            const uint4 w = philox(i, day, S_CTWIN, 0, key);
+            const uint4 w = draw4<TP>(S, i, day, S_CTWIN, 0, key);
             if (bern(w.x, P.fctcap_thr)) {
                 const uint32_t d4 = S.dur[a];
                 const int tid = 1 + below(w.y, (int)(d4 >> 24));              // :680
@@ -309,7 +333,7 @@ __device__ inline Ev agent_event_core(const Dev &S, const DevPset &P, int r, int
                 S.isovia[a] = VIA_NULL;
                 txp = 0;
                 if (P.ctstrat == 3) {
-                    const uint4 w = philox(i, day, S_CT3, 0, key);
+                    const uint4 w = draw4<TP>(S, i, day, S_CT3, 0, key);
                     const int h = st_health(st);
                     if ((h == LAT && bern(w.x, c_tab.ct3_lat_thr)) || (h == PRE && bern(w.x, c_tab.ct3_pre_thr)) ||
                         (h == ASYMP && bern(w.x, c_tab.ct3_asymp_thr)) || h == MILD || h == INF || h == MISO || h == IISO) {

@@ -39,18 +39,20 @@
 #pragma once
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 namespace cabm {
 
 constexpr int FUSED_NT = 256;          // threads per CTA
 constexpr int FUSED_LCAP = 256;        // infectors listed per pass = infectors per chunk at most
 constexpr int FUSED_EVCAP = 2048;      // contact events per chunk
-constexpr int FUSED_NEDGE = 512;       // events of a chunk that hit a later infector of the same chunk (more: the chunk is halved)
+constexpr int FUSED_NEDGE = 256;       // events of a chunk that hit a later infector of the same chunk (more: the chunk is halved)
 constexpr unsigned FUSED_TAIL_CTAS = 8;  // CTAs that copy finished curves to the host at any one time (PCIe saturates with ~8)
 constexpr int FUSED_SCAN_U = 5;        // chunks of 8 agents a thread scans at once in time_update (256 x 8 x 5 >= 10,000 agents in one go)
 static_assert(FUSED_NT == 256 && FUSED_LCAP <= FUSED_NT && FUSED_EVCAP % 32 == 0 && FUSED_EVCAP <= 2048, "thread-index roles and record fields in k_sim_fused");
-// event record: target [0:16) | transmits [16] | owner (chunk entry) [17:25) | dropped by a reduced budget [25]
-constexpr uint32_t EV_SUCC = 1u << 16, EV_DROPPED = 1u << 25, EV_NONE = 0xFFFFFFFFu;
+// event record: evy = target (EV_NONE: none); evm = transmits [0] | dropped by a reduced budget [1] | owner (chunk entry) [2:10)
+constexpr uint32_t EV_NONE = 0xFFFFFFFFu;
+constexpr uint16_t EVM_SUCC = 1, EVM_DROPPED = 2;
 
 // Small per-CTA state. It lives at the start of the dynamic shared-memory block (not in static __shared__ arrays) so that every
 // access is "block base + constant offset" from one uniform register.
@@ -66,46 +68,53 @@ struct FusedCtl {
     int nf[2], wsum[FUSED_NT / 32], wsum2[FUSED_NT / 32];
     int nb_len[5], kind;
     int infectors[4];
-    int nb, mlist, needtot, nedge;           // chunk: entries with events, list entries consumed, contact-log words reserved, DAG edges
+    int wfit[FUSED_NT / 32], wkept[FUSED_NT / 32], wneed[FUSED_NT / 32];   // per warp: entries that fit the chunk; entries with events and contact-log words up to its last fitting entry
+    int nedge;                               // DAG edges of the chunk
     int wdup[FUSED_NT / 32];
     uint32_t logn, qcnt[2];                  // contact tracing (:647-752): the replicate's log fill, index-case queues by day parity
-    int pad_[3];
+    int pad_[4];
 };
 static_assert(sizeof(FusedCtl) % 16 == 0, "the arrays behind FusedCtl need 16-byte alignment");
 
-struct FusedSmem {
+// IdxT: agent index type of the lists (u16 with the state in shared memory, u32 with the state in global memory)
+template <class IdxT> struct FusedSmemT {
     uint32_t *status; int16_t *expday; uint8_t *col; uint32_t *inf;
     uint32_t *nb_thr; uint8_t *nb_guide; const int *nb_len;
     uint32_t *touch, *dupm, *mpre, *mpost;
-    uint32_t *ev;                        // [EVCAP] event records of the chunk, in event order
+    uint32_t *evy; uint16_t *evm;        // [EVCAP] events of the chunk, in event order: target (EV_NONE: no event); transmits | dropped << 1 | owner << 2
     uint16_t *D;                         // [EVCAP] events on shared targets, in event order
     uint32_t *edges;                     // [NEDGE] event [0:11) | entry of the target [11:19) | g [19:22) | k [22:30)
-    uint16_t *list;                      // [LCAP] the day's infectious agents from the cursor on, ascending
-    uint16_t *cx;                        // chunk entries (infectors with events): agent,
+    IdxT *list;                          // [LCAP] the day's infectious agents from the cursor on, ascending
+    IdxT *cx;                            // chunk entries (infectors with events): agent,
     uint8_t *ch, *cb, *cc, *cflag;       //   health | ag << 4 | tracing << 7; budget at chunk start; budget after hits; 1 = log contacts
     int *pref, *hits;                    //   event prefix [LCAP + 1]; hits by earlier entries of the chunk
     unsigned long long *gp0;             //   budget split over the five age groups (:804) at the chunk-start budget, five packed bytes
+    uint32_t *gcum;                      //   the same split as cumulative counts of groups 1..4 (one byte each)
     uint32_t *cbase; int *clen;          //   contact-log chunk of a traced entry, contacts logged so far
     unsigned long long *dcache;          // (agent << 32 | dur) of recently infected agents
-    int *cnt;                            // NT ints scratch (seeding, first column); aliases ev
+    int *cnt;                            // NT ints scratch (seeding, first column); aliases evy
 };
 
-__host__ __device__ inline size_t fused_smem_bytes(int Np) {
+// global_state: the per-agent arrays (status, expday, column, bitmasks) stay in global memory (any popsize); only the chunk
+// buffers and tables are in shared memory
+__host__ __device__ inline size_t fused_smem_bytes(int Np, bool global_state = false) {
     size_t b = sizeof(FusedCtl);
-    b += (size_t)Np * 4;                 // status
-    b += (size_t)Np * 2;                 // expday
-    b += (size_t)Np;                     // col
-    b += (size_t)(Np / 32) * 4;          // inf
+    if (!global_state) {
+        b += (size_t)Np * 4;                 // status
+        b += (size_t)Np * 2;                 // expday
+        b += (size_t)Np;                     // col
+        b += (size_t)(Np / 32) * 4;          // inf
+        b += (size_t)(Np / 32) * 4 * 4;      // touch, dupm, mark_pre, mark_post bitmasks
+    }
     b += 5 * 256 * 4 + 5 * 512;          // nb tables
-    b += (size_t)(Np / 32) * 4 * 4;      // touch, dupm, mark_pre, mark_post bitmasks
-    b += FUSED_EVCAP * 4 + FUSED_EVCAP * 2 + FUSED_NEDGE * 4;        // ev, D, edges
-    b += FUSED_LCAP * (2 + 2 + 4 * 1 + 4 + 8 + 4 + 4) + (FUSED_LCAP + 1) * 4 + 12;   // list, cx, ch/cb/cc/cflag, hits, gp0, cbase, clen, pref
+    b += FUSED_EVCAP * 4 + FUSED_EVCAP * 2 * 2 + FUSED_NEDGE * 4;    // evy, evm, D, edges
+    b += FUSED_LCAP * ((global_state ? 4 : 2) * 2 + 4 * 1 + 4 + 8 + 4 + 4 + 4) + (FUSED_LCAP + 1) * 4 + 12;   // list, cx, ch/cb/cc/cflag, hits, gp0, cbase, clen, gcum, pref
     b += DUR_CACHE * 8;                  // dcache
     return (b + 15) / 16 * 16 + 64;
 }
 
 // get_nextday_counts :772-788 with the NB tables in shared memory
-__device__ __forceinline__ int fresh_budget_s(const FusedSmem &M, uint2 key, uint32_t i, uint32_t day, uint32_t st) {
+template <class MT> __device__ __forceinline__ int fresh_budget_s(const MT &M, uint2 key, uint32_t i, uint32_t day, uint32_t st) {
     if (st_health(st) == DED) return 0;
     uint32_t w = pick(philox(i >> 2, day, S_COUNT, 0, key), i & 3u);
     if (st & ST_ISOB) return (w < 0x80000000u) ? 0 : 1 + (int)(((unsigned long long)(w & 0x7fffffffu) * 3ull) >> 31);
@@ -116,7 +125,7 @@ __device__ __forceinline__ int fresh_budget_s(const FusedSmem &M, uint2 key, uin
     while (k < len && thr[k] <= w) ++k;
     return k;
 }
-__device__ __forceinline__ int budget_of_s(const FusedSmem &M, uint2 key, uint32_t i, int day, uint32_t st) {
+template <class MT> __device__ __forceinline__ int budget_of_s(const MT &M, uint2 key, uint32_t i, int day, uint32_t st) {
     return st_tag(st) == day ? st_rem(st) : fresh_budget_s(M, key, i, (uint32_t)day, st);
 }
 
@@ -142,35 +151,44 @@ __device__ __forceinline__ void bulk_store_wait_read_n() { asm volatile("cp.asyn
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <bool CT>      // CT = false: no replicate of the ensemble traces contacts (the tracing code is compiled out)
+// CT = false: no replicate of the ensemble traces contacts (the tracing code is compiled out).
+// GS = true: the per-agent state stays in global memory (L2) instead of shared memory — any popsize; no TMA column stores, no parking.
+template <bool CT, bool GS>
 __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work /* queue heads and tails, see below */, int split_day, unsigned tail_cta_limit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = FUSED_NT, NW = FUSED_NT / 32;
     const int N = S.N, Np = S.Np, T = S.T, nwords = S.nwords;
     FusedCtl &Z = *reinterpret_cast<FusedCtl *>(smem_raw);
-    FusedSmem M;
+    using IdxT = typename std::conditional<GS, uint32_t, uint16_t>::type;
+    FusedSmemT<IdxT> M;
     {
         unsigned char *p = smem_raw + sizeof(FusedCtl);
         M.dcache = (unsigned long long *)p; p += DUR_CACHE * 8;
         M.gp0 = (unsigned long long *)p; p += FUSED_LCAP * 8;
-        M.status = (uint32_t *)p; p += (size_t)Np * 4;
-        M.expday = (int16_t *)p; p += (size_t)Np * 2;          // Np is a multiple of 32: every array below stays 16-byte aligned
-        M.col = (uint8_t *)p; p += (size_t)Np;
-        M.inf = (uint32_t *)p; p += (size_t)nwords * 4;
+        if (!GS) {
+            M.status = (uint32_t *)p; p += (size_t)Np * 4;
+            M.expday = (int16_t *)p; p += (size_t)Np * 2;      // Np is a multiple of 32: every array below stays 16-byte aligned
+            M.col = (uint8_t *)p; p += (size_t)Np;
+            M.inf = (uint32_t *)p; p += (size_t)nwords * 4;
+            M.touch = (uint32_t *)p; p += (size_t)nwords * 4;
+            M.dupm = (uint32_t *)p; p += (size_t)nwords * 4;
+            M.mpre = (uint32_t *)p; p += (size_t)nwords * 4;
+            M.mpost = (uint32_t *)p; p += (size_t)nwords * 4;
+        } else {                                               // set per replicate (global memory)
+            M.status = nullptr; M.expday = nullptr; M.col = nullptr; M.inf = nullptr; M.touch = M.dupm = M.mpre = M.mpost = nullptr;
+        }
         M.nb_thr = (uint32_t *)p; p += 5 * 256 * 4;
-        M.ev = (uint32_t *)p; M.cnt = (int *)p; p += FUSED_EVCAP * 4;
+        M.evy = (uint32_t *)p; M.cnt = (int *)p; p += FUSED_EVCAP * 4;
         M.edges = (uint32_t *)p; p += FUSED_NEDGE * 4;
-        M.touch = (uint32_t *)p; p += (size_t)nwords * 4;
-        M.dupm = (uint32_t *)p; p += (size_t)nwords * 4;
-        M.mpre = (uint32_t *)p; p += (size_t)nwords * 4;
-        M.mpost = (uint32_t *)p; p += (size_t)nwords * 4;
         M.pref = (int *)p; p += (FUSED_LCAP + 1) * 4;
         M.hits = (int *)p; p += FUSED_LCAP * 4;
         M.cbase = (uint32_t *)p; p += FUSED_LCAP * 4;
         M.clen = (int *)p; p += FUSED_LCAP * 4;
+        M.gcum = (uint32_t *)p; p += FUSED_LCAP * 4;
+        M.list = (IdxT *)p; p += FUSED_LCAP * sizeof(IdxT);
+        M.cx = (IdxT *)p; p += FUSED_LCAP * sizeof(IdxT);
         M.D = (uint16_t *)p; p += FUSED_EVCAP * 2;
-        M.list = (uint16_t *)p; p += FUSED_LCAP * 2;
-        M.cx = (uint16_t *)p; p += FUSED_LCAP * 2;
+        M.evm = (uint16_t *)p; p += FUSED_EVCAP * 2;
         M.nb_guide = (uint8_t *)p; p += 5 * 512;
         M.nb_len = Z.nb_len;
         M.ch = (uint8_t *)p; p += FUSED_LCAP;
@@ -182,14 +200,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     for (int k = tid; k < 5 * 256; k += NT) M.nb_thr[k] = S.nb_thr[k];
     for (int k = tid; k < 5 * 512; k += NT) M.nb_guide[k] = S.nb_guide[k];
     if (tid < 5) Z.nb_len[tid] = c_tab.nb_len[tid];
-    for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; M.mpre[k] = 0; M.mpost[k] = 0; }
-    if (tid == 0) { Z.nb = 0; Z.mlist = 0; Z.needtot = 0; Z.nedge = 0; }
+    if (!GS) for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; M.mpre[k] = 0; M.mpost[k] = 0; }
+    if (tid == 0) Z.nedge = 0;
     if (tid < 4) { Z.tlat[tid] = c_tab.lat_thr[tid]; Z.tpre[tid] = c_tab.pre_thr[tid]; }
     if (tid < 40) { Z.tasy[tid] = c_tab.asy_thr[tid]; Z.tinf[tid] = c_tab.inf_thr[tid]; }
     if (tid < 25) Z.cm[tid] = c_tab.cm[tid / 5][tid % 5];
     int *const s_inc = Z.io[0][0], *const s_out = Z.io[0][1];   // first-column phase uses parity 0
     __syncthreads();
-    const bool tma_ok = S.store_hm && (N % 16 == 0);     // cp.async.bulk needs 16-byte size and alignment
+    const bool tma_ok = !GS && S.store_hm && (N % 16 == 0);     // cp.async.bulk needs a shared-memory source and 16-byte size and alignment
 
     // Two sweeps over an atomic work queue. Sweep 0 starts every replicate; with split_day > 0 a replicate that is still active
     // after split_day days is parked (state to HBM) and queued, so that the long epidemics — which bound the launch — all resume
@@ -300,11 +318,16 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 __threadfence();
             }
             Z.r = got; Z.kind = kind;
-            if (S.store_hm) bulk_store_wait_read();                              // column copies of the previous job have left shared memory
+            if (tma_ok) bulk_store_wait_read();                                  // column copies of the previous job have left shared memory
         }
         __syncthreads();
         const int r = Z.r;
         if (r < 0) break;
+        if (GS) {           // this replicate's per-agent arrays (the host zeroed the bitmasks before the launch)
+            const size_t rb_ = (size_t)r * Np, rw_ = (size_t)r * nwords;
+            M.status = S.status + rb_; M.expday = S.expday + rb_; M.col = S.col_g + rb_; M.inf = S.infmask + rw_;
+            M.touch = S.touch_g + rw_; M.dupm = S.dupm_g + rw_; M.mpre = S.mark_pre + rw_; M.mpost = S.mark_post + rw_;
+        }
         if (Z.kind == 2) {
             // -------------------------------------------------------- copy job: a finished replicate's curves -> pinned host memory
             stream_curves_to_host(r, __ldcg(&S.resume_aux[r * 2]));
@@ -358,7 +381,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid == 0) { Z.logn = 0; Z.qcnt[0] = 0; Z.qcnt[1] = 0; }
         const uint2 key = S.key[r];
         const size_t rb = (size_t)r * Np;
-        uint16_t *const grp = S.grp16 + rb;             // get_ag_dist :339-343 index tables of this replicate (global memory, read through L2/L1)
+        IdxT *grp;                                      // get_ag_dist :339-343 index tables of this replicate (global memory, read through L2/L1)
+        if constexpr (GS) grp = S.grp_idx + rb; else grp = S.grp16 + rb;
         const unsigned long long *beta = S.beta_thr + (size_t)S.pset_of[r] * T * 4;
         uint8_t *hm = S.store_hm ? S.hm + (size_t)r * T * N : nullptr;
 
@@ -433,7 +457,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #pragma unroll
                 for (int g = 0; g < 5; ++g) {
                     const unsigned m = __ballot_sync(FULL, ag == g);
-                    if (ag == g) grp[base[g] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                    if (ag == g) grp[base[g] + __popc(m & ((1u << lane) - 1u))] = (IdxT)i;
                     base[g] += __popc(m);
                 }
             }
@@ -592,8 +616,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             __syncthreads();
                             int pos = lbase + excl, tot = 0;
                             for (int w = 0; w < NW; ++w) { const int v = Z.wsum[w]; tot += v; if (w < wid) pos += v; }
-                            while (m0 && pos < FUSED_LCAP) { const int b = __ffs(m0) - 1; m0 &= m0 - 1; M.list[pos++] = (uint16_t)((wi << 5) + b); }
-                            while (m1 && pos < FUSED_LCAP) { const int b = __ffs(m1) - 1; m1 &= m1 - 1; M.list[pos++] = (uint16_t)(((wi + 1) << 5) + b); }
+                            while (m0 && pos < FUSED_LCAP) { const int b = __ffs(m0) - 1; m0 &= m0 - 1; M.list[pos++] = (IdxT)((wi << 5) + b); }
+                            while (m1 && pos < FUSED_LCAP) { const int b = __ffs(m1) - 1; m1 &= m1 - 1; M.list[pos++] = (IdxT)(((wi + 1) << 5) + b); }
                             lbase += tot;
                             __syncthreads();
                         }
@@ -632,34 +656,40 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const bool fits = have && inclE <= FUSED_EVCAP;                    // a prefix of the threads (the first entry always fits)
                             if (fits && E > 0) {
                                 const int q = nkept - 1;
-                                M.cx[q] = (uint16_t)x; M.ch[q] = (uint8_t)hx; M.cb[q] = (uint8_t)cnts; M.cc[q] = (uint8_t)cnts; M.gp0[q] = gp;
+                                M.cx[q] = (IdxT)x; M.ch[q] = (uint8_t)hx; M.cb[q] = (uint8_t)cnts; M.cc[q] = (uint8_t)cnts; M.gp0[q] = gp;
+                                {
+                                    const uint32_t c1 = (uint32_t)(gp & 0xFF), c2 = c1 + (uint32_t)((gp >> 8) & 0xFF), c3 = c2 + (uint32_t)((gp >> 16) & 0xFF), c4 = c3 + (uint32_t)((gp >> 24) & 0xFF);
+                                    M.gcum[q] = c1 | (c2 << 8) | (c3 << 16) | (c4 << 24);
+                                }
                                 M.pref[q + 1] = inclE;
                                 if (ctr) { M.cflag[q] = tr ? 1 : 0; M.cbase[q] = (uint32_t)(v2 - (tr ? 2 + E : 0)); M.clen[q] = 0; }
                             }
                             {
                                 const unsigned fm = __ballot_sync(FULL, fits);
-                                if (fm && lane == 31 - __clz(fm)) {                            // the warp's last fitting entry carries its totals
-                                    atomicMax(&Z.mlist, tid + 1); atomicMax(&Z.nb, nkept);
-                                    if (ctr) atomicMax(&Z.needtot, v2);
-                                }
+                                if (lane == 0) Z.wfit[wid] = __popc(fm);
+                                if (fm && lane == 31 - __clz(fm)) { Z.wkept[wid] = nkept; Z.wneed[wid] = v2; }   // the warp's last fitting entry carries its totals
                             }
                             if (tid == 0) M.pref[0] = 0;
                             __syncthreads();                                                   // C1
-                            const int nb = Z.nb, mlist = Z.mlist, Etot = nb ? M.pref[nb] : 0;
+                            int mlist = 0;
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) mlist += Z.wfit[w];                     // fitting entries are a prefix of the threads
+                            const int wl = (mlist - 1) >> 5;                                    // warp of the last fitting entry (mlist >= 1)
+                            const int nb = Z.wkept[wl], Etot = nb ? M.pref[nb] : 0;
                             const uint32_t base0 = Z.logn;
-                            const int needtot = ctr ? Z.needtot : 0;
+                            const int needtot = ctr ? Z.wneed[wl] : 0;
                             const bool room = ctr && base0 + (uint32_t)needtot <= S.ct_cap;
                             if (ctr && !room && needtot && tid == 0) atomicOr(&S.err[r], ERR_CT_LOG_FULL);
                             PHASE(8);
                             if (nb == 0) {                                                     // nobody in this stretch of the list has contacts today
-                                __syncthreads();
-                                if (tid == 0) { Z.nb = 0; Z.mlist = 0; Z.needtot = 0; }
+                                __syncthreads();                                               // (wfit/wkept are rewritten by the next chunk)
                                 lpos += mlist; lim = FUSED_LCAP;
                                 continue;
                             }
-                            // ---- (b) all events of the chunk, in event order: warp w draws windows [win0, win1) of 32 consecutive events.
-                            //      Owner of an event = the entry whose prefix range holds it: the (strictly increasing) prefix entries that
-                            //      fall into the window are bits of one word; q0 walks along with the windows.
+                            // ---- (b) all events of the chunk, in event order: warp w draws windows [win0, win1) of 32 consecutive events,
+                            //      two windows at a time so that their (independent) draw chains overlap. Owner of an event = the entry whose
+                            //      prefix range holds it: the (strictly increasing) prefix entries that fall into the window are bits of one
+                            //      word; q0 walks along with the windows.
                             const int nwin = (Etot + 31) >> 5, wpw = (nwin + NW - 1) / NW;
                             const int win0 = wid * wpw, win1 = min(nwin, win0 + wpw);
                             const int xlast = M.cx[nb - 1];
@@ -670,46 +700,107 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.pref[mid] <= tgt) lo = mid; else hi = mid - 1; }
                                 q0 = lo;
                             }
-                            for (int win = win0; win < win1; ++win) {
-                                const int base = win << 5, e = base + lane;
+                            auto owner_of = [&](int base) {                                    // entry of event base + lane; advances q0 to the window's last owner
                                 const int Pl = (q0 + 1 + lane <= nb) ? M.pref[q0 + 1 + lane] : 0x7FFFFFFF;      // >= base: q0 owns event base - 1
                                 const unsigned bits = __reduce_or_sync(FULL, (Pl <= base + 31) ? 1u << (Pl - base) : 0u);
                                 const int q = q0 + __popc(bits & ((2u << lane) - 1u));
                                 q0 = __shfl_sync(FULL, q, 31);
-                                uint32_t rec = EV_NONE;
-                                if (e < Etot) {
-                                    const int el = e - M.pref[q];
-                                    const unsigned long long gq = M.gp0[q];                     // round.(cm[ag]*cnts) :804
-                                    const int p1 = (int)(gq & 0xFF), p2 = p1 + (int)((gq >> 8) & 0xFF), p3 = p2 + (int)((gq >> 16) & 0xFF), p4 = p3 + (int)((gq >> 24) & 0xFF);
-                                    const int g = (el >= p1) + (el >= p2) + (el >= p3) + (el >= p4);
-                                    const int k = el - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
-                                    const int go = Z.off[g], len = Z.off[g + 1] - go;
-                                    const int xq = M.cx[q];
-                                    if (len == 0) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
-                                    else {
-                                        const uint4 w = philox(xq, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
-                                        const uint32_t y = grp[go + below(w.x, len)];                                   // :807
-                                        rec = y | (bern(w.y, Z.beta[beta_class(M.ch[q] & 0xF)]) ? EV_SUCC : 0u) | ((uint32_t)q << 17);   // :800, :823
-                                        // the target's budget for today (:811), drawn on first touch and kept in its status word (tag = today)
-                                        const uint32_t sy = M.status[y];
-                                        if (st_tag(sy) != day)
-                                            M.status[y] = (sy & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)fresh_budget_s(M, key, y, (uint32_t)day, sy) | ((uint32_t)day << 22);
-                                        // targets hit more than once (by any event of the chunk, dropped later or not) take the ordered path
-                                        const uint32_t ybit = 1u << (y & 31);
-                                        const uint32_t old = atomicOr(&M.touch[y >> 5], ybit);
-                                        if (old & ybit) atomicOr(&M.dupm[y >> 5], ybit);
-                                        // a later infector of this chunk that gets contacted starts its turn with a smaller budget (:802, :813): DAG edge
-                                        if (((M.inf[y >> 5] >> (y & 31)) & 1u) && (int)y > xq && (int)y <= xlast) {
-                                            int a = q + 1, b = nb - 1;
-                                            while (a < b) { const int mid = (a + b) >> 1; if ((int)M.cx[mid] < (int)y) a = mid + 1; else b = mid; }
-                                            if ((int)M.cx[a] == (int)y) {                        // (a listed infector without events has nothing to lose)
-                                                const int slot = atomicAdd(&Z.nedge, 1);
-                                                if (slot < FUSED_NEDGE) M.edges[slot] = (uint32_t)e | ((uint32_t)a << 11) | ((uint32_t)g << 19) | ((uint32_t)k << 22);
-                                            }
-                                        }
+                                return q;
+                            };
+                            // draw of one event (branch-free: lanes past the end repeat the last event and are masked by `ok`)
+                            auto draw = [&](int e, int q, int &idx, uint32_t &meta, bool &ok) {
+                                const int qc = min(q, nb - 1), ec = min(e, Etot - 1);
+                                const int el = ec - M.pref[qc];
+                                const uint32_t pc = M.gcum[qc];                                 // cumulative round.(cm[ag]*cnts) :804 over the groups, one byte each
+                                const int g = (el >= (int)(pc & 0xFF)) + (el >= (int)((pc >> 8) & 0xFF)) + (el >= (int)((pc >> 16) & 0xFF)) + (el >= (int)(pc >> 24));
+                                const int k = el - (int)((((unsigned long long)pc << 8) >> (8 * g)) & 0xFF);
+                                const int go = Z.off[g], len = Z.off[g + 1] - go;
+                                const uint32_t hq = M.ch[qc];
+                                const uint4 w = philox(M.cx[qc], day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                                idx = min(go + below(w.x, len), N - 1);                         // :807
+                                meta = (bern(w.y, Z.beta[beta_class(hq & 0xF)]) ? (uint32_t)EVM_SUCC : 0u) | ((uint32_t)qc << 2) | ((uint32_t)g << 26) | ((uint32_t)(len == 0) << 31);   // :800, :823
+                                ok = e < Etot && len > 0;
+                            };
+                            // marks and DAG edges of one drawn event; writes its record
+                            auto mark = [&](int e, uint32_t y, uint32_t meta, bool ok) {
+                                if (!ok) { if ((meta >> 31) && e < Etot) atomicOr(&S.err[r], ERR_EMPTY_GROUP); M.evy[e] = EV_NONE; M.evm[e] = 0; return; }
+                                // targets hit more than once (by any event of the chunk, dropped later or not) take the ordered path
+                                const uint32_t ybit = 1u << (y & 31);
+                                const uint32_t old = atomicOr(&M.touch[y >> 5], ybit);
+                                if (old & ybit) atomicOr(&M.dupm[y >> 5], ybit);
+                                const int q = (int)((meta >> 2) & 255u), xq = (int)M.cx[q];
+                                // a later infector of this chunk that gets contacted starts its turn with a smaller budget (:802, :813): DAG edge
+                                if (((M.inf[y >> 5] >> (y & 31)) & 1u) && (int)y > xq && (int)y <= xlast) {
+                                    int a = q + 1, b = nb - 1;
+                                    while (a < b) { const int mid = (a + b) >> 1; if ((int)M.cx[mid] < (int)y) a = mid + 1; else b = mid; }
+                                    if ((int)M.cx[a] == (int)y) {                                // (a listed infector without events has nothing to lose)
+                                        const int g = (int)((meta >> 26) & 7u), el = e - M.pref[q];
+                                        const int k = el - (int)((((unsigned long long)M.gcum[q] << 8) >> (8 * g)) & 0xFF);
+                                        const int slot = atomicAdd(&Z.nedge, 1);
+                                        if (slot < FUSED_NEDGE) M.edges[slot] = (uint32_t)e | ((uint32_t)a << 11) | ((uint32_t)g << 19) | ((uint32_t)k << 22);
                                     }
                                 }
-                                M.ev[e] = rec;
+                                M.evy[e] = y; M.evm[e] = (uint16_t)(meta & 0x3FFu & ~(uint32_t)EVM_DROPPED);
+                            };
+                            // NWIN windows of 32 events at once: every stage is a fully unrolled loop over the windows, so that the
+                            // independent chains (Philox, table walks, loads) of the windows interleave in one basic block
+                            auto windows = [&](int win, auto nwc) {
+                                constexpr int NWIN = decltype(nwc)::value;
+                                int q[NWIN], idx[NWIN]; uint32_t meta[NWIN], y[NWIN], sy[NWIN]; bool ok[NWIN], need[NWIN];
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) q[j] = owner_of((win + j) << 5);
+                                PHASE(2);
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) draw(((win + j) << 5) + lane, q[j], idx[j], meta[j], ok[j]);
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) y[j] = grp[idx[j]];                 // loads in flight together
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) sy[j] = M.status[y[j]];
+                                bool any_need = false;
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) { need[j] = ok[j] && st_tag(sy[j]) != day; any_need |= need[j]; }
+                                PHASE(7);
+                                // today's contact budget of targets that have none yet (:811 on first touch; get_nextday_counts :772-788), kept in
+                                // their status words (tag = today); every event of a target computes the same word
+                                if (__any_sync(FULL, any_need)) {
+                                    uint32_t w[NWIN]; int k[NWIN], len[NWIN]; const uint32_t *thr[NWIN];
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) w[j] = pick(philox(y[j] >> 2, (uint32_t)day, S_COUNT, 0, key), y[j] & 3u);
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) {
+                                        const int ag = st_ag(sy[j]);
+                                        len[j] = M.nb_len[ag]; thr[j] = M.nb_thr + ag * 256;
+                                        k[j] = M.nb_guide[ag * 512 + ((w[j] >> 24) == 255u ? 256u + ((w[j] >> 16) & 0xFFu) : (w[j] >> 24))];
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) k[j] += (k[j] < len[j] && thr[j][min(k[j], 255)] <= w[j]);
+                                    bool more = false;
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) more |= need[j] && !(sy[j] & ST_ISOB) && k[j] < len[j] && thr[j][min(k[j], 255)] <= w[j];
+                                    while (__any_sync(FULL, more)) {
+                                        more = false;
+#pragma unroll
+                                        for (int j = 0; j < NWIN; ++j) {
+                                            k[j] += (k[j] < len[j] && thr[j][min(k[j], 255)] <= w[j]);
+                                            more |= need[j] && !(sy[j] & ST_ISOB) && k[j] < len[j] && thr[j][min(k[j], 255)] <= w[j];
+                                        }
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) {
+                                        const int viso = (w[j] < 0x80000000u) ? 0 : 1 + (int)(((unsigned long long)(w[j] & 0x7fffffffu) * 3ull) >> 31);
+                                        const int v = st_health(sy[j]) == DED ? 0 : (sy[j] & ST_ISOB) ? viso : k[j];
+                                        if (need[j]) M.status[y[j]] = (sy[j] & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)v | ((uint32_t)day << 22);
+                                    }
+                                }
+                                PHASE(20);
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) mark(((win + j) << 5) + lane, y[j], meta[j], ok[j]);
+                                PHASE(21);
+                            };
+                            {
+                                int win = win0;
+                                for (; win + 2 <= win1; win += 2) windows(win, std::integral_constant<int, 2>());
+                                if (win < win1) windows(win, std::integral_constant<int, 1>());
                             }
                             PHASE(9);
                             __syncthreads();                                                   // C2
@@ -718,7 +809,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 // too many order dependences for the edge list (tiny populations with most agents infectious): take half the entries
                                 __syncthreads();
                                 for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }
-                                if (tid == 0) { Z.nb = 0; Z.mlist = 0; Z.needtot = 0; Z.nedge = 0; }
+                                if (tid == 0) Z.nedge = 0;
                                 lim = max(1, mlist >> 1);
                                 __syncthreads();
                                 continue;
@@ -732,11 +823,11 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #ifdef CABM_FUSED_DIAG
                                     if (tid == 0) t_ph[19] += 1;
 #endif
-                                    if (tid < nb) M.hits[tid] = 0;
+                                    for (int j = tid; j < ne; j += NT) M.hits[(M.edges[j] >> 11) & 255u] = 0;      // only entries with edges count
                                     __syncthreads();
                                     for (int j = tid; j < ne; j += NT) {
                                         const uint32_t ed = M.edges[j];
-                                        const int q = (int)((M.ev[ed & 2047u] >> 17) & 255u), g = (int)((ed >> 19) & 7u), k = (int)(ed >> 22);
+                                        const int q = (int)(M.evm[ed & 2047u] >> 2), g = (int)((ed >> 19) & 7u), k = (int)(ed >> 22);
                                         const int cq = M.cc[q];
                                         bool valid = cq == (int)M.cb[q];
                                         if (!valid) valid = k < (int)((gpw_pack(Z.cm + ((M.ch[q] >> 4) & 7) * 5, cq) >> (8 * g)) & 0xFF);
@@ -744,24 +835,25 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     }
                                     __syncthreads();
                                     bool chg = false;
-                                    if (tid < nb) {
-                                        const int nc = max(0, (int)M.cb[tid] - M.hits[tid]);      // admitted hits = min(budget, hits) :811-813
-                                        if (nc != (int)M.cc[tid]) { M.cc[tid] = (uint8_t)nc; chg = true; }
+                                    for (int j = tid; j < ne; j += NT) {                            // (several edges into one entry compute the same value)
+                                        const int t = (int)((M.edges[j] >> 11) & 255u);
+                                        const int nc = max(0, (int)M.cb[t] - M.hits[t]);           // admitted hits = min(budget, hits) :811-813
+                                        if (nc != (int)M.cc[t]) { M.cc[t] = (uint8_t)nc; chg = true; }
                                     }
                                     if (!__syncthreads_or(chg)) break;
                                 }
-                                // events a reduced budget no longer has: (g, k) with k >= round(cm[ag][g] * cnts')
-                                for (int e = tid; e < Etot; e += NT) {
-                                    const uint32_t rec = M.ev[e];
-                                    if (rec == EV_NONE) continue;
-                                    const int q = (int)((rec >> 17) & 255u), cq = M.cc[q];
-                                    if (cq == (int)M.cb[q]) continue;
-                                    const int el = e - M.pref[q];
-                                    const unsigned long long gq = M.gp0[q];
-                                    const int p1 = (int)(gq & 0xFF), p2 = p1 + (int)((gq >> 8) & 0xFF), p3 = p2 + (int)((gq >> 16) & 0xFF), p4 = p3 + (int)((gq >> 24) & 0xFF);
-                                    const int g = (el >= p1) + (el >= p2) + (el >= p3) + (el >= p4);
-                                    const int k = el - (g == 0 ? 0 : g == 1 ? p1 : g == 2 ? p2 : g == 3 ? p3 : p4);
-                                    if (k >= (int)((gpw_pack(Z.cm + ((M.ch[q] >> 4) & 7) * 5, cq) >> (8 * g)) & 0xFF)) M.ev[e] = rec | EV_DROPPED;
+                                // events a reduced budget no longer has: (g, k) with k >= round(cm[ag][g] * cnts'); one thread per edge walks the
+                                // events of the entry the edge points to (an entry with several edges is walked more than once, to the same effect)
+                                for (int j = tid; j < ne; j += NT) {
+                                    const int t = (int)((M.edges[j] >> 11) & 255u), cq = M.cc[t];
+                                    if (cq == (int)M.cb[t]) continue;
+                                    const unsigned long long gnew = gpw_pack(Z.cm + ((M.ch[t] >> 4) & 7) * 5, cq), gold = M.gp0[t];
+                                    int e = M.pref[t];
+                                    for (int g = 0; g < 5; ++g) {
+                                        const int n_old = (int)((gold >> (8 * g)) & 0xFF), n_new = (int)((gnew >> (8 * g)) & 0xFF);
+                                        for (int k = n_new; k < n_old; ++k) M.evm[e + k] |= EVM_DROPPED;
+                                        e += n_old;
+                                    }
                                 }
                                 __syncthreads();
                             }
@@ -773,18 +865,18 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             int ndl = 0;
                             for (int win = win0; win < win1; ++win) {
                                 const int e = (win << 5) + lane;
-                                const uint32_t rec = e < Etot ? M.ev[e] : EV_NONE;
-                                const bool live = rec != EV_NONE && !(rec & EV_DROPPED);
-                                const uint32_t y = rec & 0xFFFFu;
+                                const uint32_t y = e < Etot ? M.evy[e] : EV_NONE;
+                                const uint32_t rec = e < Etot ? M.evm[e] : 0u;
+                                const bool live = y != EV_NONE && !(rec & EVM_DROPPED);
                                 const bool shared = live && ((M.dupm[y >> 5] >> (y & 31)) & 1u);
                                 if (live && !shared) {
                                     const uint32_t sy = M.status[y];                               // tag == today since (b)
                                     const int rem = st_rem(sy);
                                     if (rem > 0) {                                                  // :812
-                                        const int q = (int)((rec >> 17) & 255u);
+                                        const int q = (int)(rec >> 2);
                                         uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)(rem - 1);     // :813
                                         if (ctr && room && M.cflag[q]) log_contact(q, y);
-                                        if (st_health(sy) == SUS && st_swap(sy) == UNDEF && (rec & EV_SUCC)) {   // :822-827
+                                        if (st_health(sy) == SUS && st_swap(sy) == UNDEF && (rec & EVM_SUCC)) {   // :822-827
                                             ns = st_set_swap(ns, LAT);
                                             S.sickfrom[rb + y] = (uint8_t)(M.ch[q] & 0xF);
                                             M.expday[y] = (int16_t)day;                             // y.exp = y.tis :826 — fires in today's time_update
@@ -803,9 +895,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 // events that share a target, compacted in event order
                                 for (int win = win0; win < win1; ++win) {
                                     const int e = (win << 5) + lane;
-                                    const uint32_t rec = e < Etot ? M.ev[e] : EV_NONE;
-                                    const uint32_t y = rec & 0xFFFFu;
-                                    const bool shared = rec != EV_NONE && !(rec & EV_DROPPED) && ((M.dupm[y >> 5] >> (y & 31)) & 1u);
+                                    const uint32_t y = e < Etot ? M.evy[e] : EV_NONE;
+                                    const bool shared = y != EV_NONE && !(M.evm[e] & EVM_DROPPED) && ((M.dupm[y >> 5] >> (y & 31)) & 1u);
                                     const unsigned dm = __ballot_sync(FULL, shared);
                                     if (shared) M.D[dpos + __popc(dm & ((1u << lane) - 1u))] = (uint16_t)e;
                                     dpos += __popc(dm);
@@ -819,18 +910,19 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 // targets' events in list (= event) order; lanes that share a target form a group led by its first event
                                 for (int base = 0; base < ndup; base += 32) {
                                     const int idx = base + lane;
-                                    const uint32_t rec = idx < ndup ? M.ev[M.D[idx]] : EV_NONE;
-                                    const uint32_t y = rec & 0xFFFFu;
-                                    const bool mine = rec != EV_NONE && (int)(y & (NW - 1)) == wid;
+                                    const int ed = idx < ndup ? (int)M.D[idx] : 0;
+                                    const uint32_t y = idx < ndup ? M.evy[ed] : EV_NONE;
+                                    const uint32_t rec = M.evm[ed];
+                                    const bool mine = y != EV_NONE && (int)(y & (NW - 1)) == wid;
                                     if (!__any_sync(FULL, mine)) continue;
-                                    const int qd = (int)((rec >> 17) & 255u);
-                                    const unsigned peers = __match_any_sync(FULL, mine ? y : 0x10000u);
+                                    const int qd = (int)(rec >> 2);
+                                    const unsigned peers = __match_any_sync(FULL, mine ? y : EV_NONE);
                                     const bool leader = mine && lane == __ffs(peers) - 1;
                                     const int n = __popc(peers), nmax = __reduce_max_sync(FULL, mine ? n : 0);
                                     const uint32_t sy = mine ? M.status[y] : 0u;
                                     int rem = st_rem(sy), xh_inf = -1;
                                     bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;                 // :822
-                                    const int hit = (mine && (rec & EV_SUCC)) ? (int)(M.ch[qd] & 0xF) : -1;     // would this event transmit (:823)?
+                                    const int hit = (mine && (rec & EVM_SUCC)) ? (int)(M.ch[qd] & 0xF) : -1;     // would this event transmit (:823)?
                                     unsigned m = peers;
                                     for (int k = 0; k < nmax; ++k) {                                          // k-th event of each target, in event order
                                         const int src = m ? __ffs(m) - 1 : lane; m &= m - 1u;
@@ -863,7 +955,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 S.ct_head[rb + xq] = base0 + M.cbase[tid];
                             }
                             for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }   // next marking is after the next C1
-                            if (tid == 0) { Z.nb = 0; Z.mlist = 0; Z.needtot = 0; Z.nedge = 0; if (room) Z.logn = base0 + (uint32_t)needtot; }
+                            if (tid == 0) { Z.nedge = 0; if (room) Z.logn = base0 + (uint32_t)needtot; }
 #ifdef CABM_FUSED_DIAG
                             if (tid == 0) t_ph[16] += Etot;
 #endif
@@ -897,7 +989,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #else
                             for (uint32_t k = wid; k < nq; k += NW)
 #endif
-                                ct_identify_warp(S, P, r, (int)qlist[k], day, M.ev + wid * (FUSED_EVCAP / NW), FUSED_EVCAP / NW, M.mpre, M.mpost);
+                                ct_identify_warp(S, P, r, (int)qlist[k], day, M.evy + wid * (FUSED_EVCAP / NW), FUSED_EVCAP / NW, M.mpre, M.mpost);
                         }
                         __syncthreads();
                         if (tid == 0) Z.qcnt[day & 1] = 0;
@@ -1091,10 +1183,11 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
     if (tid == 0 && S.store_hm) bulk_store_wait_all();     // column copies of the last fill job
 }
 
-size_t fused_smem_bytes_host(int Np) { return fused_smem_bytes(Np); }
+size_t fused_smem_bytes_host(int Np, bool global_state) { return fused_smem_bytes(Np, global_state); }
 
-int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaStream_t s) {
-    const size_t bytes = fused_smem_bytes(S.Np);
+// global_state = false: per-agent state in shared memory (popsize up to ~21k); true: in global memory (any popsize)
+int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, bool global_state, cudaStream_t s) {
+    const size_t bytes = fused_smem_bytes(S.Np, global_state);
     {   // per device: function attributes belong to the device's copy of the kernel. Handles of several host threads may get here
         // at once, so the flags sit behind a lock.
         static std::mutex mu;
@@ -1104,8 +1197,10 @@ int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaSt
         std::lock_guard<std::mutex> lock(mu);
         if (dev < 0 || dev >= 64 || !attr_set[dev]) {
             const int lim = 227 * 1024 - 512;        // the opt-in maximum per CTA minus this kernel's (diagnostic) static shared memory
-            cudaFuncSetAttribute(k_sim_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-            cudaFuncSetAttribute(k_sim_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(k_sim_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(k_sim_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(k_sim_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(k_sim_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
     }
@@ -1124,17 +1219,23 @@ int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, cudaSt
     per_sm = env_int("CABM_FUSED_CTAS_PER_SM", 1, per_sm, per_sm);
     int grid = n_sm * per_sm;
     if (grid > S.R) grid = S.R;
-    // park-and-resume only pays when there are more replicates than resident CTAs and the run is long
+    // park-and-resume only pays when there are more replicates than resident CTAs and the run is long; with the state in global
+    // memory a replicate runs from start to end on its CTA
     int split_day = (S.R > grid && S.T >= 150) ? 60 : 0;
     split_day = env_int("CABM_FUSED_SPLIT_DAY", 0, S.T - 1, split_day);
-    if (split_day >= S.T) split_day = 0;
+    if (split_day >= S.T || global_state) split_day = 0;
     cudaMemsetAsync(work, 0, 16 * sizeof(unsigned), s);
     if (split_day > 0) { cudaMemsetAsync(S.resume_list, 0xFF, (size_t)S.R * sizeof(int), s); cudaMemsetAsync(S.copy_list, 0xFF, (size_t)S.R * sizeof(int), s); }
     unsigned tail_ctas = FUSED_TAIL_CTAS;
     if (tail_ctas > (unsigned)grid / 4) tail_ctas = grid / 4 > 0 ? grid / 4 : 1;      // copiers do not resume parked replicates
     tail_ctas = (unsigned)env_int("CABM_FUSED_TAIL_CTAS", 1, grid, (int)tail_ctas);
-    if (any_ct) k_sim_fused<true><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
-    else k_sim_fused<false><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
+    if (global_state) {
+        if (any_ct) k_sim_fused<true, true><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
+        else k_sim_fused<false, true><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
+    } else {
+        if (any_ct) k_sim_fused<true, false><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
+        else k_sim_fused<false, false><<<grid, FUSED_NT, bytes, s>>>(S, work, split_day, tail_ctas);
+    }
     return 1;
 }
 

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) k_initialize(Dev S) {
     uint32_t st = st_make(SUS, UNDEF, 0, false), d4 = 0;
     if (i < S.N) {
         const uint2 key = S.key[r];
-        uint4 wa = philox(i, 0, S_INIT, 0, key), wb = philox(i, 0, S_INIT, 1, key);
+        uint4 wa = draw4<true>(S, i, 0, S_INIT, 0, key), wb = draw4<true>(S, i, 0, S_INIT, 1, key);
         int ag0 = 0;                                                   // :177 rand(Categorical)
 #pragma unroll
         for (int k = 0; k < 4; ++k) ag0 += ((unsigned long long)wa.x >= P.age_thr[k]);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_insert_infected(Dev S, int which, int h
     if (Ltot == 0 || num > Ltot) { if (tid == 0 && (num > 0 || Ltot == 0)) atomicOr(&S.err[r], ERR_NO_SUS); return; }   // :371-372
     for (int j = 0; j < num; ++j) {
         if (tid == 0) {
-            uint4 w = philox(j, 0, S_SEED, call_id, key);
+            uint4 w = draw4<true>(S, j, 0, S_SEED, call_id, key);
             int k = below(w.x, Ltot - j), t = 0;
             while (k >= cnt[t]) { k -= cnt[t]; ++t; }
             sel_tid = t; sel_k = k;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) k_insert_infected(Dev S, int which, int h
                 uint32_t st = S.status[rb + i];
                 if (!(st_health(st) == SUS && (health != INF || st_ag(st) == ag - 1))) continue;
                 if (k-- > 0) continue;
-                uint32_t ns = transition(S, P, r, i, day, st, key, health, /*seed_simple_inf=*/true, /*count_curves=*/false);
+                uint32_t ns = transition<true>(S, P, r, i, day, st, key, health, /*seed_simple_inf=*/true, /*count_curves=*/false);
                 if (health == LAT) {                                                     // x.tis = x.exp :383
                     const int ex = (int)S.texp[rb + i] - day;
                     S.entry[rb + i] = (int16_t)(day - ex); S.texp[rb + i] = S.expday[rb + i] = (int16_t)day;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
                 // ---- one infector (:798-803)
                 const uint32_t sx = __ldcg(&S.status[rb + x]);
                 const int xh = st_health(sx);
-                const int cnts = budget_of(S, key, x, day, sx);
+                const int cnts = budget_of<true>(S, key, x, day, sx);
                 if (cnts == 0) continue;
                 const unsigned long long gp = __ldg(&S.gpw[st_ag(sx) * 256 + cnts]);     // :804
                 const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF),
@@ -230,11 +230,11 @@ __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
                     uint32_t j = 0x80000000u + lane, sy = 0, w1 = 0;
                     int remy = 0;
                     if (act) {
-                        const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                        const uint4 w = draw4<true>(S, x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
                         w1 = w.y;
                         j = S.grp_idx[rb + go + below(w.x, len)];                        // :807
                         sy = __ldcg(&S.status[rb + j]);
-                        remy = budget_of(S, key, j, day, sy);                            // :811
+                        remy = budget_of<true>(S, key, j, day, sy);                            // :811
                     }
                     const unsigned peers = __match_any_sync(FULL, j);
                     const int rank = __popc(peers & lt), cntp = __popc(peers);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
             const int x = (wi << 5) + b;
             const uint32_t sx = __ldcg(&S.status[rb + x]);
             const int xh = st_health(sx);
-            int cnts = st_health(sx) == DED ? 0 : fresh_budget(S, key, x, day, sx);    // :802, the day's undiminished budget
+            int cnts = st_health(sx) == DED ? 0 : fresh_budget<true>(S, key, x, day, sx);    // :802, the day's undiminished budget
             if (hits_in) cnts = max(0, cnts - (int)((hits_in[(rb + x) >> 1] >> (16 * (x & 1))) & 0xFFFFu));
             if (cnts == 0) continue;
             const unsigned long long gp = __ldg(&S.gpw[st_ag(sx) * 256 + cnts]);     // :804
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
                     const int go = off[g], len = off[g + 1] - go;
                     if (len == 0) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
                     else {
-                        const uint4 w = philox(x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                        const uint4 w = draw4<true>(S, x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
                         j = S.grp_idx[rb + go + below(w.x, len)];                    // :807
                         if (COUNT) {
                             if ((int)j > x && ((mask[j >> 5] >> (j & 31)) & 1u)) atomicAdd(&hits_out[(rb + j) >> 1], 1u << (16 * (j & 1)));
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
                         for (;;) {
                             int rem;
                             if (st_tag(old) == day) rem = st_rem(old);
-                            else { if (fresh < 0) fresh = fresh_budget(S, key, j, day, old); rem = fresh; }
+                            else { if (fresh < 0) fresh = fresh_budget<true>(S, key, j, day, old); rem = fresh; }
                             if (rem == 0) break;                                      // :812
                             uint32_t nw = (old & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)(rem - 1) | ((uint32_t)day << 22);   // :813
                             const bool infect = st_health(old) == SUS && st_swap(old) == UNDEF && bern(w.y, bthr);           // :822-823
@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
 // One index case, handled by a whole warp: gather its traced contacts (chunks are contiguous, so the reads coalesce),
 // drop repeats (the reference's contact set is a Bool vector, :25) and draw Bernoulli(fcontactst) per distinct contact.
 constexpr int CT_GATHER = 512;          // contacts gathered in shared memory per warp; longer sets take the slow path
+template <bool TP = false>
 __device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, int x, int day, uint32_t *buf, int bufcap,
                                         uint32_t *mpre_row, uint32_t *mpost_row) {
     const int lane = threadIdx.x & 31;
@@ -399,7 +400,7 @@ __device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, i
     int n = 0;
     for (uint32_t c = head; c != CT_NONE; c = log[c]) n += (int)log[c + 1];
     auto contact = [&](uint32_t y) {
-        const uint4 w = philox(x, day, S_CTCON, y, key);
+        const uint4 w = draw4<TP>(S, x, day, S_CTCON, y, key);
         if (!bern(w.x, P.fcontact_thr)) return;               // :711
         atomicAdd(&S.totiso[r], 1ull);                        // :649
         if (y > (uint32_t)x) atomicOr(&mpre_row[y >> 5], 1u << (y & 31));
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
     const uint32_t n = *cnt;
     const uint32_t *list = S.ident_list + ((size_t)r * 2 + (day & 1)) * S.Np;
     for (uint32_t k = wid; k < n; k += 4)
-        ct_identify_warp(S, P, r, (int)list[k], day, buf[wid], CT_GATHER, S.mark_pre + (size_t)r * S.nwords, S.mark_post + (size_t)r * S.nwords);
+        ct_identify_warp<true>(S, P, r, (int)list[k], day, buf[wid], CT_GATHER, S.mark_pre + (size_t)r * S.nwords, S.mark_post + (size_t)r * S.nwords);
     __syncthreads();
     if (threadIdx.x == 0) *cnt = 0;
 }
@@ -483,7 +484,7 @@ __device__ __noinline__ uint32_t agent_event(const Dev &S, int r, int i, int day
     const int texp0 = S.texp[a];
     const int par = (day + 1) & 1;
     const DevPset &P = S.psets[S.pset_of[r]];
-    const Ev e = agent_event_core(S, P, r, i, day, S.key[r], st0, texp0, P.ctstrat != 0, pre, post,
+    const Ev e = agent_event_core<true>(S, P, r, i, day, S.key[r], st0, texp0, P.ctstrat != 0, pre, post,
                                   S.ident_cnt ? &S.ident_cnt[r * 2 + par] : nullptr, S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * S.Np : nullptr);
     if (e.newh != e.oldh) {
         if (is_infectious(e.newh) != is_infectious(e.oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
@@ -668,7 +669,7 @@ __global__ void __launch_bounds__(256) k_peek(Dev S, int field, int r, int day, 
     case 0: v = st_health(st); break;
     case 1: v = st_swap(st); break;
     case 2: v = S.sickfrom[a]; break;
-    case 3: v = budget_of(S, S.key[r], i, day, st); break;
+    case 3: v = budget_of<true>(S, S.key[r], i, day, st); break;
     case 4: v = st_ag(st) + 1; break;
     case 5: v = tis; break;
     case 6: v = (st_health(st) == SUS && st_swap(st) == LAT) ? tis : (int)S.texp[a] - (int)S.entry[a]; break;

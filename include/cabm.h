@@ -98,6 +98,23 @@ int cabm_configure(cabm_handle *h, const cabm_params *psets, int n_psets, const 
  * incidence/prevalence reductions (:259-293) and _count_infectors (:295-313), all on device.
  * Asynchronous on the handle's stream; cabm_sync or any cabm_get_* waits. */
 int cabm_run(cabm_handle *h);
+
+/* Replay tape — north_star's "replay mode feeds each kernel the reference's own uniform draws". The reference consumes one
+ * sequential RNG (Random.seed!(simnum*726) :78, then rand() at :177-181,352-356,374,455,481,487,503,535-555,561,590-612,
+ * 678-680,711,740,779-781,807,823); this library names every such draw by a key instead of a stream position (DESIGN.md §3:
+ * Philox counter = (index, day, stream, sub)). A tape lists keys with the four 32-bit words the draw shall return; draws not
+ * listed keep their Philox value. So a run of the Julia reference instrumented to log its draws per site can be replayed here
+ * draw for draw: uniforms as w = floor(u * 2^32), integerised variates (durations, contact counts) as any w of the table bin
+ * of the value (cabm_get_table). INTEGRATION.md gives the key of every draw site. The tape is consulted by the per-day
+ * kernels (cabm_run then takes CABM_PATH_MULTIKERNEL; the cabm_step_* calls); entries may be in any order, duplicates are an
+ * error; n = 0 removes the tape. The oracle has the same entry point (orc_set_tape) for parity tests. */
+typedef struct cabm_tape_entry {
+    uint64_t seed;        /* the replicate's seed as given to cabm_configure */
+    uint32_t ctr[4];      /* (index, day, stream, sub) */
+    uint32_t w[4];        /* the words the draw returns */
+} cabm_tape_entry;
+int cabm_set_tape(cabm_handle *h, const cabm_tape_entry *entries, uint64_t n);
+
 /* Waits for the run. In-model error()s of the reference (:308 "sickfrom not set right", :371-372 "No susceptibles in the
  * population to change status", :418 "swap expired, but no swap set.", :719) and implementation limits (an empty age group
  * sampled, contact log full) are recorded per replicate on the device; after a run cabm_sync and every cabm_get_* result call
@@ -122,10 +139,12 @@ enum { CABM_K_DYNTRANS = 0, CABM_K_TIME_UPDATE = 1, CABM_K_CT_IDENTIFY = 2, CABM
 int cabm_set_profiling(cabm_handle *h, int on);
 int cabm_get_profile(cabm_handle *h, float *ms /*[CABM_N_KCLASS]*/, int32_t *launches /*[CABM_N_KCLASS]*/);
 /* Execution path of cabm_run. FUSED: one persistent CTA per replicate runs all of main() with the per-agent state in
- * shared memory (needs the exact schedule and a popsize that fits, ~21k agents). MULTIKERNEL: one launch per phase per
- * day over HBM-resident state (any popsize, exact or native schedule). AUTO (default) picks FUSED when eligible. Both give
- * bit-identical results. */
-enum { CABM_PATH_AUTO = 0, CABM_PATH_MULTIKERNEL = 1, CABM_PATH_FUSED = 2 };
+ * shared memory (needs the exact schedule and a popsize that fits, ~21k agents). FUSED_GLOBAL: the same kernel with the
+ * per-agent arrays in global memory (L2) and only its work buffers in shared memory: exact schedule, any popsize.
+ * MULTIKERNEL: one launch per phase per day over HBM-resident state (any popsize, exact or native schedule; also what the
+ * cabm_step_* calls drive). AUTO (default): exact schedule -> FUSED when the population fits, else FUSED_GLOBAL; native
+ * schedule -> MULTIKERNEL. All exact paths give bit-identical results. */
+enum { CABM_PATH_AUTO = 0, CABM_PATH_MULTIKERNEL = 1, CABM_PATH_FUSED = 2, CABM_PATH_FUSED_GLOBAL = 3 };
 int cabm_set_path(cabm_handle *h, int path);
 int cabm_get_last_path(const cabm_handle *h);
 /* diagnostics of the fused path: per replicate, cycles thread 0 spent in 16 phase slots (tools/diag_fused.py names them):

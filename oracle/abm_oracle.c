@@ -44,8 +44,37 @@ struct orc_sim {
     int *grp[5]; int grplen[5]; int grps_built;
 };
 
+/* Replay tape (include/cabm.h cabm_set_tape): a sorted table of draw words keyed by (seed, counter). A draw whose
+ * key is on the tape takes the tape's four words instead of the Philox output; every other draw is unchanged. This is how an
+ * external stream — e.g. the draws of an instrumented Julia run, dumped per logical draw site — is replayed. */
+static orc_tape_entry *g_tape = NULL;
+static uint64_t g_tape_n = 0;
+static int tape_cmp(const void *a, const void *b) {
+    const orc_tape_entry *x = (const orc_tape_entry *)a, *y = (const orc_tape_entry *)b;
+    if (x->seed != y->seed) return x->seed < y->seed ? -1 : 1;
+    for (int k = 0; k < 4; ++k) if (x->ctr[k] != y->ctr[k]) return x->ctr[k] < y->ctr[k] ? -1 : 1;
+    return 0;
+}
+int orc_set_tape(const orc_tape_entry *entries, uint64_t n) {
+    free(g_tape); g_tape = NULL; g_tape_n = 0;
+    if (!entries || n == 0) return 0;
+    g_tape = (orc_tape_entry *)malloc(sizeof(orc_tape_entry) * n);
+    if (!g_tape) return fail("orc_set_tape: out of memory");
+    memcpy(g_tape, entries, sizeof(orc_tape_entry) * n);
+    qsort(g_tape, n, sizeof(orc_tape_entry), tape_cmp);
+    g_tape_n = n;
+    return 0;
+}
+
 static void draw4(const orc_sim *s, uint32_t c0, uint32_t day, uint32_t stream, uint32_t sub, uint32_t w[4]) {
     uint32_t ctr[4] = { c0, day, stream, sub };
+    if (g_tape_n) {
+        orc_tape_entry k;
+        k.seed = (uint64_t)s->key[0] | ((uint64_t)s->key[1] << 32);
+        memcpy(k.ctr, ctr, sizeof ctr);
+        const orc_tape_entry *hit = (const orc_tape_entry *)bsearch(&k, g_tape, g_tape_n, sizeof(orc_tape_entry), tape_cmp);
+        if (hit) { memcpy(w, hit->w, sizeof hit->w); return; }
+    }
     orc_philox4x32_10(ctr, s->key, w);
 }
 static inline double u01(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }

@@ -109,6 +109,9 @@ int orc_run_ensemble(const orc_params *psets, int n_psets, const int32_t *pset_o
 
 /* draw-contract primitives, exposed for known-answer tests */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* replay tape: same layout and meaning as cabm_tape_entry / cabm_set_tape (include/cabm.h). Process-wide; NULL or n = 0 clears it. */
+typedef struct orc_tape_entry { uint64_t seed; uint32_t ctr[4]; uint32_t w[4]; } orc_tape_entry;
+int orc_set_tape(const orc_tape_entry *entries, uint64_t n);
 int orc_table(const char *name, int *base, const uint32_t **thr);       /* returns length or -1 */
 void orc_gpw(int ag, int cnts, int out[5]);                              /* :804 split, ag 1..5 */
 

@@ -77,6 +77,7 @@ def lib():
         L.orc_run_ensemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_tape.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_table.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint32))]
         L.orc_gpw.argtypes = [C.c_int, C.c_int, C.c_void_p]
         _lib = L
@@ -263,3 +264,16 @@ def gpw(ag, cnts):
     out = np.zeros(5, dtype=np.int32)
     lib().orc_gpw(ag, cnts, out.ctypes.data)
     return out
+
+
+TAPE_DTYPE = np.dtype([("seed", "<u8"), ("ctr", "<u4", (4,)), ("w", "<u4", (4,))])       # orc_tape_entry
+
+
+def set_tape(entries=None):
+    """Replay tape of the oracle (process-wide): same layout and meaning as cabm_set_tape. None removes it."""
+    if entries is None or len(entries) == 0:
+        lib().orc_set_tape(None, 0)
+        return
+    a = np.ascontiguousarray(entries, dtype=TAPE_DTYPE)
+    if lib().orc_set_tape(a.ctypes.data, len(a)):
+        raise OracleError(lib().orc_last_error().decode())

@@ -101,11 +101,13 @@ def test_config_d_bit_exact_at_full_size(cv, O):
 
 
 def test_config_e_exact_schedule_at_a_million_agents(cv, O):
-    """BASELINE configs[4] population (10^6 agents, sheltered age group), exact schedule on the per-day kernels, against the
-    oracle: 60 days of one replicate, every element of the state matrix."""
+    """BASELINE configs[4] population (10^6 agents, sheltered age group), exact schedule (the fused kernel with its per-agent
+    arrays in global memory, and the per-day kernels), against the oracle: 60 days of one replicate, every element of the state matrix."""
     ip = cv.ModelParameters(β=0.0345, prov="ontario", popsize=1000000, modeltime=60, initialinf=100, quar_grp_frac=0.5, quar_grp=5)
     hm = cv.main(ip, seed=726)
-    assert cv.humans().last_path == "multikernel"
+    assert cv.humans().last_path == "fused-global"
+    hm2 = cv.main(ip, seed=726, path="multikernel")
+    assert (np.asarray(hm) == np.asarray(hm2)).all()
     sim = O.Sim(to_oracle(O, ip), 726)
     ref = sim.main()
     assert (np.asarray(hm) == np.asarray(ref)).all()

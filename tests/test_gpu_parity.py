@@ -50,7 +50,7 @@ CONFIGS = {
 
 def _cases():
     for name, kw in CONFIGS.items():
-        for path in ("multikernel", "fused"):
+        for path in ("multikernel", "fused", "fused-global"):
             yield pytest.param(name, path, id=f"{name}-{path}")
 
 
@@ -164,15 +164,17 @@ def test_stepwise_fields_follow_oracle(cv, O):
 
 def test_large_population_bit_exact(cv, O):
     """BASELINE config 5 ingredients beyond the reference's 10,000-agent limit (:113): 200,000 agents, 100 seeds, a
-    quarantined age group — exact schedule on the per-day kernels (the population does not fit shared memory)."""
+    quarantined age group — exact schedule; the population does not fit shared memory: the fused kernel keeps the per-agent arrays in
+    global memory (default), or the per-day kernels run."""
     ip = cv.ModelParameters(β=0.06, prov="ontario", popsize=200000, modeltime=40, initialinf=100, quar_grp_frac=0.5, quar_grp=5)
-    got = cv.run_ensemble(ip, 2, seeds=[726, 1452], want_hmatrix=True)
-    assert got["path"] == "multikernel"
     ref = O.run_ensemble([to_oracle(O, ip)], [0, 0], [726, 1452], nthreads=2, want_hmatrix=True)
-    assert (got["err"] == 0).all()
-    assert (got["hmatrix"] == ref["hmatrix"]).all()
-    assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all()
-    assert (got["infectors"] == ref["infectors"]).all()
+    for path, expect in (("auto", "fused-global"), ("multikernel", "multikernel")):
+        got = cv.run_ensemble(ip, 2, seeds=[726, 1452], want_hmatrix=True, path=path)
+        assert got["path"] == expect
+        assert (got["err"] == 0).all()
+        assert (got["hmatrix"] == ref["hmatrix"]).all()
+        assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all()
+        assert (got["infectors"] == ref["infectors"]).all()
 
 
 def test_odd_population_sizes_bit_exact(cv, O):
@@ -276,7 +278,8 @@ def test_fused_refuses_populations_that_do_not_fit(cv):
     ip = cv.ModelParameters(β=0.08, prov="ontario", popsize=40000, modeltime=20)
     with pytest.raises(cv.CabmError, match="fused path needs"):
         cv.run_ensemble(ip, 1, path="fused")
-    assert cv.run_ensemble(ip, 1)["path"] == "multikernel"            # auto falls back to the per-day kernels
+    assert cv.run_ensemble(ip, 1)["path"] == "fused-global"           # auto: the same kernel with the per-agent arrays in global memory
+    assert cv.run_ensemble(ip, 1, mode=cv.MODE_NATIVE)["path"] == "multikernel"
 
 
 @pytest.mark.parametrize("popsize,split", [(10000, None), (10007, None), (10000, "25")])

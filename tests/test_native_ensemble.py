@@ -117,7 +117,7 @@ def test_native_vs_exact_at_100k_agents(cv):
     seeds = [726 * (i + 1) for i in range(R)]
     a = cv.run_ensemble(ip, R, seeds=seeds, mode=cv.MODE_EXACT)
     b = cv.run_ensemble(ip, R, seeds=seeds, mode=cv.MODE_NATIVE)
-    assert a["path"] == "multikernel" and b["path"] == "multikernel" and (b["err"] == 0).all() and (a["err"] == 0).all()
+    assert a["path"] == "fused-global" and b["path"] == "multikernel" and (b["err"] == 0).all() and (a["err"] == 0).all()
     xa, xb = 1.0 - a["prev"][:, 0, -1, 0] / Nl, 1.0 - b["prev"][:, 0, -1, 0] / Nl
     assert stats.ks_2samp(xa, xb).pvalue > 0.01
     assert abs(xa.mean() - xb.mean()) < 2 * np.sqrt(xa.var(ddof=1) / R + xb.var(ddof=1) / R)

@@ -27,7 +27,7 @@ for r in order[:6]: print(r, "kcyc", met[r], "ms", met[r] * 1024 / 1.965e6, "chu
 print("takeoff count", (attack > 0.1).sum(), "mean attack", attack.mean())
 dbg = np.zeros((R, 32), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctypes.data))
 names = {22: "setup: initialize", 23: "setup: get_ag_dist", 24: "setup: insert_infected", 0: "setup: column 1 / resume reload", 1: "list",
-         8: "chunk: budgets + prefix -> C1", 9: "chunk: event generation", 10: "chunk: C2 wait + DAG", 11: "chunk: apply singles + count shared",
+         8: "chunk: budgets + prefix -> C1", 9: "chunk: event generation (rest)", 2: "  gen: owners", 3: "  gen: draws (philox)", 7: "  gen: grp + status loads", 20: "  gen: fresh budgets", 21: "  gen: marks/edges", 10: "chunk: C2 wait + DAG", 11: "chunk: apply singles + count shared",
          13: "chunk: C3 + compaction", 14: "chunk: C4 + resolve shared", 15: "chunk: C5 + link/clear", 12: "dyntrans end -> S1",
          25: "time_update: S1 -> own scan done", 26: "time_update: min-reduce", 4: "time_update: S2 wait", 5: "curves/idle", 6: "writeback",
          16: "(count) events", 17: "(count) shared-target events", 18: "(count) DAG edges", 19: "(count) DAG sweeps"}
