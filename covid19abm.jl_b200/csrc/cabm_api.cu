@@ -126,7 +126,7 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.status, A); DA(S.expday, A); DA(S.texp, A); DA(S.entry, A); DA(S.dur, A); DA(S.sickfrom, A); DA(S.isovia, A);
     DA(S.latday, A); DA(S.tracestart, A); DA(S.traceend, A); DA(S.txpday, A); DA(S.ct_head, A);
     DA(S.mark_pre, W); DA(S.mark_post, W); DA(S.infmask, W); DA(S.ct_cnt, (size_t)h->R);
-    DA(S.touch_g, W); DA(S.dupm_g, W); DA(S.col_g, A);
+    DA(S.touch_g, W); DA(S.dupm_g, W); DA(S.col_g, A); DA(S.ev_cnt, (size_t)h->R * 2);
     if ((e = cudaMemset(S.touch_g, 0, W * 4)) != cudaSuccess || (e = cudaMemset(S.dupm_g, 0, W * 4)) != cudaSuccess) return bail(e, "memset");
     DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8); DA(S.hits, A);
     if (h->N <= 65535) DA(S.grp16, A);
@@ -353,6 +353,7 @@ static int reset_state(cabm_handle *h, bool curves_too = true) {
     CU(cudaMemsetAsync(S.err, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totiso, 0, (size_t)S.R * 8, h->stream));
     CU(cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, h->stream));
     CU(cudaMemsetAsync(S.touch_g, 0, W * 4, h->stream)); CU(cudaMemsetAsync(S.dupm_g, 0, W * 4, h->stream));
+    CU(cudaMemsetAsync(S.ev_cnt, 0, (size_t)S.R * 8, h->stream));
     if (curves_too) { CU(cudaMemsetAsync(S.inc, 0, C * 4, h->stream)); CU(cudaMemsetAsync(S.prev, 0, C * 4, h->stream)); }
     CU(cudaMemsetAsync(S.infectors, 0, (size_t)S.R * 32, h->stream)); CU(cudaMemsetAsync(S.latsum, 0, (size_t)S.R * 8, h->stream));
     h->day = 1;
@@ -367,6 +368,14 @@ template <class F> static void timed(cabm_handle *h, int cls, F f) {
     h->launches += f();
     cudaEventRecord(h->pev[h->pev_used + 1], h->stream);
     h->pev_used += 2; h->pcls.push_back(cls);
+}
+
+// the per-day kernels' event list [R][Np] is only needed on that path: allocated on first use
+static int need_event_list(cabm_handle *h) {
+    if (h->S.ev_list) return CABM_OK;
+    CU(cudaMalloc((void **)&h->S.ev_list, sizeof(uint32_t) * (size_t)h->R * h->Np));
+    h->allocs.push_back(h->S.ev_list);
+    return CABM_OK;
 }
 
 static int do_dyntrans(cabm_handle *h, int day) {
@@ -398,6 +407,7 @@ extern "C" int cabm_run(cabm_handle *h) {
     CU(cudaEventRecord(h->ev0, h->stream));
     if ((rc = reset_state(h, /*curves_too=*/!use_fused))) return rc;      // the fused kernel writes every curve entry itself
     h->last_path = use_smem ? CABM_PATH_FUSED : use_global ? CABM_PATH_FUSED_GLOBAL : CABM_PATH_MULTIKERNEL;
+    if (!use_fused && (rc = need_event_list(h))) return rc;
     if (use_fused) {
         timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->any_ct != 0, use_global, h->stream); });  // :104-142 in one launch
     } else {
@@ -549,6 +559,7 @@ extern "C" int cabm_get_day(const cabm_handle *h) { return h ? h->day : -1; }
 
 extern "C" int cabm_step_initialize(cabm_handle *h) {
     int rc = need_config(h); if (rc) return rc;
+    if ((rc = need_event_list(h))) return rc;
     if ((rc = reset_state(h))) return rc;
     h->launches += launch_initialize(h->S, h->stream);
     h->launches += launch_build_groups(h->S, h->stream);
@@ -575,6 +586,7 @@ extern "C" int cabm_step_dyntrans(cabm_handle *h) {
 }
 extern "C" int cabm_step_time_update(cabm_handle *h) {
     int rc = need_config(h); if (rc) return rc;
+    if ((rc = need_event_list(h))) return rc;
     if (h->day > h->T) return fail(h, CABM_E_STATE, "day exceeds modeltime");
     do_time_update(h, h->day);
     h->day += 1;

@@ -75,6 +75,7 @@ struct Dev {
     uint32_t *mark_pre, *mark_post;          // [R][nwords] bitmasks
     uint32_t *ct_log; uint32_t *ct_cnt;      // [R][ct_cap] words: chunks [next chunk, count, targets...] per (traced agent, day); [R] words used
     uint32_t *ident_list, *ident_cnt;        // [R][2][Np], [R][2]: agents whose identification day is today / tomorrow
+    uint32_t *ev_list, *ev_cnt;              // [R][Np], [R][2]: agents with an event today (k_time_update_scan -> k_time_update_events), count by day parity
     uint32_t *grp_idx; int *grp_off;         // [R][Np], [R][8]
     uint16_t *grp16;                         // [R][Np] the same index tables as 16-bit words: the fused kernel's copy (popsize <= 65535)
     uint32_t *infmask;                       // [R][nwords]

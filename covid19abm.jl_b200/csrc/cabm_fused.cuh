@@ -142,10 +142,27 @@ __device__ __forceinline__ int gpw_sum(unsigned long long gp) {
 
 // TMA bulk store of one hmatrix column from shared memory (UBLKCP in SASS)
 __device__ __forceinline__ void bulk_store_g2s_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// The state matrix is written once and never read by the kernel: its lines are marked evict-first in L2 so that the 5 GB stream of
+// a launch does not push out what the replicates keep re-reading through L2 (age-group tables, per-agent fields of transitions).
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(s), "r"(bytes), "l"(pol) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// age-group index tables: read at random by every contact event for the whole life of the replicate -> evict-last in L2
+__device__ __forceinline__ uint32_t ld_keep(const uint16_t *p) {
+    uint64_t pol; unsigned short v;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_keep(const uint32_t *p) {
+    uint64_t pol; uint32_t v;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
 }
 __device__ __forceinline__ void bulk_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); }   // bound the queue on idle days
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -753,7 +770,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) draw(((win + j) << 5) + lane, q[j], idx[j], meta[j], ok[j]);
 #pragma unroll
-                                for (int j = 0; j < NWIN; ++j) y[j] = grp[idx[j]];                 // loads in flight together
+                                for (int j = 0; j < NWIN; ++j) y[j] = ld_keep(grp + idx[j]);       // loads in flight together
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) sy[j] = M.status[y[j]];
                                 bool any_need = false;

@@ -496,46 +496,67 @@ __device__ __noinline__ uint32_t agent_event(const Dev &S, int r, int i, int day
     return (uint32_t)e.newh;
 }
 
-__global__ void __launch_bounds__(256) k_time_update(const __grid_constant__ Dev S, int day, int any_ct) {
-    const int r = blockIdx.y;
+// Two launches per day. k_time_update_scan is the pure stream: thread per 16 consecutive agents, two 128-bit loads of event days,
+// one 128-bit load and one 128-bit store of column bytes (the next column starts as a copy of the previous one), the mark bits;
+// agents with an event today are appended to the replicate's event list (one atomicAdd per warp). k_time_update_events then runs
+// agent_event for exactly those agents, one per thread in dense warps, and patches their byte of the new column. (A single kernel
+// that handled events inside the stream stalled whole warps on one lane's dependent HBM loads: 0.10 of HBM peak on 10^6 agents.)
+__global__ void __launch_bounds__(256) k_time_update_scan(const __grid_constant__ Dev S, int day, int any_ct) {
+    const int r = blockIdx.y, lane = threadIdx.x & 31;
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (i0 >= S.N) return;
-    const size_t a0 = (size_t)r * S.Np + i0;
-    const uint4 e0 = *reinterpret_cast<const uint4 *>(S.expday + a0), e1 = *reinterpret_cast<const uint4 *>(S.expday + a0 + 8);
-    unsigned pre = 0, post = 0;
-    if (any_ct) {                                                    // marks left by today's index cases (pass A)
-        const size_t wi = (size_t)r * S.nwords + (i0 >> 5);
-        const unsigned sh = i0 & 31;
-        pre = (S.mark_pre[wi] >> sh) & 0xFFFFu; post = (S.mark_post[wi] >> sh) & 0xFFFFu;
-        if (pre) atomicAnd(&S.mark_pre[wi], ~(0xFFFFu << sh));       // consumed by this update
-        if (post) atomicAnd(&S.mark_post[wi], ~(0xFFFFu << sh));
-    }
-    const uint32_t dd = (uint32_t)day * 0x10001u;
-    const uint32_t m[8] = {__vcmples2(e0.x, dd), __vcmples2(e0.y, dd), __vcmples2(e0.z, dd), __vcmples2(e0.w, dd),
-                           __vcmples2(e1.x, dd), __vcmples2(e1.y, dd), __vcmples2(e1.z, dd), __vcmples2(e1.w, dd)};
-    const bool any = ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7]) | pre | post) != 0;   // somebody has an event today
-    const bool hm_on = S.store_hm && day < S.T;                      // column st+1 = state at the start of the next day
-    const bool vec = (S.N & 15) == 0;
-    union { uint4 v; uint8_t b[16]; } col;
-    col.v = make_uint4(0, 0, 0, 0);
-    uint8_t *cur = nullptr;
-    if (hm_on) {
-        const uint8_t *prv = S.hm + ((size_t)r * S.T + (size_t)(day - 1)) * S.N + i0;
-        cur = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
-        if (vec) col.v = *reinterpret_cast<const uint4 *>(prv);
-        else for (int k = 0; k < 16 && i0 + k < S.N; ++k) col.b[k] = prv[k];
-    }
-    if (any) {
+    const bool valid = i0 < S.N;
+    unsigned fire = 0, pre = 0, post = 0;
+    if (valid) {
+        const size_t a0 = (size_t)r * S.Np + i0;
+        const uint4 e0 = *reinterpret_cast<const uint4 *>(S.expday + a0), e1 = *reinterpret_cast<const uint4 *>(S.expday + a0 + 8);
+        if (any_ct) {                                                    // marks left by today's index cases (pass A)
+            const size_t wi = (size_t)r * S.nwords + (i0 >> 5);
+            const unsigned sh = i0 & 31;
+            pre = (S.mark_pre[wi] >> sh) & 0xFFFFu; post = (S.mark_post[wi] >> sh) & 0xFFFFu;
+            if (pre) atomicAnd(&S.mark_pre[wi], ~(0xFFFFu << sh));       // consumed by this update
+            if (post) atomicAnd(&S.mark_post[wi], ~(0xFFFFu << sh));
+        }
+        const uint32_t dd = (uint32_t)day * 0x10001u;
+        const uint32_t m[8] = {__vcmples2(e0.x, dd), __vcmples2(e0.y, dd), __vcmples2(e0.z, dd), __vcmples2(e0.w, dd),
+                               __vcmples2(e1.x, dd), __vcmples2(e1.y, dd), __vcmples2(e1.z, dd), __vcmples2(e1.w, dd)};
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const bool f = ((m[k >> 1] >> ((k & 1) * 16)) | (pre >> k) | (post >> k)) & 1u;
-            if (f && i0 + k < S.N) col.b[k] = (uint8_t)agent_event(S, r, i0 + k, day, (pre >> k) & 1u, (post >> k) & 1u);
+        for (int k = 0; k < 8; ++k) fire |= ((m[k] & 1u) | ((m[k] >> 15) & 2u)) << (2 * k);
+        fire = (fire | pre | post) & (S.N - i0 >= 16 ? 0xFFFFu : ((1u << (S.N - i0)) - 1u));
+        if (S.store_hm && day < S.T) {                                   // column st+1 = state at the start of the next day: copy, patched by the events
+            const uint8_t *prv = S.hm + ((size_t)r * S.T + (size_t)(day - 1)) * S.N + i0;
+            uint8_t *cur = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
+            if ((S.N & 15) == 0) *reinterpret_cast<uint4 *>(cur) = *reinterpret_cast<const uint4 *>(prv);
+            else for (int k = 0; k < 16 && i0 + k < S.N; ++k) cur[k] = prv[k];
         }
     }
-    if (hm_on) {
-        if (vec) *reinterpret_cast<uint4 *>(cur) = col.v;
-        else for (int k = 0; k < 16 && i0 + k < S.N; ++k) cur[k] = col.b[k];
+    // append the agents with an event: exclusive prefix of the counts over the warp, one atomicAdd per warp
+    const int c = __popc(fire);
+    if (__any_sync(FULL, c != 0)) {
+        int incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(FULL, incl, 31);
+        unsigned base = 0;
+        if (lane == 31) base = atomicAdd(&S.ev_cnt[r * 2 + (day & 1)], (unsigned)total);
+        base = __shfl_sync(FULL, base, 31);
+        uint32_t *out = S.ev_list + (size_t)r * S.Np + base + (unsigned)(incl - c);
+        while (fire) {
+            const int k = __ffs(fire) - 1; fire &= fire - 1;
+            *out++ = (uint32_t)(i0 + k) | (((pre >> k) & 1u) << 30) | (((post >> k) & 1u) << 31);
+        }
     }
+}
+
+__global__ void __launch_bounds__(256) k_time_update_events(const __grid_constant__ Dev S, int day) {
+    const int r = blockIdx.y;
+    const unsigned n = S.ev_cnt[r * 2 + (day & 1)];
+    const bool hm_on = S.store_hm && day < S.T;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t ent = S.ev_list[(size_t)r * S.Np + k];
+        const int i = (int)(ent & 0x3FFFFFFFu);
+        const uint32_t newh = agent_event(S, r, i, day, (ent >> 30) & 1u, ent >> 31);
+        if (hm_on) S.hm[((size_t)r * S.T + (size_t)day) * S.N + i] = (uint8_t)newh;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) S.ev_cnt[r * 2 + ((day + 1) & 1)] = 0;      // tomorrow's counter (read two launches from now)
 }
 
 // Seeds isolated through fpreiso at seeding keep the day-1 contact budget that initialize drew for them (:186): their
@@ -763,8 +784,10 @@ int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s) {
 }
 int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStream_t s) {
     (void)all_ct;
-    int n = 1;
-    k_time_update<<<agent_grid(S, 16), 256, 0, s>>>(S, day, any_ct ? 1 : 0);
+    int n = 2;
+    k_time_update_scan<<<agent_grid(S, 16), 256, 0, s>>>(S, day, any_ct ? 1 : 0);
+    unsigned eb = (unsigned)(S.N / 16384); if (eb < 1) eb = 1; if (eb > 64) eb = 64;
+    k_time_update_events<<<dim3(eb, (unsigned)S.R), 256, 0, s>>>(S, day);
     if (day == 1) { k_resync_isob<<<148 * 8, 256, 0, s>>>(S); ++n; }
     return n;
 }
