@@ -679,6 +679,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     M.gcum[q] = c1 | (c2 << 8) | (c3 << 16) | (c4 << 24);
                                 }
                                 M.pref[q + 1] = inclE;
+                                for (int k = inclE - E; k < inclE; ++k) M.evm[k] = (uint16_t)(q << 2);      // owner of each of its events (read back by (b))
                                 if (ctr) { M.cflag[q] = tr ? 1 : 0; M.cbase[q] = (uint32_t)(v2 - (tr ? 2 + E : 0)); M.clen[q] = 0; }
                             }
                             {
@@ -704,26 +705,11 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 continue;
                             }
                             // ---- (b) all events of the chunk, in event order: warp w draws windows [win0, win1) of 32 consecutive events,
-                            //      two windows at a time so that their (independent) draw chains overlap. Owner of an event = the entry whose
-                            //      prefix range holds it: the (strictly increasing) prefix entries that fall into the window are bits of one
-                            //      word; q0 walks along with the windows.
+                            //      two windows at a time so that their (independent) draw chains overlap. The owner (chunk entry) of every
+                            //      event was written into its record by the entry's thread during the chunk build.
                             const int nwin = (Etot + 31) >> 5, wpw = (nwin + NW - 1) / NW;
                             const int win0 = wid * wpw, win1 = min(nwin, win0 + wpw);
                             const int xlast = M.cx[nb - 1];
-                            int q0 = 0;
-                            if (win0 < win1 && win0 > 0) {                                     // owner of the event before the first window
-                                const int tgt = win0 * 32 - 1;
-                                int lo = 0, hi = nb - 1;
-                                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (M.pref[mid] <= tgt) lo = mid; else hi = mid - 1; }
-                                q0 = lo;
-                            }
-                            auto owner_of = [&](int base) {                                    // entry of event base + lane; advances q0 to the window's last owner
-                                const int Pl = (q0 + 1 + lane <= nb) ? M.pref[q0 + 1 + lane] : 0x7FFFFFFF;      // >= base: q0 owns event base - 1
-                                const unsigned bits = __reduce_or_sync(FULL, (Pl <= base + 31) ? 1u << (Pl - base) : 0u);
-                                const int q = q0 + __popc(bits & ((2u << lane) - 1u));
-                                q0 = __shfl_sync(FULL, q, 31);
-                                return q;
-                            };
                             // draw of one event (branch-free: lanes past the end repeat the last event and are masked by `ok`)
                             auto draw = [&](int e, int q, int &idx, uint32_t &meta, bool &ok) {
                                 const int qc = min(q, nb - 1), ec = min(e, Etot - 1);
@@ -738,26 +724,18 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 meta = (bern(w.y, Z.beta[beta_class(hq & 0xF)]) ? (uint32_t)EVM_SUCC : 0u) | ((uint32_t)qc << 2) | ((uint32_t)g << 26) | ((uint32_t)(len == 0) << 31);   // :800, :823
                                 ok = e < Etot && len > 0;
                             };
-                            // marks and DAG edges of one drawn event; writes its record
-                            auto mark = [&](int e, uint32_t y, uint32_t meta, bool ok) {
-                                if (!ok) { if ((meta >> 31) && e < Etot) atomicOr(&S.err[r], ERR_EMPTY_GROUP); M.evy[e] = EV_NONE; M.evm[e] = 0; return; }
-                                // targets hit more than once (by any event of the chunk, dropped later or not) take the ordered path
-                                const uint32_t ybit = 1u << (y & 31);
-                                const uint32_t old = atomicOr(&M.touch[y >> 5], ybit);
-                                if (old & ybit) atomicOr(&M.dupm[y >> 5], ybit);
-                                const int q = (int)((meta >> 2) & 255u), xq = (int)M.cx[q];
-                                // a later infector of this chunk that gets contacted starts its turn with a smaller budget (:802, :813): DAG edge
-                                if (((M.inf[y >> 5] >> (y & 31)) & 1u) && (int)y > xq && (int)y <= xlast) {
-                                    int a = q + 1, b = nb - 1;
-                                    while (a < b) { const int mid = (a + b) >> 1; if ((int)M.cx[mid] < (int)y) a = mid + 1; else b = mid; }
-                                    if ((int)M.cx[a] == (int)y) {                                // (a listed infector without events has nothing to lose)
-                                        const int g = (int)((meta >> 26) & 7u), el = e - M.pref[q];
-                                        const int k = el - (int)((((unsigned long long)M.gcum[q] << 8) >> (8 * g)) & 0xFF);
-                                        const int slot = atomicAdd(&Z.nedge, 1);
-                                        if (slot < FUSED_NEDGE) M.edges[slot] = (uint32_t)e | ((uint32_t)a << 11) | ((uint32_t)g << 19) | ((uint32_t)k << 22);
-                                    }
+                            // DAG edge of a drawn event whose target is a later infector of this chunk: that infector starts its turn with a
+                            // smaller budget (:802, :813)
+                            auto edge = [&](int e, uint32_t y, uint32_t meta) {
+                                const int q = (int)((meta >> 2) & 255u);
+                                int a = q + 1, b = nb - 1;
+                                while (a < b) { const int mid = (a + b) >> 1; if ((int)M.cx[mid] < (int)y) a = mid + 1; else b = mid; }
+                                if ((int)M.cx[a] == (int)y) {                                    // (a listed infector without events has nothing to lose)
+                                    const int g = (int)((meta >> 26) & 7u), el = e - M.pref[q];
+                                    const int k = el - (int)((((unsigned long long)M.gcum[q] << 8) >> (8 * g)) & 0xFF);
+                                    const int slot = atomicAdd(&Z.nedge, 1);
+                                    if (slot < FUSED_NEDGE) M.edges[slot] = (uint32_t)e | ((uint32_t)a << 11) | ((uint32_t)g << 19) | ((uint32_t)k << 22);
                                 }
-                                M.evy[e] = y; M.evm[e] = (uint16_t)(meta & 0x3FFu & ~(uint32_t)EVM_DROPPED);
                             };
                             // NWIN windows of 32 events at once: every stage is a fully unrolled loop over the windows, so that the
                             // independent chains (Philox, table walks, loads) of the windows interleave in one basic block
@@ -765,7 +743,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 constexpr int NWIN = decltype(nwc)::value;
                                 int q[NWIN], idx[NWIN]; uint32_t meta[NWIN], y[NWIN], sy[NWIN]; bool ok[NWIN], need[NWIN];
 #pragma unroll
-                                for (int j = 0; j < NWIN; ++j) q[j] = owner_of((win + j) << 5);
+                                for (int j = 0; j < NWIN; ++j) q[j] = (int)(M.evm[min(((win + j) << 5) + lane, Etot - 1)] >> 2);   // written by the chunk build
                                 PHASE(2);
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) draw(((win + j) << 5) + lane, q[j], idx[j], meta[j], ok[j]);
@@ -810,8 +788,23 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     }
                                 }
                                 PHASE(20);
+                                // records; targets hit more than once (by any event of the chunk, dropped later or not) take the ordered path
+                                uint32_t old[NWIN];
 #pragma unroll
-                                for (int j = 0; j < NWIN; ++j) mark(((win + j) << 5) + lane, y[j], meta[j], ok[j]);
+                                for (int j = 0; j < NWIN; ++j) old[j] = ok[j] ? atomicOr(&M.touch[y[j] >> 5], 1u << (y[j] & 31)) : 0u;
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) {
+                                    const int e = ((win + j) << 5) + lane;
+                                    M.evy[e] = ok[j] ? y[j] : EV_NONE;
+                                    M.evm[e] = ok[j] ? (uint16_t)(meta[j] & 0x3FFu & ~(uint32_t)EVM_DROPPED) : (uint16_t)0;
+                                    if (!ok[j] && (meta[j] >> 31) && e < Etot) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
+                                }
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) {
+                                    if (ok[j] && (old[j] >> (y[j] & 31)) & 1u) atomicOr(&M.dupm[y[j] >> 5], 1u << (y[j] & 31));
+                                    if (ok[j] && ((M.inf[y[j] >> 5] >> (y[j] & 31)) & 1u) && (int)y[j] > (int)M.cx[(meta[j] >> 2) & 255u] && (int)y[j] <= xlast)
+                                        edge(((win + j) << 5) + lane, y[j], meta[j]);
+                                }
                                 PHASE(21);
                             };
                             {
@@ -1029,10 +1022,12 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             post |= (unsigned long long)((M.mpost[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
                         }
                     }
-                    uint32_t anyf = 0;
+                    // earliest event day of these chunks with packed 16-bit minima (DPX VIMNMX: one instruction per pair of words); the
+                    // per-agent compares are only needed when somebody is due
+                    uint32_t cmin = 0x7FFF7FFFu;
 #pragma unroll
-                    for (int u = 0; u < FUSED_SCAN_U; ++u) anyf |= __vcmples2(ex[u].x, dd) | __vcmples2(ex[u].y, dd) | __vcmples2(ex[u].z, dd) | __vcmples2(ex[u].w, dd);
-                    if (anyf | (uint32_t)((pre | post) != 0)) {                // somebody in these chunks has an event today
+                    for (int u = 0; u < FUSED_SCAN_U; ++u) cmin = __vimin3_s16x2(cmin, __vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w));
+                    if (min((int)(short)(cmin & 0xFFFFu), (int)(short)(cmin >> 16)) <= day || (pre | post) != 0) {   // somebody in these chunks has an event today
 #pragma unroll
                         for (int u = 0; u < FUSED_SCAN_U; ++u) {
                             const uint32_t m0 = __vcmples2(ex[u].x, dd), m1 = __vcmples2(ex[u].y, dd), m2 = __vcmples2(ex[u].z, dd), m3 = __vcmples2(ex[u].w, dd);
@@ -1071,9 +1066,11 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const int i0 = b0 + u * NT * 8;
                             if (i0 < N) ex[u] = *reinterpret_cast<const uint4 *>(M.expday + i0);
                         }
-                    }
+                        cmin = 0x7FFF7FFFu;
 #pragma unroll
-                    for (int u = 0; u < FUSED_SCAN_U; ++u) mn = __vmins2(mn, __vmins2(__vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w)));
+                        for (int u = 0; u < FUSED_SCAN_U; ++u) cmin = __vimin3_s16x2(cmin, __vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w));
+                    }
+                    mn = __vmins2(mn, cmin);
                 }
                 PHASE(25);
                 {
