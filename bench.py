@@ -190,7 +190,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the timed outputs")
     ap.add_argument("--pipeline", type=int, default=3, help="handles (CUDA streams) the steps alternate over; 1 = one step after the other")
-    ap.add_argument("--path", default="auto", choices=["auto", "multikernel", "fused"], help="execution path (include/cabm.h CABM_PATH_*)")
+    ap.add_argument("--path", default="auto", choices=["auto", "multikernel", "fused", "fused-global"], help="execution path (include/cabm.h CABM_PATH_*)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -275,7 +275,7 @@ def main():
     for q in pops:
         q.check_errors()
     one_ms = pop.last_run_ms                           # one step alone on the GPU (nothing else in flight)
-    fused = pop.last_path == "fused"
+    fused = pop.last_path in ("fused", "fused-global")
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -414,7 +414,7 @@ def main():
         ms, n = prof["fused"]
         gbs = alg_bytes / (ms / n * 1e-3) / 1e9
         cap = ncu.get(args.config, {}) if (Rtot == W["R"] and hm_on == W["hm"]) else {}
-        roofline = {"kernel": "k_sim_fused", "bound": "latency",
+        roofline = {"kernel": "k_sim_fused" + ("<state in global memory>" if pop.last_path == "fused-global" else ""), "bound": "latency",
                     "bound_note": "per ncu the kernel is bound by dependent-instruction latency and barriers of the per-replicate day chain, not by a pipe: "
                                   "HBM is the roofline this line reports against (denominator), the kernel moves only the bytes it must",
                     "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),

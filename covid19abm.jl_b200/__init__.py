@@ -307,10 +307,10 @@ class Population:
 
     def profile(self):
         """{class: (milliseconds, launches)} of the last profiled run."""
-        ms = np.zeros(5, dtype=np.float32)
-        n = np.zeros(5, dtype=np.int32)
+        ms = np.zeros(6, dtype=np.float32)
+        n = np.zeros(6, dtype=np.int32)
         self._chk(self.L.cabm_get_profile(self.h, ms.ctypes.data, n.ctypes.data))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(["dyntrans", "time_update", "ct_identify", "other", "fused"])}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(["dyntrans", "time_update", "ct_identify", "other", "fused", "time_update_events"])}
 
     def set_path(self, path):
         """'auto' | 'multikernel' | 'fused' | 'fused-global' (include/cabm.h CABM_PATH_*)."""

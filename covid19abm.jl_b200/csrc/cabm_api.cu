@@ -385,7 +385,8 @@ static int do_dyntrans(cabm_handle *h, int day) {
 }
 static int do_time_update(cabm_handle *h, int day) {
     if (h->any_ct) timed(h, CABM_K_CT_IDENTIFY, [&] { return launch_ct_identify(h->S, day, h->poked, h->stream); });
-    timed(h, CABM_K_TIME_UPDATE, [&] { return launch_time_update(h->S, day, h->any_ct != 0, h->all_ct != 0, h->stream); });
+    timed(h, CABM_K_TIME_UPDATE, [&] { return launch_time_update_scan(h->S, day, h->any_ct != 0, h->stream); });
+    timed(h, CABM_K_TU_EVENTS, [&] { return launch_time_update_events(h->S, day, h->stream); });
     return CABM_OK;
 }
 

@@ -964,7 +964,15 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 c[0] = S.ct_head[rb + xq]; c[1] = (uint32_t)M.clen[tid];
                                 S.ct_head[rb + xq] = base0 + M.cbase[tid];
                             }
-                            for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }   // next marking is after the next C1
+                            if (GS) {       // (the bitmasks cover the whole population: clear the words this chunk's events marked)
+                                for (int win = win0; win < win1; ++win) {
+                                    const int e = (win << 5) + lane;
+                                    const uint32_t y = e < Etot ? M.evy[e] : EV_NONE;
+                                    if (y != EV_NONE) { M.touch[y >> 5] = 0; M.dupm[y >> 5] = 0; }
+                                }
+                            } else {
+                                for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }   // next marking is after the next C1
+                            }
                             if (tid == 0) { Z.nedge = 0; if (room) Z.logn = base0 + (uint32_t)needtot; }
 #ifdef CABM_FUSED_DIAG
                             if (tid == 0) t_ph[16] += Etot;

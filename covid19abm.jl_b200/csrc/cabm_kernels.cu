@@ -12,7 +12,7 @@ void upload_const_tables(const ConstTables &t, cudaStream_t s) {
 
 // ============================================================================ initialize :171-188
 // thread per (replicate, agent). Draw words: S_INIT block 0 = (ag, lat, pre, asymp), block 1 = (inf, quarantine).
-__global__ void __launch_bounds__(256) k_initialize(Dev S) {
+template <bool TP> __global__ void __launch_bounds__(256) k_initialize(Dev S) {
     const int r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.Np) return;
     const size_t a = (size_t)r * S.Np + i;
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) k_initialize(Dev S) {
     uint32_t st = st_make(SUS, UNDEF, 0, false), d4 = 0;
     if (i < S.N) {
         const uint2 key = S.key[r];
-        uint4 wa = draw4<true>(S, i, 0, S_INIT, 0, key), wb = draw4<true>(S, i, 0, S_INIT, 1, key);
+        uint4 wa = draw4<TP>(S, i, 0, S_INIT, 0, key), wb = draw4<TP>(S, i, 0, S_INIT, 1, key);
         int ag0 = 0;                                                   // :177 rand(Categorical)
 #pragma unroll
         for (int k = 0; k < 4; ++k) ag0 += ((unsigned long long)wa.x >= P.age_thr[k]);
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_build_groups(Dev S) {
 // CTA per replicate. Pick j takes the floor(u_j*(L-j))-th remaining susceptible in ascending index order.
 // which: 0 = main's insert_infected(PRE, initialinf, 4) :117/:119; 1 = insert_infected(REC, initialhi, 4) :120
 //        (skipped in calibration); 2 = explicit (health, num, ag) for the step API.
-__global__ void __launch_bounds__(256) k_insert_infected(Dev S, int which, int health, int num, int ag, int call_id, int day) {
+template <bool TP> __global__ void __launch_bounds__(256) k_insert_infected(Dev S, int which, int health, int num, int ag, int call_id, int day) {
     const int r = blockIdx.x, tid = threadIdx.x;
     const DevPset &P = S.psets[S.pset_of[r]];
     if (which == 0) { health = PRE; num = P.initialinf; call_id = 0; }
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_insert_infected(Dev S, int which, int h
     if (Ltot == 0 || num > Ltot) { if (tid == 0 && (num > 0 || Ltot == 0)) atomicOr(&S.err[r], ERR_NO_SUS); return; }   // :371-372
     for (int j = 0; j < num; ++j) {
         if (tid == 0) {
-            uint4 w = draw4<true>(S, j, 0, S_SEED, call_id, key);
+            uint4 w = draw4<TP>(S, j, 0, S_SEED, call_id, key);
             int k = below(w.x, Ltot - j), t = 0;
             while (k >= cnt[t]) { k -= cnt[t]; ++t; }
             sel_tid = t; sel_k = k;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) k_insert_infected(Dev S, int which, int h
                 uint32_t st = S.status[rb + i];
                 if (!(st_health(st) == SUS && (health != INF || st_ag(st) == ag - 1))) continue;
                 if (k-- > 0) continue;
-                uint32_t ns = transition<true>(S, P, r, i, day, st, key, health, /*seed_simple_inf=*/true, /*count_curves=*/false);
+                uint32_t ns = transition<TP>(S, P, r, i, day, st, key, health, /*seed_simple_inf=*/true, /*count_curves=*/false);
                 if (health == LAT) {                                                     // x.tis = x.exp :383
                     const int ex = (int)S.texp[rb + i] - day;
                     S.entry[rb + i] = (int16_t)(day - ex); S.texp[rb + i] = S.expday[rb + i] = (int16_t)day;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_first_column(Dev S) {
 // the result depends through the shared contact budgets :811-813); the lanes take that infector's contact
 // events 32 at a time. Duplicate targets inside a batch are ranked with __match_any_sync so that the outcome
 // equals processing the events one after another.
-__global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
+template <bool TP> __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
     const int r = blockIdx.x, lane = threadIdx.x;
     const DevPset &P = S.psets[S.pset_of[r]];
     const uint2 key = S.key[r];
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
                 // ---- one infector (:798-803)
                 const uint32_t sx = __ldcg(&S.status[rb + x]);
                 const int xh = st_health(sx);
-                const int cnts = budget_of<true>(S, key, x, day, sx);
+                const int cnts = budget_of<TP>(S, key, x, day, sx);
                 if (cnts == 0) continue;
                 const unsigned long long gp = __ldg(&S.gpw[st_ag(sx) * 256 + cnts]);     // :804
                 const int p1 = (int)(gp & 0xFF), p2 = p1 + (int)((gp >> 8) & 0xFF), p3 = p2 + (int)((gp >> 16) & 0xFF),
@@ -230,11 +230,11 @@ __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
                     uint32_t j = 0x80000000u + lane, sy = 0, w1 = 0;
                     int remy = 0;
                     if (act) {
-                        const uint4 w = draw4<true>(S, x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                        const uint4 w = draw4<TP>(S, x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
                         w1 = w.y;
                         j = S.grp_idx[rb + go + below(w.x, len)];                        // :807
                         sy = __ldcg(&S.status[rb + j]);
-                        remy = budget_of<true>(S, key, j, day, sy);                            // :811
+                        remy = budget_of<TP>(S, key, j, day, sy);                            // :811
                     }
                     const unsigned peers = __match_any_sync(FULL, j);
                     const int rank = __popc(peers & lt), cntp = __popc(peers);
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(32) k_dyntrans_exact(Dev S, int day) {
 // budgets and counts, per infectious target, the hits coming from lower indices; APPLY gives infector x
 // gpw(budget_x - hits_x) contacts and resolves them with CAS. COUNT runs twice (the second sweep uses the corrected
 // budgets of the first), leaving a third-order difference in the infectious fraction.
-template <bool COUNT>
+template <bool COUNT, bool TP>
 __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const uint32_t *hits_in, uint32_t *hits_out) {
     const int r = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const DevPset &P = S.psets[S.pset_of[r]];
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
             const int x = (wi << 5) + b;
             const uint32_t sx = __ldcg(&S.status[rb + x]);
             const int xh = st_health(sx);
-            int cnts = st_health(sx) == DED ? 0 : fresh_budget<true>(S, key, x, day, sx);    // :802, the day's undiminished budget
+            int cnts = st_health(sx) == DED ? 0 : fresh_budget<TP>(S, key, x, day, sx);    // :802, the day's undiminished budget
             if (hits_in) cnts = max(0, cnts - (int)((hits_in[(rb + x) >> 1] >> (16 * (x & 1))) & 0xFFFFu));
             if (cnts == 0) continue;
             const unsigned long long gp = __ldg(&S.gpw[st_ag(sx) * 256 + cnts]);     // :804
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
                     const int go = off[g], len = off[g + 1] - go;
                     if (len == 0) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
                     else {
-                        const uint4 w = draw4<true>(S, x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
+                        const uint4 w = draw4<TP>(S, x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
                         j = S.grp_idx[rb + go + below(w.x, len)];                    // :807
                         if (COUNT) {
                             if ((int)j > x && ((mask[j >> 5] >> (j & 31)) & 1u)) atomicAdd(&hits_out[(rb + j) >> 1], 1u << (16 * (j & 1)));
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
                         for (;;) {
                             int rem;
                             if (st_tag(old) == day) rem = st_rem(old);
-                            else { if (fresh < 0) fresh = fresh_budget<true>(S, key, j, day, old); rem = fresh; }
+                            else { if (fresh < 0) fresh = fresh_budget<TP>(S, key, j, day, old); rem = fresh; }
                             if (rem == 0) break;                                      // :812
                             uint32_t nw = (old & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)(rem - 1) | ((uint32_t)day << 22);   // :813
                             const bool infect = st_health(old) == SUS && st_swap(old) == UNDEF && bern(w.y, bthr);           // :822-823
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(256) k_ct_scan_identifiers(Dev S, int day) {
 
 // Pass A over the queued index cases of today (queued by yesterday's agent_update_ct, or by the scan above): the work is
 // proportional to the number of index cases, not to the population. CTA per replicate, warp per index case.
-__global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
+template <bool TP> __global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
     __shared__ uint32_t buf[4][CT_GATHER];
     const int r = blockIdx.x, wid = threadIdx.x >> 5;
     const DevPset &P = S.psets[S.pset_of[r]];
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
     const uint32_t n = *cnt;
     const uint32_t *list = S.ident_list + ((size_t)r * 2 + (day & 1)) * S.Np;
     for (uint32_t k = wid; k < n; k += 4)
-        ct_identify_warp<true>(S, P, r, (int)list[k], day, buf[wid], CT_GATHER, S.mark_pre + (size_t)r * S.nwords, S.mark_post + (size_t)r * S.nwords);
+        ct_identify_warp<TP>(S, P, r, (int)list[k], day, buf[wid], CT_GATHER, S.mark_pre + (size_t)r * S.nwords, S.mark_post + (size_t)r * S.nwords);
     __syncthreads();
     if (threadIdx.x == 0) *cnt = 0;
 }
@@ -478,13 +478,13 @@ __global__ void __launch_bounds__(128) k_ct_identify_list(Dev S, int day) {
 // identification, quarantine expiry) -> isob := iso (the value :778 sees) -> [post mark]; then the next event day.
 // The marks are the hoisted cross-agent writes of :705-716 (k_ct_identify_list). Quarantine countdown (:718-750):
 // tracedxp == txpday - day after today's update.
-__device__ __noinline__ uint32_t agent_event(const Dev &S, int r, int i, int day, bool pre, bool post) {
+template <bool TP> __device__ __noinline__ uint32_t agent_event(const Dev &S, int r, int i, int day, bool pre, bool post) {
     const size_t a = (size_t)r * S.Np + i;
     const uint32_t st0 = S.status[a];
     const int texp0 = S.texp[a];
     const int par = (day + 1) & 1;
     const DevPset &P = S.psets[S.pset_of[r]];
-    const Ev e = agent_event_core<true>(S, P, r, i, day, S.key[r], st0, texp0, P.ctstrat != 0, pre, post,
+    const Ev e = agent_event_core<TP>(S, P, r, i, day, S.key[r], st0, texp0, P.ctstrat != 0, pre, post,
                                   S.ident_cnt ? &S.ident_cnt[r * 2 + par] : nullptr, S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * S.Np : nullptr);
     if (e.newh != e.oldh) {
         if (is_infectious(e.newh) != is_infectious(e.oldh)) atomicXor(&S.infmask[(size_t)r * S.nwords + (i >> 5)], 1u << (i & 31));
@@ -546,14 +546,14 @@ __global__ void __launch_bounds__(256) k_time_update_scan(const __grid_constant_
     }
 }
 
-__global__ void __launch_bounds__(256) k_time_update_events(const __grid_constant__ Dev S, int day) {
+template <bool TP> __global__ void __launch_bounds__(256) k_time_update_events(const __grid_constant__ Dev S, int day) {
     const int r = blockIdx.y;
     const unsigned n = S.ev_cnt[r * 2 + (day & 1)];
     const bool hm_on = S.store_hm && day < S.T;
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t ent = S.ev_list[(size_t)r * S.Np + k];
         const int i = (int)(ent & 0x3FFFFFFFu);
-        const uint32_t newh = agent_event(S, r, i, day, (ent >> 30) & 1u, ent >> 31);
+        const uint32_t newh = agent_event<TP>(S, r, i, day, (ent >> 30) & 1u, ent >> 31);
         if (hm_on) S.hm[((size_t)r * S.T + (size_t)day) * S.N + i] = (uint8_t)newh;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) S.ev_cnt[r * 2 + ((day + 1) & 1)] = 0;      // tomorrow's counter (read two launches from now)
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(256) k_reduce_hmatrix(const int16_t *hm, const
 }
 
 // ============================================================================ peek / poke (tests read `humans` like test/runtests.jl)
-__global__ void __launch_bounds__(256) k_peek(Dev S, int field, int r, int day, int *out) {
+template <bool TP> __global__ void __launch_bounds__(256) k_peek(Dev S, int field, int r, int day, int *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.N) return;
     const size_t a = (size_t)r * S.Np + i;
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(256) k_peek(Dev S, int field, int r, int day, 
     case 0: v = st_health(st); break;
     case 1: v = st_swap(st); break;
     case 2: v = S.sickfrom[a]; break;
-    case 3: v = budget_of<true>(S, S.key[r], i, day, st); break;
+    case 3: v = budget_of<TP>(S, S.key[r], i, day, st); break;
     case 4: v = st_ag(st) + 1; break;
     case 5: v = tis; break;
     case 6: v = (st_health(st) == SUS && st_swap(st) == LAT) ? tis : (int)S.texp[a] - (int)S.entry[a]; break;
@@ -754,13 +754,21 @@ static inline dim3 agent_grid(const Dev &S, int per_thread) {
     return dim3((unsigned)((S.Np + 256 * per_thread - 1) / (256 * per_thread)), (unsigned)S.R);
 }
 
-int launch_initialize(const Dev &S, cudaStream_t s) { k_initialize<<<agent_grid(S, 1), 256, 0, s>>>(S); return 1; }
+int launch_initialize(const Dev &S, cudaStream_t s) {
+    if (S.tape_n) k_initialize<true><<<agent_grid(S, 1), 256, 0, s>>>(S); else k_initialize<false><<<agent_grid(S, 1), 256, 0, s>>>(S);
+    return 1;
+}
 int launch_build_groups(const Dev &S, cudaStream_t s) { k_build_groups<<<S.R, 256, 0, s>>>(S); return 1; }
 int launch_insert_infected(const Dev &S, int which, int health, int num, int ag, int call_id, int day, cudaStream_t s) {
-    k_insert_infected<<<S.R, 256, 0, s>>>(S, which, health, num, ag, call_id, day); return 1;
+    if (S.tape_n) k_insert_infected<true><<<S.R, 256, 0, s>>>(S, which, health, num, ag, call_id, day);
+    else k_insert_infected<false><<<S.R, 256, 0, s>>>(S, which, health, num, ag, call_id, day);
+    return 1;
 }
 int launch_first_column(const Dev &S, cudaStream_t s) { k_first_column<<<agent_grid(S, 1), 256, 0, s>>>(S); return 1; }
-int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s) { k_dyntrans_exact<<<S.R, 32, 0, s>>>(S, day); return 1; }
+int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s) {
+    if (S.tape_n) k_dyntrans_exact<true><<<S.R, 32, 0, s>>>(S, day); else k_dyntrans_exact<false><<<S.R, 32, 0, s>>>(S, day);
+    return 1;
+}
 int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s) {
     cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, s); cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, s);
     // two fixed-point sweeps for the budgets (first and second order in the infectious fraction), then the CAS pass
@@ -768,9 +776,15 @@ int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s) {
     uint32_t *h0 = S.hits, *h1 = S.hits + half;
     cudaMemsetAsync(S.hits, 0, half * 8, s);
     const dim3 grid((unsigned)((S.nwords + 63) / 64), (unsigned)S.R);
-    k_dyntrans_native<true><<<grid, 256, 0, s>>>(S, day, nullptr, h0);
-    k_dyntrans_native<true><<<grid, 256, 0, s>>>(S, day, h0, h1);
-    k_dyntrans_native<false><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
+    if (S.tape_n) {
+        k_dyntrans_native<true, true><<<grid, 256, 0, s>>>(S, day, nullptr, h0);
+        k_dyntrans_native<true, true><<<grid, 256, 0, s>>>(S, day, h0, h1);
+        k_dyntrans_native<false, true><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
+    } else {
+        k_dyntrans_native<true, false><<<grid, 256, 0, s>>>(S, day, nullptr, h0);
+        k_dyntrans_native<true, false><<<grid, 256, 0, s>>>(S, day, h0, h1);
+        k_dyntrans_native<false, false><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
+    }
     return 3;
 }
 int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s) {
@@ -779,15 +793,18 @@ int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s) {
         cudaMemsetAsync(S.ident_cnt, 0, (size_t)S.R * 8, s);
         k_ct_scan_identifiers<<<agent_grid(S, 1), 256, 0, s>>>(S, day); ++n;
     }
-    k_ct_identify_list<<<S.R, 128, 0, s>>>(S, day);
+    if (S.tape_n) k_ct_identify_list<true><<<S.R, 128, 0, s>>>(S, day); else k_ct_identify_list<false><<<S.R, 128, 0, s>>>(S, day);
     return n;
 }
-int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStream_t s) {
-    (void)all_ct;
-    int n = 2;
+int launch_time_update_scan(const Dev &S, int day, bool any_ct, cudaStream_t s) {
     k_time_update_scan<<<agent_grid(S, 16), 256, 0, s>>>(S, day, any_ct ? 1 : 0);
+    return 1;
+}
+int launch_time_update_events(const Dev &S, int day, cudaStream_t s) {
+    int n = 1;
     unsigned eb = (unsigned)(S.N / 16384); if (eb < 1) eb = 1; if (eb > 64) eb = 64;
-    k_time_update_events<<<dim3(eb, (unsigned)S.R), 256, 0, s>>>(S, day);
+    if (S.tape_n) k_time_update_events<true><<<dim3(eb, (unsigned)S.R), 256, 0, s>>>(S, day);
+    else k_time_update_events<false><<<dim3(eb, (unsigned)S.R), 256, 0, s>>>(S, day);
     if (day == 1) { k_resync_isob<<<148 * 8, 256, 0, s>>>(S); ++n; }
     return n;
 }
@@ -806,7 +823,10 @@ int launch_narrow(const int *a, const int *b, int16_t *out, size_t n, cudaStream
 int launch_mean_curves(const int *inc, const int *prev, double *minc, double *mprev, int R, size_t per_rep, cudaStream_t s) {
     k_mean_curves<<<(unsigned)((per_rep + 255) / 256), 256, 0, s>>>(inc, prev, minc, mprev, R, per_rep); return 1;
 }
-int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s) { k_peek<<<(S.N + 255) / 256, 256, 0, s>>>(S, field, r, day, out); return 1; }
+int launch_peek(const Dev &S, int field, int r, int day, int *out, cudaStream_t s) {
+    if (S.tape_n) k_peek<true><<<(S.N + 255) / 256, 256, 0, s>>>(S, field, r, day, out); else k_peek<false><<<(S.N + 255) / 256, 256, 0, s>>>(S, field, r, day, out);
+    return 1;
+}
 int launch_poke(const Dev &S, int field, int r, int i, int day, int value, cudaStream_t s) { k_poke<<<1, 1, 0, s>>>(S, field, r, i, day, value); return 1; }
 
 }  // namespace cabm

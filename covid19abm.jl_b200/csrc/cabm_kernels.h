@@ -13,7 +13,8 @@ int launch_first_column(const Dev &S, cudaStream_t s);
 int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s);
 int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s);
 int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s);
-int launch_time_update(const Dev &S, int day, bool any_ct, bool all_ct, cudaStream_t s);
+int launch_time_update_scan(const Dev &S, int day, bool any_ct, cudaStream_t s);
+int launch_time_update_events(const Dev &S, int day, cudaStream_t s);
 int launch_curves_finalize(const Dev &S, cudaStream_t s);
 int launch_count_infectors(const Dev &S, cudaStream_t s);
 int launch_reduce_hmatrix(const int16_t *hm, const int *ags, int M, int N, int T, int *inc, int *prev, cudaStream_t s);

@@ -133,9 +133,9 @@ int cabm_mark(cabm_handle *h);
 int cabm_ms_since_mark(cabm_handle *marked, cabm_handle *h, float *ms);
 /* Per-kernel-class device time of a run: with profiling on, cabm_run brackets every launch with CUDA events on
  * the handle's stream (and synchronises at the end); cabm_get_profile returns the summed milliseconds and the launch
- * count per class. Classes: dyntrans :790-834, time_update :399-428 (+snapshot), ct_dynamics pass A :705-716,
- * everything else (initialize, seeding, group tables, reductions), the fused whole-run kernel. */
-enum { CABM_K_DYNTRANS = 0, CABM_K_TIME_UPDATE = 1, CABM_K_CT_IDENTIFY = 2, CABM_K_OTHER = 3, CABM_K_FUSED = 4, CABM_N_KCLASS = 5 };
+ * count per class. Classes: dyntrans :790-834, time_update :399-428 streaming scan (+snapshot), ct_dynamics pass A :705-716,
+ * everything else (initialize, seeding, group tables, reductions), the fused whole-run kernel, time_update's event kernel. */
+enum { CABM_K_DYNTRANS = 0, CABM_K_TIME_UPDATE = 1, CABM_K_CT_IDENTIFY = 2, CABM_K_OTHER = 3, CABM_K_FUSED = 4, CABM_K_TU_EVENTS = 5, CABM_N_KCLASS = 6 };
 int cabm_set_profiling(cabm_handle *h, int on);
 int cabm_get_profile(cabm_handle *h, float *ms /*[CABM_N_KCLASS]*/, int32_t *launches /*[CABM_N_KCLASS]*/);
 /* Execution path of cabm_run. FUSED: one persistent CTA per replicate runs all of main() with the per-agent state in

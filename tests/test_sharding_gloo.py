@@ -47,3 +47,40 @@ def test_two_rank_shard_and_gather(tmp_path, O, cv):
         assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all()
         assert (got["infectors"] == ref["infectors"]).all() and (got["totalisolated"] == ref["totalisolated"]).all()
         assert (got["lat_inc_sum"] == ref["inc"][:, 0, :, 1].sum(axis=1)).all()
+
+
+# ------------------------------------------------------------------------------------------------ the same plumbing on GPUs
+import pytest
+
+
+def _nccl_worker(rank, world, port, out_dir, nsims):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import covid19abm_b200 as cv
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ip = cv.ModelParameters(β=0.07, prov="ontario", modeltime=120, initialinf=2, fmild=0.5, τmild=1, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3)
+    full = cv.run_ensemble_sharded(ip, nsims, rank, world, dist=dist, device_index=rank)
+    np.savez(os.path.join(out_dir, f"nccl_rank{rank}.npz"), **full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_sharded_ensemble_over_nccl(tmp_path, cv):
+    """run_ensemble_sharded on two GPUs (one process each, replicate r on rank r mod 2) with the end-of-run all_gather over
+    NCCL/NVLink: every rank ends up with the whole ensemble in replicate order, equal to the one-GPU run."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nsims = 37
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path), nsims), nprocs=2, join=True)
+    ip = cv.ModelParameters(β=0.07, prov="ontario", modeltime=120, initialinf=2, fmild=0.5, τmild=1, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3)
+    ref = cv.run_ensemble(ip, nsims)
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), f"nccl_rank{rank}.npz"))
+        for k in ("inc", "prev", "infectors", "totalisolated", "lat_inc_sum"):
+            assert (got[k] == ref[k]).all(), (rank, k)
+        assert (got["err"] == 0).all()

@@ -8,7 +8,7 @@ key = sys.argv[3] if len(sys.argv) > 3 else "samples"
 cur, hdr = None, None
 agg = collections.defaultdict(lambda: [0, 0, "", collections.Counter(), 0])
 for r in rows:
-    if len(r) == 2 and r[0] == "File Name":
+    if len(r) == 2 and r[0] in ("File Name", "File Path"):
         cur = r[1].split('/')[-1]; continue
     if r and r[0] == "Line No":
         hdr = r; ie = hdr.index('Instructions Executed'); ss = hdr.index('# Samples'); te = hdr.index('Thread Instructions Executed')
