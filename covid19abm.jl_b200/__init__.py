@@ -727,7 +727,9 @@ def gather_ensemble(local, nsims, rank, world, dist=None, device="cpu", keys=("i
     gathered = {}
     for k, t in staged.items():
         out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out.view((world * t.shape[0],) + tuple(t.shape[1:])), t)
+        # NCCL has no 16-bit integer type: the Int16 curves travel as bytes
+        ti, to = (t.view(torch.uint8), out.view(torch.uint8)) if t.dtype in (torch.int16, torch.uint16) else (t, out)
+        dist.all_gather_into_tensor(to.reshape(-1), ti.reshape(-1))
         gathered[k] = out
     if events is not None:
         events[1].record()

@@ -186,10 +186,11 @@ struct Tr { uint32_t st; int expday; int oldh, newh; };
 constexpr int DUR_CACHE = 256;          // direct-mapped shared-memory cache of `dur` words for infected agents (fused kernel)
 
 template <bool TP = false> __device__ inline Tr transition_core(const Dev &S, const DevPset &P, int r, int i, int day, uint32_t st, uint2 key,
-                                     int target /* swap to apply */, bool seed_simple_inf, unsigned long long *dcache = nullptr) {
+                                     int target /* swap to apply */, bool seed_simple_inf, unsigned long long *dcache = nullptr,
+                                     int *via_io = nullptr /* the agent's isovia held by the caller: no load, no store here */) {
     size_t a = (size_t)r * S.Np + i;
     const int oldh = st_health(st), ag = st_ag(st);
-    const uint8_t via0 = S.isovia[a];   // needed by a few targets only, but loaded here so that its latency hides behind the draws
+    const int via0 = via_io ? *via_io : (int)S.isovia[a];   // needed by a few targets only, but loaded here so that its latency hides behind the draws
     uint32_t d4;
     if (dcache) {                        // (agent << 32 | dur) — filled when the agent is infected, so the HBM load is off this path
         const unsigned long long e = dcache[i & (DUR_CACHE - 1)];
@@ -254,7 +255,7 @@ template <bool TP = false> __device__ inline Tr transition_core(const Dev &S, co
         atomicOr(&S.err[r], ERR_NO_SWAP);
         return Tr{st, 32767, oldh, oldh};
     }
-    if (via >= 0 && via0 == VIA_NULL) S.isovia[a] = (uint8_t)via;   // _set_isolation :432-444 only fills a :null isovia
+    if (via >= 0 && via0 == VIA_NULL) { if (via_io) *via_io = via; else S.isovia[a] = (uint8_t)via; }   // _set_isolation :432-444 only fills a :null isovia
     S.entry[a] = (int16_t)day;
     st = st_set_swap(st_set_health(st, newh), newsw);
     st = iso ? (st | ST_ISO | ST_ISOB) : (st & ~(ST_ISO | ST_ISOB));
@@ -288,23 +289,25 @@ template <bool TP = false> __device__ inline Ev agent_event_core(const Dev &S, c
                                       uint32_t *queue_cnt /* tomorrow's index cases */, uint32_t *queue, unsigned long long *dcache = nullptr) {
     const size_t a = (size_t)r * S.Np + i;
     int oldh = st_health(st), newh = oldh;
-    int txp = 0, txp0 = 0;
+    // the agent's tracing fields, loaded together up front (independent loads: one round trip to L2) and written back at the end
+    int txp = 0, txp0 = 0, via = 0, via_in = 0, latday = 0, ts = 0, te = 0, ts0 = 0, te0 = 0;
     if (ct) {
-        txp = txp0 = S.txpday[a];
+        txp = txp0 = S.txpday[a]; via = via_in = S.isovia[a]; latday = S.latday[a]; ts = ts0 = S.tracestart[a]; te = te0 = S.traceend[a];
         if (pre) {                                             // apply_ct_strategy :647-656 by an index case with a lower index
             st |= ST_ISO;
-            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            if (via == VIA_NULL) via = VIA_CT;
             txp = P.qdays > 0 ? day + P.qdays - 1 : 0;         // counted down once more in this same update
         }
     }
     if (texp <= day || (st_health(st) == SUS && st_swap(st) == LAT)) {      // :405 (an infection today set exp = tis :826)
-        const Tr t = transition_core<TP>(S, P, r, i, day, st, key, st_swap(st), false, dcache);
+        const int target = st_swap(st);
+        const Tr t = transition_core<TP>(S, P, r, i, day, st, key, target, false, dcache, ct ? &via : nullptr);
         st = t.st; texp = t.expday; oldh = t.oldh; newh = t.newh;
+        if (target == LAT) latday = day;                       // move_to_latent set doi = 0 (:449; transition_core wrote latday)
     }
     int ne = texp;
     if (ct) {
-        const int latday = S.latday[a], doi = day - latday;
-        int ts = S.tracestart[a], te = S.traceend[a];
+        const int doi = day - latday;
         if (st_health(st) == LAT && st_swap(st) != ASYMP && doi == 0) {      // :678
             const uint4 w = draw4<TP>(S, i, day, S_CTWIN, 0, key);
             if (bern(w.x, P.fctcap_thr)) {
@@ -313,7 +316,6 @@ template <bool TP = false> __device__ inline Ev agent_event_core(const Dev &S, c
                 const int delta = (int)(d4 & 0xFF) + (int)((d4 >> 16) & 0xFF) + tid;
                 const int q = delta - P.cdaysback;
                 ts = q > 0 ? q : 0; te = delta;
-                S.tracestart[a] = (int16_t)ts; S.traceend[a] = (int16_t)te;
                 st &= ~ST_TRACING;
                 S.ct_head[a] = CT_NONE;                                        // :687
             }
@@ -322,7 +324,7 @@ template <bool TP = false> __device__ inline Ev agent_event_core(const Dev &S, c
         if (doi == te) {                                                      // :705-716 (contacts were handled in pass A)
             st &= ~ST_TRACING;
             st |= ST_ISO;
-            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            if (via == VIA_NULL) via = VIA_CT;
             txp = P.qdays > 0 ? day + P.qdays - 1 : 0;
             atomicAdd(&S.totiso[r], 1ull);
             S.ct_head[a] = CT_NONE;
@@ -331,14 +333,14 @@ template <bool TP = false> __device__ inline Ev agent_event_core(const Dev &S, c
             if (!(st & ST_ISO)) atomicOr(&S.err[r], ERR_TRACED_NOT_ISO);
             if (txp == day) {                                                 // :734 the countdown ends today
                 st &= ~ST_ISO;
-                S.isovia[a] = VIA_NULL;
+                via = VIA_NULL;
                 txp = 0;
                 if (P.ctstrat == 3) {
                     const uint4 w = draw4<TP>(S, i, day, S_CT3, 0, key);
                     const int h = st_health(st);
                     if ((h == LAT && bern(w.x, c_tab.ct3_lat_thr)) || (h == PRE && bern(w.x, c_tab.ct3_pre_thr)) ||
                         (h == ASYMP && bern(w.x, c_tab.ct3_asymp_thr)) || h == MILD || h == INF || h == MISO || h == IISO) {
-                        st |= ST_ISO; S.isovia[a] = VIA_CT; txp = day + 14;
+                        st |= ST_ISO; via = VIA_CT; txp = day + 14;
                     }
                 }
             }
@@ -348,14 +350,15 @@ template <bool TP = false> __device__ inline Ev agent_event_core(const Dev &S, c
     if (ct) {
         if (post) {                                            // apply_ct_strategy by an index case with a higher index: after this agent's own step
             st |= ST_ISO;
-            if (S.isovia[a] == VIA_NULL) S.isovia[a] = VIA_CT;
+            if (via == VIA_NULL) via = VIA_CT;
             txp = P.qdays > 0 ? day + P.qdays : 0;
         }
         if (txp != txp0) S.txpday[a] = (int16_t)txp;
+        if (via != via_in) S.isovia[a] = (uint8_t)via;
+        if (ts != ts0 || te != te0) { S.tracestart[a] = (int16_t)ts; S.traceend[a] = (int16_t)te; }
         // next event: state expiry, tracing on, the eve of identification (to queue for pass A), identification, end of quarantine
-        const int te = S.traceend[a];
         if (te >= 0) {
-            const int latday = S.latday[a], ts = S.tracestart[a], idd = latday + te, tron = latday + ts;
+            const int idd = latday + te, tron = latday + ts;
             if (ts < te && tron > day) ne = min(ne, tron);
             if (idd - 1 > day) ne = min(ne, idd - 1);
             if (idd > day) ne = min(ne, idd);

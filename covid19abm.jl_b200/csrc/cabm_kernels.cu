@@ -397,8 +397,6 @@ __device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, i
     const uint2 key = S.key[r];
     const uint32_t *log = S.ct_log + (size_t)r * S.ct_cap;
     const uint32_t head = S.ct_head[a];
-    int n = 0;
-    for (uint32_t c = head; c != CT_NONE; c = log[c]) n += (int)log[c + 1];
     auto contact = [&](uint32_t y) {
         const uint4 w = draw4<TP>(S, x, day, S_CTCON, y, key);
         if (!bern(w.x, P.fcontact_thr)) return;               // :711
@@ -406,19 +404,29 @@ __device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, i
         if (y > (uint32_t)x) atomicOr(&mpre_row[y >> 5], 1u << (y & 31));
         else if (y < (uint32_t)x) atomicOr(&mpost_row[y >> 5], 1u << (y & 31));
     };
-    if (n <= bufcap) {
-        int o = 0;
-        for (uint32_t c = head; c != CT_NONE; c = log[c]) {
-            const int cnt = (int)log[c + 1];
-            for (int k = lane; k < cnt; k += 32) buf[o + k] = log[c + 2 + k];
-            o += cnt;
-        }
+    // one walk along the chain of the case's chunks (newest first), gathering as it goes
+    int n = 0;
+    bool fits = true;
+    for (uint32_t c = head; c != CT_NONE;) {
+        const uint32_t next = log[c];
+        const int cnt = (int)log[c + 1];
+        if (n + cnt > bufcap) { fits = false; break; }
+        for (int k = lane; k < cnt; k += 32) buf[n + k] = log[c + 2 + k];
+        n += cnt; c = next;
+    }
+    if (fits) {
         __syncwarp();
-        for (int k = lane; k < n; k += 32) {
-            const uint32_t y = buf[k];
-            bool dup = false;
-            for (int q = 0; q < k; ++q) if (buf[q] == y) { dup = true; break; }
-            if (!dup) contact(y);
+        if (n <= 32) {                                        // the usual case: the distinct contacts are the first lane of each group of equal ones
+            const uint32_t y = lane < n ? buf[lane] : 0xFFFFFF00u + (uint32_t)lane;
+            const unsigned peers = __match_any_sync(FULL, y);
+            if (lane < n && lane == __ffs(peers) - 1) contact(y);
+        } else {
+            for (int k = lane; k < n; k += 32) {
+                const uint32_t y = buf[k];
+                bool dup = false;
+                for (int q = 0; q < k; ++q) if (buf[q] == y) { dup = true; break; }
+                if (!dup) contact(y);
+            }
         }
         __syncwarp();
     } else if (lane == 0) {                                   // very long contact sets: one lane, quadratic walk

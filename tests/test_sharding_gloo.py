@@ -30,7 +30,9 @@ def _worker(rank, world, port, out_dir):
     loc = O.run_ensemble([_params(O)], [0] * len(idx), [seeds[i] for i in idx], nthreads=1)
     loc["lat_inc_sum"] = loc["inc"][:, 0, :, 1].sum(axis=1).astype(np.int64)
     loc["err"] = np.zeros(len(idx), dtype=np.uint32)
+    loc["inc"] = loc["inc"].astype(np.int16)          # the transport form of the curves (Int16: travels as bytes, NCCL has no 16-bit integers)
     full = cv.gather_ensemble(loc, NSIMS, rank, world, dist=dist, device="cpu")
+    assert full["inc"].dtype == np.int16
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **full)
     dist.barrier()
     dist.destroy_process_group()
