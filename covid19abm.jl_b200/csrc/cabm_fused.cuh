@@ -1015,7 +1015,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 }
                 // every thread looks at FUSED_SCAN_U chunks of 8 expiry days at once (independent loads and compares), then handles
                 // the few agents that have an event today (:405, marks) one after another
-                const uint32_t dd = (uint32_t)day * 0x10001u;
                 uint32_t mn = 0x7FFF7FFFu;                                     // running min of the event days that stay (2 x i16)
                 for (int b0 = tid * 8; b0 < N; b0 += NT * 8 * FUSED_SCAN_U) {
                     uint4 ex[FUSED_SCAN_U];
@@ -1037,10 +1036,16 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                     for (int u = 0; u < FUSED_SCAN_U; ++u) cmin = __vimin3_s16x2(cmin, __vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w));
                     if (min((int)(short)(cmin & 0xFFFFu), (int)(short)(cmin >> 16)) <= day || (pre | post) != 0) {   // somebody in these chunks has an event today
 #pragma unroll
-                        for (int u = 0; u < FUSED_SCAN_U; ++u) {
-                            const uint32_t m0 = __vcmples2(ex[u].x, dd), m1 = __vcmples2(ex[u].y, dd), m2 = __vcmples2(ex[u].z, dd), m3 = __vcmples2(ex[u].w, dd);
-                            const unsigned f = (m0 & 1u) | ((m0 >> 15) & 2u) | ((m1 & 1u) << 2) | ((m1 >> 13) & 8u) | ((m2 & 1u) << 4) | ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u);
-                            fire |= (unsigned long long)f << (8 * u);
+                        for (int u = 0; u < FUSED_SCAN_U; ++u) {               // per-agent compares only in chunks that hold a due day
+                            const uint32_t cu = __vmins2(__vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w));
+                            if (min((int)(short)(cu & 0xFFFFu), (int)(short)(cu >> 16)) <= day) {
+                                const uint32_t wds[4] = {ex[u].x, ex[u].y, ex[u].z, ex[u].w};
+                                unsigned f = 0;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    f |= ((unsigned)((int)(short)(wds[k] & 0xFFFFu) <= day) << (2 * k)) | ((unsigned)((int)(short)(wds[k] >> 16) <= day) << (2 * k + 1));
+                                fire |= (unsigned long long)f << (8 * u);
+                            }
                         }
                         fire |= pre | post;
                         while (fire) {

@@ -504,37 +504,48 @@ template <bool TP> __device__ __noinline__ uint32_t agent_event(const Dev &S, in
     return (uint32_t)e.newh;
 }
 
-// Two launches per day. k_time_update_scan is the pure stream: thread per 16 consecutive agents, two 128-bit loads of event days,
-// one 128-bit load and one 128-bit store of column bytes (the next column starts as a copy of the previous one), the mark bits;
+// Two launches per day. k_time_update_scan is the pure stream: thread per 32 consecutive agents, four 128-bit loads of event days,
+// two 128-bit loads and stores of column bytes (the next column starts as a copy of the previous one), the mark bits;
 // agents with an event today are appended to the replicate's event list (one atomicAdd per warp). k_time_update_events then runs
 // agent_event for exactly those agents, one per thread in dense warps, and patches their byte of the new column. (A single kernel
 // that handled events inside the stream stalled whole warps on one lane's dependent HBM loads: 0.10 of HBM peak on 10^6 agents.)
 __global__ void __launch_bounds__(256) k_time_update_scan(const __grid_constant__ Dev S, int day, int any_ct) {
+    // thread per 32 consecutive agents (one word of each mark bitmask): four 128-bit loads of event days in flight, two of column bytes
     const int r = blockIdx.y, lane = threadIdx.x & 31;
-    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 32;
     const bool valid = i0 < S.N;
     unsigned fire = 0, pre = 0, post = 0;
     if (valid) {
         const size_t a0 = (size_t)r * S.Np + i0;
-        const uint4 e0 = *reinterpret_cast<const uint4 *>(S.expday + a0), e1 = *reinterpret_cast<const uint4 *>(S.expday + a0 + 8);
+        uint4 e[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e[q] = *reinterpret_cast<const uint4 *>(S.expday + a0 + 8 * q);     // Np is padded to 32: in bounds
+        const bool hm_on = S.store_hm && day < S.T;
+        const bool vec = (S.N & 15) == 0;
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+        const uint8_t *prv = nullptr; uint8_t *cur = nullptr;
+        if (hm_on) {                                                     // column st+1 = state at the start of the next day: copy, patched by the events
+            prv = S.hm + ((size_t)r * S.T + (size_t)(day - 1)) * S.N + i0;
+            cur = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
+            if (vec) { c0 = *reinterpret_cast<const uint4 *>(prv); if (i0 + 16 < S.N) c1 = *reinterpret_cast<const uint4 *>(prv + 16); }
+        }
         if (any_ct) {                                                    // marks left by today's index cases (pass A)
             const size_t wi = (size_t)r * S.nwords + (i0 >> 5);
-            const unsigned sh = i0 & 31;
-            pre = (S.mark_pre[wi] >> sh) & 0xFFFFu; post = (S.mark_post[wi] >> sh) & 0xFFFFu;
-            if (pre) atomicAnd(&S.mark_pre[wi], ~(0xFFFFu << sh));       // consumed by this update
-            if (post) atomicAnd(&S.mark_post[wi], ~(0xFFFFu << sh));
+            pre = S.mark_pre[wi]; post = S.mark_post[wi];
+            if (pre) S.mark_pre[wi] = 0;                                 // consumed by this update (this thread owns the word)
+            if (post) S.mark_post[wi] = 0;
         }
         const uint32_t dd = (uint32_t)day * 0x10001u;
-        const uint32_t m[8] = {__vcmples2(e0.x, dd), __vcmples2(e0.y, dd), __vcmples2(e0.z, dd), __vcmples2(e0.w, dd),
-                               __vcmples2(e1.x, dd), __vcmples2(e1.y, dd), __vcmples2(e1.z, dd), __vcmples2(e1.w, dd)};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) fire |= ((m[k] & 1u) | ((m[k] >> 15) & 2u)) << (2 * k);
-        fire = (fire | pre | post) & (S.N - i0 >= 16 ? 0xFFFFu : ((1u << (S.N - i0)) - 1u));
-        if (S.store_hm && day < S.T) {                                   // column st+1 = state at the start of the next day: copy, patched by the events
-            const uint8_t *prv = S.hm + ((size_t)r * S.T + (size_t)(day - 1)) * S.N + i0;
-            uint8_t *cur = S.hm + ((size_t)r * S.T + (size_t)day) * S.N + i0;
-            if ((S.N & 15) == 0) *reinterpret_cast<uint4 *>(cur) = *reinterpret_cast<const uint4 *>(prv);
-            else for (int k = 0; k < 16 && i0 + k < S.N; ++k) cur[k] = prv[k];
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t m[4] = {__vcmples2(e[q].x, dd), __vcmples2(e[q].y, dd), __vcmples2(e[q].z, dd), __vcmples2(e[q].w, dd)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fire |= ((m[k] & 1u) | ((m[k] >> 15) & 2u)) << (8 * q + 2 * k);
+        }
+        fire = (fire | pre | post) & (S.N - i0 >= 32 ? 0xFFFFFFFFu : ((1u << (S.N - i0)) - 1u));
+        if (hm_on) {
+            if (vec) { *reinterpret_cast<uint4 *>(cur) = c0; if (i0 + 16 < S.N) *reinterpret_cast<uint4 *>(cur + 16) = c1; }
+            else for (int k = 0; k < 32 && i0 + k < S.N; ++k) cur[k] = prv[k];
         }
     }
     // append the agents with an event: exclusive prefix of the counts over the warp, one atomicAdd per warp
@@ -805,7 +816,7 @@ int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s) {
     return n;
 }
 int launch_time_update_scan(const Dev &S, int day, bool any_ct, cudaStream_t s) {
-    k_time_update_scan<<<agent_grid(S, 16), 256, 0, s>>>(S, day, any_ct ? 1 : 0);
+    k_time_update_scan<<<agent_grid(S, 32), 256, 0, s>>>(S, day, any_ct ? 1 : 0);
     return 1;
 }
 int launch_time_update_events(const Dev &S, int day, cudaStream_t s) {
