@@ -69,7 +69,7 @@ def workload(name):
     if name == "E":
         return dict(desc="configs[4]: 1,000,000 agents x 500 days, quar_grp_frac=0.5 quar_grp=5, initialinf=100, 100 replicates sharded over the GPUs",
                     psets=[dict(β=0.0345, prov="ontario", popsize=1000000, modeltime=500, initialinf=100, quar_grp_frac=0.5, quar_grp=5)],
-                    N=1000000, T=500, R=100, scaling="strong", mode=os.environ.get("CABM_BENCH_E_MODE", "native"), hm=False)
+                    N=1000000, T=500, R=100, scaling="strong", mode=os.environ.get("CABM_BENCH_E_MODE", "exact"), hm=False)
     raise SystemExit(f"unknown --config {name}")
 
 

@@ -758,26 +758,37 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 // today's contact budget of targets that have none yet (:811 on first touch; get_nextday_counts :772-788), kept in
                                 // their status words (tag = today); every event of a target computes the same word
                                 if (__any_sync(FULL, any_need)) {
-                                    uint32_t w[NWIN]; int k[NWIN], len[NWIN]; const uint32_t *thr[NWIN];
+                                    uint32_t w[NWIN]; int k[NWIN], hi[NWIN]; const uint32_t *thr[NWIN];
 #pragma unroll
                                     for (int j = 0; j < NWIN; ++j) w[j] = pick(philox(y[j] >> 2, (uint32_t)day, S_COUNT, 0, key), y[j] & 3u);
+                                    // value = #{thr <= w}: the guide brackets it (bucket of the top byte; the top bucket by the next byte), a
+                                    // three-step binary search finishes brackets of up to 7 thresholds, longer ones (the far tail) walk on
 #pragma unroll
                                     for (int j = 0; j < NWIN; ++j) {
                                         const int ag = st_ag(sy[j]);
-                                        len[j] = M.nb_len[ag]; thr[j] = M.nb_thr + ag * 256;
-                                        k[j] = M.nb_guide[ag * 512 + ((w[j] >> 24) == 255u ? 256u + ((w[j] >> 16) & 0xFFu) : (w[j] >> 24))];
+                                        const int gi = (w[j] >> 24) == 255u ? 256 + (int)((w[j] >> 16) & 0xFFu) : (int)(w[j] >> 24);
+                                        thr[j] = M.nb_thr + ag * 256;
+                                        k[j] = M.nb_guide[ag * 512 + gi];
+                                        hi[j] = gi == 511 ? M.nb_len[ag] : (int)M.nb_guide[ag * 512 + gi + 1];
                                     }
 #pragma unroll
-                                    for (int j = 0; j < NWIN; ++j) k[j] += (k[j] < len[j] && thr[j][min(k[j], 255)] <= w[j]);
+                                    for (int j = 0; j < NWIN; ++j) {
+                                        const int lo = k[j], n = min(hi[j] - lo, 7);
+                                        int c = 0;
+                                        if (c + 4 <= n && thr[j][lo + c + 3] <= w[j]) c += 4;
+                                        if (c + 2 <= n && thr[j][lo + c + 1] <= w[j]) c += 2;
+                                        if (c + 1 <= n && thr[j][lo + c] <= w[j]) c += 1;
+                                        k[j] = lo + c;
+                                    }
                                     bool more = false;
 #pragma unroll
-                                    for (int j = 0; j < NWIN; ++j) more |= need[j] && !(sy[j] & ST_ISOB) && k[j] < len[j] && thr[j][min(k[j], 255)] <= w[j];
+                                    for (int j = 0; j < NWIN; ++j) more |= need[j] && !(sy[j] & ST_ISOB) && k[j] < hi[j] && thr[j][min(k[j], 255)] <= w[j];
                                     while (__any_sync(FULL, more)) {
                                         more = false;
 #pragma unroll
                                         for (int j = 0; j < NWIN; ++j) {
-                                            k[j] += (k[j] < len[j] && thr[j][min(k[j], 255)] <= w[j]);
-                                            more |= need[j] && !(sy[j] & ST_ISOB) && k[j] < len[j] && thr[j][min(k[j], 255)] <= w[j];
+                                            k[j] += (k[j] < hi[j] && thr[j][min(k[j], 255)] <= w[j]);
+                                            more |= need[j] && !(sy[j] & ST_ISOB) && k[j] < hi[j] && thr[j][min(k[j], 255)] <= w[j];
                                         }
                                     }
 #pragma unroll
