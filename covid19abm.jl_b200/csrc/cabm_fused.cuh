@@ -654,7 +654,8 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             if (have) {
                                 x = M.list[li];
                                 const uint32_t sx = M.status[x];
-                                cnts = budget_of_s(M, key, x, day, sx);
+                                cnts = fresh_budget_s(M, key, x, (uint32_t)day, sx);
+                                if (st_tag(sx) == day) cnts = max(0, cnts - st_rem(sx));       // contacts received earlier today (:813) came off it
                                 gp = gpw_pack(Z.cm + st_ag(sx) * 5, cnts);
                                 E = gpw_sum(gp);
                                 hx = st_health(sx) | (st_ag(sx) << 4) | ((sx & ST_TRACING) ? 0x80 : 0);
@@ -751,53 +752,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 for (int j = 0; j < NWIN; ++j) y[j] = ld_keep(grp + idx[j]);       // loads in flight together
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) sy[j] = M.status[y[j]];
-                                bool any_need = false;
 #pragma unroll
-                                for (int j = 0; j < NWIN; ++j) { need[j] = ok[j] && st_tag(sy[j]) != day; any_need |= need[j]; }
+                                for (int j = 0; j < NWIN; ++j) need[j] = ok[j] && st_tag(sy[j]) != day;
                                 PHASE(7);
-                                // today's contact budget of targets that have none yet (:811 on first touch; get_nextday_counts :772-788), kept in
-                                // their status words (tag = today); every event of a target computes the same word
-                                if (__any_sync(FULL, any_need)) {
-                                    uint32_t w[NWIN]; int k[NWIN], hi[NWIN]; const uint32_t *thr[NWIN];
+                                // first touch today: start the target's count of today's contacts (tag = today, count 0). Its contact budget
+                                // (:811, get_nextday_counts :772-788) is not drawn here: it is drawn when an outcome depends on it (step (d))
 #pragma unroll
-                                    for (int j = 0; j < NWIN; ++j) w[j] = pick(philox(y[j] >> 2, (uint32_t)day, S_COUNT, 0, key), y[j] & 3u);
-                                    // value = #{thr <= w}: the guide brackets it (bucket of the top byte; the top bucket by the next byte), a
-                                    // three-step binary search finishes brackets of up to 7 thresholds, longer ones (the far tail) walk on
-#pragma unroll
-                                    for (int j = 0; j < NWIN; ++j) {
-                                        const int ag = st_ag(sy[j]);
-                                        const int gi = (w[j] >> 24) == 255u ? 256 + (int)((w[j] >> 16) & 0xFFu) : (int)(w[j] >> 24);
-                                        thr[j] = M.nb_thr + ag * 256;
-                                        k[j] = M.nb_guide[ag * 512 + gi];
-                                        hi[j] = gi == 511 ? M.nb_len[ag] : (int)M.nb_guide[ag * 512 + gi + 1];
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < NWIN; ++j) {
-                                        const int lo = k[j], n = min(hi[j] - lo, 7);
-                                        int c = 0;
-                                        if (c + 4 <= n && thr[j][lo + c + 3] <= w[j]) c += 4;
-                                        if (c + 2 <= n && thr[j][lo + c + 1] <= w[j]) c += 2;
-                                        if (c + 1 <= n && thr[j][lo + c] <= w[j]) c += 1;
-                                        k[j] = lo + c;
-                                    }
-                                    bool more = false;
-#pragma unroll
-                                    for (int j = 0; j < NWIN; ++j) more |= need[j] && !(sy[j] & ST_ISOB) && k[j] < hi[j] && thr[j][min(k[j], 255)] <= w[j];
-                                    while (__any_sync(FULL, more)) {
-                                        more = false;
-#pragma unroll
-                                        for (int j = 0; j < NWIN; ++j) {
-                                            k[j] += (k[j] < hi[j] && thr[j][min(k[j], 255)] <= w[j]);
-                                            more |= need[j] && !(sy[j] & ST_ISOB) && k[j] < hi[j] && thr[j][min(k[j], 255)] <= w[j];
-                                        }
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < NWIN; ++j) {
-                                        const int viso = (w[j] < 0x80000000u) ? 0 : 1 + (int)(((unsigned long long)(w[j] & 0x7fffffffu) * 3ull) >> 31);
-                                        const int v = st_health(sy[j]) == DED ? 0 : (sy[j] & ST_ISOB) ? viso : k[j];
-                                        if (need[j]) M.status[y[j]] = (sy[j] & ~(ST_REMMASK | ST_TAGMASK)) | (uint32_t)v | ((uint32_t)day << 22);
-                                    }
-                                }
+                                for (int j = 0; j < NWIN; ++j)
+                                    if (need[j]) M.status[y[j]] = (sy[j] & ~(ST_REMMASK | ST_TAGMASK)) | ((uint32_t)day << 22);
                                 PHASE(20);
                                 // records; targets hit more than once (by any event of the chunk, dropped later or not) take the ordered path
                                 uint32_t old[NWIN];
@@ -891,19 +853,23 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 const bool live = y != EV_NONE && !(rec & EVM_DROPPED);
                                 const bool shared = live && ((M.dupm[y >> 5] >> (y & 31)) & 1u);
                                 if (live && !shared) {
-                                    const uint32_t sy = M.status[y];                               // tag == today since (b)
-                                    const int rem = st_rem(sy);
-                                    if (rem > 0) {                                                  // :812
-                                        const int q = (int)(rec >> 2);
-                                        uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)(rem - 1);     // :813
-                                        if (ctr && room && M.cflag[q]) log_contact(q, y);
-                                        if (st_health(sy) == SUS && st_swap(sy) == UNDEF && (rec & EVM_SUCC)) {   // :822-827
+                                    // The status word counts today's contacts of y (tag == today since (b)); the event is admitted iff that
+                                    // count is still below y's budget (:812-813). The budget is only drawn when the answer matters: the event
+                                    // would transmit to a susceptible, or its infector logs contacts.
+                                    const uint32_t sy = M.status[y];
+                                    const int hits = st_rem(sy), q = (int)(rec >> 2);
+                                    uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)min(hits + 1, 255);
+                                    const bool infects = st_health(sy) == SUS && st_swap(sy) == UNDEF && (rec & EVM_SUCC);   // :822-823
+                                    const bool logs = ctr && room && M.cflag[q];
+                                    if ((infects || logs) && hits < fresh_budget_s(M, key, y, (uint32_t)day, sy)) {
+                                        if (logs) log_contact(q, y);
+                                        if (infects) {                                              // :824-827
                                             ns = st_set_swap(ns, LAT);
                                             S.sickfrom[rb + y] = (uint8_t)(M.ch[q] & 0xF);
                                             M.expday[y] = (int16_t)day;                             // y.exp = y.tis :826 — fires in today's time_update
                                         }
-                                        M.status[y] = ns;
                                     }
+                                    M.status[y] = ns;
                                 }
                                 ndl += __popc(__ballot_sync(FULL, shared));
                             }
@@ -941,22 +907,26 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                     const bool leader = mine && lane == __ffs(peers) - 1;
                                     const int n = __popc(peers), nmax = __reduce_max_sync(FULL, mine ? n : 0);
                                     const uint32_t sy = mine ? M.status[y] : 0u;
-                                    int rem = st_rem(sy), xh_inf = -1;
+                                    const int hits0 = st_rem(sy);                                            // contacts of y before this group's
+                                    int xh_inf = -1;
                                     bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;                 // :822
                                     const int hit = (mine && (rec & EVM_SUCC)) ? (int)(M.ch[qd] & 0xF) : -1;     // would this event transmit (:823)?
+                                    const bool logs = ctr && room && mine && M.cflag[qd];
+                                    // y's budget is drawn only if some event of the group would transmit to it or is logged
+                                    const bool wanted = (__ballot_sync(FULL, (hit >= 0 && sus) || logs) & peers) != 0u;
+                                    const int budget = (leader && wanted) ? fresh_budget_s(M, key, y, (uint32_t)day, sy) : 0;
                                     unsigned m = peers;
                                     for (int k = 0; k < nmax; ++k) {                                          // k-th event of each target, in event order
                                         const int src = m ? __ffs(m) - 1 : lane; m &= m - 1u;
                                         const int hs = __shfl_sync(FULL, hit, src);
                                         const int qs = __shfl_sync(FULL, qd, src);
-                                        if (leader && k < n && rem > 0) {                                     // :812
-                                            rem -= 1;                                                         // :813
+                                        if (leader && k < n && hits0 + k < budget) {                          // admitted :812-813
                                             if (ctr && room && M.cflag[qs]) log_contact(qs, y);
                                             if (sus && hs >= 0) { sus = false; xh_inf = hs; }
                                         }
                                     }
                                     if (leader) {
-                                        uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)rem;
+                                        uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)min(hits0 + n, 255);
                                         if (xh_inf >= 0) {
                                             ns = st_set_swap(ns, LAT);
                                             S.sickfrom[rb + y] = (uint8_t)xh_inf;
