@@ -190,72 +190,79 @@ template <bool TP = false> __device__ inline Tr transition_core(const Dev &S, co
                                      int *via_io = nullptr /* the agent's isovia held by the caller: no load, no store here */) {
     size_t a = (size_t)r * S.Np + i;
     const int oldh = st_health(st), ag = st_ag(st);
-    const int via0 = via_io ? *via_io : (int)S.isovia[a];   // needed by a few targets only, but loaded here so that its latency hides behind the draws
+    // dcache (fused kernel): direct-mapped shared-memory cache of the two rarely-touched fields a transition reads,
+    // entry = agent [40:64) | isovia [32:35) | dur [0:32). An infected agent makes ~5 transitions: all but the first hit.
+    int via0;
     uint32_t d4;
-    if (dcache) {                        // (agent << 32 | dur) — filled when the agent is infected, so the HBM load is off this path
+    if (dcache) {
         const unsigned long long e = dcache[i & (DUR_CACHE - 1)];
-        if ((uint32_t)(e >> 32) == (uint32_t)i) d4 = (uint32_t)e;
-        else { d4 = S.dur[a]; dcache[i & (DUR_CACHE - 1)] = ((unsigned long long)(uint32_t)i << 32) | d4; }
-    } else d4 = S.dur[a];
+        if ((uint32_t)(e >> 40) == (uint32_t)i) { d4 = (uint32_t)e; via0 = (int)((e >> 32) & 7u); }
+        else { d4 = S.dur[a]; via0 = (int)S.isovia[a]; }
+        if (via_io) via0 = *via_io;      // (with contact tracing the caller holds isovia: the cached copy is not used)
+    } else {
+        via0 = via_io ? *via_io : (int)S.isovia[a];   // needed by a few targets only, but loaded here so that its latency hides behind the draws
+        d4 = S.dur[a];
+    }
     const int d_lat = d4 & 0xFF, d_asy = (d4 >> 8) & 0xFF, d_pre = (d4 >> 16) & 0xFF, d_inf = d4 >> 24;
     bool iso = st & ST_ISO;
     int via = -1;                       // -1: unchanged
     int newh = target, newsw = UNDEF, exp = 999;
-    switch (target) {
-    case LAT: {                          // move_to_latent :446-461
-        uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key);
-        exp = d_lat; newsw = bern(w.x, P.asymp_thr[ag]) ? ASYMP : PRE;
-        if (P.calibration) { newsw = LAT; exp = 999; }
-        S.latday[a] = (int16_t)day;
-        break; }
-    case ASYMP: exp = d_asy; newsw = REC; break;                       // :464-472
-    case PRE: {                          // move_to_pre :475-488
-        uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key);
-        exp = d_pre; newsw = bern(w.x, P.mild_thr[ag]) ? MILD : INF;
-        bool active = (day == 0) || (P.tpreiso >= 1 && day >= P.tpreiso);   // main :124-125,:133-135
-        if (active && bern(w.y, P.fpreiso_thr)) { iso = true; via = VIA_PI; }
-        break; }
-    case MILD: {                         // move_to_mild :491-507
-        exp = d_inf; newsw = REC;
-        bool go = iso;
-        if (!go) { uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key); go = bern(w.x, P.fmild_thr); }
-        if (go) { newsw = MISO; exp = P.tau_mild; }
-        break; }
-    case MISO: exp = d_inf - P.tau_mild; newsw = REC; iso = true; via = VIA_MI; break;   // :510-517
-    case INF: {
-        if (seed_simple_inf) {           // move_to_infsimple :520-528
-            exp = d_inf; newsw = REC; iso = false; break;    // _set_isolation(x, false, :null) leaves isovia as is
-        }
-        // move_to_inf :530-569
-        uint4 wa = draw4<TP>(S, i, day, S_TRANS, 0, key), wb = draw4<TP>(S, i, day, S_TRANS, 1, key);
-        double h = __dadd_rn(c_tab.hlo[ag], __dmul_rn(c_tab.hspan[ag], u01(wa.x)));
-        double c = __dadd_rn(c_tab.clo[ag], __dmul_rn(c_tab.cspan[ag], u01(wa.y)));
-        unsigned long long mthr = c_tab.mh_inf_thr[ag];
-        if (P.calibration) { h = 0; c = 0; mthr = 0; }
-        int tth = (int)rint(__dadd_rn(2.0, __dmul_rn(3.0, u01(wa.z))));
-        if (u01(wa.w) < h) { exp = tth; newsw = (u01(wb.x) < c) ? ICU : HOS; }
-        else if (bern(wb.y, mthr)) { exp = d_inf; newsw = DED; }
-        else {
-            exp = d_inf; newsw = REC;
-            if (iso || bern(wb.z, P.fsevere_thr)) { exp = 1; newsw = IISO; }
-        }
-        break; }
-    case IISO: exp = d_inf - 1; newsw = REC; iso = true; via = VIA_MI; break;            // :571-578
-    case HOS: case ICU: {                // move_to_hospicu :580-622
-        uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key);
-        int psi = table_draw(w.x, c_tab.psi_base, c_tab.psi_thr, c_tab.psi_len);
-        int mu = table_draw(w.y, c_tab.mu_base, c_tab.mu_thr, c_tab.mu_len);
-        iso = true;                                                                        // :599
-        if (target == HOS) { if (bern(w.z, c_tab.mh_hos_thr[ag])) { exp = mu; newsw = DED; } else { exp = psi; newsw = REC; } }
-        else { if (bern(w.z, c_tab.mh_icu_thr[ag])) { exp = mu + 2; newsw = DED; } else { exp = psi + 2; newsw = REC; } }
-        break; }
-    case REC: exp = 999; newsw = UNDEF; break;                                             // :635-644
-    case DED: exp = 999; newsw = UNDEF; iso = true; break;                                 // :624-633
-    default:                              // :418 "swap expired, but no swap set."
+    if (target < LAT || target > DED) {      // :418 "swap expired, but no swap set."
         atomicOr(&S.err[r], ERR_NO_SWAP);
         return Tr{st, 32767, oldh, oldh};
     }
-    if (via >= 0 && via0 == VIA_NULL) { if (via_io) *via_io = via; else S.isovia[a] = (uint8_t)via; }   // _set_isolation :432-444 only fills a :null isovia
+    // Every move_to_* that draws uses the words of the same first call, so it is made once for all targets (entries without draws
+    // ignore it), and the common entries are written as selects rather than a switch: agents of one warp that enter different
+    // states on the same day then run in lockstep instead of one case after the other. Hospital-bound entries branch off.
+    const uint4 w = draw4<TP>(S, i, day, S_TRANS, 0, key);
+    if ((target == INF && !seed_simple_inf) || target == HOS || target == ICU) {
+        if (target == INF) {                 // move_to_inf :530-569
+            const uint4 wb = draw4<TP>(S, i, day, S_TRANS, 1, key);
+            double h = __dadd_rn(c_tab.hlo[ag], __dmul_rn(c_tab.hspan[ag], u01(w.x)));
+            double c = __dadd_rn(c_tab.clo[ag], __dmul_rn(c_tab.cspan[ag], u01(w.y)));
+            unsigned long long mthr = c_tab.mh_inf_thr[ag];
+            if (P.calibration) { h = 0; c = 0; mthr = 0; }
+            const int tth = (int)rint(__dadd_rn(2.0, __dmul_rn(3.0, u01(w.z))));
+            if (u01(w.w) < h) { exp = tth; newsw = (u01(wb.x) < c) ? ICU : HOS; }
+            else if (bern(wb.y, mthr)) { exp = d_inf; newsw = DED; }
+            else {
+                exp = d_inf; newsw = REC;
+                if (iso || bern(wb.z, P.fsevere_thr)) { exp = 1; newsw = IISO; }
+            }
+        } else {                             // move_to_hospicu :580-622
+            const int psi = table_draw(w.x, c_tab.psi_base, c_tab.psi_thr, c_tab.psi_len);
+            const int mu = table_draw(w.y, c_tab.mu_base, c_tab.mu_thr, c_tab.mu_len);
+            iso = true;                                                                    // :599
+            if (target == HOS) { if (bern(w.z, c_tab.mh_hos_thr[ag])) { exp = mu; newsw = DED; } else { exp = psi; newsw = REC; } }
+            else { if (bern(w.z, c_tab.mh_icu_thr[ag])) { exp = mu + 2; newsw = DED; } else { exp = psi + 2; newsw = REC; } }
+        }
+    } else {
+        const bool tLAT = target == LAT, tPRE = target == PRE, tMILD = target == MILD;
+        const bool b = bern(w.x, tLAT ? P.asymp_thr[ag] : tPRE ? P.mild_thr[ag] : P.fmild_thr);   // :455, :481, :503
+        exp = tLAT ? d_lat                                           // move_to_latent :446-461
+            : target == ASYMP ? d_asy                                // move_to_asymp :464-472
+            : tPRE ? d_pre                                           // move_to_pre :475-488
+            : (tMILD || target == INF) ? d_inf                       // move_to_mild :491-507, move_to_infsimple :520-528 (seeds)
+            : target == MISO ? d_inf - P.tau_mild                    // move_to_miso :510-517
+            : target == IISO ? d_inf - 1                             // move_to_iiso :571-578
+            : 999;                                                   // move_to_recovered :635-644, move_to_dead :624-633
+        newsw = tLAT ? (b ? ASYMP : PRE) : tPRE ? (b ? MILD : INF) : (target == REC || target == DED) ? UNDEF : REC;
+        if (tLAT) {
+            if (P.calibration) { newsw = LAT; exp = 999; }           // :457-460
+            S.latday[a] = (int16_t)day;
+        }
+        if (tPRE) {
+            const bool active = (day == 0) || (P.tpreiso >= 1 && day >= P.tpreiso);   // main :124-125,:133-135
+            if (active && bern(w.y, P.fpreiso_thr)) { iso = true; via = VIA_PI; }     // :487
+        }
+        if (tMILD && (iso || b)) { newsw = MISO; exp = P.tau_mild; }                  // :503-506
+        if (target == MISO || target == IISO) { iso = true; via = VIA_MI; }
+        if (target == INF) iso = false;                              // _set_isolation(x, false, :null) leaves isovia as is
+        if (target == DED) iso = true;
+    }
+    int newvia = via0;
+    if (via >= 0 && via0 == VIA_NULL) { newvia = via; if (via_io) *via_io = via; else S.isovia[a] = (uint8_t)via; }   // _set_isolation :432-444 only fills a :null isovia
+    if (dcache) dcache[i & (DUR_CACHE - 1)] = ((unsigned long long)(uint32_t)i << 40) | ((unsigned long long)(uint32_t)newvia << 32) | d4;
     S.entry[a] = (int16_t)day;
     st = st_set_swap(st_set_health(st, newh), newsw);
     st = iso ? (st | ST_ISO | ST_ISOB) : (st & ~(ST_ISO | ST_ISOB));

@@ -151,6 +151,7 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(s), "r"(bytes), "l"(pol) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // age-group index tables: read at random by every contact event for the whole life of the replicate -> evict-last in L2
 __device__ __forceinline__ uint32_t ld_keep(const uint16_t *p) {
     uint64_t pol; unsigned short v;
@@ -867,6 +868,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                             ns = st_set_swap(ns, LAT);
                                             S.sickfrom[rb + y] = (uint8_t)(M.ch[q] & 0xF);
                                             M.expday[y] = (int16_t)day;                             // y.exp = y.tis :826 — fires in today's time_update
+                                            prefetch_l2(S.dur + rb + y); prefetch_l2(S.isovia + rb + y);   // what that transition will read
                                         }
                                     }
                                     M.status[y] = ns;
@@ -931,6 +933,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                             ns = st_set_swap(ns, LAT);
                                             S.sickfrom[rb + y] = (uint8_t)xh_inf;
                                             M.expday[y] = (int16_t)day;
+                                            prefetch_l2(S.dur + rb + y); prefetch_l2(S.isovia + rb + y);
                                         }
                                         M.status[y] = ns;
                                     }
@@ -996,6 +999,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 }
                 // every thread looks at FUSED_SCAN_U chunks of 8 expiry days at once (independent loads and compares), then handles
                 // the few agents that have an event today (:405, marks) one after another
+                PHASE(27);
                 uint32_t mn = 0x7FFF7FFFu;                                     // running min of the event days that stay (2 x i16)
                 for (int b0 = tid * 8; b0 < N; b0 += NT * 8 * FUSED_SCAN_U) {
                     uint4 ex[FUSED_SCAN_U];
@@ -1041,8 +1045,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             const uint32_t st = M.status[i];
                             const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];      // without tracing the scan key is the expiry day
                             const int par = (day + 1) & 1;
+#ifdef CABM_FUSED_DIAG
+                            const long long t_e0 = clock64();
+#endif
                             const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, ctr, pb, qb,
                                                           &Z.qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr, M.dcache);
+#ifdef CABM_FUSED_DIAG
+                            if (e.st != 0xFFFFFFFFu) { atomicAdd((unsigned long long *)&t_ph[28], (unsigned long long)(clock64() - t_e0)); atomicAdd((unsigned long long *)&t_ph[29], 1ull); }
+#endif
                             M.status[i] = e.st;
                             M.expday[i] = (int16_t)e.ne;
                             if (ctr && e.texp != texp) S.texp[rb + i] = (int16_t)e.texp;
