@@ -113,3 +113,18 @@ def calibrate_regression(betas=None, nsims=1000, prov="newyork", device=0):
     A = np.stack([np.ones(nb), betas], axis=1)                                             # lm(hcat(ones, betas), ros) :172
     coef, *_ = np.linalg.lstsq(A, ros, rcond=None)
     return float(coef[0]), float(coef[1]), betas, ros
+
+
+def calibrate_robustness(beta, reps, prov="ontario", nsims=(500, 1000), device=0):
+    """local_run.jl:178-199: run calibration with the same beta `reps` times for each ensemble size to see the variation of R0.
+    Returns means[reps][len(nsims)]. (The reference reuses its free-running RNG; here repetition k of size ns uses its own seeds.)"""
+    means = np.zeros((reps, len(nsims)))
+    for j, ns in enumerate(nsims):
+        myp = ModelParameters(β=beta, prov=prov, modeltime=50, calibration=True, initialinf=1)
+        with Population(ns, myp.popsize, 50, device=device) as pop:
+            for k in range(reps):
+                pop.configure(myp, [726 * (1 + x + ns * (k + reps * j)) for x in range(ns)])
+                pop.run()
+                pop.check_errors()
+                means[k, j] = pop.scalars()["lat_inc_sum"].mean()
+    return means

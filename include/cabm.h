@@ -162,7 +162,9 @@ int cabm_step_insert_infected(cabm_handle *h, int health, int num, int ag, int c
 int cabm_step_dyntrans(cabm_handle *h);
 int cabm_step_time_update(cabm_handle *h);
 int cabm_get_day(const cabm_handle *h);
-/* (totalmet, totalinf) returned by the last dyntrans :833, per replicate */
+/* (totalmet, totalinf) returned by the last dyntrans :833, per replicate. Kept by the per-day kernels (cabm_step_dyntrans, the
+ * multikernel path); the fused paths do not count them — main discards them (:138) and the fused dyntrans does not even decide
+ * the admission of events whose outcome cannot matter. */
 int cabm_get_dyntrans_counters(cabm_handle *h, int32_t *totalmet, int32_t *totalinf);
 
 /* hmatrix of one replicate: Int16, popsize x modeltime, column-major (:111,:141). Needs CABM_STORE_HMATRIX. */

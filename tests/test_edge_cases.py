@@ -17,7 +17,7 @@ def both(cv, O, seeds, path, **kw):
     return got
 
 
-@pytest.mark.parametrize("path", ["fused", "multikernel"])
+@pytest.mark.parametrize("path", ["fused", "multikernel", "fused-global"])
 def test_degenerate_scenarios(cv, O, path):
     seeds = [2 ** 63 + 12345, 2 ** 40 + 7, 1]                                   # 64-bit seeds use both halves of the Philox key
     g = both(cv, O, seeds, path, β=0.0, prov="ontario", popsize=3000, modeltime=40, initialinf=4)      # no transmission
@@ -40,6 +40,18 @@ def test_degenerate_scenarios(cv, O, path):
          ctstrat=3, strat3qdays=0, fctcapture=1.0, fcontactst=1.0, cdaysback=20, asymp_props=(0, 0, 0, 0, 0), mild_props=(1, 1, 0, 0, 0))
     both(cv, O, seeds, path, β=0.6, prov="saskat", popsize=3000, modeltime=120, initialinf=30, ctstrat=1, fctcapture=1.0, fcontactst=1.0,
          cdaysback=0, τmild=40, fmild=1.0)                                          # τmild longer than any infectious period (exp <= 0, :515)
+
+
+@pytest.mark.parametrize("path", ["fused", "fused-global"])
+def test_dense_order_dependences_halve_the_chunk(cv, O, path):
+    """Small populations in which nearly everybody is infectious: most contact events of a chunk hit a later infector of the same
+    chunk, far more than its edge list holds, so the kernel halves the chunk (repeatedly) and must still reproduce the sequential
+    order bit for bit. Also long DAG chains (budgets reduced by infectors whose own budgets were reduced)."""
+    seeds = [5, 6, 7, 8]
+    both(cv, O, seeds, path, β=0.5, prov="ontario", popsize=400, modeltime=30, initialinf=399)
+    both(cv, O, seeds, path, β=0.9, prov="quebec", popsize=700, modeltime=40, initialinf=650, fmild=0.5, τmild=1, fsevere=1.0,
+         ctstrat=1, fctcapture=1.0, fcontactst=1.0, cdaysback=4)
+    both(cv, O, seeds, path, β=0.3, prov="ontario", popsize=2500, modeltime=60, initialinf=1200, initialhi=300)
 
 
 @pytest.mark.parametrize("path", ["fused", "multikernel"])

@@ -218,6 +218,8 @@ def test_local_run_outputs(cv, O, tmp_path):
     rc = O.run_ensemble([to_oracle(O, cal)], [0] * 64, [726 * x for x in range(1, 65)], nthreads=8)
     v = rc["inc"][:, 0, :, 1].sum(axis=1).astype(float)
     assert m == v.mean() and abs(sd - v.std(ddof=1)) < 1e-12
+    rb = cv.local_run.calibrate_robustness(0.05, 2, prov="ontario", nsims=(100, 200))
+    assert rb.shape == (2, 2) and (rb > 1.0).all() and (rb < 4.0).all()
     a, b, betas, ros = cv.local_run.calibrate_regression(betas=[0.03, 0.05, 0.07], nsims=200, prov="newyork")
     assert 30 < b < 60 and abs(a) < 0.6        # the author's fit: R0 = 46.1761 beta - 0.00285 (scripts/local_run.jl:174)
 
