@@ -354,7 +354,7 @@ def main():
         sd, pof = batch_of(100 + args.steps - 1)
         attack = 1.0 - prev_l[:, 0, -1, 0] / N
         order = np.argsort(-attack, kind="stable")
-        pick = sorted(set(order[:32].tolist() + list(range(0, R, max(1, R // 32)))[:32]))     # the 32 largest epidemics + 32 spread evenly
+        pick = sorted(set(order[:32].tolist() + list(range(0, R, max(1, R // 48)))[:48]))     # the 32 largest epidemics + 48 spread evenly (>= 64 distinct)
         O, ops = oracle_psets(W)
         ref = O.run_ensemble(ops, [pof[i] for i in pick], [sd[i] for i in pick], nthreads=os.cpu_count() or 1)
         ok = bool((inc_l[pick] == ref["inc"]).all() and (prev_l[pick] == ref["prev"]).all()
