@@ -60,6 +60,9 @@ def workload(name):
         ct = dict(ctstrat=1) if name == "C1" else dict(ctstrat=3, strat3qdays=14)
         return dict(desc=f"configs[2]: configs[1] + contact tracing {ct} fctcapture=0.5 fcontactst=0.5 cdaysback=3 (ctstrat=2 does not exist in the source, :165)",
                     psets=[dict(CFG, **_TRACE, **ct)], N=N_AGENTS, T=T_DAYS, R=1000, scaling="weak", mode="exact", hm=True)
+    if name == "C1HOT":          # tools only: tracing under a supercritical epidemic (the stress case of profiles/r01_configs_CDE.jsonl)
+        return dict(desc="beta=0.06 ontario, no isolation, contact tracing ctstrat=1 fctcapture=0.5 fcontactst=0.5 cdaysback=3, 10000 agents x 500 days",
+                    psets=[dict(β=0.06, prov="ontario", initialinf=1, modeltime=T_DAYS, popsize=N_AGENTS, ctstrat=1, **_TRACE)], N=N_AGENTS, T=T_DAYS, R=1000, scaling="weak", mode="exact", hm=True)
     if name == "D":
         import numpy as np
         betas = np.linspace(0.0225, 0.085, 20)                   # scripts/local_run.jl:165 range, 20 points

@@ -984,14 +984,14 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                     const uint32_t nq = Z.qcnt[day & 1];
                     if (nq) {
                         __syncthreads();        // the contact chunks linked after today's last dyntrans chunk (by many warps) are visible to every warp
-                        {   // one index case per warp at a time, each warp gathering contacts in its own slice of the event buffer
+                        {   // one index case per half-warp at a time (the chain walks are latency-bound: sixteen in flight), each group
+                            // gathering contacts in its own slice of the event buffer and deduplicating in its slice of the D/evm area
                             const uint32_t *qlist = S.ident_list + ((size_t)r * 2 + (day & 1)) * Np;
-#ifdef CABM_PASSA_SERIAL
-                            if (wid == 0) for (uint32_t k = 0; k < nq; ++k)
-#else
-                            for (uint32_t k = wid; k < nq; k += NW)
-#endif
-                                ct_identify_warp(S, P, r, (int)qlist[k], day, M.evy + wid * (FUSED_EVCAP / NW), FUSED_EVCAP / NW, M.mpre, M.mpost);
+                            const int grp = tid >> 4;
+                            constexpr int GB = FUSED_EVCAP / (2 * NW);                 // 128 words of gather buffer and of hash table per group
+                            uint32_t *const htab_all = reinterpret_cast<uint32_t *>(M.D);   // D and evm are adjacent: 2 x EVCAP x 2 B = EVCAP words
+                            for (uint32_t k = grp; k < nq; k += 2 * NW)
+                                ct_identify_warp<false, 16>(S, P, r, (int)qlist[k], day, M.evy + grp * GB, GB, htab_all + grp * GB, GB, M.mpre, M.mpost);
                         }
                         __syncthreads();
                         if (tid == 0) Z.qcnt[day & 1] = 0;

@@ -386,13 +386,15 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
 // An index case x identifies on a day fixed when it became latent (doi == traceend), so the cross-agent writes are
 // hoisted: this kernel draws Bernoulli(fcontactst) once per distinct traced contact y (:709-713) and leaves a mark —
 // "pre" if y > x (y sees the isolation in its own update today), "post" if y < x (y was already updated today).
-// One index case, handled by a whole warp: gather its traced contacts (chunks are contiguous, so the reads coalesce),
+// One index case, handled by a warp or half a warp: gather its traced contacts (chunks are contiguous, so the reads coalesce),
 // drop repeats (the reference's contact set is a Bool vector, :25) and draw Bernoulli(fcontactst) per distinct contact.
 constexpr int CT_GATHER = 512;          // contacts gathered in shared memory per warp; longer sets take the slow path
-template <bool TP = false>
+// G lanes (a warp or half a warp) handle one index case; buf/htab are that group's gather buffer and hash table (hcap a power of two)
+template <bool TP = false, int G = 32>
 __device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, int x, int day, uint32_t *buf, int bufcap,
-                                        uint32_t *mpre_row, uint32_t *mpost_row) {
-    const int lane = threadIdx.x & 31;
+                                        uint32_t *htab, int hcap, uint32_t *mpre_row, uint32_t *mpost_row) {
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const unsigned gmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
     const size_t a = (size_t)r * S.Np + x;
     const uint2 key = S.key[r];
     const uint32_t *log = S.ct_log + (size_t)r * S.ct_cap;
@@ -411,25 +413,35 @@ __device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, i
         const uint32_t next = log[c];
         const int cnt = (int)log[c + 1];
         if (n + cnt > bufcap) { fits = false; break; }
-        for (int k = lane; k < cnt; k += 32) buf[n + k] = log[c + 2 + k];
+        for (int k = gl; k < cnt; k += G) buf[n + k] = log[c + 2 + k];
         n += cnt; c = next;
     }
-    if (fits) {
-        __syncwarp();
-        if (n <= 32) {                                        // the usual case: the distinct contacts are the first lane of each group of equal ones
-            const uint32_t y = lane < n ? buf[lane] : 0xFFFFFF00u + (uint32_t)lane;
-            const unsigned peers = __match_any_sync(FULL, y);
-            if (lane < n && lane == __ffs(peers) - 1) contact(y);
-        } else {
-            for (int k = lane; k < n; k += 32) {
-                const uint32_t y = buf[k];
-                bool dup = false;
-                for (int q = 0; q < k; ++q) if (buf[q] == y) { dup = true; break; }
-                if (!dup) contact(y);
+    if (fits && 2 * n <= hcap) {
+        // distinct contacts (the reference's contact set is a Bool vector, :25): every gathered contact is inserted into a small
+        // open-addressing table; the lane whose insert claims an empty slot owns that contact
+        for (int k = gl; k < hcap; k += G) htab[k] = 0xFFFFFFFFu;
+        __syncwarp(gmask);
+        for (int k = gl; k < n; k += G) {
+            const uint32_t y = buf[k];
+            uint32_t slot = ((y * 2654435761u) >> 16) & (uint32_t)(hcap - 1);
+            for (;;) {
+                const uint32_t old = atomicCAS(&htab[slot], 0xFFFFFFFFu, y);
+                if (old == 0xFFFFFFFFu) { contact(y); break; }
+                if (old == y) break;
+                slot = (slot + 1u) & (uint32_t)(hcap - 1);
             }
         }
-        __syncwarp();
-    } else if (lane == 0) {                                   // very long contact sets: one lane, quadratic walk
+        __syncwarp(gmask);
+    } else if (fits) {
+        __syncwarp(gmask);
+        for (int k = gl; k < n; k += G) {
+            const uint32_t y = buf[k];
+            bool dup = false;
+            for (int q = 0; q < k; ++q) if (buf[q] == y) { dup = true; break; }
+            if (!dup) contact(y);
+        }
+        __syncwarp(gmask);
+    } else if (gl == 0) {                                     // very long contact sets: one lane, quadratic walk
         for (uint32_t c = head; c != CT_NONE; c = log[c]) {
             for (uint32_t k = 0; k < log[c + 1]; ++k) {
                 const uint32_t y = log[c + 2 + k];
@@ -467,8 +479,11 @@ template <bool TP> __global__ void __launch_bounds__(128) k_ct_identify_list(Dev
     uint32_t *cnt = &S.ident_cnt[r * 2 + (day & 1)];
     const uint32_t n = *cnt;
     const uint32_t *list = S.ident_list + ((size_t)r * 2 + (day & 1)) * S.Np;
-    for (uint32_t k = wid; k < n; k += 4)
-        ct_identify_warp<TP>(S, P, r, (int)list[k], day, buf[wid], CT_GATHER, S.mark_pre + (size_t)r * S.nwords, S.mark_post + (size_t)r * S.nwords);
+    const int grp = (threadIdx.x >> 4);                        // eight half-warps, one index case each at a time
+    uint32_t *gb = buf[wid] + ((threadIdx.x >> 4) & 1) * (CT_GATHER / 2);
+    for (uint32_t k = grp; k < n; k += 8)
+        ct_identify_warp<TP, 16>(S, P, r, (int)list[k], day, gb, CT_GATHER / 4, gb + CT_GATHER / 4, CT_GATHER / 4,
+                                 S.mark_pre + (size_t)r * S.nwords, S.mark_post + (size_t)r * S.nwords);
     __syncthreads();
     if (threadIdx.x == 0) *cnt = 0;
 }
