@@ -408,7 +408,7 @@ extern "C" int cabm_run(cabm_handle *h) {
     CU(cudaEventRecord(h->ev0, h->stream));
     if ((rc = reset_state(h, /*curves_too=*/!use_fused))) return rc;      // the fused kernel writes every curve entry itself
     h->last_path = use_smem ? CABM_PATH_FUSED : use_global ? CABM_PATH_FUSED_GLOBAL : CABM_PATH_MULTIKERNEL;
-    if (!use_fused && (rc = need_event_list(h))) return rc;
+    if (!use_smem && (rc = need_event_list(h))) return rc;        // per-day kernels, and the fused kernel with its state in global memory
     if (use_fused) {
         timed(h, CABM_K_FUSED, [&] { return launch_sim_fused(S, h->d_work, h->n_sm, h->any_ct != 0, use_global, h->stream); });  // :104-142 in one launch
     } else {

@@ -50,6 +50,7 @@ constexpr int FUSED_NEDGE = 256;       // events of a chunk that hit a later inf
 constexpr unsigned FUSED_TAIL_CTAS = 8;  // CTAs that copy finished curves to the host at any one time (PCIe saturates with ~8)
 constexpr int FUSED_SCAN_U = 5;        // chunks of 8 agents a thread scans at once in time_update (256 x 8 x 5 >= 10,000 agents in one go)
 static_assert(FUSED_NT == 256 && FUSED_LCAP <= FUSED_NT && FUSED_EVCAP % 32 == 0 && FUSED_EVCAP <= 2048, "thread-index roles and record fields in k_sim_fused");
+static_assert(FUSED_EVCAP / FUSED_NT <= 32, "one bit per window of a warp in the shared-target mask");
 // event record: evy = target (EV_NONE: none); evm = transmits [0] | dropped by a reduced budget [1] | owner (chunk entry) [2:10)
 constexpr uint32_t EV_NONE = 0xFFFFFFFFu;
 constexpr uint16_t EVM_SUCC = 1, EVM_DROPPED = 2;
@@ -72,7 +73,8 @@ struct FusedCtl {
     int nedge;                               // DAG edges of the chunk
     int wdup[FUSED_NT / 32];
     uint32_t logn, qcnt[2];                  // contact tracing (:647-752): the replicate's log fill, index-case queues by day parity
-    int pad_[4];
+    unsigned evn;                            // global-state variant: agents with an event today, listed by the scan
+    int pad_[3];
 };
 static_assert(sizeof(FusedCtl) % 16 == 0, "the arrays behind FusedCtl need 16-byte alignment");
 
@@ -171,8 +173,19 @@ __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.b
 
 // CT = false: no replicate of the ensemble traces contacts (the tracing code is compiled out).
 // GS = true: the per-agent state stays in global memory (L2) instead of shared memory — any popsize; no TMA column stores, no parking.
+// state-matrix column without TMA (state in global memory, or a column that is not 16-byte aligned): 16 bytes per thread and pass
+__device__ __forceinline__ void copy_column(uint8_t *dst, const uint8_t *src, int n, int tid, int nt) {
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+        const int nv = n >> 4;
+        for (int i = tid; i < nv; i += nt) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+        for (int i = (nv << 4) + tid; i < n; i += nt) dst[i] = src[i];
+    } else {
+        for (int i = tid; i < n; i += nt) dst[i] = src[i];
+    }
+}
+
 template <bool CT, bool GS>
-__global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work /* queue heads and tails, see below */, int split_day, unsigned tail_cta_limit) {
+__global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsigned *work /* queue heads and tails, see below */, int split_day, unsigned tail_cta_limit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = FUSED_NT, NW = FUSED_NT / 32;
     const int N = S.N, Np = S.Np, T = S.T, nwords = S.nwords;
@@ -556,7 +569,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         if (tid < 60) { s_inc[tid] = 0; s_out[tid] = 0; }
         if (hm) {
             if (tma_ok) { bulk_store_g2s_fence(); __syncthreads(); if (tid == 0) bulk_store(hm, M.col, (uint32_t)N); }
-            else for (int i = tid; i < N; i += NT) hm[i] = M.col[i];
+            else copy_column(hm, M.col, N, tid, NT);
         }
         __syncthreads();
 
@@ -585,6 +598,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
         // s_nextfire = earliest expiry day of any agent. A day with nobody infectious and nothing expiring changes no
         // state: it only repeats the column and the prevalence row, without a single barrier.
         if (tid < 2) Z.nf[tid] = 32767;
+        if (GS && tid == 0) Z.evn = 0;
         int nextfire = resumed ? __ldcg(&S.resume_aux[r * 2]) : 0, act = 0;    // uniform registers
         const int day_first = resumed ? split_day + 1 : 1;
         const int day_last = (!resumed && split_day > 0 && split_day < T) ? split_day : T;
@@ -783,6 +797,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                             };
                             {
                                 int win = win0;
+                                if constexpr (GS) {     // every load of a target is an L2 round trip: eight windows in flight per warp
+                                    for (; win + 8 <= win1; win += 8) windows(win, std::integral_constant<int, 8>());
+                                    if (win + 4 <= win1) { windows(win, std::integral_constant<int, 4>()); win += 4; }
+                                }
                                 for (; win + 2 <= win1; win += 2) windows(win, std::integral_constant<int, 2>());
                                 if (win < win1) windows(win, std::integral_constant<int, 1>());
                             }
@@ -847,33 +865,59 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 S.ct_log[(size_t)r * S.ct_cap + base0 + M.cbase[q] + 2u + (uint32_t)atomicAdd(&M.clen[q], 1)] = y;
                             };
                             int ndl = 0;
-                            for (int win = win0; win < win1; ++win) {
-                                const int e = (win << 5) + lane;
-                                const uint32_t y = e < Etot ? M.evy[e] : EV_NONE;
-                                const uint32_t rec = e < Etot ? M.evm[e] : 0u;
-                                const bool live = y != EV_NONE && !(rec & EVM_DROPPED);
-                                const bool shared = live && ((M.dupm[y >> 5] >> (y & 31)) & 1u);
-                                if (live && !shared) {
+                            unsigned smask = 0;                                                // bit j: this lane's event of window win0 + j shares its target
+                            auto apply = [&](int win, auto nwc) {
+                                constexpr int NWIN = decltype(nwc)::value;
+                                uint32_t y[NWIN], rec[NWIN], dm[NWIN], sy[NWIN]; bool single[NWIN];
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) {
+                                    const int e = ((win + j) << 5) + lane;
+                                    y[j] = e < Etot ? M.evy[e] : EV_NONE;
+                                    rec[j] = e < Etot ? M.evm[e] : 0u;
+                                }
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) {
+                                    single[j] = y[j] != EV_NONE && !(rec[j] & EVM_DROPPED);      // live so far
+                                    dm[j] = single[j] ? M.dupm[y[j] >> 5] : 0u;                  // (loads of all windows in flight together)
+                                }
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) {
+                                    const bool shared = single[j] && ((dm[j] >> (y[j] & 31)) & 1u);
+                                    single[j] = single[j] && !shared;
+                                    smask |= (unsigned)shared << (win + j - win0);
+                                    ndl += __popc(__ballot_sync(FULL, shared));
+                                    sy[j] = single[j] ? M.status[y[j]] : 0u;
+                                }
+#pragma unroll
+                                for (int j = 0; j < NWIN; ++j) {
+                                    if (!single[j]) continue;
                                     // The status word counts today's contacts of y (tag == today since (b)); the event is admitted iff that
                                     // count is still below y's budget (:812-813). The budget is only drawn when the answer matters: the event
                                     // would transmit to a susceptible, or its infector logs contacts.
-                                    const uint32_t sy = M.status[y];
-                                    const int hits = st_rem(sy), q = (int)(rec >> 2);
-                                    uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)min(hits + 1, 255);
-                                    const bool infects = st_health(sy) == SUS && st_swap(sy) == UNDEF && (rec & EVM_SUCC);   // :822-823
+                                    const int hits = st_rem(sy[j]), q = (int)(rec[j] >> 2);
+                                    uint32_t ns = (sy[j] & ~ST_REMMASK) | (uint32_t)min(hits + 1, 255);
+                                    const bool infects = st_health(sy[j]) == SUS && st_swap(sy[j]) == UNDEF && (rec[j] & EVM_SUCC);   // :822-823
                                     const bool logs = ctr && room && M.cflag[q];
-                                    if ((infects || logs) && hits < fresh_budget_s(M, key, y, (uint32_t)day, sy)) {
-                                        if (logs) log_contact(q, y);
+                                    if ((infects || logs) && hits < fresh_budget_s(M, key, y[j], (uint32_t)day, sy[j])) {
+                                        if (logs) log_contact(q, y[j]);
                                         if (infects) {                                              // :824-827
                                             ns = st_set_swap(ns, LAT);
-                                            S.sickfrom[rb + y] = (uint8_t)(M.ch[q] & 0xF);
-                                            M.expday[y] = (int16_t)day;                             // y.exp = y.tis :826 — fires in today's time_update
-                                            prefetch_l2(S.dur + rb + y); prefetch_l2(S.isovia + rb + y);   // what that transition will read
+                                            S.sickfrom[rb + y[j]] = (uint8_t)(M.ch[q] & 0xF);
+                                            M.expday[y[j]] = (int16_t)day;                          // y.exp = y.tis :826 — fires in today's time_update
+                                            prefetch_l2(S.dur + rb + y[j]); prefetch_l2(S.isovia + rb + y[j]);   // what that transition will read
                                         }
                                     }
-                                    M.status[y] = ns;
+                                    M.status[y[j]] = ns;
                                 }
-                                ndl += __popc(__ballot_sync(FULL, shared));
+                            };
+                            {
+                                int win = win0;
+                                if constexpr (GS) {
+                                    for (; win + 8 <= win1; win += 8) apply(win, std::integral_constant<int, 8>());
+                                    if (win + 4 <= win1) { apply(win, std::integral_constant<int, 4>()); win += 4; }
+                                    for (; win + 2 <= win1; win += 2) apply(win, std::integral_constant<int, 2>());
+                                }
+                                for (; win < win1; ++win) apply(win, std::integral_constant<int, 1>());
                             }
                             if (lane == 0) Z.wdup[wid] = ndl;
                             PHASE(11);
@@ -884,8 +928,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                                 // events that share a target, compacted in event order
                                 for (int win = win0; win < win1; ++win) {
                                     const int e = (win << 5) + lane;
-                                    const uint32_t y = e < Etot ? M.evy[e] : EV_NONE;
-                                    const bool shared = y != EV_NONE && !(M.evm[e] & EVM_DROPPED) && ((M.dupm[y >> 5] >> (y & 31)) & 1u);
+                                    const bool shared = (smask >> (win - win0)) & 1u;          // found by the apply pass above
                                     const unsigned dm = __ballot_sync(FULL, shared);
                                     if (shared) M.D[dpos + __popc(dm & ((1u << lane) - 1u))] = (uint16_t)e;
                                     dpos += __popc(dm);
@@ -1001,6 +1044,98 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 // the few agents that have an event today (:405, marks) one after another
                 PHASE(27);
                 uint32_t mn = 0x7FFF7FFFu;                                     // running min of the event days that stay (2 x i16)
+                if constexpr (GS) {
+                    // State in global memory (large populations): an event inside the stream would stall its whole warp on one lane's
+                    // dependent L2 round trips, several times per pass. So the scan only LISTS the agents with an event today (event day
+                    // reached, or marked by pass A) and keeps the minimum of the event days that stay; the listed agents are then taken one
+                    // per thread in dense warps.
+                    constexpr int U = 8;
+                    uint32_t *const evl = S.ev_list + (size_t)r * Np;
+                    const uint32_t dd = (uint32_t)day * 0x10001u;
+                    for (int bb = 0; bb < N; bb += NT * 8 * U) {             // (the same number of passes for every thread: the append is a warp collective)
+                        const int b0 = bb + tid * 8;
+                        uint4 ex[U];
+                        unsigned long long fire = 0, pre = 0, post = 0;        // 8 bits per chunk
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int i0 = b0 + u * NT * 8;
+                            ex[u] = i0 < N ? *reinterpret_cast<const uint4 *>(M.expday + i0) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
+                            if (i0 + NT * 8 * U < N) prefetch_l2(M.expday + i0 + NT * 8 * U);      // the next pass of this thread
+                            if (ctr && i0 < N) {
+                                const unsigned sh = i0 & 31;
+                                pre |= (unsigned long long)((M.mpre[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
+                                post |= (unsigned long long)((M.mpost[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            uint32_t wds[4] = {ex[u].x, ex[u].y, ex[u].z, ex[u].w};
+                            const unsigned mk = (unsigned)((pre | post) >> (8 * u)) & 0xFFu;
+                            unsigned f = 0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                uint32_t m = __vcmples2(wds[k], dd);                              // 0xFFFF per half whose day has come
+                                f |= ((m & 1u) | ((m >> 15) & 2u)) << (2 * k);
+                                m |= ((mk >> (2 * k)) & 1u ? 0xFFFFu : 0u) | ((mk >> (2 * k + 1)) & 1u ? 0xFFFF0000u : 0u);
+                                mn = __vmins2(mn, (wds[k] & ~m) | (0x7FFF7FFFu & m));             // listed agents report their new event day below
+                            }
+                            fire |= (unsigned long long)f << (8 * u);
+                        }
+                        fire |= pre | post;
+                        // append: exclusive prefix of the counts over the warp, one atomicAdd per warp
+                        const int c = __popcll(fire);
+                        if (__any_sync(FULL, c != 0)) {
+                            int incl = c;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                            unsigned base = 0;
+                            if (lane == 31) base = atomicAdd(&Z.evn, (unsigned)incl);
+                            base = __shfl_sync(FULL, base, 31) + (unsigned)(incl - c);
+                            while (fire) {
+                                const int bit = __ffsll((long long)fire) - 1; fire &= fire - 1;
+                                const int i = b0 + (bit >> 3) * NT * 8 + (bit & 7);
+                                evl[base++] = (uint32_t)i | ((uint32_t)((pre >> bit) & 1u) << 30) | ((uint32_t)((post >> bit) & 1u) << 31);
+                            }
+                        }
+                    }
+                    __syncthreads();                                           // the list is complete
+                    const unsigned nev = Z.evn;
+                    int mne = 32767;
+                    for (unsigned k = tid; k < nev; k += NT) {
+                        const uint32_t ent = evl[k];
+                        const int i = (int)(ent & 0x3FFFFFFFu);
+                        if (i >= N) continue;                                  // padding of the last block of eight
+                        const unsigned pb = (ent >> 30) & 1u, qb = ent >> 31;
+                        if (ctr) {
+                            if (pb) atomicAnd(&M.mpre[i >> 5], ~(1u << (i & 31)));
+                            if (qb) atomicAnd(&M.mpost[i >> 5], ~(1u << (i & 31)));
+                        }
+                        const uint32_t st = M.status[i];
+                        const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];
+                        const int par = (day + 1) & 1;
+#ifdef CABM_FUSED_DIAG
+                        const long long t_e0 = clock64();
+#endif
+                        const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, ctr, pb, qb,
+                                                      &Z.qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr, M.dcache);
+#ifdef CABM_FUSED_DIAG
+                        if (e.st != 0xFFFFFFFFu) { atomicAdd((unsigned long long *)&t_ph[28], (unsigned long long)(clock64() - t_e0)); atomicAdd((unsigned long long *)&t_ph[29], 1ull); }
+#endif
+                        M.status[i] = e.st;
+                        M.expday[i] = (int16_t)e.ne;
+                        mne = min(mne, e.ne);
+                        if (ctr && e.texp != texp) S.texp[rb + i] = (int16_t)e.texp;
+                        if (e.newh != e.oldh) {
+                            M.col[i] = (uint8_t)e.newh;
+                            atomicAdd(&Z.io[act & 1][0][st_ag(st) * 12 + e.newh], 1); atomicAdd(&Z.io[act & 1][1][st_ag(st) * 12 + e.oldh], 1);
+                            if (is_infectious(e.newh) != is_infectious(e.oldh)) {
+                                atomicXor(&M.inf[i >> 5], 1u << (i & 31));
+                                atomicAdd(&Z.ninf, is_infectious(e.newh) ? 1 : -1);
+                            }
+                        }
+                    }
+                    mn = __vmins2(mn, (uint32_t)(mne & 0xFFFF) | 0x7FFF0000u);
+                } else {
                 for (int b0 = tid * 8; b0 < N; b0 += NT * 8 * FUSED_SCAN_U) {
                     uint4 ex[FUSED_SCAN_U];
                     unsigned long long fire = 0, pre = 0, post = 0;            // 8 bits per chunk
@@ -1076,6 +1211,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                     }
                     mn = __vmins2(mn, cmin);
                 }
+                }
                 PHASE(25);
                 {
                     int v = min((int)(short)(mn & 0xFFFF), (int)(short)(mn >> 16));
@@ -1086,6 +1222,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 PHASE(26);
                 __syncthreads();                                               // S2
                 nextfire = Z.nf[act & 1]; ++act;
+                if (GS && tid == 0) Z.evn = 0;                                 // every thread has read the count (before S2); the next append is behind a barrier
                 PHASE(4);
             }
             // -------------------------------------------------------- column st+1 (:136 of the next day) and its curves
@@ -1119,7 +1256,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_sim_fused(Dev S, unsigned *work
                 }
                 if (hm) {
                     if (tma_ok) { if (tid == 0) { bulk_store_wait_read_n(); bulk_store(hm + (size_t)day * N, M.col, (uint32_t)N); } }
-                    else for (int i = tid; i < N; i += NT) hm[(size_t)day * N + i] = M.col[i];
+                    else copy_column(hm + (size_t)day * N, M.col, N, tid, NT);
                 }
             }
             PHASE(5);

@@ -441,19 +441,29 @@ __device__ inline void ct_identify_warp(const Dev &S, const DevPset &P, int r, i
             if (!dup) contact(y);
         }
         __syncwarp(gmask);
-    } else if (gl == 0) {                                     // very long contact sets: one lane, quadratic walk
+    } else {
+        // very long contact sets: the group walks the log itself, one entry per lane, each compared with every entry before it.
+        // Control flow is uniform over the group. (No lane may run ahead to the next index case: its gather would land in buffer
+        // slots that belong to other lanes of a case still being gathered — every branch ends with the group together.)
         for (uint32_t c = head; c != CT_NONE; c = log[c]) {
-            for (uint32_t k = 0; k < log[c + 1]; ++k) {
-                const uint32_t y = log[c + 2 + k];
-                bool dup = false;
-                for (uint32_t c2 = head; c2 != CT_NONE && !dup; c2 = log[c2]) {
-                    const uint32_t lim = c2 == c ? k : log[c2 + 1];
-                    for (uint32_t k2 = 0; k2 < lim; ++k2) if (log[c2 + 2 + k2] == y) { dup = true; break; }
+            const uint32_t cnt = log[c + 1];
+            for (uint32_t k0 = 0; k0 < cnt; k0 += G) {
+                const uint32_t k = k0 + (uint32_t)gl;
+                const bool have = k < cnt;
+                const uint32_t y = have ? log[c + 2 + k] : 0u;
+                bool dup = !have;
+                for (uint32_t c2 = head;; c2 = log[c2]) {
+                    const uint32_t n2 = c2 == c ? min(cnt, k0 + (uint32_t)G) : log[c2 + 1];
+                    for (uint32_t k2 = 0; k2 < n2; ++k2) {
+                        const uint32_t z = log[c2 + 2 + k2];
+                        if (z == y && (c2 != c || k2 < k)) dup = true;
+                    }
                     if (c2 == c) break;
                 }
                 if (!dup) contact(y);
             }
         }
+        __syncwarp(gmask);
     }
 }
 

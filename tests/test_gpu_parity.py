@@ -459,3 +459,21 @@ def test_random_scenarios_bit_exact(cv, O, block):
             assert (got["hmatrix"] == ref["hmatrix"]).all(), (path, kw)
             assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all(), (path, kw)
             assert (got["infectors"] == ref["infectors"]).all() and (got["totalisolated"] == ref["totalisolated"]).all(), (path, kw)
+
+
+def test_long_contact_sets_are_identified_the_same_way_every_run(cv, O):
+    """Index cases whose traced-contact set is longer than a group's gather buffer (seven days back at beta = 0.3: more than 128
+    entries) take the walk over the log itself. Regression: a lane that ran ahead of its group there once let the next case's
+    gather overwrite buffer slots of the case after it — a result that changed from run to run. Eight runs per path."""
+    kw = dict(β=0.3, prov="nwterrito", popsize=6000, modeltime=112, initialinf=16, seasonal=True, frelasymp=1.0, τmild=2, fmild=0.3,
+              fsevere=0.0, tpreiso=1, fpreiso=0.0, ctstrat=1, fctcapture=1.0, fcontactst=0.2, cdaysback=7)
+    ip = cv.ModelParameters(**kw)
+    seeds = [726 * (i + 1) for i in range(6)]
+    ref = O.run_ensemble([to_oracle(O, ip)], [0] * 6, seeds, nthreads=6, want_hmatrix=True)
+    assert ref["totalisolated"].sum() > 1000
+    for it in range(8):
+        for path in ("fused", "multikernel", "fused-global"):
+            got = cv.run_ensemble(ip, 6, seeds=seeds, want_hmatrix=True, path=path)
+            assert (got["totalisolated"] == ref["totalisolated"]).all(), (it, path)
+            assert (got["hmatrix"] == ref["hmatrix"]).all(), (it, path)
+            assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all(), (it, path)

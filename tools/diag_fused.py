@@ -1,7 +1,8 @@
 """Per-phase cycle counts of k_sim_fused (diagnostics build: make -C covid19abm.jl_b200/csrc diag).
-Usage: python tools/diag_fused.py [B|REF|HOT|C1] [nrep]
+Usage: python tools/diag_fused.py [B|REF|HOT|C1|E] [nrep]
   B    bench workload (BASELINE configs[1])          REF  the reference's timed scenario (test/runtests.jl:408-428)
-  HOT  beta=0.06 ontario, no isolation, no tracing   C1   beta=0.06 with contact tracing ctstrat=1"""
+  HOT  beta=0.06 ontario, no isolation, no tracing   C1   beta=0.06 with contact tracing ctstrat=1
+  E    10^6 agents (BASELINE configs[4]; the fused kernel with per-agent arrays in global memory)"""
 import os, sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 os.environ.setdefault("CABM_LIB", os.path.abspath("covid19abm.jl_b200/libcabm_b200_diag.so"))
 import numpy as np, covid19abm_b200 as cv
@@ -11,16 +12,18 @@ R = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 cfgs = {"B": CFG,
         "REF": dict(β=0.0525, prov="newyork", modeltime=300),
         "HOT": dict(β=0.06, prov="ontario", initialinf=1, modeltime=500),
-        "C1": dict(β=0.06, prov="ontario", initialinf=1, modeltime=500, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3)}
+        "C1": dict(β=0.06, prov="ontario", initialinf=1, modeltime=500, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3),
+        "E": dict(β=0.0345, prov="ontario", popsize=1000000, modeltime=500, initialinf=100, quar_grp_frac=0.5, quar_grp=5)}
 ip = cv.ModelParameters(**cfgs[which])
 T = ip.modeltime
-pop = cv.Population(R, 10000, T, store_hmatrix=False)
+NPOP = ip.popsize
+pop = cv.Population(R, NPOP, T, store_hmatrix=False)
 pop.configure(ip, seeds_for(0, 0, R)); pop.run(); pop.run()
 print("config", which, "ms", pop.last_run_ms)
 met = np.zeros(R, np.int32); inf = np.zeros(R, np.int32)
 pop._chk(pop.L.cabm_get_dyntrans_counters(pop.h, met.ctypes.data, inf.ctypes.data))
 inc, prev = pop.curves()
-attack = 1 - prev[:, 0, -1, 0] / 10000
+attack = 1 - prev[:, 0, -1, 0] / NPOP
 order = np.argsort(-met)
 print("kcycles sum", met.sum(), "max", met.max(), "mean", met.mean())
 for r in order[:6]: print(r, "kcyc", met[r], "ms", met[r] * 1024 / 1.965e6, "chunks", inf[r], "attack", attack[r], "peak inf", prev[r, 0, :, 2:8].sum(axis=1).max(), "cyc/chunk", met[r] * 1024 / max(inf[r], 1))
