@@ -755,9 +755,10 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                             };
                             // NWIN windows of 32 events at once: every stage is a fully unrolled loop over the windows, so that the
                             // independent chains (Philox, table walks, loads) of the windows interleave in one basic block
+                            unsigned lmask = 0;                                                 // bit j: this lane's event of window win0 + j found its target already touched
                             auto windows = [&](int win, auto nwc) {
                                 constexpr int NWIN = decltype(nwc)::value;
-                                int q[NWIN], idx[NWIN]; uint32_t meta[NWIN], y[NWIN], sy[NWIN]; bool ok[NWIN], need[NWIN];
+                                int q[NWIN], idx[NWIN]; uint32_t meta[NWIN], y[NWIN]; bool ok[NWIN];
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) q[j] = (int)(M.evm[min(((win + j) << 5) + lane, Etot - 1)] >> 2);   // written by the chunk build
                                 PHASE(2);
@@ -765,17 +766,9 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                 for (int j = 0; j < NWIN; ++j) draw(((win + j) << 5) + lane, q[j], idx[j], meta[j], ok[j]);
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) y[j] = ld_keep(grp + idx[j]);       // loads in flight together
-#pragma unroll
-                                for (int j = 0; j < NWIN; ++j) sy[j] = M.status[y[j]];
-#pragma unroll
-                                for (int j = 0; j < NWIN; ++j) need[j] = ok[j] && st_tag(sy[j]) != day;
                                 PHASE(7);
-                                // first touch today: start the target's count of today's contacts (tag = today, count 0). Its contact budget
-                                // (:811, get_nextday_counts :772-788) is not drawn here: it is drawn when an outcome depends on it (step (d))
-#pragma unroll
-                                for (int j = 0; j < NWIN; ++j)
-                                    if (need[j]) M.status[y[j]] = (sy[j] & ~(ST_REMMASK | ST_TAGMASK)) | ((uint32_t)day << 22);
-                                PHASE(20);
+                                // (the target's status word is not touched here: its count of today's contacts starts when the first
+                                // event is applied, step (d), where a tag older than today reads as zero contacts)
                                 // records; targets hit more than once (by any event of the chunk, dropped later or not) take the ordered path
                                 uint32_t old[NWIN];
 #pragma unroll
@@ -789,8 +782,12 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                 }
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) {
-                                    if (ok[j] && (old[j] >> (y[j] & 31)) & 1u) atomicOr(&M.dupm[y[j] >> 5], 1u << (y[j] & 31));
-                                    if (ok[j] && ((M.inf[y[j] >> 5] >> (y[j] & 31)) & 1u) && (int)y[j] > (int)M.cx[(meta[j] >> 2) & 255u] && (int)y[j] <= xlast)
+                                    if (ok[j] && (old[j] >> (y[j] & 31)) & 1u) {
+                                        atomicOr(&M.dupm[y[j] >> 5], 1u << (y[j] & 31));
+                                        lmask |= 1u << (win + j - win0);                           // this lane's event set a dupm bit (cleared by it at chunk end)
+                                    }
+                                    // a later infector of this chunk? the index range first: with a large population hardly any target is inside it
+                                    if (ok[j] && (int)y[j] > (int)M.cx[(meta[j] >> 2) & 255u] && (int)y[j] <= xlast && ((M.inf[y[j] >> 5] >> (y[j] & 31)) & 1u))
                                         edge(((win + j) << 5) + lane, y[j], meta[j]);
                                 }
                                 PHASE(21);
@@ -891,11 +888,11 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) {
                                     if (!single[j]) continue;
-                                    // The status word counts today's contacts of y (tag == today since (b)); the event is admitted iff that
+                                    // The status word counts today's contacts of y (when its tag is today); the event is admitted iff that
                                     // count is still below y's budget (:812-813). The budget is only drawn when the answer matters: the event
                                     // would transmit to a susceptible, or its infector logs contacts.
-                                    const int hits = st_rem(sy[j]), q = (int)(rec[j] >> 2);
-                                    uint32_t ns = (sy[j] & ~ST_REMMASK) | (uint32_t)min(hits + 1, 255);
+                                    const int hits = st_tag(sy[j]) == day ? st_rem(sy[j]) : 0, q = (int)(rec[j] >> 2);   // today's contacts of y so far
+                                    uint32_t ns = (sy[j] & ~(ST_REMMASK | ST_TAGMASK)) | ((uint32_t)day << 22) | (uint32_t)min(hits + 1, 255);
                                     const bool infects = st_health(sy[j]) == SUS && st_swap(sy[j]) == UNDEF && (rec[j] & EVM_SUCC);   // :822-823
                                     const bool logs = ctr && room && M.cflag[q];
                                     if ((infects || logs) && hits < fresh_budget_s(M, key, y[j], (uint32_t)day, sy[j])) {
@@ -952,7 +949,7 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                     const bool leader = mine && lane == __ffs(peers) - 1;
                                     const int n = __popc(peers), nmax = __reduce_max_sync(FULL, mine ? n : 0);
                                     const uint32_t sy = mine ? M.status[y] : 0u;
-                                    const int hits0 = st_rem(sy);                                            // contacts of y before this group's
+                                    const int hits0 = st_tag(sy) == day ? st_rem(sy) : 0;                    // contacts of y today before this group's
                                     int xh_inf = -1;
                                     bool sus = st_health(sy) == SUS && st_swap(sy) == UNDEF;                 // :822
                                     const int hit = (mine && (rec & EVM_SUCC)) ? (int)(M.ch[qd] & 0xF) : -1;     // would this event transmit (:823)?
@@ -971,7 +968,7 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                         }
                                     }
                                     if (leader) {
-                                        uint32_t ns = (sy & ~ST_REMMASK) | (uint32_t)min(hits0 + n, 255);
+                                        uint32_t ns = (sy & ~(ST_REMMASK | ST_TAGMASK)) | ((uint32_t)day << 22) | (uint32_t)min(hits0 + n, 255);
                                         if (xh_inf >= 0) {
                                             ns = st_set_swap(ns, LAT);
                                             S.sickfrom[rb + y] = (uint8_t)xh_inf;
@@ -995,7 +992,7 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                 for (int win = win0; win < win1; ++win) {
                                     const int e = (win << 5) + lane;
                                     const uint32_t y = e < Etot ? M.evy[e] : EV_NONE;
-                                    if (y != EV_NONE) { M.touch[y >> 5] = 0; M.dupm[y >> 5] = 0; }
+                                    if (y != EV_NONE) { M.touch[y >> 5] = 0; if ((lmask >> (win - win0)) & 1u) M.dupm[y >> 5] = 0; }   // (dupm bits were set by exactly these events)
                                 }
                             } else {
                                 for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }   // next marking is after the next C1
