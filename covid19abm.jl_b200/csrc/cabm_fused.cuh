@@ -46,6 +46,7 @@ namespace cabm {
 constexpr int FUSED_NT = 256;          // threads per CTA
 constexpr int FUSED_LCAP = 256;        // infectors listed per pass = infectors per chunk at most
 constexpr int FUSED_EVCAP = 2048;      // contact events per chunk
+constexpr int FUSED_HCAP = 8192;       // global-state variant: slots of the chunk's target table (four times the events of a chunk; a power of two)
 constexpr int FUSED_NEDGE = 256;       // events of a chunk that hit a later infector of the same chunk (more: the chunk is halved)
 constexpr unsigned FUSED_TAIL_CTAS = 8;  // CTAs that copy finished curves to the host at any one time (PCIe saturates with ~8)
 constexpr int FUSED_SCAN_U = 5;        // chunks of 8 agents a thread scans at once in time_update (256 x 8 x 5 >= 10,000 agents in one go)
@@ -95,6 +96,7 @@ template <class IdxT> struct FusedSmemT {
     uint32_t *cbase; int *clen;          //   contact-log chunk of a traced entry, contacts logged so far
     unsigned long long *dcache;          // (agent << 32 | dur) of recently infected agents
     int *cnt;                            // NT ints scratch (seeding, first column); aliases evy
+    uint32_t *htab;                      // global-state variant: open-addressing table of the chunk's targets (bit 31: hit more than once)
 };
 
 // global_state: the per-agent arrays (status, expday, column, bitmasks) stay in global memory (any popsize); only the chunk
@@ -112,6 +114,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int Np, bool global_state = f
     b += FUSED_EVCAP * 4 + FUSED_EVCAP * 2 * 2 + FUSED_NEDGE * 4;    // evy, evm, D, edges
     b += FUSED_LCAP * ((global_state ? 4 : 2) * 2 + 4 * 1 + 4 + 8 + 4 + 4 + 4) + (FUSED_LCAP + 1) * 4 + 12;   // list, cx, ch/cb/cc/cflag, hits, gp0, cbase, clen, gcum, pref
     b += DUR_CACHE * 8;                  // dcache
+    if (global_state) b += FUSED_HCAP * 4;   // htab
     return (b + 15) / 16 * 16 + 64;
 }
 
@@ -196,6 +199,8 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
         unsigned char *p = smem_raw + sizeof(FusedCtl);
         M.dcache = (unsigned long long *)p; p += DUR_CACHE * 8;
         M.gp0 = (unsigned long long *)p; p += FUSED_LCAP * 8;
+        M.htab = nullptr;
+        if (GS) { M.htab = (uint32_t *)p; p += FUSED_HCAP * 4; }
         if (!GS) {
             M.status = (uint32_t *)p; p += (size_t)Np * 4;
             M.expday = (int16_t *)p; p += (size_t)Np * 2;      // Np is a multiple of 32: every array below stays 16-byte aligned
@@ -232,6 +237,7 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
     for (int k = tid; k < 5 * 512; k += NT) M.nb_guide[k] = S.nb_guide[k];
     if (tid < 5) Z.nb_len[tid] = c_tab.nb_len[tid];
     if (!GS) for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; M.mpre[k] = 0; M.mpost[k] = 0; }
+    if (GS) for (int k = tid; k < FUSED_HCAP / 4; k += NT) reinterpret_cast<uint4 *>(M.htab)[k] = make_uint4(~0u, ~0u, ~0u, ~0u);
     if (tid == 0) Z.nedge = 0;
     if (tid < 4) { Z.tlat[tid] = c_tab.lat_thr[tid]; Z.tpre[tid] = c_tab.pre_thr[tid]; }
     if (tid < 40) { Z.tasy[tid] = c_tab.asy_thr[tid]; Z.tinf[tid] = c_tab.inf_thr[tid]; }
@@ -755,7 +761,6 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                             };
                             // NWIN windows of 32 events at once: every stage is a fully unrolled loop over the windows, so that the
                             // independent chains (Philox, table walks, loads) of the windows interleave in one basic block
-                            unsigned lmask = 0;                                                 // bit j: this lane's event of window win0 + j found its target already touched
                             auto windows = [&](int win, auto nwc) {
                                 constexpr int NWIN = decltype(nwc)::value;
                                 int q[NWIN], idx[NWIN]; uint32_t meta[NWIN], y[NWIN]; bool ok[NWIN];
@@ -770,25 +775,54 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                 // (the target's status word is not touched here: its count of today's contacts starts when the first
                                 // event is applied, step (d), where a tag older than today reads as zero contacts)
                                 // records; targets hit more than once (by any event of the chunk, dropped later or not) take the ordered path
-                                uint32_t old[NWIN];
+                                if constexpr (GS) {
+                                    // state in global memory: which targets the chunk hits more than once is found in a table of the chunk's
+                                    // targets in shared memory (slot = target, bit 31 = hit again) instead of two population-wide bitmasks
+                                    // in global memory (an atomic, a load and two clearing stores per event)
+                                    uint32_t slot[NWIN]; bool pend[NWIN];
 #pragma unroll
-                                for (int j = 0; j < NWIN; ++j) old[j] = ok[j] ? atomicOr(&M.touch[y[j] >> 5], 1u << (y[j] & 31)) : 0u;
+                                    for (int j = 0; j < NWIN; ++j) { slot[j] = ((y[j] * 2654435761u) >> 16) & (uint32_t)(FUSED_HCAP - 1); pend[j] = ok[j]; }
+                                    for (bool any = true; any;) {                                              // one probe of every unfinished window per round
+                                        any = false;
 #pragma unroll
-                                for (int j = 0; j < NWIN; ++j) {
-                                    const int e = ((win + j) << 5) + lane;
-                                    M.evy[e] = ok[j] ? y[j] : EV_NONE;
-                                    M.evm[e] = ok[j] ? (uint16_t)(meta[j] & 0x3FFu & ~(uint32_t)EVM_DROPPED) : (uint16_t)0;
-                                    if (!ok[j] && (meta[j] >> 31) && e < Etot) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
-                                }
-#pragma unroll
-                                for (int j = 0; j < NWIN; ++j) {
-                                    if (ok[j] && (old[j] >> (y[j] & 31)) & 1u) {
-                                        atomicOr(&M.dupm[y[j] >> 5], 1u << (y[j] & 31));
-                                        lmask |= 1u << (win + j - win0);                           // this lane's event set a dupm bit (cleared by it at chunk end)
+                                        for (int j = 0; j < NWIN; ++j) {
+                                            if (pend[j]) {
+                                                const uint32_t old = atomicCAS(&M.htab[slot[j]], 0xFFFFFFFFu, y[j]);
+                                                if (old == 0xFFFFFFFFu) pend[j] = false;                        // first event on this target
+                                                else if ((old & 0x7FFFFFFFu) == y[j]) { if (!(old >> 31)) atomicOr(&M.htab[slot[j]], 0x80000000u); pend[j] = false; }
+                                                else slot[j] = (slot[j] + 1u) & (uint32_t)(FUSED_HCAP - 1);
+                                                any |= pend[j];
+                                            }
+                                        }
                                     }
-                                    // a later infector of this chunk? the index range first: with a large population hardly any target is inside it
-                                    if (ok[j] && (int)y[j] > (int)M.cx[(meta[j] >> 2) & 255u] && (int)y[j] <= xlast && ((M.inf[y[j] >> 5] >> (y[j] & 31)) & 1u))
-                                        edge(((win + j) << 5) + lane, y[j], meta[j]);
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) {
+                                        const int e = ((win + j) << 5) + lane;
+                                        if (ok[j]) M.D[e] = (uint16_t)slot[j];                                  // read back by the apply pass (D is free until the compaction)
+                                        M.evy[e] = ok[j] ? y[j] : EV_NONE;
+                                        M.evm[e] = ok[j] ? (uint16_t)(meta[j] & 0x3FFu & ~(uint32_t)EVM_DROPPED) : (uint16_t)0;
+                                        if (!ok[j] && (meta[j] >> 31) && e < Etot) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
+                                        if (ok[j] && (int)y[j] > (int)M.cx[(meta[j] >> 2) & 255u] && (int)y[j] <= xlast && ((M.inf[y[j] >> 5] >> (y[j] & 31)) & 1u))
+                                            edge(e, y[j], meta[j]);
+                                    }
+                                } else {
+                                    uint32_t old[NWIN];
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) old[j] = ok[j] ? atomicOr(&M.touch[y[j] >> 5], 1u << (y[j] & 31)) : 0u;
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) {
+                                        const int e = ((win + j) << 5) + lane;
+                                        M.evy[e] = ok[j] ? y[j] : EV_NONE;
+                                        M.evm[e] = ok[j] ? (uint16_t)(meta[j] & 0x3FFu & ~(uint32_t)EVM_DROPPED) : (uint16_t)0;
+                                        if (!ok[j] && (meta[j] >> 31) && e < Etot) atomicOr(&S.err[r], ERR_EMPTY_GROUP);
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < NWIN; ++j) {
+                                        if (ok[j] && (old[j] >> (y[j] & 31)) & 1u) atomicOr(&M.dupm[y[j] >> 5], 1u << (y[j] & 31));
+                                        // a later infector of this chunk? the index range first: with a large population hardly any target is inside it
+                                        if (ok[j] && (int)y[j] > (int)M.cx[(meta[j] >> 2) & 255u] && (int)y[j] <= xlast && ((M.inf[y[j] >> 5] >> (y[j] & 31)) & 1u))
+                                            edge(((win + j) << 5) + lane, y[j], meta[j]);
+                                    }
                                 }
                                 PHASE(21);
                             };
@@ -807,7 +841,8 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                             if (ne > FUSED_NEDGE) {
                                 // too many order dependences for the edge list (tiny populations with most agents infectious): take half the entries
                                 __syncthreads();
-                                for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }
+                                if (GS) { for (int k = tid; k < FUSED_HCAP / 4; k += NT) reinterpret_cast<uint4 *>(M.htab)[k] = make_uint4(~0u, ~0u, ~0u, ~0u); }
+                                else for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }
                                 if (tid == 0) Z.nedge = 0;
                                 lim = max(1, mlist >> 1);
                                 __syncthreads();
@@ -875,15 +910,20 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) {
                                     single[j] = y[j] != EV_NONE && !(rec[j] & EVM_DROPPED);      // live so far
-                                    dm[j] = single[j] ? M.dupm[y[j] >> 5] : 0u;                  // (loads of all windows in flight together)
+                                    if constexpr (GS) {
+                                        dm[j] = single[j] ? M.htab[M.D[((win + j) << 5) + lane]] >> 31 : 0u;    // the slot found by the event's insert
+                                        sy[j] = single[j] ? M.status[y[j]] : 0u;                 // (nearly every target is hit once: loaded without waiting for the answer)
+                                    } else {
+                                        dm[j] = single[j] ? (M.dupm[y[j] >> 5] >> (y[j] & 31)) & 1u : 0u;
+                                    }
                                 }
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) {
-                                    const bool shared = single[j] && ((dm[j] >> (y[j] & 31)) & 1u);
+                                    const bool shared = single[j] && dm[j];
                                     single[j] = single[j] && !shared;
                                     smask |= (unsigned)shared << (win + j - win0);
                                     ndl += __popc(__ballot_sync(FULL, shared));
-                                    sy[j] = single[j] ? M.status[y[j]] : 0u;
+                                    if constexpr (!GS) sy[j] = single[j] ? M.status[y[j]] : 0u;
                                 }
 #pragma unroll
                                 for (int j = 0; j < NWIN; ++j) {
@@ -988,12 +1028,8 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                 c[0] = S.ct_head[rb + xq]; c[1] = (uint32_t)M.clen[tid];
                                 S.ct_head[rb + xq] = base0 + M.cbase[tid];
                             }
-                            if (GS) {       // (the bitmasks cover the whole population: clear the words this chunk's events marked)
-                                for (int win = win0; win < win1; ++win) {
-                                    const int e = (win << 5) + lane;
-                                    const uint32_t y = e < Etot ? M.evy[e] : EV_NONE;
-                                    if (y != EV_NONE) { M.touch[y >> 5] = 0; if ((lmask >> (win - win0)) & 1u) M.dupm[y >> 5] = 0; }   // (dupm bits were set by exactly these events)
-                                }
+                            if (GS) {
+                                for (int k = tid; k < FUSED_HCAP / 4; k += NT) reinterpret_cast<uint4 *>(M.htab)[k] = make_uint4(~0u, ~0u, ~0u, ~0u);     // next insert is after the next C1
                             } else {
                                 for (int k = tid; k < nwords; k += NT) { M.touch[k] = 0; M.dupm[k] = 0; }   // next marking is after the next C1
                             }
@@ -1351,8 +1387,8 @@ int launch_sim_fused(const Dev &S, unsigned *work, int n_sm, bool any_ct, bool g
             const int lim = 227 * 1024 - 512;        // the opt-in maximum per CTA minus this kernel's (diagnostic) static shared memory
             cudaFuncSetAttribute(k_sim_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             cudaFuncSetAttribute(k_sim_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-            cudaFuncSetAttribute(k_sim_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(k_sim_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(k_sim_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(32, true));
+            cudaFuncSetAttribute(k_sim_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(32, true));      // (independent of the population)
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
     }
