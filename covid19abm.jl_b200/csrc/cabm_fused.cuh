@@ -524,19 +524,46 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                     Z.sel_tid = t; Z.sel_k = k;
                 }
                 __syncthreads();
-                if (tid == Z.sel_tid) {
+                auto seed_agent = [&](int i, uint32_t st) {
+                    const Tr t = transition_core(S, P, r, i, 0, st, key, health, true, M.dcache);
+                    M.status[i] = (t.st & ~ST_ISOB) | (st & ST_ISOB);    // day-1 budget was drawn with the old iso (:186)
+                    M.expday[i] = (int16_t)t.expday;
+                    if (ctr) S.texp[rb + i] = (int16_t)t.expday;
+                    M.col[i] = (uint8_t)t.newh;
+                    S.sickfrom[rb + i] = INF;                             // :391
+                    if (is_infectious(t.newh)) { M.inf[i >> 5] |= 1u << (i & 31); Z.ninf += 1; }
+                };
+                if constexpr (GS) {
+                    // state in global memory: the selected thread's segment (thousands of agents) is searched by the whole CTA — each warp
+                    // counts the susceptibles of its slice with coalesced loads, the warp whose slice holds the k-th one locates it
+                    const int slo = Z.sel_tid * seg, shi = min(N, slo + seg);
+                    const int per = (((shi - slo + NW - 1) / NW) + 31) & ~31;
+                    const int wlo = min(shi, slo + wid * per), whi = min(shi, wlo + per);
+                    int c = 0;
+                    for (int i0 = wlo; i0 < whi; i0 += 32) { const int i = i0 + lane; c += (i < whi && st_health(M.status[i]) == SUS); }
+                    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+                    if (lane == 0) Z.wsum2[wid] = c;
+                    __syncthreads();
+                    int k = Z.sel_k, w = 0;
+                    while (w < NW - 1 && k >= Z.wsum2[w]) { k -= Z.wsum2[w]; ++w; }
+                    if (wid == w) {
+                        for (int i0 = wlo; i0 < whi; i0 += 32) {
+                            const int i = i0 + lane;
+                            const uint32_t st = i < whi ? M.status[i] : 0u;
+                            const unsigned b = __ballot_sync(FULL, i < whi && st_health(st) == SUS);
+                            const int n = __popc(b);
+                            if (k < n) { if (lane == (int)__fns(b, 0, k + 1)) seed_agent(i, st); break; }
+                            k -= n;
+                        }
+                        if (lane == 0) M.cnt[Z.sel_tid] -= 1;
+                    }
+                } else if (tid == Z.sel_tid) {
                     int k = Z.sel_k;
                     for (int i = lo; i < hi; ++i) {
                         const uint32_t st = M.status[i];
                         if (st_health(st) != SUS) continue;
                         if (k-- > 0) continue;
-                        const Tr t = transition_core(S, P, r, i, 0, st, key, health, true, M.dcache);
-                        M.status[i] = (t.st & ~ST_ISOB) | (st & ST_ISOB);    // day-1 budget was drawn with the old iso (:186)
-                        M.expday[i] = (int16_t)t.expday;
-                        if (ctr) S.texp[rb + i] = (int16_t)t.expday;
-                        M.col[i] = (uint8_t)t.newh;
-                        S.sickfrom[rb + i] = INF;                             // :391
-                        if (is_infectious(t.newh)) { M.inf[i >> 5] |= 1u << (i & 31); Z.ninf += 1; }
+                        seed_agent(i, st);
                         break;
                     }
                     M.cnt[tid] -= 1;
