@@ -432,6 +432,21 @@ def main():
         roofline["launch_ms_alone"] = round(ms / n, 3)
         roofline["achieved_in_timed_region"] = round(alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9, 1)
         roofline["frac_in_timed_region"] = round(alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9 / peak, 4)
+        if pop.last_path == "fused-global":
+            # state in global memory (large populations): here the per-agent fields do live in HBM, so the yardstick is SURVEY 8(d)'s own
+            # figure, 14 B per agent-day (25 B with contact tracing) at the reference's field widths, over one launch
+            per_ad = 25 if any(kw.get("ctstrat", 0) for kw in W["psets"]) else 14
+            alg_bytes = per_ad * units + hm_b
+            gbs = alg_bytes / (ms / n * 1e-3) / 1e9
+            roofline.update({"bound": "hbm", "achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "bytes_per_launch": alg_bytes,
+                             "bytes_per_agent_day": round(alg_bytes / max(units, 1), 3),
+                             "bound_note": "state in HBM, touched as random 4-byte words (32-byte sectors) by one CTA per replicate: algorithmic bytes = SURVEY 8(d)'s "
+                                           "14 B (25 B with tracing) per agent-day; `traffic` above that is sector and line over-fetch of the random accesses. ncu: long "
+                                           "scoreboard and barriers are the top stalls — the chain of dependent HBM round trips per chunk, not bandwidth, bounds it",
+                             "long_scoreboard_stall_share": cap.get("long_scoreboard_stall_share"),
+                             "achieved_in_timed_region": round(alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9, 1),
+                             "frac_in_timed_region": round(alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9 / peak, 4)})
+            roofline.pop("traffic_eliminated", None)
     else:
         # algorithmic bytes per agent-day of k_time_update in the HBM layout: expday 2 r + previous column 1 r + next column 1 w
         tu_bytes = (2 + (2 if hm_on else 0)) * R * N
