@@ -21,6 +21,7 @@ struct cabm_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mark = nullptr;
     Dev S{};
+    bool native_edges_tried = false;
     std::vector<void *> allocs;
     DevPset *d_psets = nullptr; unsigned long long *d_beta = nullptr; int psets_cap = 0;
     int *d_scratch = nullptr;          // 4*N ints for peeks
@@ -126,8 +127,7 @@ extern "C" int cabm_create(cabm_handle **out, int device, int max_replicates, in
     DA(S.status, A); DA(S.expday, A); DA(S.texp, A); DA(S.entry, A); DA(S.dur, A); DA(S.sickfrom, A); DA(S.isovia, A);
     DA(S.latday, A); DA(S.tracestart, A); DA(S.traceend, A); DA(S.txpday, A); DA(S.ct_head, A);
     DA(S.mark_pre, W); DA(S.mark_post, W); DA(S.infmask, W); DA(S.ct_cnt, (size_t)h->R);
-    DA(S.touch_g, W); DA(S.dupm_g, W); DA(S.col_g, A); DA(S.ev_cnt, (size_t)h->R * 2);
-    if ((e = cudaMemset(S.touch_g, 0, W * 4)) != cudaSuccess || (e = cudaMemset(S.dupm_g, 0, W * 4)) != cudaSuccess) return bail(e, "memset");
+    DA(S.col_g, A); DA(S.ev_cnt, (size_t)h->R * 2);
     DA(S.grp_idx, A); DA(S.grp_off, (size_t)h->R * 8); DA(S.hits, A);
     if (h->N <= 65535) DA(S.grp16, A);
     DA(S.key, (size_t)h->R); DA(S.pset_of, (size_t)h->R); DA(S.err, (size_t)h->R); DA(S.totiso, (size_t)h->R);
@@ -352,7 +352,6 @@ static int reset_state(cabm_handle *h, bool curves_too = true) {
     h->poked = false;
     CU(cudaMemsetAsync(S.err, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totiso, 0, (size_t)S.R * 8, h->stream));
     CU(cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, h->stream)); CU(cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, h->stream));
-    CU(cudaMemsetAsync(S.touch_g, 0, W * 4, h->stream)); CU(cudaMemsetAsync(S.dupm_g, 0, W * 4, h->stream));
     CU(cudaMemsetAsync(S.ev_cnt, 0, (size_t)S.R * 8, h->stream));
     if (curves_too) { CU(cudaMemsetAsync(S.inc, 0, C * 4, h->stream)); CU(cudaMemsetAsync(S.prev, 0, C * 4, h->stream)); }
     CU(cudaMemsetAsync(S.infectors, 0, (size_t)S.R * 32, h->stream)); CU(cudaMemsetAsync(S.latsum, 0, (size_t)S.R * 8, h->stream));
@@ -378,7 +377,29 @@ static int need_event_list(cabm_handle *h) {
     return CABM_OK;
 }
 
+// native schedule: list of the day's events that hit a later infector (second-order budget count walks it instead of re-drawing every
+// event). Allocated on first use; without the memory for it the schedule falls back to three full sweeps.
+static void need_native_edges(cabm_handle *h) {
+    if (h->S.nat_edges || h->native_edges_tried) return;
+    h->native_edges_tried = true;
+    const char *off = getenv("CABM_NATIVE_EDGES");
+    if (off && off[0] == '0' && off[1] == 0) return;                 // CABM_NATIVE_EDGES=0: the three-sweep form (for comparison)
+    uint32_t *e = nullptr, *c = nullptr, *v = nullptr;
+    const size_t words = (size_t)h->R * h->Np * 3;
+    if (cudaMalloc((void **)&e, words * 4) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaMalloc((void **)&c, (size_t)h->R * 4) != cudaSuccess) { cudaGetLastError(); cudaFree(e); return; }
+    const char *ver = getenv("CABM_NATIVE_VERIFY");
+    if (ver && ver[0] == '1' && ver[1] == 0) {
+        const size_t vb = (size_t)h->R * h->Np / 2 * 4;
+        if (cudaMalloc((void **)&v, vb) == cudaSuccess) { cudaMemset(v, 0, vb); h->allocs.push_back(v); } else { cudaGetLastError(); v = nullptr; }
+    }
+    cudaMemset(h->S.hits, 0, (size_t)h->R * h->Np * 4);
+    h->allocs.push_back(e); h->allocs.push_back(c);
+    h->S.nat_edges = e; h->S.nat_ecnt = c; h->S.nat_verify = v;
+}
+
 static int do_dyntrans(cabm_handle *h, int day) {
+    if (h->mode == CABM_MODE_NATIVE) need_native_edges(h);
     if (h->mode == CABM_MODE_NATIVE) timed(h, CABM_K_DYNTRANS, [&] { return launch_dyntrans_native(h->S, day, h->stream); });
     else timed(h, CABM_K_DYNTRANS, [&] { return launch_dyntrans_exact(h->S, day, h->stream); });
     return CABM_OK;

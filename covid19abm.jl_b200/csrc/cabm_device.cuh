@@ -76,10 +76,11 @@ struct Dev {
     uint32_t *ct_log; uint32_t *ct_cnt;      // [R][ct_cap] words: chunks [next chunk, count, targets...] per (traced agent, day); [R] words used
     uint32_t *ident_list, *ident_cnt;        // [R][2][Np], [R][2]: agents whose identification day is today / tomorrow
     uint32_t *ev_list, *ev_cnt;              // [R][Np], [R][2]: agents with an event today (k_time_update_scan -> k_time_update_events), count by day parity
+    uint32_t *nat_edges, *nat_ecnt;          // native schedule: [R][Np][3] events of the day whose target is a later infector (x, j, k|g<<8|budget<<16|ag<<24), [R] their number
+    uint32_t *nat_verify;                    // test aid (CABM_NATIVE_VERIFY=1): the second-order counts recomputed by a full sweep, compared on the device
     uint32_t *grp_idx; int *grp_off;         // [R][Np], [R][8]
     uint16_t *grp16;                         // [R][Np] the same index tables as 16-bit words: the fused kernel's copy (popsize <= 65535)
     uint32_t *infmask;                       // [R][nwords]
-    uint32_t *touch_g, *dupm_g;              // [R][nwords] target marks of the fused kernel when its state lives in global memory
     uint8_t *col_g;                          // [R][Np] its current hmatrix column
     uint32_t *hits;                          // 2 x [R][Np/2] of 2 x u16: native mode, contacts received from lower-indexed infectors
     uint2 *key; int *pset_of; uint32_t *err; unsigned long long *totiso; int *totalmet, *totalinf;

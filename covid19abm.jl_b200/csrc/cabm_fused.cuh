@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
         if (GS) {           // this replicate's per-agent arrays (the host zeroed the bitmasks before the launch)
             const size_t rb_ = (size_t)r * Np, rw_ = (size_t)r * nwords;
             M.status = S.status + rb_; M.expday = S.expday + rb_; M.col = S.col_g + rb_; M.inf = S.infmask + rw_;
-            M.touch = S.touch_g + rw_; M.dupm = S.dupm_g + rw_; M.mpre = S.mark_pre + rw_; M.mpost = S.mark_post + rw_;
+            M.mpre = S.mark_pre + rw_; M.mpost = S.mark_post + rw_;     // (touch/dupm: the chunk's target table M.htab takes their place)
         }
         if (Z.kind == 2) {
             // -------------------------------------------------------- copy job: a finished replicate's curves -> pinned host memory

@@ -299,6 +299,8 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
     const int *off = S.grp_off + r * 8;
     const bool ct = P.ctstrat != 0;
     const uint32_t *mask = S.infmask + (size_t)r * S.nwords;
+    // second COUNT sweep: only for a replicate whose edge list overflowed (k_native_edges did the others), or into the verify buffer
+    if (COUNT && hits_in && S.nat_edges && S.nat_ecnt[r] <= (uint32_t)S.Np && hits_out != S.nat_verify) return;
     int met = 0, ninf = 0;
     // 64 mask words (2048 agents) per block, 8 per warp
     const int w_begin = blockIdx.x * 64 + wid * 8;
@@ -332,7 +334,17 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
                         const uint4 w = draw4<TP>(S, x, day, S_DT, ((uint32_t)g << 16) | (uint32_t)k, key);
                         j = S.grp_idx[rb + go + below(w.x, len)];                    // :807
                         if (COUNT) {
-                            if ((int)j > x && ((mask[j >> 5] >> (j & 31)) & 1u)) atomicAdd(&hits_out[(rb + j) >> 1], 1u << (16 * (j & 1)));
+                            if ((int)j > x && ((mask[j >> 5] >> (j & 31)) & 1u)) {
+                                atomicAdd(&hits_out[(rb + j) >> 1], 1u << (16 * (j & 1)));
+                                if (!hits_in && S.nat_edges) {                        // first sweep: remember the event for the second-order count
+                                    const uint32_t slot = atomicAdd(&S.nat_ecnt[r], 1u);
+                                    if (slot < (uint32_t)S.Np) {
+                                        uint32_t *rec = S.nat_edges + ((size_t)r * S.Np + slot) * 3;
+                                        rec[0] = (uint32_t)x; rec[1] = j;
+                                        rec[2] = (uint32_t)k | ((uint32_t)g << 8) | ((uint32_t)cnts << 16) | ((uint32_t)st_ag(sx) << 24);
+                                    }
+                                }
+                            }
                             continue;
                         }
                         uint32_t old = __ldcg(&S.status[rb + j]);
@@ -379,6 +391,47 @@ __global__ void __launch_bounds__(256) k_dyntrans_native(Dev S, int day, const u
     }
     for (int o = 16; o; o >>= 1) { met += __shfl_xor_sync(FULL, met, o); ninf += __shfl_xor_sync(FULL, ninf, o); }
     if (!COUNT && lane == 0 && (met | ninf)) { atomicAdd(&S.totalmet[r], met); atomicAdd(&S.totalinf[r], ninf); }
+}
+
+// Second-order count of the native schedule from the first sweep's edge list: the event (g, k) of infector x still exists under
+// x's corrected budget iff k < round(cm[ag][g] * (budget - hits0[x])) (:804 is monotone in the budget, and the event's draws are
+// keyed by (x, day, g, k), so it meets the same target). One thread per edge instead of a second sweep over every event.
+__global__ void __launch_bounds__(256) k_native_edges(Dev S, const uint32_t *h0, uint32_t *h1) {
+    const int r = blockIdx.y;
+    const uint32_t n = S.nat_ecnt[r];
+    if (n > (uint32_t)S.Np) return;                                   // overflowed: the full sweep counts this replicate
+    const size_t rb = (size_t)r * S.Np;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint32_t *rec = S.nat_edges + (rb + e) * 3;
+        const uint32_t x = rec[0], j = rec[1], w = rec[2];
+        const int k = (int)(w & 0xFFu), g = (int)((w >> 8) & 7u), cnts = (int)((w >> 16) & 0xFFu), ag = (int)((w >> 24) & 7u);
+        const int c2 = max(0, cnts - (int)((h0[(rb + x) >> 1] >> (16 * (x & 1))) & 0xFFFFu));
+        if (c2 == 0) continue;
+        const unsigned long long gp = __ldg(&S.gpw[ag * 256 + c2]);
+        if (k < (int)((gp >> (8 * g)) & 0xFF)) atomicAdd(&h1[(rb + j) >> 1], 1u << (16 * (j & 1)));
+    }
+}
+// end of the day's dyntrans: the hit counters go back to zero — only the words the edges touched (all of the replicate's after an overflow)
+__global__ void __launch_bounds__(256) k_native_clean(Dev S, uint32_t *h0, uint32_t *h1) {
+    const int r = blockIdx.y;
+    const uint32_t n = S.nat_ecnt[r];
+    const size_t rb = (size_t)r * S.Np;
+    if (n > (uint32_t)S.Np) {
+        for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < (size_t)S.Np / 2; k += (size_t)gridDim.x * blockDim.x) { h0[rb / 2 + k] = 0; h1[rb / 2 + k] = 0; }
+        return;
+    }
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint32_t j = S.nat_edges[(rb + e) * 3 + 1];
+        h0[(rb + j) >> 1] = 0; h1[(rb + j) >> 1] = 0;
+    }
+}
+// test aid: the edge-list count must equal the full second sweep's
+__global__ void __launch_bounds__(256) k_native_verify(Dev S, const uint32_t *h1) {
+    const size_t n = (size_t)S.R * S.Np / 2;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        if (h1[k] != S.nat_verify[k]) atomicOr(&S.err[(2 * k) / S.Np], ERR_INTERNAL);
+        S.nat_verify[k] = 0;
+    }
 }
 
 // ============================================================================ contact tracing, pass A
@@ -815,21 +868,30 @@ int launch_dyntrans_exact(const Dev &S, int day, cudaStream_t s) {
 }
 int launch_dyntrans_native(const Dev &S, int day, cudaStream_t s) {
     cudaMemsetAsync(S.totalmet, 0, (size_t)S.R * 4, s); cudaMemsetAsync(S.totalinf, 0, (size_t)S.R * 4, s);
-    // two fixed-point sweeps for the budgets (first and second order in the infectious fraction), then the CAS pass
+    // two fixed-point counts for the budgets (first and second order in the infectious fraction), then the CAS pass. The first is a
+    // sweep over every event, which also lists the events that hit a later infector; the second only walks that list.
     const size_t half = (size_t)S.R * S.Np / 2;
     uint32_t *h0 = S.hits, *h1 = S.hits + half;
-    cudaMemsetAsync(S.hits, 0, half * 8, s);
+    int n = 3;
+    if (!S.nat_edges || day == 1) cudaMemsetAsync(S.hits, 0, half * 8, s);       // (with the edge list the counters are cleared by k_native_clean)
+    if (S.nat_edges) cudaMemsetAsync(S.nat_ecnt, 0, (size_t)S.R * 4, s);
     const dim3 grid((unsigned)((S.nwords + 63) / 64), (unsigned)S.R);
-    if (S.tape_n) {
-        k_dyntrans_native<true, true><<<grid, 256, 0, s>>>(S, day, nullptr, h0);
-        k_dyntrans_native<true, true><<<grid, 256, 0, s>>>(S, day, h0, h1);
-        k_dyntrans_native<false, true><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
-    } else {
-        k_dyntrans_native<true, false><<<grid, 256, 0, s>>>(S, day, nullptr, h0);
-        k_dyntrans_native<true, false><<<grid, 256, 0, s>>>(S, day, h0, h1);
-        k_dyntrans_native<false, false><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
+    unsigned eb = (unsigned)(S.N / 8192); if (eb < 1) eb = 1; if (eb > 32) eb = 32;
+    const dim3 egrid(eb, (unsigned)S.R);
+    if (S.tape_n) k_dyntrans_native<true, true><<<grid, 256, 0, s>>>(S, day, nullptr, h0);
+    else k_dyntrans_native<true, false><<<grid, 256, 0, s>>>(S, day, nullptr, h0);
+    if (S.nat_edges) { k_native_edges<<<egrid, 256, 0, s>>>(S, h0, h1); ++n; }
+    if (S.tape_n) k_dyntrans_native<true, true><<<grid, 256, 0, s>>>(S, day, h0, h1);            // returns at once unless the list overflowed
+    else k_dyntrans_native<true, false><<<grid, 256, 0, s>>>(S, day, h0, h1);
+    if (S.nat_edges && S.nat_verify) {
+        if (S.tape_n) k_dyntrans_native<true, true><<<grid, 256, 0, s>>>(S, day, h0, S.nat_verify);
+        else k_dyntrans_native<true, false><<<grid, 256, 0, s>>>(S, day, h0, S.nat_verify);
+        k_native_verify<<<1024, 256, 0, s>>>(S, h1); n += 2;
     }
-    return 3;
+    if (S.tape_n) k_dyntrans_native<false, true><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
+    else k_dyntrans_native<false, false><<<grid, 256, 0, s>>>(S, day, h1, nullptr);
+    if (S.nat_edges) { k_native_clean<<<egrid, 256, 0, s>>>(S, h0, h1); ++n; }
+    return n;
 }
 int launch_ct_identify(const Dev &S, int day, bool scan, cudaStream_t s) {
     int n = 1;

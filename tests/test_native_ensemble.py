@@ -124,3 +124,29 @@ def test_native_vs_exact_at_100k_agents(cv):
     ia, ib = a["prev"][:, 0, :, 9].max(axis=1).astype(np.float64), b["prev"][:, 0, :, 9].max(axis=1).astype(np.float64)
     assert stats.ks_2samp(ia, ib).pvalue > 0.01
     assert (b["prev"][:, 0].sum(axis=2) == Nl).all()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(β=0.0345, prov="ontario", initialinf=5, modeltime=200, fmild=0.5, τmild=1, fsevere=1.0, fpreiso=0.3),
+    dict(β=0.06, prov="ontario", initialinf=1, modeltime=200, ctstrat=1, fctcapture=0.5, fcontactst=0.5, cdaysback=3),
+    dict(β=0.8, prov="newyork", popsize=2048, initialinf=600, modeltime=40),          # most agents infectious: the edge list overflows
+    dict(β=0.0345, prov="ontario", popsize=200000, initialinf=50, modeltime=150),
+], ids=["B", "tracing", "overflow", "200k"])
+def test_native_edge_list_count_equals_the_full_second_sweep(cv, monkeypatch, kw):
+    """The second-order budget count of the native schedule walks the list of the first sweep's events that hit a later infector.
+    With CABM_NATIVE_VERIFY=1 the library also recomputes it by the full second sweep and compares on the device, every day
+    (a difference raises ERR_INTERNAL for the replicate)."""
+    monkeypatch.setenv("CABM_NATIVE_VERIFY", "1")
+    ip = cv.ModelParameters(**kw)
+    R = 8 if ip.popsize > 50000 else 64
+    res = cv.run_ensemble(ip, R, mode=cv.MODE_NATIVE, strict=False)
+    assert res["path"] == "multikernel"
+    assert (res["err"] == 0).all(), res["err"]
+    attack = 1 - res["prev"][:, 0, -1, 0] / ip.popsize
+    assert attack.max() > 0.05                                                        # the check saw real epidemics
+    monkeypatch.setenv("CABM_NATIVE_VERIFY", "0")
+    monkeypatch.setenv("CABM_NATIVE_EDGES", "0")                                      # three full sweeps: the same distribution of outcomes
+    res3 = cv.run_ensemble(ip, R, mode=cv.MODE_NATIVE, strict=False)
+    assert (res3["err"] == 0).all()
+    a3 = 1 - res3["prev"][:, 0, -1, 0] / ip.popsize
+    assert abs(attack.mean() - a3.mean()) < 4 * np.sqrt((attack.var() + a3.var()) / R) + 1e-3
