@@ -74,7 +74,7 @@ struct FusedCtl {
     int nedge;                               // DAG edges of the chunk
     int wdup[FUSED_NT / 32];
     uint32_t logn, qcnt[2];                  // contact tracing (:647-752): the replicate's log fill, index-case queues by day parity
-    unsigned evn;                            // global-state variant: agents with an event today, listed by the scan
+    unsigned evn;                            // agents with an event today, listed by the time_update scan
     int pad_[3];
 };
 static_assert(sizeof(FusedCtl) % 16 == 0, "the arrays behind FusedCtl need 16-byte alignment");
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
         // s_nextfire = earliest expiry day of any agent. A day with nobody infectious and nothing expiring changes no
         // state: it only repeats the column and the prevalence row, without a single barrier.
         if (tid < 2) Z.nf[tid] = 32767;
-        if (GS && tid == 0) Z.evn = 0;
+        if (tid == 0) Z.evn = 0;
         int nextfire = resumed ? __ldcg(&S.resume_aux[r * 2]) : 0, act = 0;    // uniform registers
         const int day_first = resumed ? split_day + 1 : 1;
         const int day_last = (!resumed && split_day > 0 && split_day < T) ? split_day : T;
@@ -1100,78 +1100,26 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                         if (tid == 0) Z.qcnt[day & 1] = 0;
                     }
                 }
-                // every thread looks at FUSED_SCAN_U chunks of 8 expiry days at once (independent loads and compares), then handles
-                // the few agents that have an event today (:405, marks) one after another
+                // every thread looks at U chunks of 8 next-event days at once (independent 128-bit loads, packed 16-bit minima)
                 PHASE(27);
                 uint32_t mn = 0x7FFF7FFFu;                                     // running min of the event days that stay (2 x i16)
-                if constexpr (GS) {
-                    // State in global memory (large populations): an event inside the stream would stall its whole warp on one lane's
-                    // dependent L2 round trips, several times per pass. So the scan only LISTS the agents with an event today (event day
-                    // reached, or marked by pass A) and keeps the minimum of the event days that stay; the listed agents are then taken one
-                    // per thread in dense warps.
-                    constexpr int U = 8;
-                    uint32_t *const evl = S.ev_list + (size_t)r * Np;
+                {
+                    // The scan only LISTS the agents with an event today (event day reached, or marked by pass A) and keeps the minimum
+                    // of the event days that stay; the listed agents are then taken one per thread in dense warps. (Handled inside the
+                    // stream, a lane's event stalls its whole warp for the length of the event's dependent chain — several times per pass
+                    // when the state is in global memory, and once per event a lane holds on a heavy day in shared memory.)
+                    constexpr int U = GS ? 8 : FUSED_SCAN_U;
+                    uint32_t *const evl = GS ? S.ev_list + (size_t)r * Np : M.evy;          // (the event buffer is free between dyntrans and the next chunk build)
+                    const unsigned ecap = GS ? (unsigned)Np : (unsigned)FUSED_EVCAP;        // shared memory: what does not fit is handled in place
                     const uint32_t dd = (uint32_t)day * 0x10001u;
-                    for (int bb = 0; bb < N; bb += NT * 8 * U) {             // (the same number of passes for every thread: the append is a warp collective)
-                        const int b0 = bb + tid * 8;
-                        uint4 ex[U];
-                        unsigned long long fire = 0, pre = 0, post = 0;        // 8 bits per chunk
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const int i0 = b0 + u * NT * 8;
-                            ex[u] = i0 < N ? *reinterpret_cast<const uint4 *>(M.expday + i0) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
-                            if (i0 + NT * 8 * U < N) prefetch_l2(M.expday + i0 + NT * 8 * U);      // the next pass of this thread
-                            if (ctr && i0 < N) {
-                                const unsigned sh = i0 & 31;
-                                pre |= (unsigned long long)((M.mpre[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
-                                post |= (unsigned long long)((M.mpost[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            uint32_t wds[4] = {ex[u].x, ex[u].y, ex[u].z, ex[u].w};
-                            const unsigned mk = (unsigned)((pre | post) >> (8 * u)) & 0xFFu;
-                            unsigned f = 0;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                uint32_t m = __vcmples2(wds[k], dd);                              // 0xFFFF per half whose day has come
-                                f |= ((m & 1u) | ((m >> 15) & 2u)) << (2 * k);
-                                m |= ((mk >> (2 * k)) & 1u ? 0xFFFFu : 0u) | ((mk >> (2 * k + 1)) & 1u ? 0xFFFF0000u : 0u);
-                                mn = __vmins2(mn, (wds[k] & ~m) | (0x7FFF7FFFu & m));             // listed agents report their new event day below
-                            }
-                            fire |= (unsigned long long)f << (8 * u);
-                        }
-                        fire |= pre | post;
-                        // append: exclusive prefix of the counts over the warp, one atomicAdd per warp
-                        const int c = __popcll(fire);
-                        if (__any_sync(FULL, c != 0)) {
-                            int incl = c;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                            unsigned base = 0;
-                            if (lane == 31) base = atomicAdd(&Z.evn, (unsigned)incl);
-                            base = __shfl_sync(FULL, base, 31) + (unsigned)(incl - c);
-                            while (fire) {
-                                const int bit = __ffsll((long long)fire) - 1; fire &= fire - 1;
-                                const int i = b0 + (bit >> 3) * NT * 8 + (bit & 7);
-                                evl[base++] = (uint32_t)i | ((uint32_t)((pre >> bit) & 1u) << 30) | ((uint32_t)((post >> bit) & 1u) << 31);
-                            }
-                        }
-                    }
-                    __syncthreads();                                           // the list is complete
-                    const unsigned nev = Z.evn;
                     int mne = 32767;
-                    for (unsigned k = tid; k < nev; k += NT) {
-                        const uint32_t ent = evl[k];
-                        const int i = (int)(ent & 0x3FFFFFFFu);
-                        if (i >= N) continue;                                  // padding of the last block of eight
-                        const unsigned pb = (ent >> 30) & 1u, qb = ent >> 31;
+                    auto do_event = [&](int i, unsigned pb, unsigned qb) {
                         if (ctr) {
                             if (pb) atomicAnd(&M.mpre[i >> 5], ~(1u << (i & 31)));
                             if (qb) atomicAnd(&M.mpost[i >> 5], ~(1u << (i & 31)));
                         }
                         const uint32_t st = M.status[i];
-                        const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];
+                        const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];      // without tracing the scan key is the expiry day
                         const int par = (day + 1) & 1;
 #ifdef CABM_FUSED_DIAG
                         const long long t_e0 = clock64();
@@ -1193,84 +1141,74 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                 atomicAdd(&Z.ninf, is_infectious(e.newh) ? 1 : -1);
                             }
                         }
-                    }
-                    mn = __vmins2(mn, (uint32_t)(mne & 0xFFFF) | 0x7FFF0000u);
-                } else {
-                for (int b0 = tid * 8; b0 < N; b0 += NT * 8 * FUSED_SCAN_U) {
-                    uint4 ex[FUSED_SCAN_U];
-                    unsigned long long fire = 0, pre = 0, post = 0;            // 8 bits per chunk
+                    };
+                    for (int bb = 0; bb < N; bb += NT * 8 * U) {             // (the same number of passes for every thread: the append is a warp collective)
+                        const int b0 = bb + tid * 8;
+                        uint4 ex[U];
+                        unsigned long long fire = 0, pre = 0, post = 0;        // 8 bits per chunk
 #pragma unroll
-                    for (int u = 0; u < FUSED_SCAN_U; ++u) {
-                        const int i0 = b0 + u * NT * 8;
-                        ex[u] = i0 < N ? *reinterpret_cast<const uint4 *>(M.expday + i0) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
-                        if (ctr && i0 < N) {
-                            const unsigned sh = i0 & 31;
-                            pre |= (unsigned long long)((M.mpre[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
-                            post |= (unsigned long long)((M.mpost[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
+                        for (int u = 0; u < U; ++u) {
+                            const int i0 = b0 + u * NT * 8;
+                            ex[u] = i0 < N ? *reinterpret_cast<const uint4 *>(M.expday + i0) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
+                            if (GS && i0 + NT * 8 * U < N) prefetch_l2(M.expday + i0 + NT * 8 * U);      // the next pass of this thread
+                            if (ctr && i0 < N) {
+                                const unsigned sh = i0 & 31;
+                                pre |= (unsigned long long)((M.mpre[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
+                                post |= (unsigned long long)((M.mpost[i0 >> 5] >> sh) & 0xFFu) << (8 * u);
+                            }
                         }
-                    }
-                    // earliest event day of these chunks with packed 16-bit minima (DPX VIMNMX: one instruction per pair of words); the
-                    // per-agent compares are only needed when somebody is due
-                    uint32_t cmin = 0x7FFF7FFFu;
+                        // earliest event day of these chunks with packed 16-bit minima (DPX VIMNMX: one instruction per pair of words); the
+                        // per-agent compares are only needed when somebody is due
+                        uint32_t cmin = 0x7FFF7FFFu;
 #pragma unroll
-                    for (int u = 0; u < FUSED_SCAN_U; ++u) cmin = __vimin3_s16x2(cmin, __vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w));
-                    if (min((int)(short)(cmin & 0xFFFFu), (int)(short)(cmin >> 16)) <= day || (pre | post) != 0) {   // somebody in these chunks has an event today
+                        for (int u = 0; u < U; ++u) cmin = __vimin3_s16x2(cmin, __vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w));
+                        if (min((int)(short)(cmin & 0xFFFFu), (int)(short)(cmin >> 16)) <= day || (pre | post) != 0) {
 #pragma unroll
-                        for (int u = 0; u < FUSED_SCAN_U; ++u) {               // per-agent compares only in chunks that hold a due day
-                            const uint32_t cu = __vmins2(__vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w));
-                            if (min((int)(short)(cu & 0xFFFFu), (int)(short)(cu >> 16)) <= day) {
-                                const uint32_t wds[4] = {ex[u].x, ex[u].y, ex[u].z, ex[u].w};
+                            for (int u = 0; u < U; ++u) {
+                                uint32_t wds[4] = {ex[u].x, ex[u].y, ex[u].z, ex[u].w};
+                                const unsigned mk = (unsigned)((pre | post) >> (8 * u)) & 0xFFu;
                                 unsigned f = 0;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    f |= ((unsigned)((int)(short)(wds[k] & 0xFFFFu) <= day) << (2 * k)) | ((unsigned)((int)(short)(wds[k] >> 16) <= day) << (2 * k + 1));
+                                for (int k = 0; k < 4; ++k) {
+                                    uint32_t m = __vcmples2(wds[k], dd);                              // 0xFFFF per half whose day has come
+                                    f |= ((m & 1u) | ((m >> 15) & 2u)) << (2 * k);
+                                    m |= ((mk >> (2 * k)) & 1u ? 0xFFFFu : 0u) | ((mk >> (2 * k + 1)) & 1u ? 0xFFFF0000u : 0u);
+                                    mn = __vmins2(mn, (wds[k] & ~m) | (0x7FFF7FFFu & m));             // listed agents report their new event day below
+                                }
                                 fire |= (unsigned long long)f << (8 * u);
                             }
+                            fire |= pre | post;
+                        } else {
+                            mn = __vmins2(mn, cmin);
                         }
-                        fire |= pre | post;
-                        while (fire) {
-                            const int bit = __ffsll((long long)fire) - 1; fire &= fire - 1;
-                            const int i = b0 + (bit >> 3) * NT * 8 + (bit & 7);
-                            if (i >= N) continue;
-                            const unsigned pb = (unsigned)(pre >> bit) & 1u, qb = (unsigned)(post >> bit) & 1u;
-                            if (ctr) {
-                                if (pb) atomicAnd(&M.mpre[i >> 5], ~(1u << (i & 31)));
-                                if (qb) atomicAnd(&M.mpost[i >> 5], ~(1u << (i & 31)));
-                            }
-                            const uint32_t st = M.status[i];
-                            const int texp = ctr ? (int)S.texp[rb + i] : (int)M.expday[i];      // without tracing the scan key is the expiry day
-                            const int par = (day + 1) & 1;
-#ifdef CABM_FUSED_DIAG
-                            const long long t_e0 = clock64();
-#endif
-                            const Ev e = agent_event_core(S, P, r, i, day, key, st, texp, ctr, pb, qb,
-                                                          &Z.qcnt[par], S.ident_list ? S.ident_list + ((size_t)r * 2 + par) * Np : nullptr, M.dcache);
-#ifdef CABM_FUSED_DIAG
-                            if (e.st != 0xFFFFFFFFu) { atomicAdd((unsigned long long *)&t_ph[28], (unsigned long long)(clock64() - t_e0)); atomicAdd((unsigned long long *)&t_ph[29], 1ull); }
-#endif
-                            M.status[i] = e.st;
-                            M.expday[i] = (int16_t)e.ne;
-                            if (ctr && e.texp != texp) S.texp[rb + i] = (int16_t)e.texp;
-                            if (e.newh != e.oldh) {
-                                M.col[i] = (uint8_t)e.newh;
-                                atomicAdd(&Z.io[act & 1][0][st_ag(st) * 12 + e.newh], 1); atomicAdd(&Z.io[act & 1][1][st_ag(st) * 12 + e.oldh], 1);
-                                if (is_infectious(e.newh) != is_infectious(e.oldh)) {
-                                    atomicXor(&M.inf[i >> 5], 1u << (i & 31));
-                                    atomicAdd(&Z.ninf, is_infectious(e.newh) ? 1 : -1);
-                                }
+                        if (fire && b0 + (U - 1) * NT * 8 + 8 > N) {           // the last block of eight may run past the population: drop the padding
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int nv = N - (b0 + u * NT * 8);
+                                if (nv < 8) fire &= ~((nv <= 0 ? 0xFFull : ((0xFFull << nv) & 0xFFull)) << (8 * u));
                             }
                         }
-#pragma unroll
-                        for (int u = 0; u < FUSED_SCAN_U; ++u) {               // with the new expiry days
-                            const int i0 = b0 + u * NT * 8;
-                            if (i0 < N) ex[u] = *reinterpret_cast<const uint4 *>(M.expday + i0);
+                        // append (a thread with listed agents reserves its slots with one shared-memory atomic)
+                        if (fire) {
+                            unsigned base = atomicAdd(&Z.evn, (unsigned)__popcll(fire));
+                            while (fire) {
+                                const int bit = __ffsll((long long)fire) - 1; fire &= fire - 1;
+                                const int i = b0 + (bit >> 3) * NT * 8 + (bit & 7);
+                                const unsigned pb = (unsigned)(pre >> bit) & 1u, qb = (unsigned)(post >> bit) & 1u;
+                                if (base < ecap) evl[base++] = (uint32_t)i | (pb << 30) | (qb << 31);
+                                else do_event(i, pb, qb);                      // (list full: a day with thousands of events in shared-memory mode)
+                            }
                         }
-                        cmin = 0x7FFF7FFFu;
-#pragma unroll
-                        for (int u = 0; u < FUSED_SCAN_U; ++u) cmin = __vimin3_s16x2(cmin, __vmins2(ex[u].x, ex[u].y), __vmins2(ex[u].z, ex[u].w));
                     }
-                    mn = __vmins2(mn, cmin);
-                }
+                    __syncthreads();                                           // the list is complete
+                    const unsigned nev = min(Z.evn, ecap);
+                    // listed event k goes to warp k mod 8, lane k / 8: a few dozen events of different kinds (different branches of the
+                    // state machine) spread over all warps instead of serialising in one
+                    for (unsigned k = (unsigned)(wid + NW * lane); k < nev; k += NT) {
+                        const uint32_t ent = evl[k];
+                        do_event((int)(ent & 0x3FFFFFFFu), (ent >> 30) & 1u, ent >> 31);
+                    }
+                    mn = __vmins2(mn, (uint32_t)(mne & 0xFFFF) | 0x7FFF0000u);
                 }
                 PHASE(25);
                 {
@@ -1282,7 +1220,7 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                 PHASE(26);
                 __syncthreads();                                               // S2
                 nextfire = Z.nf[act & 1]; ++act;
-                if (GS && tid == 0) Z.evn = 0;                                 // every thread has read the count (before S2); the next append is behind a barrier
+                if (tid == 0) Z.evn = 0;                                 // every thread has read the count (before S2); the next append is behind a barrier
                 PHASE(4);
             }
             // -------------------------------------------------------- column st+1 (:136 of the next day) and its curves
