@@ -1200,7 +1200,9 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                             }
                         }
                     }
+                    PHASE(30);
                     __syncthreads();                                           // the list is complete
+                    PHASE(31);
                     const unsigned nev = min(Z.evn, ecap);
                     // listed event k goes to warp k mod 8, lane k / 8: a few dozen events of different kinds (different branches of the
                     // state machine) spread over all warps instead of serialising in one

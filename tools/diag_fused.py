@@ -32,7 +32,7 @@ dbg = np.zeros((R, 32), np.int64); pop._chk(pop.L.cabm_get_debug(pop.h, dbg.ctyp
 names = {22: "setup: initialize", 23: "setup: get_ag_dist", 24: "setup: insert_infected", 0: "setup: column 1 / resume reload", 1: "list",
          8: "chunk: budgets + prefix -> C1", 9: "chunk: event generation (rest)", 2: "  gen: owners", 3: "  gen: draws (philox)", 7: "  gen: grp + status loads", 20: "  gen: fresh budgets", 21: "  gen: marks/edges", 10: "chunk: C2 wait + DAG", 11: "chunk: apply singles + count shared",
          13: "chunk: C3 + compaction", 14: "chunk: C4 + resolve shared", 15: "chunk: C5 + link/clear", 12: "dyntrans end -> S1",
-         27: "time_update: S1 -> scan start (nf reset, pass A)", 25: "time_update: own scan + events", 26: "time_update: min-reduce", 4: "time_update: S2 wait", 5: "curves/idle", 6: "writeback",
+         27: "time_update: S1 -> scan start (nf reset, pass A)", 30: "time_update: scan + list", 31: "time_update: list barrier", 25: "time_update: listed events", 26: "time_update: min-reduce", 4: "time_update: S2 wait", 5: "curves/idle", 6: "writeback",
          28: "(sum over threads) cycles inside agent_event_core", 29: "(count) time_update events", 16: "(count) events", 17: "(count) shared-target events", 18: "(count) DAG edges", 19: "(count) DAG sweeps"}
 big = attack > 0.1
 print("phase kcycles  take-off mean | extinct mean | per chunk (take-off)")
