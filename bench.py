@@ -432,7 +432,9 @@ def main():
         roofline["launch_ms_alone"] = round(ms / n, 3)
         roofline["achieved_in_timed_region"] = round(alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9, 1)
         roofline["frac_in_timed_region"] = round(alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9 / peak, 4)
-        if pop.last_path == "fused-global":
+        if pop.last_path == "fused-global" and R * N * 12 <= 126e6:
+            roofline["bound_note"] += "; state in global memory but L2-resident at this size (%.0f MB of per-agent words): SURVEY 8(d)'s HBM yardstick applies only above L2 capacity" % (R * N * 12 / 1e6)
+        if pop.last_path == "fused-global" and R * N * 12 > 126e6:
             # state in global memory (large populations): here the per-agent fields do live in HBM, so the yardstick is SURVEY 8(d)'s own
             # figure, 14 B per agent-day (25 B with contact tracing) at the reference's field widths, over one launch
             per_ad = 25 if any(kw.get("ctstrat", 0) for kw in W["psets"]) else 14
