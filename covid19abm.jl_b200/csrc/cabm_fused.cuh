@@ -1188,9 +1188,21 @@ __global__ void __launch_bounds__(FUSED_NT, GS ? 1 : 2) k_sim_fused(Dev S, unsig
                                 if (nv < 8) fire &= ~((nv <= 0 ? 0xFFull : ((0xFFull << nv) & 0xFFull)) << (8 * u));
                             }
                         }
-                        // append (a thread with listed agents reserves its slots with one shared-memory atomic)
+                        // append. Shared-memory variant: a thread with listed agents reserves its slots with one atomic (a few dozen a day).
+                        // Global-state variant (thousands a day): one atomic per warp, slots by a prefix over the lanes.
+                        unsigned wbase = 0;
+                        if constexpr (GS) {
+                            const int wc = __popcll(fire);
+                            if (__any_sync(FULL, wc != 0)) {
+                                int wincl = wc;
+#pragma unroll
+                                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, wincl, o); if (lane >= o) wincl += v; }
+                                if (lane == 31) wbase = atomicAdd(&Z.evn, (unsigned)wincl);
+                                wbase = __shfl_sync(FULL, wbase, 31) + (unsigned)(wincl - wc);
+                            }
+                        }
                         if (fire) {
-                            unsigned base = atomicAdd(&Z.evn, (unsigned)__popcll(fire));
+                            unsigned base = GS ? wbase : atomicAdd(&Z.evn, (unsigned)__popcll(fire));
                             while (fire) {
                                 const int bit = __ffsll((long long)fire) - 1; fire &= fire - 1;
                                 const int i = b0 + (bit >> 3) * NT * 8 + (bit & 7);
