@@ -17,8 +17,9 @@
 // dyntrans keeps the reference's sequential semantics (:797-832) without walking the infectors one after another. A day's
 // infectious agents are listed in ascending index order and taken in CHUNKS of up to 256 infectors / FUSED_EVCAP contact events;
 // inside a chunk everything is parallel:
-//   * every potential event (infector x, age group g, slot k) of the chunk is drawn at once (:807) — targets, transmission
-//     draws, and the targets' lazy contact budgets (written into their status words: tag = today);
+//   * every potential event (infector x, age group g, slot k) of the chunk is drawn at once (:807) — targets and transmission
+//     draws; a target's status word counts the day's contacts (tag = today) from the first event applied to it, and its own
+//     lazy contact budget is drawn only when an outcome depends on it;
 //   * the only order dependence BETWEEN infectors is x's own budget (:802), which earlier infectors reduce when they contact x
 //     (:813). Such events (target infectious, later in the same chunk) are rare; they are collected as the edges of a DAG and
 //     resolved by relaxation: hits on x -> smaller budget -> fewer events of x (the reduced budget's events are a subset of the
@@ -34,8 +35,14 @@
 //                 copy jobs (curves -> pinned host memory, a few "copier" CTAs), fill jobs (idle tails of curves and state matrix)
 //   per replicate initialize :171-188 -> get_ag_dist :339-343 -> insert_infected :360-395 -> column 1 -> day loop -> write-back
 //   per active day infector list -> chunks { budgets + prefix | C1 | events | C2 | [DAG sweeps] | apply singles, count shared | C3 |
-//                 compact shared | C4 | resolve shared | C5 } -> time_update scan + events | S2 -> curves row + TMA store of the column
+//                 compact shared | C4 | resolve shared | C5 } -> [pass A of contact tracing] -> time_update: scan lists the agents with
+//                 an event | barrier | listed events, dense | S2 -> curves row + TMA store of the column
 //   idle days     (nobody infectious, nothing due) repeat column and prevalence row; an idle tail is filled in one go
+//
+// Template GS ("global state", any population size): the same algorithm with status/expday/column/bitmasks left in global memory.
+// Every per-agent access is then an L2/HBM round trip, so that variant keeps eight event windows in flight per warp, finds the
+// targets a chunk hits more than once in a shared-memory table of the chunk's targets (M.htab) instead of population-wide bitmasks,
+// and touches a target's status word once per event.
 #pragma once
 #include <cstdlib>
 #include <mutex>
