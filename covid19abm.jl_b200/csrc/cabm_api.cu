@@ -391,9 +391,9 @@ static void need_native_edges(cabm_handle *h) {
     const char *ver = getenv("CABM_NATIVE_VERIFY");
     if (ver && ver[0] == '1' && ver[1] == 0) {
         const size_t vb = (size_t)h->R * h->Np / 2 * 4;
-        if (cudaMalloc((void **)&v, vb) == cudaSuccess) { cudaMemset(v, 0, vb); h->allocs.push_back(v); } else { cudaGetLastError(); v = nullptr; }
+        if (cudaMalloc((void **)&v, vb) == cudaSuccess) { cudaMemsetAsync(v, 0, vb, h->stream); h->allocs.push_back(v); } else { cudaGetLastError(); v = nullptr; }
     }
-    cudaMemset(h->S.hits, 0, (size_t)h->R * h->Np * 4);
+    cudaMemsetAsync(h->S.hits, 0, (size_t)h->R * h->Np * 4, h->stream);     // from here on k_native_clean keeps the counters at zero between days
     h->allocs.push_back(e); h->allocs.push_back(c);
     h->S.nat_edges = e; h->S.nat_ecnt = c; h->S.nat_verify = v;
 }
