@@ -137,9 +137,6 @@ template <class MT> __device__ __forceinline__ int fresh_budget_s(const MT &M, u
     while (k < len && thr[k] <= w) ++k;
     return k;
 }
-template <class MT> __device__ __forceinline__ int budget_of_s(const MT &M, uint2 key, uint32_t i, int day, uint32_t st) {
-    return st_tag(st) == day ? st_rem(st) : fresh_budget_s(M, key, i, (uint32_t)day, st);
-}
 
 // gpw = Int.(round.(cm[ag]*cnts)) :804 (half-to-even) packed as five bytes; cm row in shared memory
 __device__ __forceinline__ unsigned long long gpw_pack(const double *cm_row, int cnts) {
