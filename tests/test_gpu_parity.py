@@ -477,3 +477,22 @@ def test_long_contact_sets_are_identified_the_same_way_every_run(cv, O):
             assert (got["totalisolated"] == ref["totalisolated"]).all(), (it, path)
             assert (got["hmatrix"] == ref["hmatrix"]).all(), (it, path)
             assert (got["inc"] == ref["inc"]).all() and (got["prev"] == ref["prev"]).all(), (it, path)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(β=0.8, prov="newyork", popsize=4097, modeltime=59, initialinf=10, ctstrat=1, fctcapture=0.7, fcontactst=0.2, cdaysback=5),
+    dict(β=0.3, prov="ontario", popsize=6000, modeltime=80, initialinf=16, ctstrat=3, strat3qdays=7, fctcapture=1.0, fcontactst=0.7, cdaysback=7),
+    dict(β=0.1, prov="quebec", popsize=12345, modeltime=70, initialinf=12, initialhi=50, fmild=0.3, τmild=2, fsevere=0.6, fpreiso=0.3),
+], ids=["ct1-dense", "ct3-long-sets", "no-tracing"])
+def test_repeated_runs_are_identical(cv, kw):
+    """Poor man's race detector (compute-sanitizer is not available on the test boxes): the same ensemble five times per path — every
+    byte of the state matrices, the curves and the tracing counter must repeat. (Cross-warp hazards show up as run-to-run differences
+    on heavy days; the comparison with the oracle is in the tests above.)"""
+    ip = cv.ModelParameters(**kw)
+    seeds = [991 * (i + 3) for i in range(6)]
+    for path in ("fused", "fused-global", "multikernel"):
+        first = cv.run_ensemble(ip, 6, seeds=seeds, want_hmatrix=True, path=path)
+        for it in range(4):
+            again = cv.run_ensemble(ip, 6, seeds=seeds, want_hmatrix=True, path=path)
+            for k in ("hmatrix", "inc", "prev", "totalisolated", "infectors"):
+                assert (again[k] == first[k]).all(), (path, it, k)
